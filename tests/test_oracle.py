@@ -1,0 +1,124 @@
+"""CPU tests: the oracle restatement against the golden vectors produced by running the
+unmodified reference (oracle/make_golden.py).  This is the pin for every parity claim."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import (attn_forward, attn_backward, func_attention, words_similarity, ce_tail,
+                    words_loss, words_loss_backward, synth_attention_inputs, synth_words_loss_inputs,
+                    normalised_max_err)
+from tests.cases import ATTN_CASES, WL_CASES, SUBSAMPLE, F64_SKIP
+
+DT = {"f32": torch.float32, "f64": torch.float64}
+# fp64: restatement must equal the reference to rounding; fp32: both are fp32 evaluations
+# with different summation orders, so agreement is at fp32 rounding level (SURVEY §8 parity note).
+TOL = {"f64": 1e-12, "f32": 2e-6}
+
+
+def _load(golden_dir, name, tag):
+    return np.load(os.path.join(golden_dir, f"{name}_{tag}.npz"))
+
+
+def _sub(name, t):
+    step = SUBSAMPLE.get(name, 1)
+    flat = t.reshape(-1)
+    return flat[::step] if step > 1 and flat.numel() > 100000 else t
+
+
+def _checksum(t):
+    t = t.double()
+    return np.array([t.sum().item(), t.abs().sum().item()])
+
+
+@pytest.mark.parametrize("tag", ["f32", "f64"])
+@pytest.mark.parametrize("name", list(ATTN_CASES))
+def test_attention_oracle_matches_reference(golden_dir, name, tag):
+    if tag == "f64" and name in F64_SKIP:
+        pytest.skip("no fp64 fixture kept for this case")
+    B, idf, cdf, L, ih, iw, seed, masked, with_ga = ATTN_CASES[name]
+    g = _load(golden_dir, name, tag)
+    d = synth_attention_inputs(B, idf, cdf, L, ih, iw, seed=seed, dtype=DT[tag], with_g_attn=with_ga)
+    in_sum = np.concatenate([_checksum(d[k]) for k in ("x", "context", "weight", "g_c")])
+    np.testing.assert_allclose(in_sum, g["in_sum"], rtol=1e-12, err_msg="synthetic input generator drifted")
+    mask = d["mask"] if masked else None
+    c, attn, _ = attn_forward(d["x"], d["context"], d["weight"], mask)
+    dX, dW, dCtx, _ = attn_backward(d["x"], d["context"], d["weight"], mask, d["g_c"], d.get("g_attn"))
+    for key, val in dict(c_code=c, attn=attn, dX=dX, dW=dW, dCtx=dCtx).items():
+        ref = torch.from_numpy(g[key])
+        err = normalised_max_err(_sub(name, val).reshape(ref.shape), ref)
+        assert err <= TOL[tag], f"{name}/{key}: {err:.3e}"
+
+
+def test_mask_quirk_is_mod_B_not_per_sample(golden_dir):
+    """the reference masks pixel (b,q) with caption (b*Q+q) mod B."""
+    name = "attn_b3_q64_rag"
+    B, idf, cdf, L, ih, iw, seed, masked, with_ga = ATTN_CASES[name]
+    g = _load(golden_dir, name, "f64")
+    d = synth_attention_inputs(B, idf, cdf, L, ih, iw, seed=seed, dtype=torch.float64, with_g_attn=with_ga)
+    _, attn_ref, _ = attn_forward(d["x"], d["context"], d["weight"], d["mask"], "reference")
+    _, attn_ps, _ = attn_forward(d["x"], d["context"], d["weight"], d["mask"], "per_sample")
+    ref = torch.from_numpy(g["attn"])
+    assert normalised_max_err(attn_ref, ref) < 1e-12
+    assert normalised_max_err(attn_ps, ref) > 1e-2
+
+
+@pytest.mark.parametrize("tag", ["f32", "f64"])
+def test_func_attention_oracle(golden_dir, tag):
+    g = _load(golden_dir, "func_attention", tag)
+    wc, attn = func_attention(torch.from_numpy(g["query"]), torch.from_numpy(g["context"]), 4.0)
+    assert normalised_max_err(wc, torch.from_numpy(g["wc"])) <= TOL[tag]
+    assert normalised_max_err(attn, torch.from_numpy(g["attn"])) <= TOL[tag]
+
+
+@pytest.mark.parametrize("tag", ["f32", "f64"])
+@pytest.mark.parametrize("name", list(WL_CASES))
+def test_words_loss_oracle_matches_reference(golden_dir, name, tag):
+    if tag == "f64" and name in F64_SKIP:
+        pytest.skip("no fp64 fixture kept for this case")
+    B, nef, L, ih, iw, seed, gammas, use_cls, use_lab = WL_CASES[name]
+    g = _load(golden_dir, name, tag)
+    d = synth_words_loss_inputs(B, nef, L, ih, iw, seed=seed, dtype=DT[tag], n_classes=max(2, B // 2))
+    np.testing.assert_allclose(np.concatenate([_checksum(d["img_features"]), _checksum(d["words_emb"])]),
+                               g["in_sum"], rtol=1e-12)
+    loss0, loss1, att_maps = words_loss(d["img_features"], d["words_emb"], d["labels"] if use_lab else None,
+                                        d["cap_lens"], d["class_ids"] if use_cls else None, B, *gammas)
+    assert len(att_maps) == B
+    for i, a in enumerate(att_maps):
+        ref = torch.from_numpy(g[f"att_{i}"])
+        assert a.shape == ref.shape == (1, int(d["cap_lens"][i]), ih, iw)
+        assert normalised_max_err(a, ref) <= TOL[tag]
+    if not use_lab:
+        assert loss0 is None and loss1 is None
+        return
+    tol = TOL[tag] * (1 if tag == "f64" else 5)
+    assert abs(loss0.item() - g["loss0"].item()) <= tol * max(1.0, abs(g["loss0"].item()))
+    assert abs(loss1.item() - g["loss1"].item()) <= tol * max(1.0, abs(g["loss1"].item()))
+    sim = words_similarity(d["img_features"], d["words_emb"], d["cap_lens"].tolist(), *gammas)
+    _, _, sim_m = ce_tail(sim, d["labels"], d["class_ids"] if use_cls else None)
+    assert normalised_max_err(sim_m, torch.from_numpy(g["sim_masked"])) <= tol
+    # gradient of loss0 + loss1 through the hand-derived backward
+    sim_leaf = sim.detach().clone().requires_grad_(True)
+    l0, l1, _ = ce_tail(sim_leaf, d["labels"], d["class_ids"] if use_cls else None)
+    (l0 + l1).backward()
+    d_img, d_words = words_loss_backward(d["img_features"], d["words_emb"], d["cap_lens"].tolist(),
+                                         sim_leaf.grad, *gammas)
+    gtol = 1e-10 if tag == "f64" else 2e-5
+    assert normalised_max_err(d_img, torch.from_numpy(g["d_img"])) <= gtol
+    assert normalised_max_err(d_words, torch.from_numpy(g["d_words"])) <= gtol
+
+
+def test_words_similarity_row_sharding_is_exact():
+    """Row-sharded evaluation reproduces the unsharded matrix bit for bit."""
+    d = synth_words_loss_inputs(6, 32, 9, 5, 5, seed=5, dtype=torch.float64)
+    lens = d["cap_lens"].tolist()
+    full, maps = words_similarity(d["img_features"], d["words_emb"], lens, 4.0, 5.0, 10.0, want_att_maps=True)
+    parts, pmaps = [], []
+    for r0 in (0, 3):
+        s, m = words_similarity(d["img_features"][r0:r0 + 3], d["words_emb"], lens, 4.0, 5.0, 10.0,
+                                want_att_maps=True, row_offset=r0)
+        parts.append(s)
+        pmaps += m
+    assert torch.equal(torch.cat(parts, 0), full)
+    assert all(torch.equal(a, b) for a, b in zip(maps, pmaps))
