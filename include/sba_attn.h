@@ -1,0 +1,129 @@
+/*
+ * sba_attn.h - C ABI of libsba_attn.so: the B200 (sm_100a) word-region attention hot path
+ * of zhengfei0908/SBA-GAN.
+ *
+ * The reference has no native boundary: its hot path is Python calling torch ops.  Each
+ * entry point below names the reference interface it replaces (paths relative to
+ * AttnGAN2/code in the reference tree).  A reference-side binding (ctypes) is shown in
+ * INTEGRATION.md; the in-repo one is sba_gan_b200/_abi.py.
+ *
+ * Contract:
+ *  - plain pointers and sizes only; every pointer is DEVICE memory owned by the caller;
+ *  - nothing here allocates, frees or synchronises; all work is enqueued on `stream`
+ *    (a cudaStream_t passed as void*, e.g. torch.cuda.current_stream().cuda_stream);
+ *  - returns SBA_OK (0) or a non-zero sba_status; the message is in sba_last_error()
+ *    (thread-local); no C++ exception crosses this boundary;
+ *  - stateless and re-entrant (one process per GPU under torchrun is fine);
+ *  - big pixel tensors must be contiguous; 16-byte aligned bases enable the 128-bit path;
+ *  - there is no CPU implementation behind these symbols.
+ */
+#ifndef SBA_ATTN_H_
+#define SBA_ATTN_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SBA_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define SBA_API __attribute__((visibility("default")))
+#else
+#define SBA_API
+#endif
+
+typedef enum {
+    SBA_OK = 0,
+    SBA_ERR_ARG = 1,         /* null pointer / non-positive size */
+    SBA_ERR_UNSUPPORTED = 2, /* shape outside what the kernels cover (e.g. L > 32) */
+    SBA_ERR_ALIGN = 3,       /* pointer alignment */
+    SBA_ERR_CUDA = 4         /* launch failure; message carries cudaGetErrorString */
+} sba_status;
+
+/* element type of the big per-pixel tensors (x, c_code, attn, g_c, g_attn, dX);
+ * arithmetic is always fp32; small per-caption tensors are always fp32. */
+enum { SBA_F32 = 0, SBA_BF16 = 1 };
+
+/* how the B x L caption padding mask is applied to pixel (b, q):
+ *  REFERENCE : caption (b*Q + q) mod B  - bug-compatible with mask.repeat(queryL, 1)
+ *              at GlobalAttention.py:104-108; the default everywhere;
+ *  PER_SAMPLE: caption b. */
+enum { SBA_MASK_REFERENCE = 0, SBA_MASK_PER_SAMPLE = 1 };
+
+/* kernel family: AUTO picks the fastest one that supports the shape */
+enum { SBA_ALGO_AUTO = 0, SBA_ALGO_SIMT = 1, SBA_ALGO_MMA = 2 };
+
+SBA_API int sba_abi_version(void);
+SBA_API const char* sba_last_error(void);
+
+/* Number of kernels the last successful call on this thread launched (bench.py's
+ * gpu_launches). */
+SBA_API int sba_last_launch_count(void);
+
+/* ---- GlobalAttentionGeneral.forward  (GlobalAttention.py:82-121) -------------------
+ * x        [B, idf, Q]   dtype      input regions (NCHW, Q = ih*iw)
+ * ctx      [B, cdf, L]   fp32       word features
+ * W        [idf, cdf]    fp32       conv_context.weight ([idf,cdf,1,1], GlobalAttention.py:25-28,75)
+ * mask     [B, L] uint8  nullable   1 = padding word (applyMask, GlobalAttention.py:79-80)
+ * c_code   [B, idf, Q]   dtype  out weightedContext
+ * attn     [B, L, Q]     dtype  out attention map
+ * srcT     [B, idf, L]   fp32   out sourceT = W.ctx, kept for the backward
+ * mask_bits[B] uint32    scratch    (only touched when mask != NULL)
+ */
+SBA_API int sba_attn_fwd(const void* x, const float* ctx, const float* W, const uint8_t* mask,
+                 void* c_code, void* attn, float* srcT, uint32_t* mask_bits,
+                 int B, int idf, int cdf, int L, int Q,
+                 int dtype, int mask_mode, int algo, void* stream);
+
+/* ---- autograd backward of the above ------------------------------
+ * srcT     [B, idf, L] fp32         from the forward
+ * mask_bits[B] uint32               from the forward (ignored when mask == NULL)
+ * g_c      [B, idf, Q] dtype        grad of c_code
+ * g_attn   [B, L, Q]   dtype nullable grad of attn (NULL in GAN training: attn is discarded,
+ *                                   trainer_bert.py:267)
+ * dX       [B, idf, Q] dtype  out
+ * dSrc     [B, idf, L] fp32   out   grad of sourceT (also the reduction workspace)
+ * dW       [idf, cdf]  fp32   out   nullable
+ * dCtx     [B, cdf, L] fp32   out   nullable (words are detached in GAN training)
+ */
+SBA_API int sba_attn_bwd(const void* x, const float* ctx, const float* W, const uint8_t* mask,
+                 const float* srcT, const uint32_t* mask_bits,
+                 const void* g_c, const void* g_attn,
+                 void* dX, float* dSrc, float* dW, float* dCtx,
+                 int B, int idf, int cdf, int L, int Q,
+                 int dtype, int mask_mode, int algo, void* stream);
+
+/* ---- DAMSM region-word similarity: func_attention + cosine + LSE --------------------
+ * (GlobalAttention.py:31-69, miscc/losses.py:11-17, 72-123)
+ * sim[j, i] = g3 * log sum_{t < len_i} exp(g2 * cos(words[i,:,t], wc_{j,i}[:,t]))
+ * for local image rows j in [0, B_img) against all B_cap captions.
+ * img      [B_img, nef, R] fp32     region features (R = 17*17)
+ * words    [B_cap, nef, Lw] fp32    word embeddings, Lw = padded width
+ * cap_lens [B_cap] int32            true lengths, 1 <= len <= min(Lw, 32)
+ * sim      [B_img, B_cap] fp32 out
+ * att_diag [B_cap, Lw, R] fp32 out nullable: row i holds the region attention of pair
+ *          (image row_offset-relative j = i - row_offset, caption i) when that image is
+ *          local (the att_maps of losses.py:92); rows of non-local images are left alone
+ * stats    [B_img, B_cap, 2] fp32 out nullable: (E, reserved) per pair for the backward
+ */
+SBA_API size_t sba_words_sim_workspace_bytes(int B_img, int B_cap, int nef, int R, int Lw);
+SBA_API int sba_words_sim_fwd(const float* img, const float* words, const int32_t* cap_lens,
+                      float* sim, float* att_diag, void* workspace,
+                      int B_img, int B_cap, int row_offset, int nef, int R, int Lw,
+                      float gamma1, float gamma2, float gamma3, float eps, void* stream);
+
+/* gradient of sim w.r.t. img (always) and words (nullable; DAMSM pre-training only).
+ * d_img [B_img, nef, R] and d_words [B_cap, nef, Lw] are OVERWRITTEN (zero-filled then
+ * accumulated). */
+SBA_API int sba_words_sim_bwd(const float* img, const float* words, const int32_t* cap_lens,
+                      const float* d_sim, float* d_img, float* d_words, void* workspace,
+                      int B_img, int B_cap, int row_offset, int nef, int R, int Lw,
+                      float gamma1, float gamma2, float gamma3, float eps, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SBA_ATTN_H_ */

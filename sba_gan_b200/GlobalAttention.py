@@ -1,0 +1,51 @@
+"""Drop-in replacement for AttnGAN2/code/GlobalAttention.py of zhengfei0908/SBA-GAN.
+
+Same names, signatures and state_dict layout, so ``from GlobalAttention import
+GlobalAttentionGeneral as ATT_NET`` (model.py:12, model_bert.py:12) and ``from
+GlobalAttention import func_attention`` (miscc/losses.py:7) keep working once this module
+is first on ``sys.path`` under that name (see ``sba_gan_b200.install``).  The arithmetic
+runs in hand-written sm_100a kernels behind libsba_attn.so; there is no CPU path.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from .functional import word_region_attention
+from .losses import func_attention  # noqa: F401  (re-exported: GlobalAttention.py:31-69)
+
+
+def conv1x1(in_planes, out_planes):
+    """1x1 convolution without bias (GlobalAttention.py:25-28)."""
+    return nn.Conv2d(in_planes, out_planes, kernel_size=1, stride=1, padding=0, bias=False)
+
+
+class GlobalAttentionGeneral(nn.Module):
+    """Word -> region attention of the generator (GlobalAttention.py:72-121).
+
+    ``conv_context`` stays a real bias-free ``nn.Conv2d(cdf, idf, 1)`` so that reference
+    checkpoints load (key ``...att.conv_context.weight`` [idf, cdf, 1, 1]) and
+    ``weights_init`` (miscc/utils.py:286-289, matches class names containing "Conv")
+    initialises it; only its weight tensor is read by the fused kernel.
+
+    mask_mode "reference" reproduces the reference's ``mask.repeat(queryL, 1)`` row order
+    (pixel (b, q) masked with caption (b*Q + q) mod B); "per_sample" uses caption b.
+    """
+
+    mask_mode = "reference"
+    algo = "auto"
+
+    def __init__(self, idf, cdf):
+        super().__init__()
+        self.conv_context = conv1x1(cdf, idf)
+        self.sm = nn.Softmax(dim=1)   # kept for attribute compatibility; unused
+        self.mask = None
+
+    def applyMask(self, mask):
+        self.mask = mask  # batch x sourceL, sticky until the next call (GlobalAttention.py:79-80)
+
+    def forward(self, input, context):
+        """input: batch x idf x ih x iw (queryL = ih*iw); context: batch x cdf x sourceL
+        returns (weightedContext batch x idf x ih x iw, attn batch x sourceL x ih x iw)."""
+        return word_region_attention(input, context, self.conv_context.weight, self.mask,
+                                     mask_mode=self.mask_mode, algo=self.algo)

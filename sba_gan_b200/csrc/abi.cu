@@ -1,0 +1,141 @@
+// extern "C" boundary of libsba_attn.so (declared in include/sba_attn.h).
+// Validates arguments, picks a kernel family, enqueues on the caller's stream.
+#include <cstdarg>
+#include <cstring>
+
+#include "kernels.h"
+
+namespace sba {
+
+namespace {
+thread_local char g_err[512] = "";
+thread_local int g_launches = 0;
+}  // namespace
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+void add_launches(int n) { g_launches += n; }
+
+int check_launch(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("%s: %s", what, cudaGetErrorString(e));
+        return SBA_ERR_CUDA;
+    }
+    return SBA_OK;
+}
+
+namespace {
+
+int check_attn_shape(const char* fn, int B, int idf, int cdf, int L, int Q, int dtype, int mask_mode, int algo) {
+    if (B <= 0 || idf <= 0 || cdf <= 0 || L <= 0 || Q <= 0) {
+        set_error("%s: sizes must be positive (B=%d idf=%d cdf=%d L=%d Q=%d)", fn, B, idf, cdf, L, Q);
+        return SBA_ERR_ARG;
+    }
+    if (L > kMaxWords) {
+        set_error("%s: L=%d words exceeds the supported maximum of %d", fn, L, kMaxWords);
+        return SBA_ERR_UNSUPPORTED;
+    }
+    if (idf > 1024) {
+        set_error("%s: idf=%d exceeds the supported maximum of 1024", fn, idf);
+        return SBA_ERR_UNSUPPORTED;
+    }
+    if (dtype != SBA_F32 && dtype != SBA_BF16) {
+        set_error("%s: unknown dtype %d", fn, dtype);
+        return SBA_ERR_ARG;
+    }
+    if (mask_mode != SBA_MASK_REFERENCE && mask_mode != SBA_MASK_PER_SAMPLE) {
+        set_error("%s: unknown mask_mode %d", fn, mask_mode);
+        return SBA_ERR_ARG;
+    }
+    if (algo != SBA_ALGO_AUTO && algo != SBA_ALGO_SIMT && algo != SBA_ALGO_MMA) {
+        set_error("%s: unknown algo %d", fn, algo);
+        return SBA_ERR_ARG;
+    }
+    if ((size_t)B * idf * Q >= ((size_t)1 << 40)) {
+        set_error("%s: tensor too large", fn);
+        return SBA_ERR_UNSUPPORTED;
+    }
+    return SBA_OK;
+}
+
+}  // namespace
+}  // namespace sba
+
+using namespace sba;
+
+extern "C" {
+
+int sba_abi_version(void) { return SBA_ABI_VERSION; }
+const char* sba_last_error(void) { return g_err; }
+int sba_last_launch_count(void) { return g_launches; }
+
+int sba_attn_fwd(const void* x, const float* ctx, const float* W, const uint8_t* mask, void* c_code, void* attn,
+                 float* srcT, uint32_t* mask_bits, int B, int idf, int cdf, int L, int Q, int dtype, int mask_mode,
+                 int algo, void* stream) {
+    g_launches = 0;
+    g_err[0] = 0;
+    if (!x || !ctx || !W || !c_code || !attn || !srcT || (mask && !mask_bits)) {
+        set_error("sba_attn_fwd: null pointer argument");
+        return SBA_ERR_ARG;
+    }
+    int rc = check_attn_shape("sba_attn_fwd", B, idf, cdf, L, Q, dtype, mask_mode, algo);
+    if (rc) return rc;
+    AttnShape s{B, idf, cdf, L, Q, dtype, mask_mode};
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (algo == SBA_ALGO_MMA) {
+        set_error("sba_attn_fwd: SBA_ALGO_MMA is not available for this shape");
+        return SBA_ERR_UNSUPPORTED;
+    }
+    rc = simt_project(ctx, W, mask, srcT, mask_bits, s, st);
+    if (rc) return rc;
+    return simt_attn_fwd(x, srcT, mask ? mask_bits : nullptr, c_code, attn, s, st);
+}
+
+int sba_attn_bwd(const void* x, const float* ctx, const float* W, const uint8_t* mask, const float* srcT,
+                 const uint32_t* mask_bits, const void* g_c, const void* g_attn, void* dX, float* dSrc, float* dW,
+                 float* dCtx, int B, int idf, int cdf, int L, int Q, int dtype, int mask_mode, int algo, void* stream) {
+    g_launches = 0;
+    g_err[0] = 0;
+    if (!x || !ctx || !W || !srcT || !g_c || !dX || !dSrc || (mask && !mask_bits)) {
+        set_error("sba_attn_bwd: null pointer argument");
+        return SBA_ERR_ARG;
+    }
+    int rc = check_attn_shape("sba_attn_bwd", B, idf, cdf, L, Q, dtype, mask_mode, algo);
+    if (rc) return rc;
+    AttnShape s{B, idf, cdf, L, Q, dtype, mask_mode};
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (algo == SBA_ALGO_MMA) {
+        set_error("sba_attn_bwd: SBA_ALGO_MMA is not available for this shape");
+        return SBA_ERR_UNSUPPORTED;
+    }
+    cudaError_t e = cudaMemsetAsync(dSrc, 0, (size_t)B * idf * L * sizeof(float), st);
+    if (e != cudaSuccess) {
+        set_error("sba_attn_bwd: memset: %s", cudaGetErrorString(e));
+        return SBA_ERR_CUDA;
+    }
+    rc = simt_attn_bwd(x, srcT, mask ? mask_bits : nullptr, g_c, g_attn, dX, dSrc, s, st);
+    if (rc) return rc;
+    return simt_attn_bwd_epilogue(ctx, W, dSrc, dW, dCtx, s, st);
+}
+
+size_t sba_words_sim_workspace_bytes(int, int, int, int, int) { return 0; }
+
+int sba_words_sim_fwd(const float*, const float*, const int32_t*, float*, float*, void*, int, int, int, int, int, int,
+                      float, float, float, float, void*) {
+    set_error("sba_words_sim_fwd: not built yet");
+    return SBA_ERR_UNSUPPORTED;
+}
+
+int sba_words_sim_bwd(const float*, const float*, const int32_t*, const float*, float*, float*, void*, int, int, int,
+                      int, int, int, float, float, float, float, void*) {
+    set_error("sba_words_sim_bwd: not built yet");
+    return SBA_ERR_UNSUPPORTED;
+}
+
+}  // extern "C"

@@ -1,0 +1,22 @@
+// Internal launch interface between abi.cu and the kernel translation units.
+#pragma once
+#include "common.cuh"
+
+namespace sba {
+
+struct AttnShape {
+    int B, idf, cdf, L, Q;
+    int dtype, mask_mode;
+};
+
+// attn_simt.cu - CUDA-core (FFMA + warp-shuffle) kernels, any shape with L <= 32
+int simt_project(const float* ctx, const float* W, const uint8_t* mask, float* srcT, uint32_t* mask_bits,
+                 const AttnShape& s, cudaStream_t st);
+int simt_attn_fwd(const void* x, const float* srcT, const uint32_t* mask_bits, void* c_code, void* attn,
+                  const AttnShape& s, cudaStream_t st);
+int simt_attn_bwd(const void* x, const float* srcT, const uint32_t* mask_bits, const void* g_c,
+                  const void* g_attn, void* dX, float* dSrc, const AttnShape& s, cudaStream_t st);
+int simt_attn_bwd_epilogue(const float* ctx, const float* W, const float* dSrc, float* dW, float* dCtx,
+                           const AttnShape& s, cudaStream_t st);
+
+}  // namespace sba

@@ -1,0 +1,115 @@
+"""torch.autograd wrappers over the C ABI: device memory and streams are PyTorch's, the
+arithmetic is libsba_attn.so's.  Mirrors AttnGAN2/code/GlobalAttention.py:82-121."""
+from __future__ import annotations
+
+import torch
+
+from . import _abi
+
+_DTYPES = {torch.float32: _abi.SBA_F32, torch.bfloat16: _abi.SBA_BF16}
+_MASK_MODES = {"reference": _abi.SBA_MASK_REFERENCE, "per_sample": _abi.SBA_MASK_PER_SAMPLE}
+_ALGOS = {"auto": _abi.SBA_ALGO_AUTO, "simt": _abi.SBA_ALGO_SIMT, "mma": _abi.SBA_ALGO_MMA}
+
+# kernels launched by this process through the ABI (bench.py reports it as gpu_launches)
+launch_counter = {"n": 0}
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError(
+                "sba_gan_b200: the word-region attention path runs only on CUDA tensors "
+                "(B200, sm_100a); there is no CPU fallback")
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def attn_forward_raw(x, context, weight, mask_u8, mask_mode, algo):
+    """x B x idf x ih x iw (fp32|bf16, contiguous), context B x cdf x L, weight idf x cdf.
+    Returns (c_code, attn, srcT fp32, mask_bits|None)."""
+    lib = _abi.load()
+    B, idf, ih, iw = x.shape
+    Q = ih * iw
+    cdf, L = context.shape[1], context.shape[2]
+    ctx32 = context.detach().to(torch.float32).contiguous()
+    w32 = weight.detach().reshape(idf, cdf).to(torch.float32).contiguous()
+    c_code = torch.empty_like(x)
+    attn = torch.empty((B, L, ih, iw), dtype=x.dtype, device=x.device)
+    srcT = torch.empty((B, idf, L), dtype=torch.float32, device=x.device)
+    mask_bits = torch.empty((B,), dtype=torch.int32, device=x.device) if mask_u8 is not None else None
+    rc = lib.sba_attn_fwd(_ptr(x), _ptr(ctx32), _ptr(w32), _ptr(mask_u8), _ptr(c_code), _ptr(attn), _ptr(srcT),
+                          _ptr(mask_bits), B, idf, cdf, L, Q, _DTYPES[x.dtype], mask_mode, algo, _stream())
+    _abi.check(rc, "sba_attn_fwd")
+    launch_counter["n"] += _abi.last_launch_count()
+    return c_code, attn, srcT, mask_bits, ctx32, w32
+
+
+class _WordRegionAttention(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, context, weight, mask_u8, mask_mode, algo):
+        _require_cuda(x, context, weight, mask_u8)
+        if x.dtype not in _DTYPES:
+            raise RuntimeError(f"sba_gan_b200: unsupported dtype {x.dtype} (float32 or bfloat16)")
+        x = x.contiguous()
+        c_code, attn, srcT, mask_bits, ctx32, w32 = attn_forward_raw(x, context, weight, mask_u8, mask_mode, algo)
+        ctx.save_for_backward(x, ctx32, w32, mask_u8, srcT, mask_bits)
+        ctx.meta = (mask_mode, algo, context.dtype, weight.dtype, tuple(weight.shape))
+        return c_code, attn
+
+    @staticmethod
+    def backward(ctx, g_c, g_attn):
+        x, ctx32, w32, mask_u8, srcT, mask_bits = ctx.saved_tensors
+        mask_mode, algo, ctx_dtype, w_dtype, w_shape = ctx.meta
+        lib = _abi.load()
+        B, idf, ih, iw = x.shape
+        Q = ih * iw
+        cdf, L = ctx32.shape[1], ctx32.shape[2]
+        need_x, need_ctx, need_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]
+        if g_c is None:
+            g_c = torch.zeros_like(x)
+        g_c = g_c.to(x.dtype).contiguous()
+        if g_attn is not None:
+            g_attn = g_attn.to(x.dtype).contiguous()
+        dX = torch.empty_like(x)
+        dSrc = torch.empty((B, idf, L), dtype=torch.float32, device=x.device)
+        dW = torch.empty((idf, cdf), dtype=torch.float32, device=x.device) if need_w else None
+        dCtx = torch.empty((B, cdf, L), dtype=torch.float32, device=x.device) if need_ctx else None
+        rc = lib.sba_attn_bwd(_ptr(x), _ptr(ctx32), _ptr(w32), _ptr(mask_u8), _ptr(srcT), _ptr(mask_bits), _ptr(g_c),
+                              _ptr(g_attn), _ptr(dX), _ptr(dSrc), _ptr(dW), _ptr(dCtx), B, idf, cdf, L, Q,
+                              _DTYPES[x.dtype], mask_mode, algo, _stream())
+        _abi.check(rc, "sba_attn_bwd")
+        launch_counter["n"] += _abi.last_launch_count()
+        return (dX if need_x else None,
+                dCtx.to(ctx_dtype) if need_ctx else None,
+                dW.reshape(w_shape).to(w_dtype) if need_w else None,
+                None, None, None)
+
+
+def word_region_attention(x, context, weight, mask=None, mask_mode="reference", algo="auto"):
+    """Fused GlobalAttentionGeneral.forward (GlobalAttention.py:82-121).
+
+    x B x idf x ih x iw; context B x cdf x L; weight [idf, cdf, 1, 1] (conv_context.weight);
+    mask B x L bool/uint8 (True = padding word) or None.
+    Returns (weightedContext B x idf x ih x iw, attn B x L x ih x iw), differentiable in
+    x, context and weight.
+    """
+    if x.dim() != 4 or context.dim() != 3:
+        raise RuntimeError("word_region_attention: x must be B x idf x ih x iw and context B x cdf x L")
+    if context.shape[0] != x.shape[0]:
+        raise RuntimeError("word_region_attention: batch sizes of input and context differ")
+    if weight.numel() != x.shape[1] * context.shape[1]:
+        raise RuntimeError("word_region_attention: conv_context.weight must be [idf, cdf, 1, 1]")
+    mask_u8 = None
+    if mask is not None:
+        if mask.shape[0] != x.shape[0] or mask.shape[-1] != context.shape[2] or mask.dim() != 2:
+            # the reference would fail in masked_fill_ on the same mismatch (GlobalAttention.py:107-108)
+            raise RuntimeError(f"word_region_attention: mask {tuple(mask.shape)} does not match "
+                               f"batch {x.shape[0]} x sourceL {context.shape[2]}")
+        mask_u8 = mask.detach().to(device=x.device, dtype=torch.uint8).contiguous()
+    return _WordRegionAttention.apply(x, context, weight, mask_u8, _MASK_MODES[mask_mode], _ALGOS[algo])

@@ -1,0 +1,196 @@
+"""GPU parity tests for kernels (a)/(b): the fused GlobalAttentionGeneral forward/backward
+through the drop-in module (-> autograd Function -> C ABI -> sm_100a kernels) against
+  * the golden vectors produced by the unmodified reference (tests/golden), and
+  * the CPU oracle on the same seeded inputs.
+Tolerances are BASELINE.json's, as normalised max error (SURVEY.md §8 parity metric):
+attention maps and c_code 1e-5 (fp32) / 2e-2 (bf16); gradients 1e-4 (fp32)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import attn_forward, attn_backward, synth_attention_inputs, normalised_max_err
+from tests.cases import ATTN_CASES, SUBSAMPLE
+
+pytestmark = pytest.mark.gpu
+
+TOL_FWD_F32 = 1e-5
+TOL_GRAD_F32 = 1e-4
+TOL_BF16 = 2e-2
+ALGOS = ["simt"]
+
+
+def _module(idf, cdf, weight, dtype=torch.float32, algo="auto", mask_mode="reference"):
+    from sba_gan_b200 import GlobalAttentionGeneral
+    m = GlobalAttentionGeneral(idf, cdf).cuda().to(dtype)
+    with torch.no_grad():
+        m.conv_context.weight.copy_(weight.to(dtype))
+    m.algo = algo
+    m.mask_mode = mask_mode
+    return m
+
+
+def _run(d, masked, algo="auto", dtype=torch.float32, mask_mode="reference", ctx_grad=True):
+    B, idf = d["x"].shape[:2]
+    cdf = d["context"].shape[1]
+    m = _module(idf, cdf, d["weight"], dtype, algo, mask_mode)
+    x = d["x"].cuda().to(dtype).requires_grad_(True)
+    ctx = d["context"].cuda().to(dtype).requires_grad_(ctx_grad)
+    m.applyMask(d["mask"].cuda() if masked else None)
+    c, attn = m(x, ctx)
+    loss = (c.float() * d["g_c"].cuda().float()).sum()
+    if "g_attn" in d:
+        loss = loss + (attn.float() * d["g_attn"].cuda().float()).sum()
+    loss.backward()
+    torch.cuda.synchronize()
+    return dict(c_code=c.detach(), attn=attn.detach(), dX=x.grad, dW=m.conv_context.weight.grad,
+                dCtx=ctx.grad if ctx_grad else None)
+
+
+def _sub(name, t):
+    step = SUBSAMPLE.get(name, 1)
+    flat = t.reshape(-1)
+    return flat[::step] if step > 1 and flat.numel() > 100000 else t
+
+
+@pytest.mark.parametrize("algo", ALGOS)
+@pytest.mark.parametrize("name", list(ATTN_CASES))
+def test_matches_reference_golden(golden_dir, name, algo):
+    B, idf, cdf, L, ih, iw, seed, masked, with_ga = ATTN_CASES[name]
+    g = np.load(os.path.join(golden_dir, f"{name}_f32.npz"))
+    d = synth_attention_inputs(B, idf, cdf, L, ih, iw, seed=seed, with_g_attn=with_ga)
+    out = _run(d, masked, algo)
+    for key, tol in (("c_code", TOL_FWD_F32), ("attn", TOL_FWD_F32), ("dX", TOL_GRAD_F32), ("dW", TOL_GRAD_F32),
+                     ("dCtx", TOL_GRAD_F32)):
+        ref = torch.from_numpy(g[key])
+        err = normalised_max_err(_sub(name, out[key].cpu()).reshape(ref.shape), ref)
+        assert err <= tol, f"{name}/{key}: {err:.3e} > {tol}"
+
+
+SWEEP = [
+    # B, idf, L, ih, iw, masked, mask_mode, with_g_attn
+    (1, 32, 18, 64, 64, True, "reference", False),
+    (10, 32, 18, 64, 64, True, "reference", True),     # BASELINE configs[0] shape
+    (3, 32, 20, 32, 32, True, "per_sample", True),
+    (2, 48, 12, 16, 16, True, "reference", False),     # coco GF_DIM
+    (2, 128, 25, 8, 8, True, "reference", True),       # default GF_DIM, longest yml caption
+    (3, 32, 15, 17, 17, True, "reference", True),      # odd Q: scalar path
+    (2, 32, 32, 8, 8, False, "reference", True),       # maximum L
+    (5, 32, 1, 4, 4, False, "reference", False),       # single word: attn == 1
+    (20, 32, 18, 64, 64, True, "reference", False),    # yml batch size
+    (4, 16, 7, 2, 2, True, "reference", True),         # tiny
+]
+
+
+@pytest.mark.parametrize("algo", ALGOS)
+@pytest.mark.parametrize("spec", SWEEP)
+def test_shape_sweep_vs_oracle(spec, algo):
+    B, idf, L, ih, iw, masked, mask_mode, with_ga = spec
+    d = synth_attention_inputs(B, idf, 256, L, ih, iw, seed=100 + B + idf + L, with_g_attn=with_ga, min_len=1)
+    out = _run(d, masked, algo, mask_mode=mask_mode)
+    d64 = {k: (v.double() if v.is_floating_point() else v) for k, v in d.items()}
+    mask = d["mask"] if masked else None
+    c, attn, _ = attn_forward(d64["x"], d64["context"], d64["weight"], mask, mask_mode)
+    dX, dW, dCtx, _ = attn_backward(d64["x"], d64["context"], d64["weight"], mask, d64["g_c"], d64.get("g_attn"),
+                                    mask_mode)
+    ref = dict(c_code=c, attn=attn, dX=dX, dW=dW, dCtx=dCtx)
+    for key, tol in (("c_code", TOL_FWD_F32), ("attn", TOL_FWD_F32), ("dX", TOL_GRAD_F32), ("dW", TOL_GRAD_F32),
+                     ("dCtx", TOL_GRAD_F32)):
+        err = normalised_max_err(out[key].cpu(), ref[key])
+        assert err <= tol, f"{spec}/{key}: {err:.3e} > {tol}"
+
+
+@pytest.mark.parametrize("algo", ALGOS)
+@pytest.mark.parametrize("hw", [64, 128])
+def test_full_size_fp32(hw, algo):
+    """BASELINE configs[1] shape (B=64, idf 32, L 18, 64x64 / 128x128) against the fp32
+    oracle, plus the size-independent properties: attention rows sum to 1, masked words get
+    exactly 0 weight, gradients of masked words' scores vanish."""
+    B, idf, cdf, L = 64, 32, 256, 18
+    d = synth_attention_inputs(B, idf, cdf, L, hw, hw, seed=1234)
+    out = _run(d, True, algo, ctx_grad=False)
+    c, attn, _ = attn_forward(d["x"], d["context"], d["weight"], d["mask"])
+    assert normalised_max_err(out["c_code"].cpu(), c) <= TOL_FWD_F32
+    assert normalised_max_err(out["attn"].cpu(), attn) <= TOL_FWD_F32
+    a = out["attn"].double()
+    assert (a.sum(dim=1) - 1).abs().max().item() < 1e-5
+    from oracle.attention import pixel_mask
+    pm = pixel_mask(d["mask"], B, hw * hw).cuda()                      # B x Q x L
+    assert out["attn"].reshape(B, L, -1).transpose(1, 2)[pm].abs().max().item() == 0.0
+    dX, dW, _, _ = attn_backward(d["x"], d["context"], d["weight"], d["mask"], d["g_c"])
+    assert normalised_max_err(out["dX"].cpu(), dX) <= TOL_GRAD_F32
+    assert normalised_max_err(out["dW"].cpu(), dW) <= TOL_GRAD_F32
+
+
+@pytest.mark.parametrize("algo", ALGOS)
+@pytest.mark.parametrize("spec", [(10, 32, 18, 64, 64, True), (3, 48, 12, 16, 16, False), (64, 32, 18, 64, 64, True)])
+def test_bf16_io(spec, algo):
+    """bf16 tensors, fp32 arithmetic.  Oracle = fp32 reference maths on the bf16-rounded
+    inputs (SURVEY.md §8 parity note); tolerance 2e-2."""
+    B, idf, L, ih, iw, masked = spec
+    d = synth_attention_inputs(B, idf, 256, L, ih, iw, seed=7, with_g_attn=True)
+    out = _run(d, masked, algo, dtype=torch.bfloat16)
+    r = {k: (v.to(torch.bfloat16).double() if v.is_floating_point() else v) for k, v in d.items()}
+    mask = d["mask"] if masked else None
+    c, attn, _ = attn_forward(r["x"], r["context"], r["weight"], mask)
+    dX, dW, dCtx, _ = attn_backward(r["x"], r["context"], r["weight"], mask, r["g_c"], r["g_attn"])
+    for key, ref in (("c_code", c), ("attn", attn), ("dX", dX), ("dW", dW), ("dCtx", dCtx)):
+        assert out[key].dtype == torch.bfloat16
+        err = normalised_max_err(out[key].float().cpu(), ref)
+        assert err <= TOL_BF16, f"{spec}/{key}: {err:.3e}"
+
+
+def test_fully_masked_caption_gives_nan_like_reference():
+    """softmax over all -inf is NaN in the reference (GlobalAttention.py:108-109)."""
+    d = synth_attention_inputs(2, 32, 256, 6, 4, 4, seed=3)
+    mask = torch.zeros(2, 6, dtype=torch.bool)
+    mask[1, :] = True
+    m = _module(32, 256, d["weight"], mask_mode="per_sample")
+    m.applyMask(mask.cuda())
+    c, attn = m(d["x"].cuda(), d["context"].cuda())
+    cr, ar, _ = attn_forward(d["x"], d["context"], d["weight"], mask, "per_sample")
+    assert torch.isnan(attn[1]).all() and torch.isnan(ar[1]).all()
+    assert normalised_max_err(attn[0].cpu(), ar[0]) <= TOL_FWD_F32
+    assert normalised_max_err(c[0].cpu(), cr[0]) <= TOL_FWD_F32
+
+
+def test_sticky_mask_and_eval_mode():
+    """applyMask state persists across calls and the module works under no_grad / eval()
+    (trainer_bert.py:366, 422)."""
+    d = synth_attention_inputs(4, 32, 256, 18, 8, 8, seed=9)
+    m = _module(32, 256, d["weight"]).eval()
+    m.applyMask(d["mask"].cuda())
+    with torch.no_grad():
+        c1, a1 = m(d["x"].cuda(), d["context"].cuda())
+        c2, a2 = m(d["x"].cuda(), d["context"].cuda())
+    assert torch.equal(c1, c2) and torch.equal(a1, a2)
+    m.applyMask(None)
+    with torch.no_grad():
+        _, a3 = m(d["x"].cuda(), d["context"].cuda())
+    assert not torch.equal(a1, a3)
+    assert c1.shape == (4, 32, 8, 8) and a1.shape == (4, 18, 8, 8)
+
+
+def test_error_behaviour():
+    from sba_gan_b200 import word_region_attention
+    x = torch.zeros(2, 32, 4, 4, device="cuda")
+    w = torch.zeros(32, 256, 1, 1, device="cuda")
+    with pytest.raises(RuntimeError, match="exceeds the supported maximum"):
+        word_region_attention(x, torch.zeros(2, 256, 33, device="cuda"), w)
+    with pytest.raises(RuntimeError, match="mask"):
+        word_region_attention(x, torch.zeros(2, 256, 5, device="cuda"), w, torch.zeros(3, 5, dtype=torch.bool))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        word_region_attention(x.cpu(), torch.zeros(2, 256, 5), w.cpu())
+    with pytest.raises(RuntimeError, match="unsupported dtype"):
+        word_region_attention(x.half(), torch.zeros(2, 256, 5, device="cuda").half(), w.half())
+
+
+def test_non_contiguous_input_is_made_contiguous():
+    d = synth_attention_inputs(2, 32, 256, 18, 8, 8, seed=10)
+    m = _module(32, 256, d["weight"])
+    xt = d["x"].cuda().permute(0, 1, 3, 2)          # non-contiguous view
+    c, attn = m(xt, d["context"].cuda())
+    cr, ar, _ = attn_forward(xt.cpu().contiguous(), d["context"], d["weight"], None)
+    assert normalised_max_err(c.cpu(), cr) <= TOL_FWD_F32
+    assert normalised_max_err(attn.cpu(), ar) <= TOL_FWD_F32
