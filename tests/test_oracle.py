@@ -122,3 +122,15 @@ def test_words_similarity_row_sharding_is_exact():
         pmaps += m
     assert torch.equal(torch.cat(parts, 0), full)
     assert all(torch.equal(a, b) for a, b in zip(maps, pmaps))
+
+
+def test_cpu_timing_path_agrees_with_oracle():
+    """bench.py's CPU baseline (oracle/cpu_path.py, the reference's op sequence) computes the
+    same thing as the closed-form oracle."""
+    from oracle.cpu_path import attn_fwd_bwd_autograd
+    d = synth_attention_inputs(5, 32, 256, 18, 8, 8, seed=77)
+    c, a, dx, dw = attn_fwd_bwd_autograd(d["x"], d["context"], d["weight"], d["mask"], d["g_c"])
+    cr, ar, _ = attn_forward(d["x"], d["context"], d["weight"], d["mask"])
+    dX, dW, _, _ = attn_backward(d["x"], d["context"], d["weight"], d["mask"], d["g_c"])
+    for got, ref in ((c, cr), (a, ar), (dx, dX), (dw, dW)):
+        assert normalised_max_err(got.reshape(ref.shape), ref) <= 2e-6
