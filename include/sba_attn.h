@@ -99,29 +99,36 @@ SBA_API int sba_attn_bwd(const void* x, const float* ctx, const float* W, const 
 /* ---- DAMSM region-word similarity: func_attention + cosine + LSE --------------------
  * (GlobalAttention.py:31-69, miscc/losses.py:11-17, 72-123)
  * sim[j, i] = g3 * log sum_{t < len_i} exp(g2 * cos(words[i,:,t], wc_{j,i}[:,t]))
- * for local image rows j in [0, B_img) against all B_cap captions.
- * img      [B_img, nef, R] fp32     region features (R = 17*17)
- * words    [B_cap, nef, Lw] fp32    word embeddings, Lw = padded width
- * cap_lens [B_cap] int32            true lengths, 1 <= len <= min(Lw, 32)
+ * for local image rows j in [0, B_img) against all B_cap captions (rows = images,
+ * cols = captions, like `similarities` at losses.py:115).
+ * img      [B_img, nef, R] fp32     region features (R = ih*iw = 17*17 <= 320)
+ * words    [B_cap, nef, Lw] fp32    word embeddings, Lw = padded width (<= 32), nef <= 256
+ * cap_lens [B_cap] int32            true lengths, 1 <= len <= Lw
  * sim      [B_img, B_cap] fp32 out
- * att_diag [B_cap, Lw, R] fp32 out nullable: row i holds the region attention of pair
- *          (image row_offset-relative j = i - row_offset, caption i) when that image is
- *          local (the att_maps of losses.py:92); rows of non-local images are left alone
- * stats    [B_img, B_cap, 2] fp32 out nullable: (E, reserved) per pair for the backward
+ * att_diag [B_cap, Lw, R] fp32 out nullable: row i receives the region attention of pair
+ *          (local image j = i - row_offset, caption i) when that image is local - the
+ *          att_maps of losses.py:92; other rows are left untouched
  */
-SBA_API size_t sba_words_sim_workspace_bytes(int B_img, int B_cap, int nef, int R, int Lw);
 SBA_API int sba_words_sim_fwd(const float* img, const float* words, const int32_t* cap_lens,
-                      float* sim, float* att_diag, void* workspace,
+                      float* sim, float* att_diag,
                       int B_img, int B_cap, int row_offset, int nef, int R, int Lw,
                       float gamma1, float gamma2, float gamma3, float eps, void* stream);
 
-/* gradient of sim w.r.t. img (always) and words (nullable; DAMSM pre-training only).
- * d_img [B_img, nef, R] and d_words [B_cap, nef, Lw] are OVERWRITTEN (zero-filled then
- * accumulated). */
+/* Gradient of sim w.r.t. img (always) and words (d_words nullable: only DAMSM pre-training
+ * needs it, pretrain_DAMSM_bert.py:86-92).  d_img [B_img, nef, R] and d_words
+ * [B_cap, nef, Lw] are overwritten.  `workspace` holds per-pair intermediates
+ * (sba_words_sim_bwd_workspace_bytes, 256-byte aligned). */
+SBA_API size_t sba_words_sim_bwd_workspace_bytes(int B_img, int B_cap, int nef, int R, int Lw);
 SBA_API int sba_words_sim_bwd(const float* img, const float* words, const int32_t* cap_lens,
                       const float* d_sim, float* d_img, float* d_words, void* workspace,
                       int B_img, int B_cap, int row_offset, int nef, int R, int Lw,
                       float gamma1, float gamma2, float gamma3, float eps, void* stream);
+
+/* ---- func_attention (GlobalAttention.py:31-69) as a standalone operator -------------
+ * query [B, nef, T], context [B, nef, R]  ->  wc [B, nef, T], attn [B, T, R]
+ * (batch element b of the query attends over batch element b of the context). */
+SBA_API int sba_func_attention(const float* query, const float* context, float* wc, float* attn,
+                       int B, int nef, int T, int R, float gamma1, void* stream);
 
 #ifdef __cplusplus
 }

@@ -124,18 +124,69 @@ int sba_attn_bwd(const void* x, const float* ctx, const float* W, const uint8_t*
     return simt_attn_bwd_epilogue(ctx, W, dSrc, dW, dCtx, s, st);
 }
 
-size_t sba_words_sim_workspace_bytes(int, int, int, int, int) { return 0; }
-
-int sba_words_sim_fwd(const float*, const float*, const int32_t*, float*, float*, void*, int, int, int, int, int, int,
-                      float, float, float, float, void*) {
-    set_error("sba_words_sim_fwd: not built yet");
-    return SBA_ERR_UNSUPPORTED;
+static int check_words_shape(const char* fn, int B_img, int B_cap, int nef, int R, int Lw) {
+    if (B_img <= 0 || B_cap <= 0 || nef <= 0 || R <= 0 || Lw <= 0) {
+        set_error("%s: sizes must be positive (B_img=%d B_cap=%d nef=%d R=%d Lw=%d)", fn, B_img, B_cap, nef, R, Lw);
+        return SBA_ERR_ARG;
+    }
+    if (Lw > kMaxWords) {
+        set_error("%s: Lw=%d words exceeds the supported maximum of %d", fn, Lw, kMaxWords);
+        return SBA_ERR_UNSUPPORTED;
+    }
+    return SBA_OK;
 }
 
-int sba_words_sim_bwd(const float*, const float*, const int32_t*, const float*, float*, float*, void*, int, int, int,
-                      int, int, int, float, float, float, float, void*) {
-    set_error("sba_words_sim_bwd: not built yet");
-    return SBA_ERR_UNSUPPORTED;
+int sba_words_sim_fwd(const float* img, const float* words, const int32_t* cap_lens, float* sim, float* att_diag,
+                      int B_img, int B_cap, int row_offset, int nef, int R, int Lw, float gamma1, float gamma2,
+                      float gamma3, float eps, void* stream) {
+    g_launches = 0;
+    g_err[0] = 0;
+    if (!img || !words || !cap_lens || !sim) {
+        set_error("sba_words_sim_fwd: null pointer argument");
+        return SBA_ERR_ARG;
+    }
+    int rc = check_words_shape("sba_words_sim_fwd", B_img, B_cap, nef, R, Lw);
+    if (rc) return rc;
+    return words_sim_fwd(img, words, cap_lens, sim, att_diag, nullptr, B_img, B_cap, row_offset, nef, R, Lw, gamma1,
+                         gamma2, gamma3, eps, 0, static_cast<cudaStream_t>(stream));
+}
+
+size_t sba_words_sim_bwd_workspace_bytes(int B_img, int B_cap, int nef, int R, int Lw) {
+    if (B_img <= 0 || B_cap <= 0 || nef <= 0 || R <= 0 || Lw <= 0) return 0;
+    return words_bwd_workspace_bytes(B_img, B_cap, nef, R, Lw);
+}
+
+int sba_words_sim_bwd(const float* img, const float* words, const int32_t* cap_lens, const float* d_sim, float* d_img,
+                      float* d_words, void* workspace, int B_img, int B_cap, int row_offset, int nef, int R, int Lw,
+                      float gamma1, float gamma2, float gamma3, float eps, void* stream) {
+    g_launches = 0;
+    g_err[0] = 0;
+    if (!img || !words || !cap_lens || !d_sim || !d_img || !workspace) {
+        set_error("sba_words_sim_bwd: null pointer argument");
+        return SBA_ERR_ARG;
+    }
+    if (reinterpret_cast<uintptr_t>(workspace) % 256 != 0) {
+        set_error("sba_words_sim_bwd: workspace must be 256-byte aligned");
+        return SBA_ERR_ALIGN;
+    }
+    int rc = check_words_shape("sba_words_sim_bwd", B_img, B_cap, nef, R, Lw);
+    if (rc) return rc;
+    return words_sim_bwd(img, words, cap_lens, d_sim, d_img, d_words, workspace, B_img, B_cap, row_offset, nef, R, Lw,
+                         gamma1, gamma2, gamma3, eps, static_cast<cudaStream_t>(stream));
+}
+
+int sba_func_attention(const float* query, const float* context, float* wc, float* attn, int B, int nef, int T, int R,
+                       float gamma1, void* stream) {
+    g_launches = 0;
+    g_err[0] = 0;
+    if (!query || !context || !wc || !attn) {
+        set_error("sba_func_attention: null pointer argument");
+        return SBA_ERR_ARG;
+    }
+    int rc = check_words_shape("sba_func_attention", B, B, nef, R, T);
+    if (rc) return rc;
+    return words_sim_fwd(context, query, nullptr, nullptr, attn, wc, B, B, 0, nef, R, T, gamma1, 1.f, 1.f, 1e-8f, 1,
+                         static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

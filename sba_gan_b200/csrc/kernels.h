@@ -19,4 +19,13 @@ int simt_attn_bwd(const void* x, const float* srcT, const uint32_t* mask_bits, c
 int simt_attn_bwd_epilogue(const float* ctx, const float* W, const float* dSrc, float* dW, float* dCtx,
                            const AttnShape& s, cudaStream_t st);
 
+// words_loss.cu - fused DAMSM region-word similarity (kernel c) and its backward
+size_t words_bwd_workspace_bytes(int B_img, int B_cap, int nef, int R, int Lw);
+int words_sim_fwd(const float* img, const float* words, const int* cap_lens, float* sim, float* att_diag, float* wc_out,
+                  int B_img, int B_cap, int row_offset, int nef, int R, int Lw, float g1, float g2, float g3, float eps,
+                  int paired, cudaStream_t st);
+int words_sim_bwd(const float* img, const float* words, const int* cap_lens, const float* d_sim, float* d_img,
+                  float* d_words, void* workspace, int B_img, int B_cap, int row_offset, int nef, int R, int Lw, float g1,
+                  float g2, float g3, float eps, cudaStream_t st);
+
 }  // namespace sba

@@ -1,0 +1,151 @@
+"""GPU parity tests for kernel (c): fused DAMSM words_loss (forward, backward, att_maps,
+None modes) and func_attention, against the reference golden vectors and the CPU oracle.
+Tolerances (BASELINE.json): words_loss 1e-5, gradients 1e-4, normalised max error."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from oracle import normalised_max_err, synth_words_loss_inputs
+from tests.cases import WL_CASES
+
+pytestmark = pytest.mark.gpu
+
+TOL_LOSS = 1e-5
+TOL_GRAD = 1e-4
+
+
+def _run(d, B, gammas, use_cls, use_lab, need_words_grad=True):
+    from sba_gan_b200 import words_loss
+    img = d["img_features"].cuda().requires_grad_(True)
+    words = d["words_emb"].cuda().requires_grad_(need_words_grad)
+    l0, l1, maps = words_loss(img, words, d["labels"].cuda() if use_lab else None, d["cap_lens"].cuda(),
+                              d["class_ids"] if use_cls else None, B, *gammas)
+    if use_lab:
+        (l0 + l1).backward()
+    torch.cuda.synchronize()
+    return l0, l1, maps, img.grad, words.grad
+
+
+@pytest.mark.parametrize("name", list(WL_CASES))
+def test_matches_reference_golden(golden_dir, name):
+    B, nef, L, ih, iw, seed, gammas, use_cls, use_lab = WL_CASES[name]
+    g = np.load(os.path.join(golden_dir, f"{name}_f32.npz"))
+    d = synth_words_loss_inputs(B, nef, L, ih, iw, seed=seed, n_classes=max(2, B // 2))
+    l0, l1, maps, d_img, d_words = _run(d, B, gammas, use_cls, use_lab)
+    assert len(maps) == B
+    for i, a in enumerate(maps):
+        ref = torch.from_numpy(g[f"att_{i}"])
+        assert tuple(a.shape) == tuple(ref.shape)
+        assert normalised_max_err(a.cpu(), ref) <= TOL_LOSS, f"{name}/att_{i}"
+    if not use_lab:
+        assert l0 is None and l1 is None
+        return
+    assert abs(l0.item() - g["loss0"].item()) <= TOL_LOSS * max(1.0, abs(g["loss0"].item()))
+    assert abs(l1.item() - g["loss1"].item()) <= TOL_LOSS * max(1.0, abs(g["loss1"].item()))
+    assert normalised_max_err(d_img.cpu(), torch.from_numpy(g["d_img"])) <= TOL_GRAD
+    assert normalised_max_err(d_words.cpu(), torch.from_numpy(g["d_words"])) <= TOL_GRAD
+    from sba_gan_b200.losses import words_similarity, class_mask
+    sim = words_similarity(d["img_features"].cuda(), d["words_emb"].cuda(), d["cap_lens"].cuda(), *gammas)
+    if use_cls:
+        sim = sim.masked_fill(class_mask(d["class_ids"], sim.device), float("-inf"))
+    assert normalised_max_err(sim.cpu(), torch.from_numpy(g["sim_masked"])) <= TOL_LOSS
+
+
+@pytest.mark.parametrize("spec", [
+    # B, nef, L, ih, iw, gammas
+    (48, 256, 18, 17, 17, (4.0, 5.0, 10.0)),     # BASELINE configs[2], B=48
+    (5, 256, 12, 17, 17, (4.0, 5.0, 10.0)),      # bird_attn2 WORDS_NUM-ish
+    (6, 256, 20, 17, 17, (5.0, 5.0, 10.0)),      # default WORDS_NUM (24-word kernel)
+    (4, 256, 25, 17, 17, (4.0, 5.0, 10.0)),      # longest yml caption (32-word kernel)
+    (3, 128, 32, 9, 9, (4.0, 5.0, 10.0)),        # maximum words
+    (7, 48, 5, 3, 4, (1.0, 2.0, 3.0)),           # tiny / odd
+    (9, 256, 18, 17, 17, (10.0, 5.0, 10.0)),     # sharp gamma1
+])
+def test_vs_oracle_fp64(spec):
+    B, nef, L, ih, iw, gammas = spec
+    d = synth_words_loss_inputs(B, nef, L, ih, iw, seed=300 + B, min_len=1, n_classes=max(2, B // 3))
+    l0, l1, maps, d_img, d_words = _run(d, B, gammas, True, True)
+    img64, words64 = d["img_features"].double(), d["words_emb"].double()
+    lens = d["cap_lens"].tolist()
+    sim = oracle.words_similarity(img64, words64, lens, *gammas).requires_grad_(True)
+    r0, r1, _ = oracle.ce_tail(sim, d["labels"], d["class_ids"])
+    (r0 + r1).backward()
+    rd_img, rd_words = oracle.words_loss_backward(img64, words64, lens, sim.grad, *gammas)
+    assert abs(l0.item() - r0.item()) <= TOL_LOSS * max(1.0, abs(r0.item())), (l0.item(), r0.item())
+    assert abs(l1.item() - r1.item()) <= TOL_LOSS * max(1.0, abs(r1.item()))
+    assert normalised_max_err(d_img.cpu(), rd_img) <= TOL_GRAD
+    assert normalised_max_err(d_words.cpu(), rd_words) <= TOL_GRAD
+    _, _, rmaps = oracle.words_loss(img64, words64, None, d["cap_lens"], None, B, *gammas)
+    assert max(normalised_max_err(a.cpu(), b) for a, b in zip(maps, rmaps)) <= TOL_LOSS
+
+
+def test_full_size_b256_rows_and_sharding():
+    """BASELINE configs[2] at B=256: the oracle takes ~30 s for the whole matrix, so check
+    (i) 6 image rows against the oracle, (ii) row-sharded evaluation (4 shards, as on 4 GPUs)
+    reproduces the unsharded matrix bit for bit, (iii) the diagonal dominates for matched
+    pairs is NOT assumed (random data) but every entry is finite."""
+    from sba_gan_b200.losses import words_similarity
+    B = 256
+    d = synth_words_loss_inputs(B, 256, 18, 17, 17, seed=1234)
+    img, words, lens = d["img_features"].cuda(), d["words_emb"].cuda(), d["cap_lens"].cuda()
+    full = words_similarity(img, words, lens, 4.0, 5.0, 10.0)
+    assert torch.isfinite(full).all()
+    parts = [words_similarity(img[r:r + 64], words, lens, 4.0, 5.0, 10.0, row_offset=r) for r in range(0, B, 64)]
+    assert torch.equal(torch.cat(parts, 0), full)
+    rows = [0, 1, 77, 128, 200, 255]
+    ref = oracle.words_similarity(d["img_features"][rows].double(), d["words_emb"].double(), d["cap_lens"].tolist(),
+                                  4.0, 5.0, 10.0)
+    assert normalised_max_err(full[rows].cpu(), ref) <= TOL_LOSS
+
+
+def test_gan_training_mode_words_detached():
+    """trainer_bert.py:257 detaches the words: only d_img is produced."""
+    d = synth_words_loss_inputs(6, 256, 18, 17, 17, seed=8)
+    l0, l1, _, d_img, d_words = _run(d, 6, (4.0, 5.0, 10.0), True, True, need_words_grad=False)
+    assert d_words is None and d_img is not None
+    sim = oracle.words_similarity(d["img_features"].double(), d["words_emb"].double(), d["cap_lens"].tolist(),
+                                  4.0, 5.0, 10.0).requires_grad_(True)
+    r0, r1, _ = oracle.ce_tail(sim, d["labels"], d["class_ids"])
+    (r0 + r1).backward()
+    rd_img, _ = oracle.words_loss_backward(d["img_features"].double(), d["words_emb"].double(),
+                                           d["cap_lens"].tolist(), sim.grad, 4.0, 5.0, 10.0)
+    assert normalised_max_err(d_img.cpu(), rd_img) <= TOL_GRAD
+
+
+@pytest.mark.parametrize("tag", ["f32"])
+def test_func_attention_golden(golden_dir, tag):
+    from sba_gan_b200 import func_attention
+    g = np.load(os.path.join(golden_dir, f"func_attention_{tag}.npz"))
+    wc, attn = func_attention(torch.from_numpy(g["query"]).cuda(), torch.from_numpy(g["context"]).cuda(), 4.0)
+    assert tuple(wc.shape) == g["wc"].shape and tuple(attn.shape) == g["attn"].shape
+    assert normalised_max_err(wc.cpu(), torch.from_numpy(g["wc"])) <= TOL_LOSS
+    assert normalised_max_err(attn.cpu(), torch.from_numpy(g["attn"])) <= TOL_LOSS
+
+
+def test_gammas_default_to_reference_cfg():
+    """With the reference's miscc.config imported, the drop-in reads cfg.TRAIN.SMOOTH like
+    losses.py:91,106,123; here a stand-in module plays that role."""
+    import sys
+    import types
+    from sba_gan_b200 import words_loss
+    d = synth_words_loss_inputs(4, 64, 9, 5, 5, seed=2)
+    smooth = types.SimpleNamespace(GAMMA1=4.0, GAMMA2=5.0, GAMMA3=10.0)
+    mod = types.ModuleType("miscc.config")
+    mod.cfg = types.SimpleNamespace(TRAIN=types.SimpleNamespace(SMOOTH=smooth))
+    saved = sys.modules.get("miscc.config")
+    sys.modules["miscc.config"] = mod
+    try:
+        l0, l1, _ = words_loss(d["img_features"].cuda(), d["words_emb"].cuda(), d["labels"].cuda(), d["cap_lens"],
+                               d["class_ids"], 4)
+    finally:
+        if saved is None:
+            sys.modules.pop("miscc.config")
+        else:
+            sys.modules["miscc.config"] = saved
+    r0, r1, _ = oracle.words_loss(d["img_features"].double(), d["words_emb"].double(), d["labels"], d["cap_lens"],
+                                  d["class_ids"], 4, 4.0, 5.0, 10.0)
+    assert abs(l0.item() - r0.item()) <= TOL_LOSS * max(1.0, abs(r0.item()))
+    assert abs(l1.item() - r1.item()) <= TOL_LOSS * max(1.0, abs(r1.item()))
