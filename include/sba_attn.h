@@ -71,16 +71,17 @@ SBA_API int sba_last_launch_count(void);
  * c_code   [B, idf, Q]   dtype  out weightedContext
  * attn     [B, L, Q]     dtype  out attention map
  * srcT     [B, idf, L]   fp32   out sourceT = W.ctx, kept for the backward
- * mask_bits[B] uint32    scratch    (only touched when mask != NULL)
+ * scratch  [3*B] uint32  scratch    [0,B): caption mask bit words (kept for the backward),
+ *                                   [B,3B): per-sample ready counters / max|srcT| of this launch
  */
 SBA_API int sba_attn_fwd(const void* x, const float* ctx, const float* W, const uint8_t* mask,
-                 void* c_code, void* attn, float* srcT, uint32_t* mask_bits,
+                 void* c_code, void* attn, float* srcT, uint32_t* scratch,
                  int B, int idf, int cdf, int L, int Q,
                  int dtype, int mask_mode, int algo, void* stream);
 
 /* ---- autograd backward of the above ------------------------------
  * srcT     [B, idf, L] fp32         from the forward
- * mask_bits[B] uint32               from the forward (ignored when mask == NULL)
+ * scratch  [3*B] uint32             from the forward (mask words; ignored when mask == NULL)
  * g_c      [B, idf, Q] dtype        grad of c_code
  * g_attn   [B, L, Q]   dtype nullable grad of attn (NULL in GAN training: attn is discarded,
  *                                   trainer_bert.py:267)
@@ -90,7 +91,7 @@ SBA_API int sba_attn_fwd(const void* x, const float* ctx, const float* W, const 
  * dCtx     [B, cdf, L] fp32   out   nullable (words are detached in GAN training)
  */
 SBA_API int sba_attn_bwd(const void* x, const float* ctx, const float* W, const uint8_t* mask,
-                 const float* srcT, const uint32_t* mask_bits,
+                 const float* srcT, const uint32_t* scratch,
                  const void* g_c, const void* g_attn,
                  void* dX, float* dSrc, float* dW, float* dCtx,
                  int B, int idf, int cdf, int L, int Q,

@@ -80,7 +80,7 @@ int sba_attn_fwd(const void* x, const float* ctx, const float* W, const uint8_t*
                  int algo, void* stream) {
     g_launches = 0;
     g_err[0] = 0;
-    if (!x || !ctx || !W || !c_code || !attn || !srcT || (mask && !mask_bits)) {
+    if (!x || !ctx || !W || !c_code || !attn || !srcT || !mask_bits) {
         set_error("sba_attn_fwd: null pointer argument");
         return SBA_ERR_ARG;
     }
@@ -88,10 +88,12 @@ int sba_attn_fwd(const void* x, const float* ctx, const float* W, const uint8_t*
     if (rc) return rc;
     AttnShape s{B, idf, cdf, L, Q, dtype, mask_mode};
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (algo == SBA_ALGO_MMA) {
-        set_error("sba_attn_fwd: SBA_ALGO_MMA is not available for this shape");
+    const bool can_mma = mma_supports(s);
+    if (algo == SBA_ALGO_MMA && !can_mma) {
+        set_error("sba_attn_fwd: SBA_ALGO_MMA does not cover idf=%d L=%d Q=%d cdf=%d B=%d", idf, L, Q, cdf, B);
         return SBA_ERR_UNSUPPORTED;
     }
+    if (algo != SBA_ALGO_SIMT && can_mma) return mma_attn_fwd(x, ctx, W, mask, c_code, attn, srcT, mask_bits, s, st);
     rc = simt_project(ctx, W, mask, srcT, mask_bits, s, st);
     if (rc) return rc;
     return simt_attn_fwd(x, srcT, mask ? mask_bits : nullptr, c_code, attn, s, st);
@@ -110,10 +112,6 @@ int sba_attn_bwd(const void* x, const float* ctx, const float* W, const uint8_t*
     if (rc) return rc;
     AttnShape s{B, idf, cdf, L, Q, dtype, mask_mode};
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (algo == SBA_ALGO_MMA) {
-        set_error("sba_attn_bwd: SBA_ALGO_MMA is not available for this shape");
-        return SBA_ERR_UNSUPPORTED;
-    }
     cudaError_t e = cudaMemsetAsync(dSrc, 0, (size_t)B * idf * L * sizeof(float), st);
     if (e != cudaSuccess) {
         set_error("sba_attn_bwd: memset: %s", cudaGetErrorString(e));

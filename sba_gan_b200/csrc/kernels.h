@@ -19,6 +19,11 @@ int simt_attn_bwd(const void* x, const float* srcT, const uint32_t* mask_bits, c
 int simt_attn_bwd_epilogue(const float* ctx, const float* W, const float* dSrc, float* dW, float* dCtx,
                            const AttnShape& s, cudaStream_t st);
 
+// attn_mma_fwd.cu / attn_mma_bwd.cu - tensor-core (mma.sync) family with TMA-staged tiles
+bool mma_supports(const AttnShape& s);
+int mma_attn_fwd(const void* x, const float* ctx, const float* W, const uint8_t* mask, void* c_code, void* attn,
+                 float* srcT, uint32_t* mask_bits, const AttnShape& s, cudaStream_t st);
+
 // words_loss.cu - fused DAMSM region-word similarity (kernel c) and its backward
 size_t words_bwd_workspace_bytes(int B_img, int B_cap, int nef, int R, int Lw);
 int words_sim_fwd(const float* img, const float* words, const int* cap_lens, float* sim, float* att_diag, float* wc_out,

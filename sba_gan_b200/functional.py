@@ -42,7 +42,7 @@ def attn_forward_raw(x, context, weight, mask_u8, mask_mode, algo):
     c_code = torch.empty_like(x)
     attn = torch.empty((B, L, ih, iw), dtype=x.dtype, device=x.device)
     srcT = torch.empty((B, idf, L), dtype=torch.float32, device=x.device)
-    mask_bits = torch.empty((B,), dtype=torch.int32, device=x.device) if mask_u8 is not None else None
+    mask_bits = torch.empty((3 * B,), dtype=torch.int32, device=x.device)   # scratch words, see sba_attn.h
     rc = lib.sba_attn_fwd(_ptr(x), _ptr(ctx32), _ptr(w32), _ptr(mask_u8), _ptr(c_code), _ptr(attn), _ptr(srcT),
                           _ptr(mask_bits), B, idf, cdf, L, Q, _DTYPES[x.dtype], mask_mode, algo, _stream())
     _abi.check(rc, "sba_attn_fwd")

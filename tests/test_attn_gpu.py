@@ -18,7 +18,12 @@ pytestmark = pytest.mark.gpu
 TOL_FWD_F32 = 1e-5
 TOL_GRAD_F32 = 1e-4
 TOL_BF16 = 2e-2
-ALGOS = ["simt"]
+ALGOS = ["simt", "mma"]
+
+
+def _mma_ok(idf, L, Q, B=1):
+    """shapes the tensor-core family covers (sba::mma_supports); others must be refused."""
+    return idf in (32, 48) and 9 <= L <= 32 and Q % 128 == 0
 
 
 def _module(idf, cdf, weight, dtype=torch.float32, algo="auto", mask_mode="reference"):
@@ -58,6 +63,8 @@ def _sub(name, t):
 @pytest.mark.parametrize("name", list(ATTN_CASES))
 def test_matches_reference_golden(golden_dir, name, algo):
     B, idf, cdf, L, ih, iw, seed, masked, with_ga = ATTN_CASES[name]
+    if algo == "mma" and not _mma_ok(idf, L, ih * iw):
+        pytest.skip("shape not covered by the tensor-core family")
     g = np.load(os.path.join(golden_dir, f"{name}_f32.npz"))
     d = synth_attention_inputs(B, idf, cdf, L, ih, iw, seed=seed, with_g_attn=with_ga)
     out = _run(d, masked, algo)
@@ -80,6 +87,11 @@ SWEEP = [
     (5, 32, 1, 4, 4, False, "reference", False),       # single word: attn == 1
     (20, 32, 18, 64, 64, True, "reference", False),    # yml batch size
     (4, 16, 7, 2, 2, True, "reference", True),         # tiny
+    (3, 48, 12, 16, 16, True, "reference", True),      # coco GF_DIM, 2 word tiles
+    (7, 32, 25, 16, 8, True, "reference", True),       # 4 word tiles, B does not divide Q
+    (5, 48, 20, 32, 16, True, "per_sample", False),    # default WORDS_NUM
+    (2, 32, 9, 16, 16, False, "reference", True),      # smallest L of the tensor-core family
+    (130, 32, 18, 16, 8, True, "reference", False),    # more samples than CTAs-per-sample logic assumes
 ]
 
 
@@ -87,6 +99,8 @@ SWEEP = [
 @pytest.mark.parametrize("spec", SWEEP)
 def test_shape_sweep_vs_oracle(spec, algo):
     B, idf, L, ih, iw, masked, mask_mode, with_ga = spec
+    if algo == "mma" and not _mma_ok(idf, L, ih * iw):
+        pytest.skip("shape not covered by the tensor-core family")
     d = synth_attention_inputs(B, idf, 256, L, ih, iw, seed=100 + B + idf + L, with_g_attn=with_ga, min_len=1)
     out = _run(d, masked, algo, mask_mode=mask_mode)
     d64 = {k: (v.double() if v.is_floating_point() else v) for k, v in d.items()}
@@ -129,6 +143,8 @@ def test_bf16_io(spec, algo):
     """bf16 tensors, fp32 arithmetic.  Oracle = fp32 reference maths on the bf16-rounded
     inputs (SURVEY.md §8 parity note); tolerance 2e-2."""
     B, idf, L, ih, iw, masked = spec
+    if algo == "mma" and not _mma_ok(idf, L, ih * iw):
+        pytest.skip("shape not covered by the tensor-core family")
     d = synth_attention_inputs(B, idf, 256, L, ih, iw, seed=7, with_g_attn=True)
     out = _run(d, masked, algo, dtype=torch.bfloat16)
     r = {k: (v.to(torch.bfloat16).double() if v.is_floating_point() else v) for k, v in d.items()}
@@ -170,6 +186,14 @@ def test_sticky_mask_and_eval_mode():
         _, a3 = m(d["x"].cuda(), d["context"].cuda())
     assert not torch.equal(a1, a3)
     assert c1.shape == (4, 32, 8, 8) and a1.shape == (4, 18, 8, 8)
+
+
+def test_mma_refuses_uncovered_shapes():
+    from sba_gan_b200 import word_region_attention
+    x = torch.zeros(2, 32, 4, 4, device="cuda")
+    w = torch.zeros(32, 256, 1, 1, device="cuda")
+    with pytest.raises(RuntimeError, match="does not cover"):
+        word_region_attention(x, torch.zeros(2, 256, 12, device="cuda"), w, algo="mma")
 
 
 def test_error_behaviour():

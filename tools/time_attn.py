@@ -26,33 +26,45 @@ for hw in (64, 128):
     lens = torch.randint(5, L + 1, (B,))
     mask = (torch.arange(L)[None] >= lens[:, None]).to(torch.uint8).to(dev)
     srcT = torch.empty(B, idf, L, device=dev)
-    mb = torch.empty(B, dtype=torch.int32, device=dev)
+    mb = torch.empty(3 * B, dtype=torch.int32, device=dev)
     dSrc = torch.empty(B, idf, L, device=dev)
     dW = torch.empty(idf, cdf, device=dev)
-    st = torch.cuda.current_stream().cuda_stream
+    st_holder = [torch.cuda.current_stream().cuda_stream]
     dcode = _DTYPES[dt]
 
     def fwd(k):
         x, g, c, a, dx = sets[k % nset]
         rc = lib.sba_attn_fwd(x.data_ptr(), ctx.data_ptr(), W.data_ptr(), mask.data_ptr(), c.data_ptr(), a.data_ptr(),
-                              srcT.data_ptr(), mb.data_ptr(), B, idf, cdf, L, Q, dcode, 0, algo, st)
+                              srcT.data_ptr(), mb.data_ptr(), B, idf, cdf, L, Q, dcode, 0, algo, st_holder[0])
         _abi.check(rc, "fwd")
 
     def bwd(k):
         x, g, c, a, dx = sets[k % nset]
         rc = lib.sba_attn_bwd(x.data_ptr(), ctx.data_ptr(), W.data_ptr(), mask.data_ptr(), srcT.data_ptr(), mb.data_ptr(),
                               g.data_ptr(), None, dx.data_ptr(), dSrc.data_ptr(), dW.data_ptr(), None, B, idf, cdf, L, Q,
-                              dcode, 0, algo, st)
+                              dcode, 0, algo, st_holder[0])
         _abi.check(rc, "bwd")
 
     def timeit(fn, n=30):
+        """device time per call: n calls (rotating buffer sets) captured in one CUDA graph"""
         for k in range(5):
             fn(k)
         torch.cuda.synchronize()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.stream(side):
+            st_holder[0] = torch.cuda.current_stream().cuda_stream
+            with torch.cuda.graph(gr, stream=side):
+                st_holder[0] = torch.cuda.current_stream().cuda_stream
+                for k in range(n):
+                    fn(k)
+        st_holder[0] = torch.cuda.current_stream().cuda_stream
+        gr.replay()
+        torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
         e0.record()
-        for k in range(n):
-            fn(k)
+        gr.replay()
         e1.record()
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) / n * 1e-3
