@@ -32,6 +32,8 @@ int check_launch(const char* what) {
 
 namespace {
 
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
 int check_attn_shape(const char* fn, int B, int idf, int cdf, int L, int Q, int dtype, int mask_mode, int algo) {
     if (B <= 0 || idf <= 0 || cdf <= 0 || L <= 0 || Q <= 0) {
         set_error("%s: sizes must be positive (B=%d idf=%d cdf=%d L=%d Q=%d)", fn, B, idf, cdf, L, Q);
@@ -88,9 +90,9 @@ int sba_attn_fwd(const void* x, const float* ctx, const float* W, const uint8_t*
     if (rc) return rc;
     AttnShape s{B, idf, cdf, L, Q, dtype, mask_mode};
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const bool can_mma = mma_supports(s);
+    const bool can_mma = mma_supports(s) && aligned16(x);
     if (algo == SBA_ALGO_MMA && !can_mma) {
-        set_error("sba_attn_fwd: SBA_ALGO_MMA does not cover idf=%d L=%d Q=%d cdf=%d B=%d", idf, L, Q, cdf, B);
+        set_error("sba_attn_fwd: SBA_ALGO_MMA does not cover idf=%d L=%d Q=%d cdf=%d B=%d (or x is not 16-byte aligned)", idf, L, Q, cdf, B);
         return SBA_ERR_UNSUPPORTED;
     }
     if (algo != SBA_ALGO_SIMT && can_mma) return mma_attn_fwd(x, ctx, W, mask, c_code, attn, srcT, mask_bits, s, st);
@@ -117,7 +119,13 @@ int sba_attn_bwd(const void* x, const float* ctx, const float* W, const uint8_t*
         set_error("sba_attn_bwd: memset: %s", cudaGetErrorString(e));
         return SBA_ERR_CUDA;
     }
-    rc = simt_attn_bwd(x, srcT, mask ? mask_bits : nullptr, g_c, g_attn, dX, dSrc, s, st);
+    const bool can_mma = mma_supports(s) && aligned16(x) && aligned16(g_c);
+    if (algo == SBA_ALGO_MMA && !can_mma) {
+        set_error("sba_attn_bwd: SBA_ALGO_MMA does not cover idf=%d L=%d Q=%d cdf=%d B=%d (or x / g_c is not 16-byte aligned)", idf, L, Q, cdf, B);
+        return SBA_ERR_UNSUPPORTED;
+    }
+    if (algo != SBA_ALGO_SIMT && can_mma) rc = mma_attn_bwd(x, srcT, mask, g_c, g_attn, dX, dSrc, s, st);
+    else rc = simt_attn_bwd(x, srcT, mask ? mask_bits : nullptr, g_c, g_attn, dX, dSrc, s, st);
     if (rc) return rc;
     return simt_attn_bwd_epilogue(ctx, W, dSrc, dW, dCtx, s, st);
 }

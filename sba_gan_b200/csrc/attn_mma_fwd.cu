@@ -55,10 +55,6 @@ struct SrcFrags {
     uint32_t bc8[NSPLIT][NC8];                           // c-phase  B: k = word (last 8)
 };
 
-// Channel held by MMA k-index kk of k-step ks (fp32 path): lane c owns channels c, c+4, c+8,
-// c+12 of the step so that its four LDS.32 gathers hit four different 8-bank groups.
-__device__ __forceinline__ int chan_of(int ks, int c, int j) { return 16 * ks + c + 4 * j; }
-
 // Build the register-resident sourceT fragments of sample b from global memory (written by
 // phase 0 of this launch, possibly by another SM: L1 is bypassed with __ldcg).
 template <typename T, int IDF, int NT, class Frags>
@@ -148,22 +144,6 @@ __device__ __forceinline__ void project_phase(const float* __restrict__ ctx, con
         named_bar_sync(1, kConsumers);
         if (tid == 0) atomicAdd(ready + b, 1u);
     }
-}
-
-__device__ __forceinline__ uint32_t ld_acquire(const uint32_t* p) {
-    uint32_t v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ float ex2_approx(float x) {
-    float y;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-__device__ __forceinline__ float rcp_approx(float x) {
-    float y;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
 }
 
 template <typename T, int IDF, int NT>
@@ -268,9 +248,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_attn_fwd_mma(const FwdParams p)
                     xv[ks][2 * j + 1] = rowp[8];    // pixel g + 8
                     amax = fmaxf(amax, fmaxf(fabsf(xv[ks][2 * j]), fabsf(xv[ks][2 * j + 1])));
                 }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(&bar_empty[stage]));
-            amax = warp_max(amax);
+            amax = warp_absmax_redux(amax);
             float sc_x;
             pow2_scale(amax, sc_x, inv_x);
 #pragma unroll
@@ -293,8 +271,6 @@ __global__ void __launch_bounds__(kThreads, 2) k_attn_fwd_mma(const FwdParams p)
                              : "=r"(a_hi[ks][0]), "=r"(a_hi[ks][1]), "=r"(a_hi[ks][2]), "=r"(a_hi[ks][3])
                              : "r"(addr));
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(&bar_empty[stage]));
         }
 
         // ---- S = x^T . srcT  (GlobalAttention.py:102) ------------------------------------------
@@ -434,6 +410,13 @@ __global__ void __launch_bounds__(kThreads, 2) k_attn_fwd_mma(const FwdParams p)
                 off += 8u * (unsigned)Q;
             }
         }
+
+        // Release the stage only here, behind the output stores: mbarrier.arrive is a release, so
+        // ptxas cannot hoist it above them, and they depend on every fragment load of the tile.
+        // (Arriving right after the ldmatrix / LDS instructions were ISSUED let the producer's next
+        // bulk copy overwrite the stage while loads of a slow warp were still queued.)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&bar_empty[stage]));
 
         if (++t == TPS) { t = 0; ++b; }
         if (++stage == NST) { stage = 0; phase ^= 1; }

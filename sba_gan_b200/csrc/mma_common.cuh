@@ -130,6 +130,34 @@ __device__ __forceinline__ float quad_sum(float v) {
     return v + __shfl_xor_sync(0xffffffffu, v, 2);
 }
 
+
+// Channel held by MMA k-index of k-step ks on the fp32 path: lane c owns channels c, c+4, c+8,
+// c+12 of the step (k = 2c, 2c+1, 2c+8, 2c+9) so that its four LDS.32 gathers hit four
+// different 8-bank groups.  The same permutation is applied to the sourceT operand.
+__device__ __forceinline__ int chan_of(int ks, int c, int j) { return 16 * ks + c + 4 * j; }
+
+__device__ __forceinline__ uint32_t ld_acquire(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// max over the warp of non-negative floats (their bit patterns order like unsigned integers)
+__device__ __forceinline__ float warp_absmax_redux(float nonneg) {
+    uint32_t r;
+    asm volatile("redux.sync.max.u32 %0, %1, 0xffffffff;" : "=r"(r) : "r"(__float_as_uint(nonneg)));
+    return __uint_as_float(r);
+}
+
 constexpr int TQ = 128;            // pixels per CTA tile: 8 consumer warps x one 16-pixel m-tile
 constexpr int kConsumerWarps = 8;
 constexpr int kConsumers = kConsumerWarps * 32;

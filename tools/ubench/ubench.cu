@@ -151,6 +151,69 @@ __global__ void k_mma(float* out, int iters) {
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+
+// warp-matrix data movement used by the tensor-core attention kernels
+template <int ILP>
+__global__ void k_movm(float* out, int iters) {
+    uint32_t v[ILP];
+#pragma unroll
+    for (int j = 0; j < ILP; ++j) v[j] = threadIdx.x * 7 + j;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int j = 0; j < ILP; ++j) asm volatile("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;" : "=r"(v[j]) : "r"(v[j]));
+    }
+    uint32_t s = 0;
+#pragma unroll
+    for (int j = 0; j < ILP; ++j) s ^= v[j];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = (float)s;
+}
+// KIND 0: ldmatrix.x4.trans, 1: stmatrix.x4.trans, 2: LDG.64 hitting L1 (256 B per warp, 12 KB table)
+template <int KIND>
+__global__ void k_matmove(float* out, const uint2* __restrict__ tab, int iters) {
+    __shared__ __align__(128) uint16_t sm[8 * 32 * 72];
+    for (int i = threadIdx.x; i < 8 * 32 * 72; i += blockDim.x) sm[i] = (uint16_t)i;
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t base = (uint32_t)__cvta_generic_to_shared(sm + warp * 32 * 72 + (lane & 15) * 72 + (lane >> 4) * 8);
+    uint32_t a0 = lane, a1 = 1, a2 = 2, a3 = 3, acc = 0;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            if constexpr (KIND == 0) {
+                uint32_t r0, r1, r2, r3;
+                asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(base + (u & 1) * 16 * 72 * 2));
+                acc ^= r0 ^ r1 ^ r2 ^ r3;
+            } else if constexpr (KIND == 1) {
+                asm volatile("stmatrix.sync.aligned.m8n8.x4.trans.shared.b16 [%0], {%1,%2,%3,%4};" :: "r"(base + (u & 1) * 16 * 72 * 2), "r"(a0 + u), "r"(a1), "r"(a2), "r"(a3) : "memory");
+            } else {
+                const uint2 v = __ldg(tab + ((it * 8 + u) % 48) * 32 + lane);
+                acc ^= v.x ^ v.y;
+            }
+        }
+    }
+    if (KIND == 1) { __syncthreads(); acc = sm[threadIdx.x]; }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = (float)acc;
+}
+// fp32 -> fp16 hi/lo split (the conversion load of the 3xFP16 scheme), 2 values per iteration
+template <int ILP>
+__global__ void k_split(float* out, int iters, float sc) {
+    float x[ILP], y[ILP]; uint32_t acc = 0;
+#pragma unroll
+    for (int j = 0; j < ILP; ++j) { x[j] = threadIdx.x * 0.37f + j; y[j] = j * 1.1f; }
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int j = 0; j < ILP; ++j) {
+            const float s0 = x[j] * sc, s1 = y[j] * sc;
+            const __half2 h = __floats2half2_rn(s0, s1);
+            const float2 hf = __half22float2(h);
+            const __half2 l = __floats2half2_rn(s0 - hf.x, s1 - hf.y);
+            acc ^= *reinterpret_cast<const uint32_t*>(&h) + *reinterpret_cast<const uint32_t*>(&l);
+            x[j] += 1.0f; y[j] += 0.5f;
+        }
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = (float)acc;
+}
+
 __global__ void k_copy(const float4* __restrict__ in, float4* __restrict__ out, size_t n) {
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -219,6 +282,22 @@ int main() {
         printf("{\"bench\": \"mma_sync_bf16_m16n8k16\", \"warps_per_sm\": %d, \"tflops\": %.1f}\n", warps_per_sm, warps * iters * 8 * 2.0 * 16 * 8 * 16 / ms / 1e9);
         ms = timeit([&] { k_mma<2, 8><<<blocks, threads>>>(out, iters); });
         printf("{\"bench\": \"mma_sync_tf32_m16n8k8\", \"warps_per_sm\": %d, \"tflops\": %.1f}\n", warps_per_sm, warps * iters * 8 * 2.0 * 16 * 8 * 8 / ms / 1e9);
+    }
+
+    for (int warps_per_sm : {8, 16}) {
+        int threads = 256, blocks = nsm * warps_per_sm * 32 / threads; double warps = (double)blocks * threads / 32;
+        float ms = timeit([&] { k_movm<8><<<blocks, threads>>>(out, iters); });
+        printf("{\"bench\": \"movmatrix\", \"warps_per_sm\": %d, \"warp_inst_per_clk_per_sm_at_1965\": %.3f}\n", warps_per_sm, warps * iters * 8 / (ms * 1e-3) / nsm / 1.965e9);
+        uint2* tab; CK(cudaMalloc(&tab, 48 * 32 * 8)); CK(cudaMemset(tab, 1, 48 * 32 * 8));
+        ms = timeit([&] { k_matmove<0><<<blocks, threads>>>(out, tab, 1024); });
+        printf("{\"bench\": \"ldmatrix_x4_trans\", \"warps_per_sm\": %d, \"warp_inst_per_clk_per_sm_at_1965\": %.3f}\n", warps_per_sm, warps * 1024 * 8 / (ms * 1e-3) / nsm / 1.965e9);
+        ms = timeit([&] { k_matmove<1><<<blocks, threads>>>(out, tab, 1024); });
+        printf("{\"bench\": \"stmatrix_x4_trans\", \"warps_per_sm\": %d, \"warp_inst_per_clk_per_sm_at_1965\": %.3f}\n", warps_per_sm, warps * 1024 * 8 / (ms * 1e-3) / nsm / 1.965e9);
+        ms = timeit([&] { k_matmove<2><<<blocks, threads>>>(out, tab, 1024); });
+        printf("{\"bench\": \"ldg64_l1_hit\", \"warps_per_sm\": %d, \"warp_inst_per_clk_per_sm_at_1965\": %.3f}\n", warps_per_sm, warps * 1024 * 8 / (ms * 1e-3) / nsm / 1.965e9);
+        ms = timeit([&] { k_split<8><<<blocks, threads>>>(out, iters, 1.5f); });
+        printf("{\"bench\": \"fp16_split_pair\", \"warps_per_sm\": %d, \"warp_pairs_per_clk_per_sm_at_1965\": %.3f}\n", warps_per_sm, warps * iters * 8 / (ms * 1e-3) / nsm / 1.965e9);
+        CK(cudaFree(tab));
     }
     {
         size_t n = (size_t)1 << 28;  // 4 GiB of float4? no: 2^28 float4 = 4 GiB; use 2^26 = 1 GiB
