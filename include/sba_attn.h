@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SBA_ABI_VERSION 1
+#define SBA_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define SBA_API __attribute__((visibility("default")))
@@ -86,7 +86,8 @@ SBA_API int sba_attn_fwd(const void* x, const float* ctx, const float* W, const 
  * g_attn   [B, L, Q]   dtype nullable grad of attn (NULL in GAN training: attn is discarded,
  *                                   trainer_bert.py:267)
  * dX       [B, idf, Q] dtype  out
- * dSrc     [B, idf, L] fp32   out   grad of sourceT (also the reduction workspace)
+ * dSrc     [B*idf*L + B + 1] fp32 out: grad of sourceT [B, idf, L] (also the reduction workspace),
+ *                                   followed by B + 1 scratch words (per-sample completion counters)
  * dW       [idf, cdf]  fp32   out   nullable
  * dCtx     [B, cdf, L] fp32   out   nullable (words are detached in GAN training)
  */

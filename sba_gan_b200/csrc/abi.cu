@@ -114,18 +114,18 @@ int sba_attn_bwd(const void* x, const float* ctx, const float* W, const uint8_t*
     if (rc) return rc;
     AttnShape s{B, idf, cdf, L, Q, dtype, mask_mode};
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    cudaError_t e = cudaMemsetAsync(dSrc, 0, (size_t)B * idf * L * sizeof(float), st);
-    if (e != cudaSuccess) {
-        set_error("sba_attn_bwd: memset: %s", cudaGetErrorString(e));
-        return SBA_ERR_CUDA;
-    }
     const bool can_mma = mma_supports(s) && aligned16(x) && aligned16(g_c);
     if (algo == SBA_ALGO_MMA && !can_mma) {
         set_error("sba_attn_bwd: SBA_ALGO_MMA does not cover idf=%d L=%d Q=%d cdf=%d B=%d (or x / g_c is not 16-byte aligned)", idf, L, Q, cdf, B);
         return SBA_ERR_UNSUPPORTED;
     }
-    if (algo != SBA_ALGO_SIMT && can_mma) rc = mma_attn_bwd(x, srcT, mask, g_c, g_attn, dX, dSrc, s, st);
-    else rc = simt_attn_bwd(x, srcT, mask ? mask_bits : nullptr, g_c, g_attn, dX, dSrc, s, st);
+    if (algo != SBA_ALGO_SIMT && can_mma) return mma_attn_bwd(x, ctx, W, srcT, mask, g_c, g_attn, dX, dSrc, dW, dCtx, s, st);
+    cudaError_t e = cudaMemsetAsync(dSrc, 0, (size_t)B * idf * L * sizeof(float), st);
+    if (e != cudaSuccess) {
+        set_error("sba_attn_bwd: memset: %s", cudaGetErrorString(e));
+        return SBA_ERR_CUDA;
+    }
+    rc = simt_attn_bwd(x, srcT, mask ? mask_bits : nullptr, g_c, g_attn, dX, dSrc, s, st);
     if (rc) return rc;
     return simt_attn_bwd_epilogue(ctx, W, dSrc, dW, dCtx, s, st);
 }

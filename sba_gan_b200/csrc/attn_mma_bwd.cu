@@ -39,7 +39,12 @@ struct BwdParams {
     const uint8_t* mask;
     void* dX;
     float* dSrc;
-    int B, L, Q, mask_mode;
+    const float* ctx;     // [B, cdf, L]   (epilogue)
+    const float* W;       // [idf, cdf]    (epilogue, dCtx only)
+    float* dW;            // [idf, cdf]    nullable
+    float* dCtx;          // [B, cdf, L]   nullable
+    uint32_t* cnt;        // [B] per-sample completion counters, [B] "dW is zeroed" flag; zero on entry
+    int B, L, Q, cdf, mask_mode;
     int tiles_per_sample;
     int n_tiles;
     int nst;
@@ -62,6 +67,8 @@ struct BwdCfg {
     static constexpr int NF_C8 = HAS_K8 ? NC8 / 2 : 0;          // dX phase: k = last 8 words, two n-tiles per entry
     static constexpr int NFB = NF_S + NF_C16 + NF_C8;
     static constexpr int TAB_BYTES = HALF ? NSPLIT * NFB * 32 * 8 : 0;   // fragment table in shared memory (fp32 only)
+    static constexpr int EPI_BYTES = IDF * 32 * 4;                       // dSrc[b] staged for the dW / dCtx epilogue
+    static constexpr int SCR_BYTES = TAB_BYTES > EPI_BYTES ? TAB_BYTES : EPI_BYTES;   // the two never live together
 };
 
 // One fragment entry (the four sourceT values lane (g, c) contributes to fragment fb).
@@ -112,9 +119,10 @@ __global__ void __launch_bounds__(kThreads, 2) k_attn_bwd_mma(const BwdParams p)
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int NST = p.nst;
     uint2* tab = reinterpret_cast<uint2*>(smem_raw + (size_t)NST * C::STAGE_BYTES);                        // [NSPLIT*NFB][32]
-    uint32_t* mb_s = reinterpret_cast<uint32_t*>(smem_raw + (size_t)NST * C::STAGE_BYTES + C::TAB_BYTES);  // [B]
+    uint32_t* mb_s = reinterpret_cast<uint32_t*>(smem_raw + (size_t)NST * C::STAGE_BYTES + C::SCR_BYTES);  // [B]
     __shared__ __align__(8) unsigned long long bar_full[kMaxStages], bar_empty[kMaxStages];
     __shared__ float red_s[kConsumerWarps];
+    __shared__ int fin_s;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, c = lane & 3;
@@ -134,7 +142,16 @@ __global__ void __launch_bounds__(kThreads, 2) k_attn_bwd_mma(const BwdParams p)
             mb_s[cap] = bits;
         }
     }
+    // CTA 0 zeroes dW and then raises the flag the per-sample finishers wait on before their atomics
+    if (blockIdx.x == 0 && p.dW != nullptr) {
+        for (int o = tid; o < IDF * p.cdf; o += kThreads) p.dW[o] = 0.f;
+        __threadfence();
+    }
     __syncthreads();
+    if (blockIdx.x == 0 && tid == 0) {
+        __threadfence();
+        atomicExch(p.cnt + p.B, 1u);
+    }
 
     const int w_begin = (int)(((long long)blockIdx.x * p.n_tiles) / gridDim.x);
     const int w_end = (int)(((long long)(blockIdx.x + 1) * p.n_tiles) / gridDim.x);
@@ -189,6 +206,65 @@ __global__ void __launch_bounds__(kThreads, 2) k_attn_bwd_mma(const BwdParams p)
                     }
             }
     };
+    // Per-sample epilogue, fused behind the dSrc reduction: the LAST CTA to flush its share of
+    // sample bb (completion counter == number of CTAs whose tile range touches bb) forms
+    //   dW     += dSrc[bb] . ctx[bb]^T     (conv_context weight grad; atomics over samples)
+    //   dCtx[bb] = W^T . dSrc[bb]          (conv_context input grad)
+    // while the other CTAs keep streaming.  All eight consumer warps call this together.
+    auto finish_sample = [&](int bb) {
+        flush_dsrc(bb);
+        __threadfence();
+        named_bar_sync(1, kConsumers);
+        if (tid == 0) {
+            const long long G = gridDim.x, N = p.n_tiles;
+            const int k0 = (int)((((long long)bb * TPS + 1) * G - 1) / N);
+            const int k1 = (int)((((long long)(bb + 1) * TPS) * G - 1) / N);
+            const uint32_t old = atomicAdd(p.cnt + bb, 1u);
+            fin_s = (old + 1u == (uint32_t)(k1 - k0 + 1)) ? 1 : 0;
+        }
+        named_bar_sync(1, kConsumers);
+        if (fin_s == 0 || (p.dW == nullptr && p.dCtx == nullptr)) return;
+        __threadfence();
+        float* ds = reinterpret_cast<float*>(tab);                 // [IDF][L]; the fragment table is dead here
+        const float* db = p.dSrc + (size_t)bb * IDF * L;
+        for (int o = tid; o < IDF * L; o += kConsumers) ds[o] = __ldcg(db + o);
+        if (p.dW != nullptr) {
+            if (lane == 0) while (ld_acquire(p.cnt + p.B) == 0u) __nanosleep(32);
+            __syncwarp();
+        }
+        named_bar_sync(1, kConsumers);
+        const float* cb = p.ctx + (size_t)bb * p.cdf * L;
+        for (int cc = tid; cc < p.cdf; cc += kConsumers) {
+            if (p.dW != nullptr) {
+                float cv[NT * 8];
+#pragma unroll
+                for (int l = 0; l < NT * 8; ++l) cv[l] = (l < L) ? __ldg(cb + (size_t)cc * L + l) : 0.f;
+                for (int i = 0; i < IDF; ++i) {
+                    float acc = 0.f;
+#pragma unroll
+                    for (int l = 0; l < NT * 8; ++l)
+                        if (l < L) acc = fmaf(ds[i * L + l], cv[l], acc);
+                    atomicAdd(p.dW + (size_t)i * p.cdf + cc, acc);
+                }
+            }
+            if (p.dCtx != nullptr) {
+                float acc[NT * 8];
+#pragma unroll
+                for (int l = 0; l < NT * 8; ++l) acc[l] = 0.f;
+                for (int i = 0; i < IDF; ++i) {
+                    const float wv = __ldg(p.W + (size_t)i * p.cdf + cc);
+#pragma unroll
+                    for (int l = 0; l < NT * 8; ++l)
+                        if (l < L) acc[l] = fmaf(wv, ds[i * L + l], acc[l]);
+                }
+                float* dc = p.dCtx + ((size_t)bb * p.cdf + cc) * L;
+#pragma unroll
+                for (int l = 0; l < NT * 8; ++l)
+                    if (l < L) dc[l] = acc[l];
+            }
+        }
+        named_bar_sync(1, kConsumers);      // ds is re-used (fragment table / next epilogue)
+    };
     // B-operand fragment fb of split sp (0 = hi, 1 = lo)
     auto frag = [&](int sp, int fb) -> uint2 {
         if constexpr (HALF) return tab[(sp * NFB + fb) * 32 + lane];
@@ -206,7 +282,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_attn_bwd_mma(const BwdParams p)
 
     for (int w = w_begin; w < w_end; ++w) {
         if (b != cur_b) {
-            if (cur_b >= 0) flush_dsrc(cur_b);
+            if (cur_b >= 0) finish_sample(cur_b);
             cur_b = b;
             const float* sb = p.srcT + (size_t)b * IDF * L;
             if constexpr (HALF) {
@@ -570,7 +646,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_attn_bwd_mma(const BwdParams p)
         cap0 += step_mod;
         if (cap0 >= Bu) cap0 -= Bu;
     }
-    if (cur_b >= 0) flush_dsrc(cur_b);
+    if (cur_b >= 0) finish_sample(cur_b);
 }
 
 template <typename T, int IDF, int NT, bool HAS_GA>
@@ -592,7 +668,7 @@ int launch_bwd_mma(const BwdParams& p0, cudaStream_t st) {
         }
         max_ctas = sms * (per_sm > 2 ? 2 : per_sm);
     }
-    const size_t fixed = (size_t)C::TAB_BYTES + (size_t)p.B * 4 + 16;
+    const size_t fixed = (size_t)C::SCR_BYTES + (size_t)p.B * 4 + 16;
     int nst = fixed < (size_t)kSmemCap ? (int)(((size_t)kSmemCap - fixed) / C::STAGE_BYTES) : 0;
     if (nst > kMaxStages) nst = kMaxStages;
     if (nst < 2) {
@@ -600,6 +676,11 @@ int launch_bwd_mma(const BwdParams& p0, cudaStream_t st) {
         return SBA_ERR_UNSUPPORTED;
     }
     p.nst = nst;
+    cudaError_t e = cudaMemsetAsync(p.dSrc, 0, ((size_t)p.B * IDF * p.L + p.B + 1) * sizeof(float), st);
+    if (e != cudaSuccess) {
+        set_error("attn_bwd(mma): memset: %s", cudaGetErrorString(e));
+        return SBA_ERR_CUDA;
+    }
     const int grid = p.n_tiles < max_ctas ? p.n_tiles : max_ctas;
     kern<<<grid, kThreads, kSmemCap, st>>>(p);
     add_launches(1);
@@ -623,11 +704,13 @@ int dispatch_ga(const BwdParams& p, int NT, cudaStream_t st) {
 
 }  // namespace
 
-int mma_attn_bwd(const void* x, const float* srcT, const uint8_t* mask, const void* g_c, const void* g_attn, void* dX,
-                 float* dSrc, const AttnShape& s, cudaStream_t st) {
+int mma_attn_bwd(const void* x, const float* ctx, const float* W, const float* srcT, const uint8_t* mask, const void* g_c,
+                 const void* g_attn, void* dX, float* dSrc, float* dW, float* dCtx, const AttnShape& s, cudaStream_t st) {
     BwdParams p{};
     p.x = x; p.g = g_c; p.ga = g_attn; p.srcT = srcT; p.mask = mask; p.dX = dX; p.dSrc = dSrc;
-    p.B = s.B; p.L = s.L; p.Q = s.Q; p.mask_mode = s.mask_mode;
+    p.ctx = ctx; p.W = W; p.dW = dW; p.dCtx = dCtx;
+    p.cnt = reinterpret_cast<uint32_t*>(dSrc + (size_t)s.B * s.idf * s.L);
+    p.B = s.B; p.L = s.L; p.Q = s.Q; p.cdf = s.cdf; p.mask_mode = s.mask_mode;
     p.tiles_per_sample = s.Q / mma::TQ;
     p.n_tiles = s.B * p.tiles_per_sample;
     const int NT = (s.L + 7) / 8;

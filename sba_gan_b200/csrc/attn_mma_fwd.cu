@@ -99,50 +99,40 @@ __device__ __forceinline__ void load_src_frags(Frags& f, const float* __restrict
     }
 }
 
-// Phase 0 of both attention kernels' forward: srcT = W . ctx (GlobalAttention.py:95-97),
-// computed ONCE per sample by the whole grid: unit u = (sample, group of 8 output channels),
-// one warp per channel, lanes = 8 words x 4 quarters of the cdf reduction.  Each unit bumps
-// ready[b]; consumers of sample b wait for ready[b] == IDF/8.  src_max[b] = max |srcT[b]|.
+// srcT = W . ctx (the bias-free 1x1 conv_context, GlobalAttention.py:95-97) as its own small
+// grid, launched in front of the streaming kernel with programmatic dependent launch: block u =
+// (sample, group of 8 output channels), one warp per channel, lanes = 8 words x 4 quarters of
+// the cdf reduction.  The streaming kernel starts prefetching x tiles while this runs and only
+// its consumers wait (griddepcontrol.wait) before they read srcT.
 template <int IDF, int NT>
-__device__ __forceinline__ void project_phase(const float* __restrict__ ctx, const float* __restrict__ W,
-                                              float* __restrict__ srcT, uint32_t* ready, uint32_t* src_max, int B, int cdf,
-                                              int L, int tid) {
-    const int warp = tid >> 5, lane = tid & 31, lg = lane & 7, kq = lane >> 3;
+__global__ void __launch_bounds__(256) k_project_mma(const float* __restrict__ ctx, const float* __restrict__ W,
+                                                     float* __restrict__ srcT, int cdf, int L) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, lg = lane & 7, kq = lane >> 3;
     constexpr int RG = IDF / 8;
-    for (int u = blockIdx.x; u < B * RG; u += gridDim.x) {
-        const int b = u / RG, i = (u - b * RG) * 8 + warp;
-        const float* wrow = W + (size_t)i * cdf;
-        const float* cb = ctx + (size_t)b * cdf * L;
-        float acc[NT];
+    const int u = blockIdx.x, b = u / RG, i = (u - b * RG) * 8 + warp;
+    const float* wrow = W + (size_t)i * cdf;
+    const float* cb = ctx + (size_t)b * cdf * L;
+    float acc[NT];
 #pragma unroll
-        for (int n = 0; n < NT; ++n) acc[n] = 0.f;
-        const int c_lo = (cdf * kq) >> 2, c_hi = (cdf * (kq + 1)) >> 2;
-#pragma unroll 4
-        for (int cc = c_lo; cc < c_hi; ++cc) {
-            const float wv = __ldg(wrow + cc);
-#pragma unroll
-            for (int n = 0; n < NT; ++n) {
-                const int l = lg + 8 * n;
-                const float v = (l < L) ? __ldg(cb + (size_t)cc * L + l) : 0.f;
-                acc[n] = fmaf(wv, v, acc[n]);
-            }
-        }
-        float lmax = 0.f;
+    for (int n = 0; n < NT; ++n) acc[n] = 0.f;
+    const int c_lo = (cdf * kq) >> 2, c_hi = (cdf * (kq + 1)) >> 2;
+#pragma unroll 8
+    for (int cc = c_lo; cc < c_hi; ++cc) {
+        const float wv = __ldg(wrow + cc);
 #pragma unroll
         for (int n = 0; n < NT; ++n) {
-            acc[n] += __shfl_xor_sync(0xffffffffu, acc[n], 8);
-            acc[n] += __shfl_xor_sync(0xffffffffu, acc[n], 16);
             const int l = lg + 8 * n;
-            if (kq == 0 && l < L) {
-                srcT[((size_t)b * IDF + i) * L + l] = acc[n];
-                lmax = fmaxf(lmax, fabsf(acc[n]));
-            }
+            const float v = (l < L) ? __ldg(cb + (size_t)cc * L + l) : 0.f;
+            acc[n] = fmaf(wv, v, acc[n]);
         }
-        lmax = warp_max(lmax);
-        if (lane == 0) atomicMax(src_max + b, __float_as_uint(lmax));
-        __threadfence();
-        named_bar_sync(1, kConsumers);
-        if (tid == 0) atomicAdd(ready + b, 1u);
+    }
+#pragma unroll
+    for (int n = 0; n < NT; ++n) {
+        acc[n] += __shfl_xor_sync(0xffffffffu, acc[n], 8);
+        acc[n] += __shfl_xor_sync(0xffffffffu, acc[n], 16);
+        const int l = lg + 8 * n;
+        if (kq == 0 && l < L) srcT[((size_t)b * IDF + i) * L + l] = acc[n];
     }
 }
 
@@ -162,8 +152,6 @@ __global__ void __launch_bounds__(kThreads, 2) k_attn_fwd_mma(const FwdParams p)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, c = lane & 3;
     const int L = p.L, Q = p.Q, TPS = p.tiles_per_sample;
-    uint32_t* ready = p.mask_bits + p.B;          // scratch layout: [B] mask bits | [B] ready | [B] max|srcT| bits
-    uint32_t* src_max = p.mask_bits + 2 * p.B;
 
     if (tid == 0) {
 #pragma unroll
@@ -207,7 +195,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_attn_fwd_mma(const FwdParams p)
     }
 
     // ---------------------------------- consumer warps ---------------------------------------
-    project_phase<IDF, NT>(p.ctx, p.W, p.srcT, ready, src_max, p.B, p.cdf, L, tid);
+    asm volatile("griddepcontrol.wait;" ::: "memory");      // srcT of k_project_mma is complete and visible
 
     SrcFrags<KS, NT, NC8, NK16, HAS_K8, NSPLIT> f;
     float inv_src = 1.f;
@@ -222,12 +210,13 @@ __global__ void __launch_bounds__(kThreads, 2) k_attn_fwd_mma(const FwdParams p)
     for (int w = w_begin; w < w_end; ++w) {
         if (b != cur_b) {
             cur_b = b;
-            if (lane == 0) {
-                while (ld_acquire(ready + b) < (uint32_t)(IDF / 8)) __nanosleep(64);
-            }
-            __syncwarp();
             float sc_src = 1.f;
-            if (HALF) pow2_scale(__uint_as_float(__ldcg(src_max + b)), sc_src, inv_src);
+            if (HALF) {
+                const float* sb = p.srcT + (size_t)b * IDF * L;
+                float lm = 0.f;
+                for (int o = lane; o < IDF * L; o += 32) lm = fmaxf(lm, fabsf(__ldcg(sb + o)));
+                pow2_scale(warp_absmax_redux(lm), sc_src, inv_src);
+            }
             load_src_frags<T, IDF, NT>(f, p.srcT + (size_t)b * IDF * L, L, sc_src, g, c);
         }
 
@@ -430,7 +419,7 @@ int launch_fwd_mma(const FwdParams& p, cudaStream_t st) {
     using C = FwdCfg<T, IDF, NT>;
     const size_t smem = (size_t)C::NST * C::STAGE_BYTES + (size_t)p.B * 4 + 16;
     auto kern = k_attn_fwd_mma<T, IDF, NT>;
-    static int max_ctas = 0;     // co-resident CTAs (the ready-flag wait needs every CTA resident)
+    static int max_ctas = 0;     // one persistent wave: two CTAs per SM
     if (max_ctas == 0) {
         int dev = 0, sms = 0, per_sm = 0;
         cudaGetDevice(&dev);
@@ -447,14 +436,26 @@ int launch_fwd_mma(const FwdParams& p, cudaStream_t st) {
         set_error("attn_fwd(mma): %zu bytes of shared memory needed (B=%d)", smem, p.B);
         return SBA_ERR_UNSUPPORTED;
     }
-    cudaError_t e = cudaMemsetAsync(p.mask_bits + p.B, 0, 2 * (size_t)p.B * sizeof(uint32_t), st);
+    k_project_mma<IDF, NT><<<p.B * (IDF / 8), 256, 0, st>>>(p.ctx, p.W, p.srcT, p.cdf, p.L);
+    int rc = check_launch("project(mma)");
+    if (rc) return rc;
+    const int grid = p.n_tiles < max_ctas ? p.n_tiles : max_ctas;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = 100 * 1024;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, p);
     if (e != cudaSuccess) {
-        set_error("attn_fwd(mma): memset: %s", cudaGetErrorString(e));
+        set_error("attn_fwd(mma): launch: %s", cudaGetErrorString(e));
         return SBA_ERR_CUDA;
     }
-    const int grid = p.n_tiles < max_ctas ? p.n_tiles : max_ctas;
-    kern<<<grid, kThreads, 100 * 1024, st>>>(p);
-    add_launches(1);
+    add_launches(2);
     return check_launch("attn_fwd(mma)");
 }
 

@@ -23,8 +23,9 @@ int simt_attn_bwd_epilogue(const float* ctx, const float* W, const float* dSrc, 
 bool mma_supports(const AttnShape& s);
 int mma_attn_fwd(const void* x, const float* ctx, const float* W, const uint8_t* mask, void* c_code, void* attn,
                  float* srcT, uint32_t* mask_bits, const AttnShape& s, cudaStream_t st);
-int mma_attn_bwd(const void* x, const float* srcT, const uint8_t* mask, const void* g_c, const void* g_attn, void* dX,
-                 float* dSrc, const AttnShape& s, cudaStream_t st);
+// dSrc holds B*idf*L floats followed by B+1 scratch words; dW / dCtx (nullable) are formed inside the kernel
+int mma_attn_bwd(const void* x, const float* ctx, const float* W, const float* srcT, const uint8_t* mask, const void* g_c,
+                 const void* g_attn, void* dX, float* dSrc, float* dW, float* dCtx, const AttnShape& s, cudaStream_t st);
 
 // words_loss.cu - fused DAMSM region-word similarity (kernel c) and its backward
 size_t words_bwd_workspace_bytes(int B_img, int B_cap, int nef, int R, int Lw);

@@ -77,7 +77,7 @@ class _WordRegionAttention(torch.autograd.Function):
         if g_attn is not None:
             g_attn = g_attn.to(x.dtype).contiguous()
         dX = torch.empty_like(x)
-        dSrc = torch.empty((B, idf, L), dtype=torch.float32, device=x.device)
+        dSrc = torch.empty((B * idf * L + B + 1,), dtype=torch.float32, device=x.device)   # + scratch words, see sba_attn.h
         dW = torch.empty((idf, cdf), dtype=torch.float32, device=x.device) if need_w else None
         dCtx = torch.empty((B, cdf, L), dtype=torch.float32, device=x.device) if need_ctx else None
         rc = lib.sba_attn_bwd(_ptr(x), _ptr(ctx32), _ptr(w32), _ptr(mask_u8), _ptr(srcT), _ptr(mask_bits), _ptr(g_c),

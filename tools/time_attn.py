@@ -27,7 +27,7 @@ for hw in (64, 128):
     mask = (torch.arange(L)[None] >= lens[:, None]).to(torch.uint8).to(dev)
     srcT = torch.empty(B, idf, L, device=dev)
     mb = torch.empty(3 * B, dtype=torch.int32, device=dev)
-    dSrc = torch.empty(B, idf, L, device=dev)
+    dSrc = torch.empty(B * idf * L + B + 1, device=dev)
     dW = torch.empty(idf, cdf, device=dev)
     st_holder = [torch.cuda.current_stream().cuda_stream]
     dcode = _DTYPES[dt]
