@@ -54,7 +54,7 @@ enum { SBA_F32 = 0, SBA_BF16 = 1 };
 enum { SBA_MASK_REFERENCE = 0, SBA_MASK_PER_SAMPLE = 1 };
 
 /* kernel family: AUTO picks the fastest one that supports the shape */
-enum { SBA_ALGO_AUTO = 0, SBA_ALGO_SIMT = 1, SBA_ALGO_MMA = 2 };
+enum { SBA_ALGO_AUTO = 0, SBA_ALGO_SIMT = 1, SBA_ALGO_MMA = 2, SBA_ALGO_TCGEN05 = 3 };
 
 SBA_API int sba_abi_version(void);
 SBA_API const char* sba_last_error(void);

@@ -55,7 +55,7 @@ int check_attn_shape(const char* fn, int B, int idf, int cdf, int L, int Q, int 
         set_error("%s: unknown mask_mode %d", fn, mask_mode);
         return SBA_ERR_ARG;
     }
-    if (algo != SBA_ALGO_AUTO && algo != SBA_ALGO_SIMT && algo != SBA_ALGO_MMA) {
+    if (algo < SBA_ALGO_AUTO || algo > SBA_ALGO_TCGEN05) {
         set_error("%s: unknown algo %d", fn, algo);
         return SBA_ERR_ARG;
     }
@@ -91,6 +91,14 @@ int sba_attn_fwd(const void* x, const float* ctx, const float* W, const uint8_t*
     AttnShape s{B, idf, cdf, L, Q, dtype, mask_mode};
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const bool can_mma = mma_supports(s) && aligned16(x);
+    const bool can_tc5 = tc5_supports(s) && aligned16(x);
+    if (algo == SBA_ALGO_TCGEN05) {
+        if (!can_tc5) {
+            set_error("sba_attn_fwd: SBA_ALGO_TCGEN05 does not cover idf=%d L=%d Q=%d B=%d (or x is not 16-byte aligned)", idf, L, Q, B);
+            return SBA_ERR_UNSUPPORTED;
+        }
+        return tc5_attn_fwd(x, ctx, W, mask, c_code, attn, srcT, mask_bits, s, st);
+    }
     if (algo == SBA_ALGO_MMA && !can_mma) {
         set_error("sba_attn_fwd: SBA_ALGO_MMA does not cover idf=%d L=%d Q=%d cdf=%d B=%d (or x is not 16-byte aligned)", idf, L, Q, cdf, B);
         return SBA_ERR_UNSUPPORTED;

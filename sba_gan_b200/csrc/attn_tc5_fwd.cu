@@ -1,0 +1,564 @@
+// Kernel (a): fused GlobalAttentionGeneral forward on the 5th-generation tensor cores
+// (SBA_ALGO_TCGEN05): TMA tensor loads -> tcgen05.mma -> TMEM -> one pixel per thread.
+//
+// One persistent CTA = 1 TMA producer warp + 1 MMA-issuing warp + 4 consumer warps, working
+// through a contiguous range of 128-pixel tiles:
+//   producer : 2-D TMA box loads of the [idf x 128 px] tile of x (128-byte swizzled rows) into a
+//              shared-memory ring; the tile as it lands is the MN-major A operand of MMA1.
+//   MMA warp : MMA1  S[128 x 32]  = x_tile^T . (log2e * sourceT)      (K = idf)
+//              MMA2  c[128 x idf] = P . sourceT^T                     (A = P in TMEM, K = words)
+//              completion is signalled with tcgen05.commit on mbarriers.
+//   consumers: thread = pixel.  tcgen05.ld S row -> masked softmax over words in registers (no
+//              shuffles) -> attention map stored one pixel per lane (128 B per warp and word)
+//              -> P written back to TMEM as MMA2's A operand -> tcgen05.ld c row -> stored.
+// The B operands (sourceT of the current sample, both orientations, zero padded) are rebuilt in
+// shared memory by the consumers whenever the tile range enters a new sample.
+// bf16 tensors: single bf16 MMAs.  fp32 tensors: 3xTF32 - every operand is split into a tf32
+// "hi" part and a residual "lo" part and multiplied as hi.hi + lo.hi + hi.lo (~2^-21 relative);
+// the hi part of x is the tile itself (the tensor core reads the top 19 bits), its lo part
+// x - trunc(x) is written by the consumers into a second shared-memory tile.
+//
+// Reference semantics: AttnGAN2/code/GlobalAttention.py:82-121 (oracle/attention.py).
+#include "kernels.h"
+#include "tc5_common.cuh"
+
+namespace sba {
+namespace tc5 {
+
+int make_tile_map(CUtensorMap* out, const void* base, int dtype, int rows, int cols, int box_rows) {
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn encode = nullptr;
+    if (encode == nullptr) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+        if (e != cudaSuccess || fn == nullptr || qres != cudaDriverEntryPointSuccess) {
+            set_error("cuTensorMapEncodeTiled is not available from this driver: %s", cudaGetErrorString(e));
+            return SBA_ERR_CUDA;
+        }
+        encode = reinterpret_cast<EncodeFn>(fn);
+    }
+    const int es = dtype == SBA_F32 ? 4 : 2;
+    const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    const cuuint64_t gstride[1] = {(cuuint64_t)cols * es};
+    const cuuint32_t box[2] = {(cuuint32_t)(128 / es), (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = encode(out, dtype == SBA_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                        const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        // 32-bit MN-major UMMA operands exist only in the 32-byte-atom flavour of the 128-byte swizzle
+                        dtype == SBA_F32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed (CUresult %d) for a %d x %d tensor", (int)r, rows, cols);
+        return SBA_ERR_CUDA;
+    }
+    return SBA_OK;
+}
+
+}  // namespace tc5
+
+namespace {
+using namespace tc5;
+
+struct Tc5FwdParams {
+    const float* srcT;
+    const uint8_t* mask;
+    void* c_code;
+    void* attn;
+    uint32_t* mask_bits;
+    int B, L, Q, mask_mode;
+    int tiles_per_sample;
+    int n_tiles;
+};
+
+constexpr int pow2_cols(int n) { return n <= 32 ? 32 : n <= 64 ? 64 : n <= 128 ? 128 : n <= 256 ? 256 : 512; }
+
+template <typename T, int IDF, int NQ>
+struct Tc5FwdCfg {
+    static constexpr bool F32 = sizeof(T) == 4;
+    static constexpr int ES = (int)sizeof(T);
+    static constexpr int LP = 4 * NQ;                          // words held per thread (L rounded up to 4)
+    static constexpr int BOX_PX = 128 / ES;                    // pixels per 128-byte box row
+    static constexpr int NBOX = TQ / BOX_PX;                   // boxes per tile: 2 (bf16) / 4 (fp32)
+    static constexpr int BOX_BYTES = IDF * 128;
+    static constexpr int STAGE_BYTES = NBOX * BOX_BYTES;       // = IDF * TQ * ES
+    static constexpr int KMMA = 32 / ES;                       // K per instruction: 16 (bf16) / 8 (tf32)
+    static constexpr int KS1 = IDF / KMMA;                     // MMA1 k-steps (channels)
+    static constexpr int KSTEP_A = KMMA * 128;                 // bytes between k-steps of the swizzled x tile
+    static constexpr int K2 = ((LP + KMMA - 1) / KMMA) * KMMA; // MMA2 K extent (words, zero padded)
+    static constexpr int KS2 = K2 / KMMA;
+    static constexpr int NS = 32;                              // MMA1 N (words, zero padded)
+    static constexpr int KCH1 = IDF * ES / 16, KCH2 = K2 * ES / 16;
+    static constexpr int B1_BYTES = NS * IDF * ES;
+    static constexpr int B2_BYTES = IDF * K2 * ES;
+    static constexpr int NSPLIT = F32 ? 2 : 1;
+    static constexpr int NST = F32 ? 3 : 4;                    // x ring depth
+    static constexpr int NLO = F32 ? 2 : 0;                    // lo tiles
+    static constexpr int PC = F32 ? K2 : K2 / 2;               // TMEM columns of one P operand
+    static constexpr int COL_S = 0, COL_P = 64, COL_PLO = 96, COL_C = F32 ? 128 : 96;
+    static constexpr int TMEM_COLS = pow2_cols(COL_C + IDF);
+    static constexpr int SMEM_BYTES = (NST + NLO) * STAGE_BYTES + NSPLIT * (B1_BYTES + B2_BYTES);
+    // MN-major x tile: bf16 = SWIZZLE_128B atoms of 8 channel rows (1024 B); tf32 = SWIZZLE_128B_BASE32B
+    // atoms of 4 channel rows (512 B), the only MN-major layout 32-bit operands have
+    static constexpr uint32_t A_SWIZZLE = F32 ? kSwizzle128B_Base32B : kSwizzle128B;
+    static constexpr uint32_t A_SBO = F32 ? 512 : 1024;
+    static constexpr uint32_t IDESC1 = make_idesc(F32 ? 2 : 1, 1, 0, TQ, NS);
+    static constexpr uint32_t IDESC2 = make_idesc(F32 ? 2 : 1, 0, 0, TQ, IDF);
+    static_assert(IDF % 16 == 0 && IDF <= 128, "idf must be a multiple of 16");
+    static_assert(LP <= 32 && PC <= 32 && COL_PLO + PC <= 128, "at most 32 words");
+};
+
+// srcT = W . ctx (the bias-free 1x1 conv_context, GlobalAttention.py:95-97): block = (sample,
+// 8 output channels), warp = channel, lanes = 8 words x 4 quarters of the cdf reduction.
+template <int NT>
+__global__ void __launch_bounds__(256) k_project_tc5(const float* __restrict__ ctx, const float* __restrict__ W,
+                                                     float* __restrict__ srcT, int idf, int cdf, int L) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, lg = lane & 7, kq = lane >> 3;
+    const int rg = idf / 8;
+    const int u = blockIdx.x, b = u / rg, i = (u - b * rg) * 8 + warp;
+    const float* wrow = W + (size_t)i * cdf;
+    const float* cb = ctx + (size_t)b * cdf * L;
+    float acc[NT];
+#pragma unroll
+    for (int n = 0; n < NT; ++n) acc[n] = 0.f;
+    const int c_lo = (cdf * kq) >> 2, c_hi = (cdf * (kq + 1)) >> 2;
+#pragma unroll 8
+    for (int cc = c_lo; cc < c_hi; ++cc) {
+        const float wv = __ldg(wrow + cc);
+#pragma unroll
+        for (int n = 0; n < NT; ++n) {
+            const int l = lg + 8 * n;
+            const float v = (l < L) ? __ldg(cb + (size_t)cc * L + l) : 0.f;
+            acc[n] = fmaf(wv, v, acc[n]);
+        }
+    }
+#pragma unroll
+    for (int n = 0; n < NT; ++n) {
+        acc[n] += __shfl_xor_sync(0xffffffffu, acc[n], 8);
+        acc[n] += __shfl_xor_sync(0xffffffffu, acc[n], 16);
+        const int l = lg + 8 * n;
+        if (kq == 0 && l < L) srcT[((size_t)b * idf + i) * L + l] = acc[n];
+    }
+}
+
+template <typename T, int IDF, int NQ>
+__global__ void __launch_bounds__(kThreads, Tc5FwdCfg<T, IDF, NQ>::F32 ? 2 : 3)
+    k_attn_fwd_tc5(const __grid_constant__ CUtensorMap tmx, const Tc5FwdParams p) {
+    using C = Tc5FwdCfg<T, IDF, NQ>;
+    constexpr bool F32 = C::F32;
+    constexpr int LP = C::LP, NST = C::NST, ES = C::ES;
+    constexpr float kLog2e = 1.4426950408889634f;
+
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;        // SWIZZLE_128B atoms are 1024-byte aligned
+    unsigned char* sgen = smem_raw + (sbase - smem_u32(smem_raw));
+    const uint32_t s_x = sbase;                                           // [NST] x tiles
+    const uint32_t s_lo = s_x + NST * C::STAGE_BYTES;                     // [NLO] x - trunc(x) tiles (fp32)
+    const uint32_t s_b1 = s_lo + C::NLO * C::STAGE_BYTES;                 // [NSPLIT] log2e * sourceT, rows = words
+    const uint32_t s_b2 = s_b1 + C::NSPLIT * C::B1_BYTES;                 // [NSPLIT] sourceT, rows = channels
+    unsigned char* g_lo = sgen + NST * C::STAGE_BYTES;
+    unsigned char* g_b1 = g_lo + C::NLO * C::STAGE_BYTES;
+    unsigned char* g_b2 = g_b1 + C::NSPLIT * C::B1_BYTES;
+    uint32_t* mb_s = reinterpret_cast<uint32_t*>(g_b2 + C::NSPLIT * C::B2_BYTES);   // [B] caption mask words
+
+    __shared__ __align__(8) unsigned long long bar_x_full[NST], bar_x_empty[NST], bar_s_full[2], bar_s_free[2],
+        bar_lo_ready[2], bar_p_ready, bar_c_full, bar_b_ready;
+    __shared__ uint32_t tmem_base_s;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int L = p.L, Q = p.Q, TPS = p.tiles_per_sample;
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < NST; ++s) {
+            mbar_init(smem_u32(&bar_x_full[s]), 1);
+            mbar_init(smem_u32(&bar_x_empty[s]), 1);
+        }
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(smem_u32(&bar_s_full[s]), 1);
+            mbar_init(smem_u32(&bar_s_free[s]), kConsumers);
+            mbar_init(smem_u32(&bar_lo_ready[s]), kConsumers);
+        }
+        mbar_init(smem_u32(&bar_p_ready), kConsumers);
+        mbar_init(smem_u32(&bar_c_full), 1);
+        mbar_init(smem_u32(&bar_b_ready), kConsumers);
+        fence_barrier_init();
+        prefetch_tensormap(&tmx);
+    }
+    if (warp == kMmaWarp) tmem_alloc(smem_u32(&tmem_base_s), C::TMEM_COLS);
+    if (p.mask != nullptr) {
+        for (int cap = tid; cap < p.B; cap += kThreads) {
+            uint32_t bits = 0;
+            for (int l = 0; l < L; ++l) bits |= (p.mask[(size_t)cap * L + l] ? 1u : 0u) << l;
+            mb_s[cap] = bits;
+            if (blockIdx.x == 0) p.mask_bits[cap] = bits;
+        }
+    }
+    // zero the B operand buffers once: the padding (words >= L) is never written again
+    for (int o = tid; o < C::NSPLIT * (C::B1_BYTES + C::B2_BYTES) / 16; o += kThreads)
+        reinterpret_cast<uint4*>(g_b1)[o] = make_uint4(0u, 0u, 0u, 0u);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+
+    const int w_begin = (int)(((long long)blockIdx.x * p.n_tiles) / gridDim.x);
+    const int w_end = (int)(((long long)(blockIdx.x + 1) * p.n_tiles) / gridDim.x);
+    const int n_local = w_end - w_begin;
+    const int b0 = w_begin / TPS, t0 = w_begin - b0 * TPS;
+
+    if (warp == kProducerWarp) {
+        // --------------------------------- TMA producer -----------------------------------------
+        if (lane == 0) {
+            int b = b0, t = t0;
+            for (int j = 0; j < n_local; ++j) {
+                const int stage = j % NST;
+                if (j >= NST) mbar_wait(smem_u32(&bar_x_empty[stage]), (uint32_t)((j / NST) - 1) & 1u);
+                const uint32_t full = smem_u32(&bar_x_full[stage]);
+                mbar_expect_tx(full, (uint32_t)C::STAGE_BYTES);
+                const uint32_t dst = s_x + stage * C::STAGE_BYTES;
+#pragma unroll
+                for (int bx = 0; bx < C::NBOX; ++bx)
+                    tma_load_2d(dst + bx * C::BOX_BYTES, &tmx, t * TQ + bx * C::BOX_PX, b * IDF, full);
+                if (++t == TPS) { t = 0; ++b; }
+            }
+        }
+    } else if (warp == kMmaWarp) {
+        // --------------------------------- MMA issuer -------------------------------------------
+        if (lane == 0) {
+            // MMA1(j): S[j & 1] = x_tile^T . B1   (3xTF32: hi.hi + hi.lo + lo.hi)
+            auto mma1 = [&](int j) {
+                const int stage = j % NST, buf = j & 1;
+                mbar_wait(smem_u32(&bar_x_full[stage]), (uint32_t)(j / NST) & 1u);
+                if constexpr (F32) mbar_wait(smem_u32(&bar_lo_ready[buf]), (uint32_t)(j >> 1) & 1u);
+                if (j >= 2) mbar_wait(smem_u32(&bar_s_free[buf]), (uint32_t)((j >> 1) - 1) & 1u);
+                tc_fence_after();
+                const uint32_t d = tmem_base + C::COL_S + 32 * buf;
+                const uint32_t a_hi = s_x + stage * C::STAGE_BYTES;
+                const uint32_t a_lo = s_lo + buf * C::STAGE_BYTES;
+#pragma unroll
+                for (int ks = 0; ks < C::KS1; ++ks) {
+                    const uint64_t da = smem_desc(a_hi + ks * C::KSTEP_A, C::BOX_BYTES, C::A_SBO, C::A_SWIZZLE);
+                    const uint64_t db = smem_desc(s_b1 + ks * 256, 128, C::KCH1 * 128, kSwizzleNone);
+                    umma_ss<F32>(d, da, db, C::IDESC1, ks > 0 ? 1u : 0u);
+                    if constexpr (F32) {
+                        const uint64_t dal = smem_desc(a_lo + ks * C::KSTEP_A, C::BOX_BYTES, C::A_SBO, C::A_SWIZZLE);
+                        const uint64_t dbl = smem_desc(s_b1 + C::B1_BYTES + ks * 256, 128, C::KCH1 * 128, kSwizzleNone);
+                        umma_ss<F32>(d, da, dbl, C::IDESC1, 1u);
+                        umma_ss<F32>(d, dal, db, C::IDESC1, 1u);
+                    }
+                }
+                umma_commit(smem_u32(&bar_x_empty[stage]));
+                umma_commit(smem_u32(&bar_s_full[buf]));
+            };
+            // MMA2(j): c = P . B2
+            auto mma2 = [&](int j) {
+                mbar_wait(smem_u32(&bar_p_ready), (uint32_t)j & 1u);
+                tc_fence_after();
+                const uint32_t d = tmem_base + C::COL_C;
+#pragma unroll
+                for (int ks = 0; ks < C::KS2; ++ks) {
+                    const uint32_t a = tmem_base + C::COL_P + ks * 8;        // 8 columns per k-step either way
+                    const uint64_t db = smem_desc(s_b2 + ks * 256, 128, C::KCH2 * 128, kSwizzleNone);
+                    umma_ts<F32>(d, a, db, C::IDESC2, ks > 0 ? 1u : 0u);
+                    if constexpr (F32) {
+                        const uint64_t dbl = smem_desc(s_b2 + C::B2_BYTES + ks * 256, 128, C::KCH2 * 128, kSwizzleNone);
+                        umma_ts<F32>(d, a, dbl, C::IDESC2, 1u);
+                        umma_ts<F32>(d, tmem_base + C::COL_PLO + ks * 8, db, C::IDESC2, 1u);
+                    }
+                }
+                umma_commit(smem_u32(&bar_c_full));
+            };
+            int t = t0;
+            uint32_t nb = 0;
+            if (n_local > 0) {
+                mbar_wait(smem_u32(&bar_b_ready), nb & 1u);
+                ++nb;
+                mma1(0);
+            }
+            for (int j = 0; j < n_local; ++j) {
+                const bool has_next = j + 1 < n_local;
+                const bool next_same = has_next && (t + 1 < TPS);
+                if (next_same) mma1(j + 1);          // runs ahead of the softmax of tile j
+                mma2(j);
+                if (has_next && !next_same) {
+                    mbar_wait(smem_u32(&bar_b_ready), nb & 1u);     // operands of the next sample are in place
+                    ++nb;
+                    mma1(j + 1);
+                }
+                if (++t == TPS) t = 0;
+            }
+        }
+    } else {
+        // --------------------------------- consumers: thread = pixel ----------------------------
+        const int ct = tid - 64;                       // 0..127
+        const int cw = warp & 3;                       // TMEM lane quarter this warp may access
+        const int px = cw * 32 + lane;                 // pixel (= accumulator row) within the tile
+        const uint32_t tl = tmem_base + ((uint32_t)(cw * 32) << 16);
+        const uint32_t pad_bits = (L < 32) ? ~((1u << L) - 1u) : 0u;
+        const uint32_t Bu = (uint32_t)p.B;
+        const uint32_t step_mod = (uint32_t)TQ % Bu;
+        // reference mask order: pixel n = b*Q + q uses caption n mod B (GlobalAttention.py:104-108)
+        uint32_t cap = (uint32_t)(((unsigned long long)w_begin * TQ + px) % Bu);
+        int b = b0, t = t0, cur_b = -1;
+
+        // fp32: lo tile of local tile j = x - trunc(x), elementwise on the swizzled image
+        auto make_lo = [&](int j) {
+            if constexpr (F32) {
+                const int stage = j % NST;
+                mbar_wait(smem_u32(&bar_x_full[stage]), (uint32_t)(j / NST) & 1u);
+                const float4* xs = reinterpret_cast<const float4*>(sgen + stage * C::STAGE_BYTES);
+                float4* lo = reinterpret_cast<float4*>(g_lo + (j & 1) * C::STAGE_BYTES);
+#pragma unroll
+                for (int r = 0; r < C::STAGE_BYTES / 16 / kConsumers; ++r) {
+                    float4 v = xs[r * kConsumers + ct];
+                    v.x -= tf32_trunc(v.x); v.y -= tf32_trunc(v.y); v.z -= tf32_trunc(v.z); v.w -= tf32_trunc(v.w);
+                    lo[r * kConsumers + ct] = v;
+                }
+                fence_proxy_async();
+                mbar_arrive(smem_u32(&bar_lo_ready[j & 1]));
+            }
+        };
+
+        asm volatile("griddepcontrol.wait;" ::: "memory");      // srcT of k_project_tc5 is complete and visible
+        if (n_local > 0) make_lo(0);
+
+        for (int j = 0; j < n_local; ++j) {
+            if (b != cur_b) {
+                // ---- operands of sample b: B1[word][channel] = log2e*srcT, B2[channel][word] = srcT ----
+                cur_b = b;
+                const float* sb = p.srcT + (size_t)b * IDF * L;
+                for (int o = ct; o < IDF * L; o += kConsumers) {
+                    const int ch = o / L, l = o - ch * L;
+                    const float v = __ldcg(sb + o), v1 = v * kLog2e;
+                    const uint32_t o1 = kmajor_off<ES>(l, ch, C::KCH1), o2 = kmajor_off<ES>(ch, l, C::KCH2);
+                    if constexpr (F32) {
+                        const float h1 = tf32_rna(v1), h2 = tf32_rna(v);
+                        *reinterpret_cast<float*>(g_b1 + o1) = h1;
+                        *reinterpret_cast<float*>(g_b1 + C::B1_BYTES + o1) = tf32_rna(v1 - h1);
+                        *reinterpret_cast<float*>(g_b2 + o2) = h2;
+                        *reinterpret_cast<float*>(g_b2 + C::B2_BYTES + o2) = tf32_rna(v - h2);
+                    } else {
+                        *reinterpret_cast<__nv_bfloat16*>(g_b1 + o1) = __float2bfloat16_rn(v1);
+                        *reinterpret_cast<__nv_bfloat16*>(g_b2 + o2) = __float2bfloat16_rn(v);
+                    }
+                }
+                fence_proxy_async();
+                mbar_arrive(smem_u32(&bar_b_ready));
+            }
+            if (j + 1 < n_local) make_lo(j + 1);
+
+            // ---- S row of this pixel (already in the log2 domain) ---------------------------------
+            const int buf = j & 1;
+            mbar_wait(smem_u32(&bar_s_full[buf]), (uint32_t)(j >> 1) & 1u);
+            tc_fence_after();
+            uint32_t sr[LP];
+            tmem_ld<LP>(tl + C::COL_S + 32 * buf, sr);
+            tmem_wait_ld();
+            tc_fence_before();
+            mbar_arrive(smem_u32(&bar_s_free[buf]));
+
+            // ---- mask (GlobalAttention.py:104-108) + softmax over words (:109) -----------------------
+            uint32_t mb = pad_bits;
+            if (p.mask != nullptr) mb |= mb_s[p.mask_mode == SBA_MASK_PER_SAMPLE ? (uint32_t)b : cap];
+            float s[LP];
+            float m = -INFINITY;
+#pragma unroll
+            for (int l = 0; l < LP; ++l) {
+                s[l] = ((mb >> l) & 1u) ? -INFINITY : __uint_as_float(sr[l]);
+                m = fmaxf(m, s[l]);
+            }
+            float sum = 0.f;
+#pragma unroll
+            for (int l = 0; l < LP; ++l) {
+                s[l] = mma::ex2_approx(s[l] - m);          // all-masked row: -inf - -inf = NaN, as the reference
+                sum += s[l];
+            }
+            const float inv = mma::rcp_approx(sum);
+#pragma unroll
+            for (int l = 0; l < LP; ++l) s[l] *= inv;
+
+            // ---- P -> TMEM (A operand of MMA2) ---------------------------------------------------
+            if constexpr (F32) {
+                uint32_t ph[C::K2], pl[C::K2];
+#pragma unroll
+                for (int l = 0; l < C::K2; ++l) {
+                    if (l < LP) {
+                        const float h = tf32_trunc(s[l]);
+                        ph[l] = __float_as_uint(h);
+                        pl[l] = __float_as_uint(s[l] - h);
+                    } else {
+                        ph[l] = 0u;
+                        pl[l] = 0u;
+                    }
+                }
+                tmem_st<C::K2>(tl + C::COL_P, ph);
+                tmem_st<C::K2>(tl + C::COL_PLO, pl);
+            } else {
+                uint32_t pk[C::PC];
+#pragma unroll
+                for (int i = 0; i < C::PC; ++i) pk[i] = (2 * i < LP) ? mma::pack_bf16(s[2 * i], s[2 * i + 1]) : 0u;
+                tmem_st<C::PC>(tl + C::COL_P, pk);
+            }
+            tmem_wait_st();
+            tc_fence_before();
+            mbar_arrive(smem_u32(&bar_p_ready));
+
+            // ---- attention map: lane = pixel, one 128-byte (fp32) row segment per warp and word ---
+            const int q = t * TQ + px;
+            {
+                T* ap = static_cast<T*>(p.attn) + (size_t)b * L * Q + q;
+#pragma unroll
+                for (int l = 0; l < LP; ++l) {
+                    if (l < L) {
+                        if constexpr (F32) ap[(size_t)l * Q] = s[l];
+                        else ap[(size_t)l * Q] = __float2bfloat16_rn(s[l]);
+                    }
+                }
+            }
+
+            // ---- c row of this pixel ---------------------------------------------------------------
+            mbar_wait(smem_u32(&bar_c_full), (uint32_t)j & 1u);
+            tc_fence_after();
+            T* cp = static_cast<T*>(p.c_code) + (size_t)b * IDF * Q + q;
+#pragma unroll
+            for (int h = 0; h < IDF / 16; ++h) {
+                uint32_t cr[16];
+                tmem_ld<16>(tl + C::COL_C + 16 * h, cr);
+                tmem_wait_ld();
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    if constexpr (F32) cp[(size_t)(16 * h + i) * Q] = __uint_as_float(cr[i]);
+                    else cp[(size_t)(16 * h + i) * Q] = __float2bfloat16_rn(__uint_as_float(cr[i]));
+                }
+            }
+
+            if (++t == TPS) { t = 0; ++b; }
+            cap += step_mod;
+            if (cap >= Bu) cap -= Bu;
+        }
+        tc_fence_before();
+    }
+
+    __syncthreads();
+    if (warp == kMmaWarp) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, C::TMEM_COLS);
+    }
+}
+
+template <typename T, int IDF, int NQ>
+int launch_fwd_tc5(const void* x, const float* ctx, const float* W, float* srcT, int cdf, const Tc5FwdParams& p,
+                   int dtype, cudaStream_t st) {
+    using C = Tc5FwdCfg<T, IDF, NQ>;
+    auto kern = k_attn_fwd_tc5<T, IDF, NQ>;
+    const size_t smem = (size_t)C::SMEM_BYTES + (size_t)p.B * 4 + 1024 + 16;
+    static int max_ctas = 0;
+    static size_t smem_set = 0;
+    if (smem > 200 * 1024) {
+        set_error("attn_fwd(tcgen05): %zu bytes of shared memory needed (B=%d)", smem, p.B);
+        return SBA_ERR_UNSUPPORTED;
+    }
+    if (max_ctas == 0 || smem > smem_set) {
+        int dev = 0, sms = 0, per_sm = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem);
+        if (e != cudaSuccess || per_sm < 1 || sms < 1) {
+            set_error("attn_fwd(tcgen05): occupancy query failed: %s", cudaGetErrorString(e));
+            return SBA_ERR_CUDA;
+        }
+        const int tmem_limit = 512 / C::TMEM_COLS;      // all resident CTAs must fit their TMEM allocation
+        if (per_sm > tmem_limit) per_sm = tmem_limit;
+        max_ctas = sms * per_sm;
+        smem_set = smem;
+    }
+    CUtensorMap tmx;
+    int rc = make_tile_map(&tmx, x, dtype, p.B * IDF, p.Q, IDF);
+    if (rc) return rc;
+    const int NT = (p.L + 7) / 8;
+    const int pgrid = p.B * (IDF / 8);
+    switch (NT) {
+        case 1: k_project_tc5<1><<<pgrid, 256, 0, st>>>(ctx, W, srcT, IDF, cdf, p.L); break;
+        case 2: k_project_tc5<2><<<pgrid, 256, 0, st>>>(ctx, W, srcT, IDF, cdf, p.L); break;
+        case 3: k_project_tc5<3><<<pgrid, 256, 0, st>>>(ctx, W, srcT, IDF, cdf, p.L); break;
+        default: k_project_tc5<4><<<pgrid, 256, 0, st>>>(ctx, W, srcT, IDF, cdf, p.L); break;
+    }
+    rc = check_launch("project(tcgen05)");
+    if (rc) return rc;
+    const int grid = p.n_tiles < max_ctas ? p.n_tiles : max_ctas;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem_set;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmx, p);
+    if (e != cudaSuccess) {
+        set_error("attn_fwd(tcgen05): launch: %s", cudaGetErrorString(e));
+        return SBA_ERR_CUDA;
+    }
+    add_launches(2);
+    return check_launch("attn_fwd(tcgen05)");
+}
+
+template <typename T, int IDF>
+int dispatch_nq(const void* x, const float* ctx, const float* W, float* srcT, int cdf, const Tc5FwdParams& p, int dtype,
+                cudaStream_t st) {
+    switch ((p.L + 3) / 4) {
+        case 1: return launch_fwd_tc5<T, IDF, 1>(x, ctx, W, srcT, cdf, p, dtype, st);
+        case 2: return launch_fwd_tc5<T, IDF, 2>(x, ctx, W, srcT, cdf, p, dtype, st);
+        case 3: return launch_fwd_tc5<T, IDF, 3>(x, ctx, W, srcT, cdf, p, dtype, st);
+        case 4: return launch_fwd_tc5<T, IDF, 4>(x, ctx, W, srcT, cdf, p, dtype, st);
+        case 5: return launch_fwd_tc5<T, IDF, 5>(x, ctx, W, srcT, cdf, p, dtype, st);
+        case 6: return launch_fwd_tc5<T, IDF, 6>(x, ctx, W, srcT, cdf, p, dtype, st);
+        case 7: return launch_fwd_tc5<T, IDF, 7>(x, ctx, W, srcT, cdf, p, dtype, st);
+        case 8: return launch_fwd_tc5<T, IDF, 8>(x, ctx, W, srcT, cdf, p, dtype, st);
+        default: return -1;
+    }
+}
+
+}  // namespace
+
+bool tc5_supports(const AttnShape& s) {
+    if (s.idf != 32 && s.idf != 48 && s.idf != 64) return false;
+    if (s.L < 1 || s.L > 32) return false;
+    if (s.Q % tc5::TQ != 0) return false;
+    if (s.B > 4096 || (unsigned long long)s.B * s.Q >= (1ull << 31)) return false;
+    return true;
+}
+
+int tc5_attn_fwd(const void* x, const float* ctx, const float* W, const uint8_t* mask, void* c_code, void* attn,
+                 float* srcT, uint32_t* mask_bits, const AttnShape& s, cudaStream_t st) {
+    Tc5FwdParams p{};
+    p.srcT = srcT; p.mask = mask; p.c_code = c_code; p.attn = attn; p.mask_bits = mask_bits;
+    p.B = s.B; p.L = s.L; p.Q = s.Q; p.mask_mode = s.mask_mode;
+    p.tiles_per_sample = s.Q / tc5::TQ;
+    p.n_tiles = s.B * p.tiles_per_sample;
+    int rc = -1;
+    if (s.dtype == SBA_F32) {
+        if (s.idf == 32) rc = dispatch_nq<float, 32>(x, ctx, W, srcT, s.cdf, p, s.dtype, st);
+        else if (s.idf == 48) rc = dispatch_nq<float, 48>(x, ctx, W, srcT, s.cdf, p, s.dtype, st);
+        else if (s.idf == 64) rc = dispatch_nq<float, 64>(x, ctx, W, srcT, s.cdf, p, s.dtype, st);
+    } else {
+        if (s.idf == 32) rc = dispatch_nq<__nv_bfloat16, 32>(x, ctx, W, srcT, s.cdf, p, s.dtype, st);
+        else if (s.idf == 48) rc = dispatch_nq<__nv_bfloat16, 48>(x, ctx, W, srcT, s.cdf, p, s.dtype, st);
+        else if (s.idf == 64) rc = dispatch_nq<__nv_bfloat16, 64>(x, ctx, W, srcT, s.cdf, p, s.dtype, st);
+    }
+    if (rc == -1) {
+        set_error("attn_fwd(tcgen05): unsupported shape idf=%d L=%d", s.idf, s.L);
+        return SBA_ERR_UNSUPPORTED;
+    }
+    return rc;
+}
+
+}  // namespace sba

@@ -1,0 +1,211 @@
+// Building blocks of the tcgen05 attention family (attn_tc5_fwd.cu / attn_tc5_bwd.cu):
+// 2-D TMA tensor loads, UMMA shared-memory / instruction descriptors, tcgen05.mma issue,
+// TMEM allocation and TMEM <-> register transfers.
+//
+// Why tcgen05 fits although idf = 32 and L = 18 are tiny: the M dimension of every contraction
+// on this path is the PIXEL index.  A 128-pixel tile of x (as TMA delivers it: [channel][pixel],
+// 128-byte swizzled rows) is a legal MN-major A operand, so
+//     S[128 px x 32 words] = x_tile^T . sourceT      (M = 128, N = 32, K = idf)
+//     c[128 px x idf]      = P[128 x words] . sourceT^T   (A = P from TMEM, K = words)
+// run as UMMA instructions issued by one thread, with the accumulators in TMEM.  tcgen05.ld
+// (32x32b) hands every thread one whole pixel row, so the softmax over words needs no
+// shuffles and the outputs are written one pixel per lane, 128 contiguous bytes per warp.
+#pragma once
+#include <cuda.h>
+
+#include "common.cuh"
+#include "mma_common.cuh"
+
+namespace sba {
+namespace tc5 {
+
+using mma::smem_u32;
+using mma::mbar_init;
+using mma::mbar_expect_tx;
+using mma::mbar_arrive;
+using mma::fence_barrier_init;
+
+// Bounded mbarrier wait: a protocol bug traps (-> a CUDA error the ABI reports) instead of
+// hanging the GPU box.  try_wait itself suspends for a HW time slice, so the bound is seconds.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    uint32_t spins = 0;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (!done && ++spins > (1u << 24)) __trap();
+    } while (!done);
+}
+
+// ---- TMA: 2-D tensor-map box load, completion on an mbarrier --------------------------------
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(bar)
+        : "memory");
+}
+__device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* tm) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(tm) : "memory");
+}
+// generic-proxy shared-memory writes -> visible to the async proxy (UMMA operand reads)
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ---- TMEM ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {      // whole warp
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {       // whole warp
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// all previously issued tcgen05.mma of this thread complete -> one arrival on the mbarrier
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// 32x32b: thread t of warp w reads / writes N consecutive 32-bit columns of TMEM lane 32*(w%4)+t
+#define SBA_R4(a, o) "=r"(a[o]), "=r"(a[o + 1]), "=r"(a[o + 2]), "=r"(a[o + 3])
+#define SBA_W4(a, o) "r"(a[o]), "r"(a[o + 1]), "r"(a[o + 2]), "r"(a[o + 3])
+template <int OFF, class A>
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, A& r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];" : SBA_R4(r, OFF) : "r"(taddr) : "memory");
+}
+template <int OFF, class A>
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, A& r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : SBA_R4(r, OFF), SBA_R4(r, OFF + 4)
+                 : "r"(taddr)
+                 : "memory");
+}
+template <int OFF, class A>
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, A& r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : SBA_R4(r, OFF), SBA_R4(r, OFF + 4), SBA_R4(r, OFF + 8), SBA_R4(r, OFF + 12)
+        : "r"(taddr)
+        : "memory");
+}
+template <int OFF, class A>
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const A& r) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr), SBA_W4(r, OFF) : "memory");
+}
+template <int OFF, class A>
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const A& r) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), SBA_W4(r, OFF),
+                 SBA_W4(r, OFF + 4)
+                 : "memory");
+}
+template <int OFF, class A>
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const A& r) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+        SBA_W4(r, OFF), SBA_W4(r, OFF + 4), SBA_W4(r, OFF + 8), SBA_W4(r, OFF + 12)
+        : "memory");
+}
+#undef SBA_R4
+#undef SBA_W4
+
+// N columns (N % 4 == 0) starting at register index OFF, as the fewest x16 / x8 / x4 transfers
+template <int N, int OFF = 0, class A>
+__device__ __forceinline__ void tmem_ld(uint32_t taddr, A& r) {
+    if constexpr (N >= 16) { tmem_ld16<OFF>(taddr, r); tmem_ld<N - 16, OFF + 16>(taddr + 16, r); }
+    else if constexpr (N >= 8) { tmem_ld8<OFF>(taddr, r); tmem_ld<N - 8, OFF + 8>(taddr + 8, r); }
+    else if constexpr (N >= 4) { tmem_ld4<OFF>(taddr, r); tmem_ld<N - 4, OFF + 4>(taddr + 4, r); }
+}
+template <int N, int OFF = 0, class A>
+__device__ __forceinline__ void tmem_st(uint32_t taddr, const A& r) {
+    if constexpr (N >= 16) { tmem_st16<OFF>(taddr, r); tmem_st<N - 16, OFF + 16>(taddr + 16, r); }
+    else if constexpr (N >= 8) { tmem_st8<OFF>(taddr, r); tmem_st<N - 8, OFF + 8>(taddr + 8, r); }
+    else if constexpr (N >= 4) { tmem_st4<OFF>(taddr, r); tmem_st<N - 4, OFF + 4>(taddr + 4, r); }
+}
+
+// ---- UMMA descriptors ---------------------------------------------------------------------------
+// Shared-memory matrix descriptor (sm_100): start address [0,14) and leading / stride byte
+// offsets [16,30) / [32,46) in 16-byte units, version 1 at [46,48), swizzle mode at [61,64).
+constexpr uint32_t kSwizzleNone = 0, kSwizzle128B_Base32B = 1, kSwizzle128B = 2;
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t swizzle) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | ((uint64_t)1 << 46) | ((uint64_t)swizzle << 61);
+}
+// Instruction descriptor: fp32 accumulate; fmt 1 = bf16 (kind::f16), 2 = tf32 (kind::tf32);
+// a_mn / b_mn = 1 when that operand is MN-major (M or N contiguous in shared memory).
+constexpr uint32_t make_idesc(int fmt, int a_mn, int b_mn, int M, int N) {
+    return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
+           ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// D[tmem] (+)= A[smem] . B[smem]^T ; one thread issues for the CTA
+template <bool TF32>
+__device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    if constexpr (TF32) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+            "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+            : "memory");
+    } else {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+            "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+            : "memory");
+    }
+}
+// D[tmem] (+)= A[tmem] . B[smem]^T
+template <bool TF32>
+__device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    if constexpr (TF32) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+            "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+            : "memory");
+    } else {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+            "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+            : "memory");
+    }
+}
+
+// ---- tf32 splitting -----------------------------------------------------------------------------
+// The tensor core reads the top 19 bits of an fp32 word (sign, 8 exponent, 10 mantissa bits).
+__device__ __forceinline__ float tf32_trunc(float v) { return __uint_as_float(__float_as_uint(v) & 0xffffe000u); }
+__device__ __forceinline__ float tf32_rna(float v) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+    return __uint_as_float(r);
+}
+
+// K-major, non-swizzled canonical operand: 8-row x 16-byte core matrices of 128 contiguous bytes;
+// core (row block rb, k chunk kc) at (rb * KCH + kc) * 128, KCH = chunks along K.
+// Descriptor: LBO = 128 (next k chunk), SBO = KCH * 128 (next 8 rows); one MMA consumes 2 chunks.
+template <int ES>   // element size in bytes
+__device__ __forceinline__ uint32_t kmajor_off(int row, int k, int kch) {
+    constexpr int EPC = 16 / ES;
+    return (uint32_t)((((row >> 3) * kch + k / EPC) << 7) + ((row & 7) << 4) + (k % EPC) * ES);
+}
+
+constexpr int TQ = 128;               // pixels per tile = UMMA M
+constexpr int kProducerWarp = 0, kMmaWarp = 1, kFirstConsumerWarp = 2;
+constexpr int kConsumers = 128;
+constexpr int kThreads = 64 + kConsumers;
+
+// Host side: cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda).
+// 2-D view [rows = B*idf][cols = Q] of a contiguous NCHW tensor; box = idf rows x 128 bytes of
+// pixels, 128-byte swizzle (bf16: the MN-major SWIZZLE_128B UMMA atom, 8 rows x 128 B; fp32: the
+// 32-byte-atom flavour SWIZZLE_128B_BASE32B, 4 rows x 128 B).
+int make_tile_map(CUtensorMap* out, const void* base, int dtype, int rows, int cols, int box_rows);
+
+}  // namespace tc5
+}  // namespace sba

@@ -8,7 +8,7 @@ from . import _abi
 
 _DTYPES = {torch.float32: _abi.SBA_F32, torch.bfloat16: _abi.SBA_BF16}
 _MASK_MODES = {"reference": _abi.SBA_MASK_REFERENCE, "per_sample": _abi.SBA_MASK_PER_SAMPLE}
-_ALGOS = {"auto": _abi.SBA_ALGO_AUTO, "simt": _abi.SBA_ALGO_SIMT, "mma": _abi.SBA_ALGO_MMA}
+_ALGOS = {"auto": _abi.SBA_ALGO_AUTO, "simt": _abi.SBA_ALGO_SIMT, "mma": _abi.SBA_ALGO_MMA, "tc5": _abi.SBA_ALGO_TCGEN05}
 
 # kernels launched by this process through the ABI (bench.py reports it as gpu_launches)
 launch_counter = {"n": 0}
@@ -57,6 +57,9 @@ class _WordRegionAttention(torch.autograd.Function):
         if x.dtype not in _DTYPES:
             raise RuntimeError(f"sba_gan_b200: unsupported dtype {x.dtype} (float32 or bfloat16)")
         x = x.contiguous()
+        # an unused output (attn is discarded in training, trainer_bert.py:267) must reach backward as
+        # None, not as a materialised zero tensor the kernel would have to stream
+        ctx.set_materialize_grads(False)
         c_code, attn, srcT, mask_bits, ctx32, w32 = attn_forward_raw(x, context, weight, mask_u8, mask_mode, algo)
         ctx.save_for_backward(x, ctx32, w32, mask_u8, srcT, mask_bits)
         ctx.meta = (mask_mode, algo, context.dtype, weight.dtype, tuple(weight.shape))
