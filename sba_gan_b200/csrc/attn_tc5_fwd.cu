@@ -19,13 +19,16 @@
 // x - trunc(x) is written by the consumers into a second shared-memory tile.
 //
 // Reference semantics: AttnGAN2/code/GlobalAttention.py:82-121 (oracle/attention.py).
+#include <cstdlib>
+
 #include "kernels.h"
 #include "tc5_common.cuh"
 
 namespace sba {
 namespace tc5 {
 
-int make_tile_map(CUtensorMap* out, const void* base, int dtype, int rows, int cols, int box_rows) {
+int make_tile_map(CUtensorMap* out, const void* base, int dtype, int rows, int cols, int box_rows, int box_cols,
+                  bool swizzle) {
     typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -43,15 +46,17 @@ int make_tile_map(CUtensorMap* out, const void* base, int dtype, int rows, int c
     const int es = dtype == SBA_F32 ? 4 : 2;
     const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
     const cuuint64_t gstride[1] = {(cuuint64_t)cols * es};
-    const cuuint32_t box[2] = {(cuuint32_t)(128 / es), (cuuint32_t)box_rows};
+    const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
     const cuuint32_t estr[2] = {1, 1};
+    // 32-bit MN-major UMMA operands exist only in the 32-byte-atom flavour of the 128-byte swizzle
+    const CUtensorMapSwizzle sw = !swizzle ? CU_TENSOR_MAP_SWIZZLE_NONE
+                                  : dtype == SBA_F32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B;
     CUresult r = encode(out, dtype == SBA_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
-                        const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        // 32-bit MN-major UMMA operands exist only in the 32-byte-atom flavour of the 128-byte swizzle
-                        dtype == SBA_F32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                        const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
-        set_error("cuTensorMapEncodeTiled failed (CUresult %d) for a %d x %d tensor", (int)r, rows, cols);
+        set_error("cuTensorMapEncodeTiled failed (CUresult %d) for a %d x %d tensor, box %d x %d", (int)r, rows, cols,
+                  box_rows, box_cols);
         return SBA_ERR_CUDA;
     }
     return SBA_OK;
@@ -95,17 +100,22 @@ struct Tc5FwdCfg {
     static constexpr int B2_BYTES = IDF * K2 * ES;
     static constexpr int NSPLIT = F32 ? 2 : 1;
     static constexpr int NST = F32 ? 3 : 4;                    // x ring depth
-    static constexpr int NLO = F32 ? 2 : 0;                    // lo tiles
+    static constexpr int NLO = F32 ? 1 : 0;                    // lo tile (fp32)
     static constexpr int PC = F32 ? K2 : K2 / 2;               // TMEM columns of one P operand
     static constexpr int COL_S = 0, COL_P = 64, COL_PLO = 96, COL_C = F32 ? 128 : 96;
     static constexpr int TMEM_COLS = pow2_cols(COL_C + IDF);
-    static constexpr int SMEM_BYTES = (NST + NLO) * STAGE_BYTES + NSPLIT * (B1_BYTES + B2_BYTES);
+    // per-warp output staging: [LP words][32 px] and [IDF channels][32 px], dense rows (TMA store boxes)
+    static constexpr int OUT_ROW = 32 * ES;
+    static constexpr int OUT_A_BYTES = LP * OUT_ROW, OUT_C_BYTES = IDF * OUT_ROW;
+    static constexpr int OUT_WARP_BYTES = OUT_A_BYTES + OUT_C_BYTES;
+    static constexpr int SMEM_BYTES = (NST + NLO) * STAGE_BYTES + NSPLIT * (B1_BYTES + B2_BYTES) + 4 * OUT_WARP_BYTES;
     // MN-major x tile: bf16 = SWIZZLE_128B atoms of 8 channel rows (1024 B); tf32 = SWIZZLE_128B_BASE32B
     // atoms of 4 channel rows (512 B), the only MN-major layout 32-bit operands have
     static constexpr uint32_t A_SWIZZLE = F32 ? kSwizzle128B_Base32B : kSwizzle128B;
     static constexpr uint32_t A_SBO = F32 ? 512 : 1024;
     static constexpr uint32_t IDESC1 = make_idesc(F32 ? 2 : 1, 1, 0, TQ, NS);
     static constexpr uint32_t IDESC2 = make_idesc(F32 ? 2 : 1, 0, 0, TQ, IDF);
+    static constexpr int CTAS_PER_SM = 512 / TMEM_COLS;        // resident CTAs must all fit their TMEM allocation
     static_assert(IDF % 16 == 0 && IDF <= 128, "idf must be a multiple of 16");
     static_assert(LP <= 32 && PC <= 32 && COL_PLO + PC <= 128, "at most 32 words");
 };
@@ -144,32 +154,41 @@ __global__ void __launch_bounds__(256) k_project_tc5(const float* __restrict__ c
     }
 }
 
+// one arrival per consumer warp: every lane orders its tcgen05 / shared-memory traffic first
+__device__ __forceinline__ void warp_arrive(uint32_t bar, int lane) {
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar);
+}
+
 template <typename T, int IDF, int NQ>
-__global__ void __launch_bounds__(kThreads, Tc5FwdCfg<T, IDF, NQ>::F32 ? 2 : 3)
-    k_attn_fwd_tc5(const __grid_constant__ CUtensorMap tmx, const Tc5FwdParams p) {
+__global__ void __launch_bounds__(kThreads, Tc5FwdCfg<T, IDF, NQ>::CTAS_PER_SM)
+    k_attn_fwd_tc5(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tma_attn,
+                   const __grid_constant__ CUtensorMap tma_c, const Tc5FwdParams p) {
     using C = Tc5FwdCfg<T, IDF, NQ>;
     constexpr bool F32 = C::F32;
     constexpr int LP = C::LP, NST = C::NST, ES = C::ES;
     constexpr float kLog2e = 1.4426950408889634f;
 
     extern __shared__ unsigned char smem_raw[];
-    const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;        // SWIZZLE_128B atoms are 1024-byte aligned
+    const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;        // swizzle atoms want 1024-byte alignment
     unsigned char* sgen = smem_raw + (sbase - smem_u32(smem_raw));
     const uint32_t s_x = sbase;                                           // [NST] x tiles
-    const uint32_t s_lo = s_x + NST * C::STAGE_BYTES;                     // [NLO] x - trunc(x) tiles (fp32)
+    const uint32_t s_lo = s_x + NST * C::STAGE_BYTES;                     // [NLO] x - trunc(x) tile (fp32)
     const uint32_t s_b1 = s_lo + C::NLO * C::STAGE_BYTES;                 // [NSPLIT] log2e * sourceT, rows = words
     const uint32_t s_b2 = s_b1 + C::NSPLIT * C::B1_BYTES;                 // [NSPLIT] sourceT, rows = channels
+    const uint32_t s_out = s_b2 + C::NSPLIT * C::B2_BYTES;                // [4 warps] output staging
     unsigned char* g_lo = sgen + NST * C::STAGE_BYTES;
     unsigned char* g_b1 = g_lo + C::NLO * C::STAGE_BYTES;
     unsigned char* g_b2 = g_b1 + C::NSPLIT * C::B1_BYTES;
-    uint32_t* mb_s = reinterpret_cast<uint32_t*>(g_b2 + C::NSPLIT * C::B2_BYTES);   // [B] caption mask words
+    unsigned char* g_out = g_b2 + C::NSPLIT * C::B2_BYTES;
+    uint32_t* mb_s = reinterpret_cast<uint32_t*>(g_out + 4 * C::OUT_WARP_BYTES);   // [B] caption mask words
 
-    __shared__ __align__(8) unsigned long long bar_x_full[NST], bar_x_empty[NST], bar_s_full[2], bar_s_free[2],
-        bar_lo_ready[2], bar_p_ready, bar_c_full, bar_b_ready;
+    __shared__ __align__(8) unsigned long long bar_x_full[NST], bar_x_empty[NST], bar_s_full[2], bar_s_free[2], bar_lo_ready,
+        bar_p_ready, bar_c_full, bar_b_ready;
     __shared__ uint32_t tmem_base_s;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int L = p.L, Q = p.Q, TPS = p.tiles_per_sample;
+    const int L = p.L, TPS = p.tiles_per_sample;
 
     if (tid == 0) {
 #pragma unroll
@@ -180,14 +199,16 @@ __global__ void __launch_bounds__(kThreads, Tc5FwdCfg<T, IDF, NQ>::F32 ? 2 : 3)
 #pragma unroll
         for (int s = 0; s < 2; ++s) {
             mbar_init(smem_u32(&bar_s_full[s]), 1);
-            mbar_init(smem_u32(&bar_s_free[s]), kConsumers);
-            mbar_init(smem_u32(&bar_lo_ready[s]), kConsumers);
+            mbar_init(smem_u32(&bar_s_free[s]), 4);
         }
-        mbar_init(smem_u32(&bar_p_ready), kConsumers);
+        mbar_init(smem_u32(&bar_lo_ready), 4);
+        mbar_init(smem_u32(&bar_p_ready), 4);
         mbar_init(smem_u32(&bar_c_full), 1);
-        mbar_init(smem_u32(&bar_b_ready), kConsumers);
+        mbar_init(smem_u32(&bar_b_ready), 4);
         fence_barrier_init();
         prefetch_tensormap(&tmx);
+        prefetch_tensormap(&tma_attn);
+        prefetch_tensormap(&tma_c);
     }
     if (warp == kMmaWarp) tmem_alloc(smem_u32(&tmem_base_s), C::TMEM_COLS);
     if (p.mask != nullptr) {
@@ -234,19 +255,18 @@ __global__ void __launch_bounds__(kThreads, Tc5FwdCfg<T, IDF, NQ>::F32 ? 2 : 3)
             auto mma1 = [&](int j) {
                 const int stage = j % NST, buf = j & 1;
                 mbar_wait(smem_u32(&bar_x_full[stage]), (uint32_t)(j / NST) & 1u);
-                if constexpr (F32) mbar_wait(smem_u32(&bar_lo_ready[buf]), (uint32_t)(j >> 1) & 1u);
+                if constexpr (F32) mbar_wait(smem_u32(&bar_lo_ready), (uint32_t)j & 1u);
                 if (j >= 2) mbar_wait(smem_u32(&bar_s_free[buf]), (uint32_t)((j >> 1) - 1) & 1u);
                 tc_fence_after();
                 const uint32_t d = tmem_base + C::COL_S + 32 * buf;
                 const uint32_t a_hi = s_x + stage * C::STAGE_BYTES;
-                const uint32_t a_lo = s_lo + buf * C::STAGE_BYTES;
 #pragma unroll
                 for (int ks = 0; ks < C::KS1; ++ks) {
                     const uint64_t da = smem_desc(a_hi + ks * C::KSTEP_A, C::BOX_BYTES, C::A_SBO, C::A_SWIZZLE);
                     const uint64_t db = smem_desc(s_b1 + ks * 256, 128, C::KCH1 * 128, kSwizzleNone);
                     umma_ss<F32>(d, da, db, C::IDESC1, ks > 0 ? 1u : 0u);
                     if constexpr (F32) {
-                        const uint64_t dal = smem_desc(a_lo + ks * C::KSTEP_A, C::BOX_BYTES, C::A_SBO, C::A_SWIZZLE);
+                        const uint64_t dal = smem_desc(s_lo + ks * C::KSTEP_A, C::BOX_BYTES, C::A_SBO, C::A_SWIZZLE);
                         const uint64_t dbl = smem_desc(s_b1 + C::B1_BYTES + ks * 256, 128, C::KCH1 * 128, kSwizzleNone);
                         umma_ss<F32>(d, da, dbl, C::IDESC1, 1u);
                         umma_ss<F32>(d, dal, db, C::IDESC1, 1u);
@@ -283,11 +303,15 @@ __global__ void __launch_bounds__(kThreads, Tc5FwdCfg<T, IDF, NQ>::F32 ? 2 : 3)
             for (int j = 0; j < n_local; ++j) {
                 const bool has_next = j + 1 < n_local;
                 const bool next_same = has_next && (t + 1 < TPS);
-                if (next_same) mma1(j + 1);          // runs ahead of the softmax of tile j
+                // bf16: S of the next tile is produced ahead of the softmax of this one; fp32: the lo tile of
+                // the next tile is written only after P of this one, so MMA2 goes first
+                if (!F32 && next_same) mma1(j + 1);
                 mma2(j);
                 if (has_next && !next_same) {
                     mbar_wait(smem_u32(&bar_b_ready), nb & 1u);     // operands of the next sample are in place
                     ++nb;
+                    mma1(j + 1);
+                } else if (F32 && next_same) {
                     mma1(j + 1);
                 }
                 if (++t == TPS) t = 0;
@@ -305,6 +329,10 @@ __global__ void __launch_bounds__(kThreads, Tc5FwdCfg<T, IDF, NQ>::F32 ? 2 : 3)
         // reference mask order: pixel n = b*Q + q uses caption n mod B (GlobalAttention.py:104-108)
         uint32_t cap = (uint32_t)(((unsigned long long)w_begin * TQ + px) % Bu);
         int b = b0, t = t0, cur_b = -1;
+        // this warp's output staging: lane = pixel column
+        const uint32_t so_a = s_out + cw * C::OUT_WARP_BYTES, so_c = so_a + C::OUT_A_BYTES;
+        T* go_a = reinterpret_cast<T*>(g_out + cw * C::OUT_WARP_BYTES) + lane;
+        T* go_c = reinterpret_cast<T*>(g_out + cw * C::OUT_WARP_BYTES + C::OUT_A_BYTES) + lane;
 
         // fp32: lo tile of local tile j = x - trunc(x), elementwise on the swizzled image
         auto make_lo = [&](int j) {
@@ -312,7 +340,7 @@ __global__ void __launch_bounds__(kThreads, Tc5FwdCfg<T, IDF, NQ>::F32 ? 2 : 3)
                 const int stage = j % NST;
                 mbar_wait(smem_u32(&bar_x_full[stage]), (uint32_t)(j / NST) & 1u);
                 const float4* xs = reinterpret_cast<const float4*>(sgen + stage * C::STAGE_BYTES);
-                float4* lo = reinterpret_cast<float4*>(g_lo + (j & 1) * C::STAGE_BYTES);
+                float4* lo = reinterpret_cast<float4*>(g_lo);
 #pragma unroll
                 for (int r = 0; r < C::STAGE_BYTES / 16 / kConsumers; ++r) {
                     float4 v = xs[r * kConsumers + ct];
@@ -320,7 +348,7 @@ __global__ void __launch_bounds__(kThreads, Tc5FwdCfg<T, IDF, NQ>::F32 ? 2 : 3)
                     lo[r * kConsumers + ct] = v;
                 }
                 fence_proxy_async();
-                mbar_arrive(smem_u32(&bar_lo_ready[j & 1]));
+                warp_arrive(smem_u32(&bar_lo_ready), lane);
             }
         };
 
@@ -330,6 +358,7 @@ __global__ void __launch_bounds__(kThreads, Tc5FwdCfg<T, IDF, NQ>::F32 ? 2 : 3)
         for (int j = 0; j < n_local; ++j) {
             if (b != cur_b) {
                 // ---- operands of sample b: B1[word][channel] = log2e*srcT, B2[channel][word] = srcT ----
+                // (every MMA that read the previous sample's operands has completed: c_full of tile j-1)
                 cur_b = b;
                 const float* sb = p.srcT + (size_t)b * IDF * L;
                 for (int o = ct; o < IDF * L; o += kConsumers) {
@@ -348,9 +377,8 @@ __global__ void __launch_bounds__(kThreads, Tc5FwdCfg<T, IDF, NQ>::F32 ? 2 : 3)
                     }
                 }
                 fence_proxy_async();
-                mbar_arrive(smem_u32(&bar_b_ready));
+                warp_arrive(smem_u32(&bar_b_ready), lane);
             }
-            if (j + 1 < n_local) make_lo(j + 1);
 
             // ---- S row of this pixel (already in the log2 domain) ---------------------------------
             const int buf = j & 1;
@@ -360,7 +388,7 @@ __global__ void __launch_bounds__(kThreads, Tc5FwdCfg<T, IDF, NQ>::F32 ? 2 : 3)
             tmem_ld<LP>(tl + C::COL_S + 32 * buf, sr);
             tmem_wait_ld();
             tc_fence_before();
-            mbar_arrive(smem_u32(&bar_s_free[buf]));
+            warp_arrive(smem_u32(&bar_s_free[buf]), lane);
 
             // ---- mask (GlobalAttention.py:104-108) + softmax over words (:109) -----------------------
             uint32_t mb = pad_bits;
@@ -406,25 +434,31 @@ __global__ void __launch_bounds__(kThreads, Tc5FwdCfg<T, IDF, NQ>::F32 ? 2 : 3)
             }
             tmem_wait_st();
             tc_fence_before();
-            mbar_arrive(smem_u32(&bar_p_ready));
+            warp_arrive(smem_u32(&bar_p_ready), lane);
 
-            // ---- attention map: lane = pixel, one 128-byte (fp32) row segment per warp and word ---
-            const int q = t * TQ + px;
-            {
-                T* ap = static_cast<T*>(p.attn) + (size_t)b * L * Q + q;
+            if (j + 1 < n_local) make_lo(j + 1);       // fp32: MMA1(j) has completed, the lo tile is free
+
+            // ---- attention map: staged [word][32 px] per warp, one TMA box store -------------------
+            const int q0 = t * TQ + cw * 32;
+            if (lane == 0) bulk_wait_read<1>();        // the previous attn store has finished reading its staging
+            __syncwarp();
 #pragma unroll
-                for (int l = 0; l < LP; ++l) {
-                    if (l < L) {
-                        if constexpr (F32) ap[(size_t)l * Q] = s[l];
-                        else ap[(size_t)l * Q] = __float2bfloat16_rn(s[l]);
-                    }
-                }
+            for (int l = 0; l < LP; ++l) {
+                if constexpr (F32) go_a[l * 32] = s[l];
+                else go_a[l * 32] = __float2bfloat16_rn(s[l]);
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+                tma_store_2d(&tma_attn, q0, b * L, so_a);
+                bulk_commit();
             }
 
             // ---- c row of this pixel ---------------------------------------------------------------
             mbar_wait(smem_u32(&bar_c_full), (uint32_t)j & 1u);
             tc_fence_after();
-            T* cp = static_cast<T*>(p.c_code) + (size_t)b * IDF * Q + q;
+            if (lane == 0) bulk_wait_read<1>();        // the previous c store has finished reading its staging
+            __syncwarp();
 #pragma unroll
             for (int h = 0; h < IDF / 16; ++h) {
                 uint32_t cr[16];
@@ -432,15 +466,22 @@ __global__ void __launch_bounds__(kThreads, Tc5FwdCfg<T, IDF, NQ>::F32 ? 2 : 3)
                 tmem_wait_ld();
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
-                    if constexpr (F32) cp[(size_t)(16 * h + i) * Q] = __uint_as_float(cr[i]);
-                    else cp[(size_t)(16 * h + i) * Q] = __float2bfloat16_rn(__uint_as_float(cr[i]));
+                    if constexpr (F32) go_c[(16 * h + i) * 32] = __uint_as_float(cr[i]);
+                    else go_c[(16 * h + i) * 32] = __float2bfloat16_rn(__uint_as_float(cr[i]));
                 }
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+                tma_store_2d(&tma_c, q0, b * IDF, so_c);
+                bulk_commit();
             }
 
             if (++t == TPS) { t = 0; ++b; }
             cap += step_mod;
             if (cap >= Bu) cap -= Bu;
         }
+        if (lane == 0) bulk_wait<0>();                 // all output stores have landed before the CTA retires
         tc_fence_before();
     }
 
@@ -457,29 +498,36 @@ int launch_fwd_tc5(const void* x, const float* ctx, const float* W, float* srcT,
     using C = Tc5FwdCfg<T, IDF, NQ>;
     auto kern = k_attn_fwd_tc5<T, IDF, NQ>;
     const size_t smem = (size_t)C::SMEM_BYTES + (size_t)p.B * 4 + 1024 + 16;
-    static int max_ctas = 0;
+    static int sms = 0;
     static size_t smem_set = 0;
-    if (smem > 200 * 1024) {
+    if (smem > 220 * 1024) {
         set_error("attn_fwd(tcgen05): %zu bytes of shared memory needed (B=%d)", smem, p.B);
         return SBA_ERR_UNSUPPORTED;
     }
-    if (max_ctas == 0 || smem > smem_set) {
-        int dev = 0, sms = 0, per_sm = 0;
+    if (sms == 0 || smem > smem_set) {
+        int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem);
-        if (e != cudaSuccess || per_sm < 1 || sms < 1) {
-            set_error("attn_fwd(tcgen05): occupancy query failed: %s", cudaGetErrorString(e));
+        if (e != cudaSuccess || sms < 1) {
+            set_error("attn_fwd(tcgen05): cudaFuncSetAttribute(%zu B): %s", smem, cudaGetErrorString(e));
+            sms = 0;
             return SBA_ERR_CUDA;
         }
-        const int tmem_limit = 512 / C::TMEM_COLS;      // all resident CTAs must fit their TMEM allocation
-        if (per_sm > tmem_limit) per_sm = tmem_limit;
-        max_ctas = sms * per_sm;
         smem_set = smem;
     }
-    CUtensorMap tmx;
-    int rc = make_tile_map(&tmx, x, dtype, p.B * IDF, p.Q, IDF);
+    // Resident CTAs per SM: the occupancy API answers 1 for kernels that allocate tensor memory, the
+    // hardware co-schedules as many as registers, shared memory and the 512 TMEM columns allow.
+    int per_sm = (int)((227 * 1024) / (smem_set + 1024));
+    if (per_sm > C::CTAS_PER_SM) per_sm = C::CTAS_PER_SM;
+    if (per_sm < 1) per_sm = 1;
+    if (getenv("SBA_TC5_CTAS_PER_SM")) per_sm = atoi(getenv("SBA_TC5_CTAS_PER_SM"));
+    const int max_ctas = sms * per_sm;
+    CUtensorMap tmx, tma_attn, tma_c;
+    const int es = dtype == SBA_F32 ? 4 : 2;
+    int rc = make_tile_map(&tmx, x, dtype, p.B * IDF, p.Q, IDF, 128 / es, true);
+    if (!rc) rc = make_tile_map(&tma_attn, p.attn, dtype, p.B * p.L, p.Q, p.L, 32, false);
+    if (!rc) rc = make_tile_map(&tma_c, p.c_code, dtype, p.B * IDF, p.Q, IDF, 32, false);
     if (rc) return rc;
     const int NT = (p.L + 7) / 8;
     const int pgrid = p.B * (IDF / 8);
@@ -502,7 +550,7 @@ int launch_fwd_tc5(const void* x, const float* ctx, const float* W, float* srcT,
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmx, p);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmx, tma_attn, tma_c, p);
     if (e != cudaSuccess) {
         set_error("attn_fwd(tcgen05): launch: %s", cudaGetErrorString(e));
         return SBA_ERR_CUDA;

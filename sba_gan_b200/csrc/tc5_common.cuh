@@ -26,19 +26,20 @@ using mma::mbar_arrive;
 using mma::fence_barrier_init;
 
 // Bounded mbarrier wait: a protocol bug traps (-> a CUDA error the ABI reports) instead of
-// hanging the GPU box.  try_wait itself suspends for a HW time slice, so the bound is seconds.
+// hanging the GPU box.  Every try_wait suspends for up to the hinted 20 us, so the bound is
+// between tens of milliseconds and ~1 s - far beyond any legitimate wait on this path.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t done;
     uint32_t spins = 0;
     do {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(done)
-            : "r"(bar), "r"(parity)
+            : "r"(bar), "r"(parity), "r"(20000u)      // suspend-time hint (ns): sleep in hardware, not in a spin loop
             : "memory");
-        if (!done && ++spins > (1u << 24)) __trap();
+        if (!done && ++spins > (1u << 16)) __trap();
     } while (!done);
 }
 
@@ -49,6 +50,18 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm,
         ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(bar)
         : "memory");
 }
+// shared -> global box store (bulk async-group completion)
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, int c0, int c1, uint32_t src) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(tm), "r"(c0), "r"(c1),
+                 "r"(src)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all but the N most recent bulk groups of this thread have finished READING shared memory
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* tm) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(tm) : "memory");
 }
@@ -202,10 +215,13 @@ constexpr int kConsumers = 128;
 constexpr int kThreads = 64 + kConsumers;
 
 // Host side: cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda).
-// 2-D view [rows = B*idf][cols = Q] of a contiguous NCHW tensor; box = idf rows x 128 bytes of
-// pixels, 128-byte swizzle (bf16: the MN-major SWIZZLE_128B UMMA atom, 8 rows x 128 B; fp32: the
-// 32-byte-atom flavour SWIZZLE_128B_BASE32B, 4 rows x 128 B).
-int make_tile_map(CUtensorMap* out, const void* base, int dtype, int rows, int cols, int box_rows);
+// 2-D view [rows][cols = Q] of a contiguous [B, rows_per_sample, Q] tensor with a box of
+// box_rows x box_cols elements.  swizzle = true (loads of x / g_c; box_cols * es must be 128):
+// 128-byte swizzle in the flavour the MN-major UMMA operand needs - bf16: SWIZZLE_128B atoms of
+// 8 rows x 128 B; fp32: SWIZZLE_128B_ATOM_32B (UMMA SWIZZLE_128B_BASE32B), 4 rows x 128 B.
+// swizzle = false (stores): dense box rows.
+int make_tile_map(CUtensorMap* out, const void* base, int dtype, int rows, int cols, int box_rows, int box_cols,
+                  bool swizzle);
 
 }  // namespace tc5
 }  // namespace sba
