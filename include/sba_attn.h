@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SBA_ABI_VERSION 2
+#define SBA_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define SBA_API __attribute__((visibility("default")))
@@ -53,7 +53,10 @@ enum { SBA_F32 = 0, SBA_BF16 = 1 };
  *  PER_SAMPLE: caption b. */
 enum { SBA_MASK_REFERENCE = 0, SBA_MASK_PER_SAMPLE = 1 };
 
-/* kernel family: AUTO picks the fastest one that supports the shape */
+/* kernel family: AUTO picks the fastest one that supports the shape
+ *  SIMT    : CUDA-core FFMA + warp shuffles, any shape with L <= 32
+ *  MMA     : warp-level mma.sync with TMA-staged tiles
+ *  TCGEN05 : tcgen05.mma with TMEM accumulators, TMA tensor loads / stores, one pixel per thread */
 enum { SBA_ALGO_AUTO = 0, SBA_ALGO_SIMT = 1, SBA_ALGO_MMA = 2, SBA_ALGO_TCGEN05 = 3 };
 
 SBA_API int sba_abi_version(void);
@@ -72,7 +75,7 @@ SBA_API int sba_last_launch_count(void);
  * attn     [B, L, Q]     dtype  out attention map
  * srcT     [B, idf, L]   fp32   out sourceT = W.ctx, kept for the backward
  * scratch  [3*B] uint32  scratch    [0,B): caption mask bit words (kept for the backward),
- *                                   [B,3B): per-sample ready counters / max|srcT| of this launch
+ *                                   [B,3B): free for the kernels of this launch
  */
 SBA_API int sba_attn_fwd(const void* x, const float* ctx, const float* W, const uint8_t* mask,
                  void* c_code, void* attn, float* srcT, uint32_t* scratch,

@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_PKG, "lib", "libsba_attn.so")
 SBA_F32, SBA_BF16 = 0, 1
 SBA_MASK_REFERENCE, SBA_MASK_PER_SAMPLE = 0, 1
 SBA_ALGO_AUTO, SBA_ALGO_SIMT, SBA_ALGO_MMA, SBA_ALGO_TCGEN05 = 0, 1, 2, 3
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 # every symbol include/sba_attn.h declares: (restype, argtypes)
 SYMBOLS = {

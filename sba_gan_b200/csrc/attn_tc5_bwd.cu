@@ -1,0 +1,544 @@
+// Kernel (b): fused backward of GlobalAttentionGeneral on the 5th-generation tensor cores
+// (SBA_ALGO_TCGEN05, bf16 tensors).  Same skeleton as attn_tc5_fwd.cu: one persistent CTA =
+// 1 TMA producer warp + 1 MMA-issuing warp + 4 consumer warps (thread = pixel), contiguous
+// ranges of 128-pixel tiles.  Per tile (formulas: SURVEY.md §8a-4, oracle/attention.py):
+//   TMA      : the [idf x 128 px] tiles of g_c and x land interleaved box by box, so that the same
+//              bytes are (i) two MN-major A operands (pixels = M) and (ii) ONE K-major A operand
+//              [g ; x] with 2*idf rows (pixels = K).
+//   MMA1     : S  = x^T . sourceT      dP = g^T . sourceT                     (K = idf)
+//   consumers: P = masked softmax(S) (recomputed, not re-read from HBM)
+//              dS = P * (dP [+ g_attn] - sum_l P dP)
+//              P and dS are written (bf16, 128-byte swizzled rows [word][pixel]) into one
+//              shared-memory operand buffer PB.
+//   MMA2     : dX   = dS . sourceT^T          (A = the dS rows of PB, MN-major; K = words)
+//              dSrc += [g ; x] . [P | dS]     (A = the staged tiles, B = PB, K = 128 pixels;
+//                                              the accumulator stays in TMEM across all tiles of a
+//                                              sample: rows = g / x channels, columns = P / dS words;
+//                                              its diagonal blocks are g.P and x.dS)
+//   consumers: dX row of the pixel -> staged -> TMA box store.
+// When the tile range leaves a sample the consumers add the two diagonal blocks of the TMEM
+// accumulator into dSrc[b] with fp32 atomics, and the last CTA to do so for that sample forms
+// dW += dSrc[b] . ctx[b]^T and dCtx[b] = W^T . dSrc[b] while the others keep streaming.
+// dSrc / dW / the per-sample counters are zeroed by a small kernel in front (programmatic
+// dependent launch: this kernel only waits for it before its first atomic).
+#include <cstdlib>
+
+#include "kernels.h"
+#include "tc5_common.cuh"
+
+namespace sba {
+namespace {
+using namespace tc5;
+
+struct Tc5BwdParams {
+    const float* srcT;
+    const uint8_t* mask;
+    const void* ga;       // [B, L, Q] nullable
+    float* dSrc;          // [B, idf, L]
+    const float* ctx;     // [B, cdf, L]   (epilogue)
+    const float* W;       // [idf, cdf]    (epilogue, dCtx only)
+    float* dW;            // [idf, cdf]    nullable
+    float* dCtx;          // [B, cdf, L]   nullable
+    uint32_t* cnt;        // [B] per-sample completion counters (zeroed by k_zero_tc5)
+    int B, L, Q, cdf, mask_mode;
+    int tiles_per_sample;
+    int n_tiles;
+};
+
+constexpr int pow2_cols(int n) { return n <= 32 ? 32 : n <= 64 ? 64 : n <= 128 ? 128 : n <= 256 ? 256 : 512; }
+
+template <int IDF, int NQ>
+struct Tc5BwdCfg {
+    static constexpr int ES = 2;                                // bf16
+    static constexpr int LP = 4 * NQ;                           // words held per thread
+    static constexpr int RP = (LP + 7) / 8 * 8;                 // P rows of PB (whole 8-row swizzle atoms)
+    static constexpr int K2 = (LP + 15) / 16 * 16;              // dS rows of PB = K extent of the dX MMA
+    static constexpr int NR = RP + K2;                          // PB rows
+    static constexpr int ND = 2 * RP;                           // N of the dSrc MMA: P words | dS words
+    static constexpr int BOX_PX = 64, NBOX = TQ / BOX_PX;       // 128-byte box rows
+    static constexpr int BOX_BYTES = IDF * 128;
+    static constexpr int STAGE_BYTES = 2 * NBOX * BOX_BYTES;    // g and x tiles, boxes interleaved (g0 x0 g1 x1)
+    static constexpr int KS1 = IDF / 16;                        // MMA1 k-steps (channels)
+    static constexpr int KS2 = K2 / 16;                         // dX k-steps (words)
+    static constexpr int KS3 = TQ / 16;                         // dSrc k-steps (pixels)
+    static constexpr int NS = 32;                               // MMA1 N (words, zero padded)
+    static constexpr int KCH1 = IDF * ES / 16, KCH2 = K2 * ES / 16;
+    static constexpr int B1_BYTES = NS * IDF * ES, B2_BYTES = IDF * K2 * ES;
+    static constexpr int PB_KBLOCK = NR * 128;                  // bytes of one 64-pixel block of PB
+    static constexpr int PB_BYTES = NBOX * PB_KBLOCK;
+    static constexpr int NST = 2;
+    static constexpr int MD = 2 * IDF <= 64 ? 64 : 128;         // M of the dSrc MMA
+    static constexpr int COL_S = 0, COL_DP = 32, COL_DX = 0 /* aliases S */, COL_ACC = 64;
+    static constexpr int TMEM_COLS = pow2_cols((IDF > 64 ? IDF : 64) + ND);
+    static constexpr int OUT_WARP_BYTES = IDF * 32 * ES;        // per-warp dX staging [channel][32 px]
+    static constexpr int SMEM_BYTES = NST * STAGE_BYTES + PB_BYTES + B1_BYTES + B2_BYTES + 4 * OUT_WARP_BYTES;
+    static constexpr uint32_t IDESC1 = make_idesc(1, 1, 0, TQ, NS);      // A = tile, MN-major
+    static constexpr uint32_t IDESC2 = make_idesc(1, 1, 0, TQ, IDF);     // A = dS rows of PB, MN-major
+    static constexpr uint32_t IDESC3 = make_idesc(1, 0, 0, MD, ND);      // A = [g ; x], B = PB, both K-major
+    static constexpr int CTAS_PER_SM = 512 / TMEM_COLS;
+    static_assert(IDF % 16 == 0 && 2 * IDF <= 128, "idf must be a multiple of 16, at most 64");
+    static_assert(LP <= 32 && IDF <= 64, "at most 32 words");
+    static_assert(4 * OUT_WARP_BYTES >= IDF * 32 * 4, "dX staging doubles as the epilogue's dSrc[b] buffer");
+};
+
+// zero dSrc, the per-sample counters and dW; the streaming kernel waits for this grid only before its
+// first atomic (griddepcontrol.wait), so the fill overlaps its prologue and first tiles
+__global__ void __launch_bounds__(256) k_zero_tc5(float* __restrict__ a, size_t na, float* __restrict__ b, size_t nb) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    const size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x, step = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = i0; i < na; i += step) a[i] = 0.f;
+    if (b != nullptr)
+        for (size_t i = i0; i < nb; i += step) b[i] = 0.f;
+}
+
+__device__ __forceinline__ void warp_arrive(uint32_t bar, int lane) {
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar);
+}
+
+template <int IDF, int NQ, bool HAS_GA>
+__global__ void __launch_bounds__(kThreads, Tc5BwdCfg<IDF, NQ>::CTAS_PER_SM > 3 ? 3 : Tc5BwdCfg<IDF, NQ>::CTAS_PER_SM)
+    k_attn_bwd_tc5(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_g,
+                   const __grid_constant__ CUtensorMap tm_dx, const Tc5BwdParams p) {
+    using C = Tc5BwdCfg<IDF, NQ>;
+    using T = __nv_bfloat16;
+    constexpr int LP = C::LP, RP = C::RP, NST = C::NST;
+    constexpr float kLog2e = 1.4426950408889634f;
+
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    unsigned char* sgen = smem_raw + (sbase - smem_u32(smem_raw));
+    const uint32_t s_st = sbase;                                  // [NST] staged g / x tiles
+    const uint32_t s_pb = s_st + NST * C::STAGE_BYTES;            // PB: [64-px block][row][128 B]
+    const uint32_t s_b1 = s_pb + C::PB_BYTES;                     // sourceT, rows = words
+    const uint32_t s_b2 = s_b1 + C::B1_BYTES;                     // sourceT, rows = channels
+    const uint32_t s_out = s_b2 + C::B2_BYTES;                    // [4 warps] dX staging
+    unsigned char* g_pb = sgen + NST * C::STAGE_BYTES;
+    unsigned char* g_b1 = g_pb + C::PB_BYTES;
+    unsigned char* g_b2 = g_b1 + C::B1_BYTES;
+    unsigned char* g_out = g_b2 + C::B2_BYTES;
+    uint32_t* mb_s = reinterpret_cast<uint32_t*>(g_out + 4 * C::OUT_WARP_BYTES);   // [B] caption mask words
+
+    __shared__ __align__(8) unsigned long long bar_x_full[NST], bar_x_empty[NST], bar_s_full, bar_ds_ready, bar_c_full,
+        bar_dx_free, bar_b_ready;
+    __shared__ uint32_t tmem_base_s;
+    __shared__ int fin_s;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int L = p.L, Q = p.Q, TPS = p.tiles_per_sample;
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < NST; ++s) {
+            mbar_init(smem_u32(&bar_x_full[s]), 1);
+            mbar_init(smem_u32(&bar_x_empty[s]), 1);
+        }
+        mbar_init(smem_u32(&bar_s_full), 1);
+        mbar_init(smem_u32(&bar_ds_ready), 4);
+        mbar_init(smem_u32(&bar_c_full), 1);
+        mbar_init(smem_u32(&bar_dx_free), 4);
+        mbar_init(smem_u32(&bar_b_ready), 4);
+        fence_barrier_init();
+        prefetch_tensormap(&tm_x);
+        prefetch_tensormap(&tm_g);
+        prefetch_tensormap(&tm_dx);
+    }
+    if (warp == kMmaWarp) tmem_alloc(smem_u32(&tmem_base_s), C::TMEM_COLS);
+    if (p.mask != nullptr) {
+        for (int cap = tid; cap < p.B; cap += kThreads) {
+            uint32_t bits = 0;
+            for (int l = 0; l < L; ++l) bits |= (p.mask[(size_t)cap * L + l] ? 1u : 0u) << l;
+            mb_s[cap] = bits;
+        }
+    }
+    // zero PB and the B operand buffers once: padding rows / words are never written again
+    for (int o = tid; o < (C::PB_BYTES + C::B1_BYTES + C::B2_BYTES) / 16; o += kThreads)
+        reinterpret_cast<uint4*>(g_pb)[o] = make_uint4(0u, 0u, 0u, 0u);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+
+    const int w_begin = (int)(((long long)blockIdx.x * p.n_tiles) / gridDim.x);
+    const int w_end = (int)(((long long)(blockIdx.x + 1) * p.n_tiles) / gridDim.x);
+    const int n_local = w_end - w_begin;
+    const int b0 = w_begin / TPS, t0 = w_begin - b0 * TPS;
+
+    if (warp == kProducerWarp) {
+        // --------------------------------- TMA producer -----------------------------------------
+        if (lane == 0) {
+            int b = b0, t = t0;
+            for (int j = 0; j < n_local; ++j) {
+                const int stage = j % NST;
+                if (j >= NST) mbar_wait(smem_u32(&bar_x_empty[stage]), (uint32_t)((j / NST) - 1) & 1u);
+                const uint32_t full = smem_u32(&bar_x_full[stage]);
+                mbar_expect_tx(full, (uint32_t)C::STAGE_BYTES);
+                const uint32_t dst = s_st + stage * C::STAGE_BYTES;
+#pragma unroll
+                for (int bx = 0; bx < C::NBOX; ++bx) {
+                    tma_load_2d(dst + (2 * bx) * C::BOX_BYTES, &tm_g, t * TQ + bx * C::BOX_PX, b * IDF, full);
+                    tma_load_2d(dst + (2 * bx + 1) * C::BOX_BYTES, &tm_x, t * TQ + bx * C::BOX_PX, b * IDF, full);
+                }
+                if (++t == TPS) { t = 0; ++b; }
+            }
+        }
+    } else if (warp == kMmaWarp) {
+        // --------------------------------- MMA issuer -------------------------------------------
+        if (lane == 0) {
+            int t = t0;
+            uint32_t nb = 0;
+            bool first_of_sample = true;
+            for (int j = 0; j < n_local; ++j) {
+                const int stage = j % NST;
+                const uint32_t st = s_st + stage * C::STAGE_BYTES;
+                if (first_of_sample) {
+                    mbar_wait(smem_u32(&bar_b_ready), nb & 1u);     // operands of this sample are in place
+                    ++nb;
+                }
+                if (j > 0) mbar_wait(smem_u32(&bar_dx_free), (uint32_t)(j - 1) & 1u);   // dX(j-1) has left the S columns
+                mbar_wait(smem_u32(&bar_x_full[stage]), (uint32_t)(j / NST) & 1u);
+                tc_fence_after();
+                // MMA1: S = x^T . B1, dP = g^T . B1  (tiles are MN-major A operands: 64-px blocks 2 boxes apart)
+#pragma unroll
+                for (int ks = 0; ks < C::KS1; ++ks) {
+                    const uint64_t db = smem_desc(s_b1 + ks * 256, 128, C::KCH1 * 128, kSwizzleNone);
+                    const uint64_t dax = smem_desc(st + C::BOX_BYTES + ks * 2048, 2 * C::BOX_BYTES, 1024, kSwizzle128B);
+                    const uint64_t dag = smem_desc(st + ks * 2048, 2 * C::BOX_BYTES, 1024, kSwizzle128B);
+                    umma_ss<false>(tmem_base + C::COL_S, dax, db, C::IDESC1, ks > 0 ? 1u : 0u);
+                    umma_ss<false>(tmem_base + C::COL_DP, dag, db, C::IDESC1, ks > 0 ? 1u : 0u);
+                }
+                umma_commit(smem_u32(&bar_s_full));
+
+                mbar_wait(smem_u32(&bar_ds_ready), (uint32_t)j & 1u);
+                tc_fence_after();
+                // MMA2a: dX = dS . B2  (A = dS rows of PB, MN-major: pixel blocks PB_KBLOCK apart)
+#pragma unroll
+                for (int ks = 0; ks < C::KS2; ++ks) {
+                    const uint64_t da = smem_desc(s_pb + (RP + 16 * ks) * 128, C::PB_KBLOCK, 1024, kSwizzle128B);
+                    const uint64_t db = smem_desc(s_b2 + ks * 256, 128, C::KCH2 * 128, kSwizzleNone);
+                    umma_ss<false>(tmem_base + C::COL_DX, da, db, C::IDESC2, ks > 0 ? 1u : 0u);
+                }
+                // MMA2b: acc (+)= [g ; x] . [P | dS]  (both K-major, K = pixels: 16 per step, 4 steps per 64-px block)
+#pragma unroll
+                for (int ks = 0; ks < C::KS3; ++ks) {
+                    const uint64_t da = smem_desc(st + (ks >> 2) * 2 * C::BOX_BYTES + (ks & 3) * 32, 16, 1024, kSwizzle128B);
+                    const uint64_t db = smem_desc(s_pb + (ks >> 2) * C::PB_KBLOCK + (ks & 3) * 32, 16, 1024, kSwizzle128B);
+                    umma_ss<false>(tmem_base + C::COL_ACC, da, db, C::IDESC3, (ks > 0 || !first_of_sample) ? 1u : 0u);
+                }
+                umma_commit(smem_u32(&bar_x_empty[stage]));
+                umma_commit(smem_u32(&bar_c_full));
+                first_of_sample = false;
+                if (++t == TPS) { t = 0; first_of_sample = true; }
+            }
+        }
+    } else {
+        // --------------------------------- consumers: thread = pixel ----------------------------
+        const int ct = tid - 64;
+        const int cw = warp & 3;
+        const int px = cw * 32 + lane;
+        const uint32_t tl = tmem_base + ((uint32_t)(cw * 32) << 16);
+        const uint32_t pad_bits = (L < 32) ? ~((1u << L) - 1u) : 0u;
+        const uint32_t Bu = (uint32_t)p.B;
+        const uint32_t step_mod = (uint32_t)TQ % Bu;
+        uint32_t cap = (uint32_t)(((unsigned long long)w_begin * TQ + px) % Bu);
+        int b = b0, t = t0, cur_b = -1;
+        const uint32_t so = s_out + cw * C::OUT_WARP_BYTES;
+        T* go = reinterpret_cast<T*>(g_out + cw * C::OUT_WARP_BYTES) + lane;
+        // PB element (row n, this pixel): block (px / 64), row n, 16-byte chunks XOR-swizzled with n & 7
+        unsigned char* pb_px = g_pb + (px >> 6) * C::PB_KBLOCK;
+        const uint32_t pb_col = (uint32_t)(px & 63) * 2;
+        bool waited_zero = false;
+
+        // Add this CTA's share of dSrc[bb] (the diagonal blocks of the TMEM accumulator) to global memory;
+        // the last CTA of the sample forms dW / dCtx.  Called by all consumer warps together.
+        auto finish_sample = [&](int bb) {
+            if (!waited_zero) {
+                asm volatile("griddepcontrol.wait;" ::: "memory");      // k_zero_tc5 has cleared dSrc / dW / counters
+                waited_zero = true;
+            }
+            // accumulator row r of this lane: M = 64 -> lanes 0..15 of each quarter hold rows 16*cw + lane
+            const int row = C::MD == 64 ? 16 * cw + lane : 32 * cw + lane;
+            const bool valid = (C::MD == 64 ? lane < 16 : true) && row < 2 * IDF;
+            const bool is_x = row >= IDF;
+            const int ch = is_x ? row - IDF : row;
+            uint32_t av[LP];
+            tc_fence_after();
+            // column block: g rows take the P columns [0, LP), x rows the dS columns [RP, RP + LP)
+            {
+                uint32_t a0[LP], a1[LP];
+                tmem_ld<LP>(tl + C::COL_ACC, a0);
+                tmem_ld<LP>(tl + C::COL_ACC + RP, a1);
+                tmem_wait_ld();
+#pragma unroll
+                for (int l = 0; l < LP; ++l) av[l] = is_x ? a1[l] : a0[l];
+            }
+            if (valid) {
+                float* db = p.dSrc + ((size_t)bb * IDF + ch) * L;
+#pragma unroll
+                for (int l = 0; l < LP; ++l)
+                    if (l < L) atomicAdd(db + l, __uint_as_float(av[l]));
+            }
+            tc_fence_before();
+            __threadfence();
+            mma::named_bar_sync(1, kConsumers);
+            if (ct == 0) {
+                const long long G = gridDim.x, N = p.n_tiles;
+                const int k0 = (int)((((long long)bb * TPS + 1) * G - 1) / N);
+                const int k1 = (int)((((long long)(bb + 1) * TPS) * G - 1) / N);
+                const uint32_t old = atomicAdd(p.cnt + bb, 1u);
+                fin_s = (old + 1u == (uint32_t)(k1 - k0 + 1)) ? 1 : 0;
+            }
+            mma::named_bar_sync(1, kConsumers);
+            if (fin_s == 0 || (p.dW == nullptr && p.dCtx == nullptr)) return;
+            __threadfence();
+            if (lane == 0) bulk_wait_read<0>();         // the dX staging doubles as the dSrc[bb] buffer
+            mma::named_bar_sync(1, kConsumers);
+            float* ds = reinterpret_cast<float*>(g_out);             // [IDF][L]
+            const float* dsg = p.dSrc + (size_t)bb * IDF * L;
+            for (int o = ct; o < IDF * L; o += kConsumers) ds[o] = __ldcg(dsg + o);
+            mma::named_bar_sync(1, kConsumers);
+            const float* cb = p.ctx + (size_t)bb * p.cdf * L;
+            for (int cc = ct; cc < p.cdf; cc += kConsumers) {
+                if (p.dW != nullptr) {
+                    float cv[LP];
+#pragma unroll
+                    for (int l = 0; l < LP; ++l) cv[l] = (l < L) ? __ldg(cb + (size_t)cc * L + l) : 0.f;
+                    for (int i = 0; i < IDF; ++i) {
+                        float acc = 0.f;
+#pragma unroll
+                        for (int l = 0; l < LP; ++l)
+                            if (l < L) acc = fmaf(ds[i * L + l], cv[l], acc);
+                        atomicAdd(p.dW + (size_t)i * p.cdf + cc, acc);
+                    }
+                }
+                if (p.dCtx != nullptr) {
+                    float acc[LP];
+#pragma unroll
+                    for (int l = 0; l < LP; ++l) acc[l] = 0.f;
+                    for (int i = 0; i < IDF; ++i) {
+                        const float wv = __ldg(p.W + (size_t)i * p.cdf + cc);
+#pragma unroll
+                        for (int l = 0; l < LP; ++l)
+                            if (l < L) acc[l] = fmaf(wv, ds[i * L + l], acc[l]);
+                    }
+                    float* dc = p.dCtx + ((size_t)bb * p.cdf + cc) * L;
+#pragma unroll
+                    for (int l = 0; l < LP; ++l)
+                        if (l < L) dc[l] = acc[l];
+                }
+            }
+            fence_proxy_async();
+            mma::named_bar_sync(1, kConsumers);      // ds goes back to being the dX staging
+        };
+
+        for (int j = 0; j < n_local; ++j) {
+            if (b != cur_b) {
+                if (cur_b >= 0) finish_sample(cur_b);   // every MMA of the previous sample has completed (c_full)
+                cur_b = b;
+                // ---- operands of sample b: B1[word][channel] = B2[channel][word] = srcT ----
+                const float* sb = p.srcT + (size_t)b * IDF * L;
+                for (int o = ct; o < IDF * L; o += kConsumers) {
+                    const int ch = o / L, l = o - ch * L;
+                    const __nv_bfloat16 v = __float2bfloat16_rn(__ldg(sb + o));
+                    *reinterpret_cast<__nv_bfloat16*>(g_b1 + kmajor_off<2>(l, ch, C::KCH1)) = v;
+                    *reinterpret_cast<__nv_bfloat16*>(g_b2 + kmajor_off<2>(ch, l, C::KCH2)) = v;
+                }
+                fence_proxy_async();
+                warp_arrive(smem_u32(&bar_b_ready), lane);
+            }
+            const int q = t * TQ + px;
+            float ga[HAS_GA ? LP : 1];
+            if constexpr (HAS_GA) {
+                const T* gp = static_cast<const T*>(p.ga) + (size_t)b * L * Q + q;
+#pragma unroll
+                for (int l = 0; l < LP; ++l) ga[l] = (l < L) ? __bfloat162float(gp[(size_t)l * Q]) : 0.f;
+            }
+
+            // ---- S and dP rows of this pixel ---------------------------------------------------------
+            mbar_wait(smem_u32(&bar_s_full), (uint32_t)j & 1u);
+            tc_fence_after();
+            uint32_t sr[LP], dr[LP];
+            tmem_ld<LP>(tl + C::COL_S, sr);
+            tmem_ld<LP>(tl + C::COL_DP, dr);
+            tmem_wait_ld();
+
+            // ---- P = masked softmax over words (recomputed; GlobalAttention.py:104-109) ---------------
+            uint32_t mb = pad_bits;
+            if (p.mask != nullptr) mb |= mb_s[p.mask_mode == SBA_MASK_PER_SAMPLE ? (uint32_t)b : cap];
+            float s[LP];
+            float m = -INFINITY;
+#pragma unroll
+            for (int l = 0; l < LP; ++l) {
+                s[l] = ((mb >> l) & 1u) ? -INFINITY : __uint_as_float(sr[l]);
+                m = fmaxf(m, s[l]);
+            }
+            const float ml = m * kLog2e;
+            float sum = 0.f;
+#pragma unroll
+            for (int l = 0; l < LP; ++l) {
+                s[l] = mma::ex2_approx(fmaf(s[l], kLog2e, -ml));    // all-masked row: NaN, as the reference
+                sum += s[l];
+            }
+            const float inv = mma::rcp_approx(sum);
+            // ---- dS = P * (dP [+ g_attn] - sum_l P dP)  (masked / padded words have P = 0) --------------
+            float d[LP];
+            float dot = 0.f;
+#pragma unroll
+            for (int l = 0; l < LP; ++l) {
+                s[l] *= inv;
+                d[l] = __uint_as_float(dr[l]);
+                if constexpr (HAS_GA) d[l] += ga[l];
+                dot = fmaf(s[l], d[l], dot);
+            }
+            // ---- P and dS into PB: rows [0, LP) and [RP, RP + LP), bf16, swizzled ------------------------
+#pragma unroll
+            for (int l = 0; l < LP; ++l) {
+                const float ds = s[l] * (d[l] - dot);
+                *reinterpret_cast<__nv_bfloat16*>(pb_px + l * 128 + (pb_col ^ ((l & 7) << 4))) = __float2bfloat16_rn(s[l]);
+                *reinterpret_cast<__nv_bfloat16*>(pb_px + (RP + l) * 128 + (pb_col ^ ((l & 7) << 4))) = __float2bfloat16_rn(ds);
+            }
+            fence_proxy_async();
+            tc_fence_before();
+            warp_arrive(smem_u32(&bar_ds_ready), lane);
+
+            // ---- dX row of this pixel: staged [channel][32 px] per warp, one TMA box store ---------------
+            mbar_wait(smem_u32(&bar_c_full), (uint32_t)j & 1u);
+            tc_fence_after();
+            if (lane == 0) bulk_wait_read<0>();        // the previous dX store has finished reading the staging
+            __syncwarp();
+#pragma unroll
+            for (int h = 0; h < IDF / 16; ++h) {
+                uint32_t cr[16];
+                tmem_ld<16>(tl + C::COL_DX + 16 * h, cr);
+                tmem_wait_ld();
+#pragma unroll
+                for (int i = 0; i < 16; ++i) go[(16 * h + i) * 32] = __float2bfloat16_rn(__uint_as_float(cr[i]));
+            }
+            tc_fence_before();
+            warp_arrive(smem_u32(&bar_dx_free), lane);
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+                tma_store_2d(&tm_dx, t * TQ + cw * 32, b * IDF, so);
+                bulk_commit();
+            }
+
+            if (++t == TPS) { t = 0; ++b; }
+            cap += step_mod;
+            if (cap >= Bu) cap -= Bu;
+        }
+        if (cur_b >= 0) finish_sample(cur_b);
+        if (lane == 0) bulk_wait<0>();
+        tc_fence_before();
+    }
+
+    __syncthreads();
+    if (warp == kMmaWarp) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, C::TMEM_COLS);
+    }
+}
+
+template <int IDF, int NQ, bool HAS_GA>
+int launch_bwd_tc5(const void* x, const void* g, void* dX, const Tc5BwdParams& p, cudaStream_t st) {
+    using C = Tc5BwdCfg<IDF, NQ>;
+    auto kern = k_attn_bwd_tc5<IDF, NQ, HAS_GA>;
+    const size_t smem = (size_t)C::SMEM_BYTES + (size_t)p.B * 4 + 1024 + 16;
+    static int sms = 0;
+    static size_t smem_set = 0;
+    if (smem > 220 * 1024) {
+        set_error("attn_bwd(tcgen05): %zu bytes of shared memory needed (B=%d)", smem, p.B);
+        return SBA_ERR_UNSUPPORTED;
+    }
+    if (sms == 0 || smem > smem_set) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess || sms < 1) {
+            set_error("attn_bwd(tcgen05): cudaFuncSetAttribute(%zu B): %s", smem, cudaGetErrorString(e));
+            sms = 0;
+            return SBA_ERR_CUDA;
+        }
+        smem_set = smem;
+    }
+    int per_sm = (int)((227 * 1024) / (smem_set + 1024));
+    if (per_sm > C::CTAS_PER_SM) per_sm = C::CTAS_PER_SM;
+    if (per_sm > 3) per_sm = 3;
+    if (per_sm < 1) per_sm = 1;
+    if (getenv("SBA_TC5_CTAS_PER_SM")) per_sm = atoi(getenv("SBA_TC5_CTAS_PER_SM"));
+    const int max_ctas = sms * per_sm;
+    CUtensorMap tm_x, tm_g, tm_dx;
+    int rc = make_tile_map(&tm_x, x, SBA_BF16, p.B * IDF, p.Q, IDF, 64, true);
+    if (!rc) rc = make_tile_map(&tm_g, g, SBA_BF16, p.B * IDF, p.Q, IDF, 64, true);
+    if (!rc) rc = make_tile_map(&tm_dx, dX, SBA_BF16, p.B * IDF, p.Q, IDF, 32, false);
+    if (rc) return rc;
+    const size_t n_src = (size_t)p.B * IDF * p.L + p.B + 1;       // dSrc and the counter words behind it
+    k_zero_tc5<<<64, 256, 0, st>>>(p.dSrc, n_src, p.dW, p.dW ? (size_t)IDF * p.cdf : 0);
+    rc = check_launch("zero(tcgen05)");
+    if (rc) return rc;
+    const int grid = p.n_tiles < max_ctas ? p.n_tiles : max_ctas;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem_set;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tm_x, tm_g, tm_dx, p);
+    if (e != cudaSuccess) {
+        set_error("attn_bwd(tcgen05): launch: %s", cudaGetErrorString(e));
+        return SBA_ERR_CUDA;
+    }
+    add_launches(2);
+    return check_launch("attn_bwd(tcgen05)");
+}
+
+template <int IDF, bool HAS_GA>
+int dispatch_nq(const void* x, const void* g, void* dX, const Tc5BwdParams& p, cudaStream_t st) {
+    switch ((p.L + 3) / 4) {
+        case 1: return launch_bwd_tc5<IDF, 1, HAS_GA>(x, g, dX, p, st);
+        case 2: return launch_bwd_tc5<IDF, 2, HAS_GA>(x, g, dX, p, st);
+        case 3: return launch_bwd_tc5<IDF, 3, HAS_GA>(x, g, dX, p, st);
+        case 4: return launch_bwd_tc5<IDF, 4, HAS_GA>(x, g, dX, p, st);
+        case 5: return launch_bwd_tc5<IDF, 5, HAS_GA>(x, g, dX, p, st);
+        case 6: return launch_bwd_tc5<IDF, 6, HAS_GA>(x, g, dX, p, st);
+        case 7: return launch_bwd_tc5<IDF, 7, HAS_GA>(x, g, dX, p, st);
+        case 8: return launch_bwd_tc5<IDF, 8, HAS_GA>(x, g, dX, p, st);
+        default: return -1;
+    }
+}
+
+template <int IDF>
+int dispatch_ga(const void* x, const void* g, void* dX, const Tc5BwdParams& p, cudaStream_t st) {
+    return p.ga != nullptr ? dispatch_nq<IDF, true>(x, g, dX, p, st) : dispatch_nq<IDF, false>(x, g, dX, p, st);
+}
+
+}  // namespace
+
+bool tc5_bwd_supports(const AttnShape& s) { return tc5_supports(s) && s.dtype == SBA_BF16; }
+
+int tc5_attn_bwd(const void* x, const float* ctx, const float* W, const float* srcT, const uint8_t* mask, const void* g_c,
+                 const void* g_attn, void* dX, float* dSrc, float* dW, float* dCtx, const AttnShape& s, cudaStream_t st) {
+    Tc5BwdParams p{};
+    p.srcT = srcT; p.mask = mask; p.ga = g_attn; p.dSrc = dSrc; p.ctx = ctx; p.W = W; p.dW = dW; p.dCtx = dCtx;
+    p.cnt = reinterpret_cast<uint32_t*>(dSrc + (size_t)s.B * s.idf * s.L);
+    p.B = s.B; p.L = s.L; p.Q = s.Q; p.cdf = s.cdf; p.mask_mode = s.mask_mode;
+    p.tiles_per_sample = s.Q / tc5::TQ;
+    p.n_tiles = s.B * p.tiles_per_sample;
+    int rc = -1;
+    if (s.idf == 32) rc = dispatch_ga<32>(x, g_c, dX, p, st);
+    else if (s.idf == 48) rc = dispatch_ga<48>(x, g_c, dX, p, st);
+    else if (s.idf == 64) rc = dispatch_ga<64>(x, g_c, dX, p, st);
+    if (rc == -1) {
+        set_error("attn_bwd(tcgen05): unsupported shape idf=%d L=%d", s.idf, s.L);
+        return SBA_ERR_UNSUPPORTED;
+    }
+    return rc;
+}
+
+}  // namespace sba

@@ -68,7 +68,10 @@ namespace {
 using namespace tc5;
 
 struct Tc5FwdParams {
-    const float* srcT;
+    float* srcT;
+    const float* ctx;     // [B, cdf, L]
+    const float* W;       // [idf, cdf]
+    int cdf;
     const uint8_t* mask;
     void* c_code;
     void* attn;
@@ -120,37 +123,58 @@ struct Tc5FwdCfg {
     static_assert(LP <= 32 && PC <= 32 && COL_PLO + PC <= 128, "at most 32 words");
 };
 
-// srcT = W . ctx (the bias-free 1x1 conv_context, GlobalAttention.py:95-97): block = (sample,
-// 8 output channels), warp = channel, lanes = 8 words x 4 quarters of the cdf reduction.
-template <int NT>
-__global__ void __launch_bounds__(256) k_project_tc5(const float* __restrict__ ctx, const float* __restrict__ W,
+// srcT = W . ctx (the bias-free 1x1 conv_context, GlobalAttention.py:95-97) as a small grid in
+// front of the streaming kernel, chained with programmatic dependent launch: block = (sample,
+// 8 output channels); warp = one quarter of the cdf reduction, lane = word.  Everything a warp
+// needs is requested up front (its W slice through warp-private shared memory, 32 ctx rows at
+// a time in registers), so the kernel lasts about two memory round trips.
+__global__ void __launch_bounds__(128) k_project_tc5(const float* __restrict__ ctx, const float* __restrict__ W,
                                                      float* __restrict__ srcT, int idf, int cdf, int L) {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, lg = lane & 7, kq = lane >> 3;
+    __shared__ __align__(16) float w_s[4][8][64];
+    __shared__ float red_s[4][8][32];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int rg = idf / 8;
-    const int u = blockIdx.x, b = u / rg, i = (u - b * rg) * 8 + warp;
-    const float* wrow = W + (size_t)i * cdf;
-    const float* cb = ctx + (size_t)b * cdf * L;
-    float acc[NT];
+    const int b = blockIdx.x / rg, i0 = (blockIdx.x - b * rg) * 8;
+    const int kq = cdf / 4, cbeg = warp * kq;          // this warp's slice of the reduction (cdf % 16 == 0)
+    const int lw = lane < L ? lane : L - 1;
+    const float* cb = ctx + (size_t)b * cdf * L + lw;
+    float acc[8];
 #pragma unroll
-    for (int n = 0; n < NT; ++n) acc[n] = 0.f;
-    const int c_lo = (cdf * kq) >> 2, c_hi = (cdf * (kq + 1)) >> 2;
-#pragma unroll 8
-    for (int cc = c_lo; cc < c_hi; ++cc) {
-        const float wv = __ldg(wrow + cc);
+    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+    for (int sub = 0; sub < kq; sub += 64) {
+        const int kc = kq - sub < 64 ? kq - sub : 64;  // multiple of 4
+        const int c0 = cbeg + sub;
+        __syncwarp();
+        for (int o = lane; o < 8 * (kc / 4); o += 32) {
+            const int r = o / (kc / 4), c4 = o - r * (kc / 4);
+            reinterpret_cast<float4*>(&w_s[warp][r][0])[c4] =
+                __ldg(reinterpret_cast<const float4*>(W + (size_t)(i0 + r) * cdf + c0) + c4);
+        }
+        __syncwarp();
+        for (int h = 0; h < kc; h += 32) {
+            float v[32];
 #pragma unroll
-        for (int n = 0; n < NT; ++n) {
-            const int l = lg + 8 * n;
-            const float v = (l < L) ? __ldg(cb + (size_t)cc * L + l) : 0.f;
-            acc[n] = fmaf(wv, v, acc[n]);
+            for (int c = 0; c < 32; ++c) v[c] = (h + c < kc) ? __ldg(cb + (size_t)(c0 + h + c) * L) : 0.f;
+#pragma unroll
+            for (int c = 0; c < 32; c += 4) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const float4 w4 = *reinterpret_cast<const float4*>(&w_s[warp][k][(h + c) & 63]);
+                    acc[k] = fmaf(w4.x, v[c], acc[k]);
+                    acc[k] = fmaf(w4.y, v[c + 1], acc[k]);
+                    acc[k] = fmaf(w4.z, v[c + 2], acc[k]);
+                    acc[k] = fmaf(w4.w, v[c + 3], acc[k]);
+                }
+            }
         }
     }
 #pragma unroll
-    for (int n = 0; n < NT; ++n) {
-        acc[n] += __shfl_xor_sync(0xffffffffu, acc[n], 8);
-        acc[n] += __shfl_xor_sync(0xffffffffu, acc[n], 16);
-        const int l = lg + 8 * n;
-        if (kq == 0 && l < L) srcT[((size_t)b * idf + i) * L + l] = acc[n];
+    for (int k = 0; k < 8; ++k) red_s[warp][k][lane] = acc[k];
+    __syncthreads();
+    for (int o = tid; o < 8 * 32; o += 128) {
+        const int k = o >> 5, l = o & 31;
+        if (l < L) srcT[((size_t)b * idf + i0 + k) * L + l] = red_s[0][k][l] + red_s[1][k][l] + red_s[2][k][l] + red_s[3][k][l];
     }
 }
 
@@ -493,8 +517,11 @@ __global__ void __launch_bounds__(kThreads, Tc5FwdCfg<T, IDF, NQ>::CTAS_PER_SM)
 }
 
 template <typename T, int IDF, int NQ>
-int launch_fwd_tc5(const void* x, const float* ctx, const float* W, float* srcT, int cdf, const Tc5FwdParams& p,
-                   int dtype, cudaStream_t st) {
+int launch_fwd_tc5(const void* x, const Tc5FwdParams& p, int dtype, cudaStream_t st) {
+    const float* ctx = p.ctx;
+    const float* W = p.W;
+    float* srcT = p.srcT;
+    const int cdf = p.cdf;
     using C = Tc5FwdCfg<T, IDF, NQ>;
     auto kern = k_attn_fwd_tc5<T, IDF, NQ>;
     const size_t smem = (size_t)C::SMEM_BYTES + (size_t)p.B * 4 + 1024 + 16;
@@ -529,14 +556,8 @@ int launch_fwd_tc5(const void* x, const float* ctx, const float* W, float* srcT,
     if (!rc) rc = make_tile_map(&tma_attn, p.attn, dtype, p.B * p.L, p.Q, p.L, 32, false);
     if (!rc) rc = make_tile_map(&tma_c, p.c_code, dtype, p.B * IDF, p.Q, IDF, 32, false);
     if (rc) return rc;
-    const int NT = (p.L + 7) / 8;
     const int pgrid = p.B * (IDF / 8);
-    switch (NT) {
-        case 1: k_project_tc5<1><<<pgrid, 256, 0, st>>>(ctx, W, srcT, IDF, cdf, p.L); break;
-        case 2: k_project_tc5<2><<<pgrid, 256, 0, st>>>(ctx, W, srcT, IDF, cdf, p.L); break;
-        case 3: k_project_tc5<3><<<pgrid, 256, 0, st>>>(ctx, W, srcT, IDF, cdf, p.L); break;
-        default: k_project_tc5<4><<<pgrid, 256, 0, st>>>(ctx, W, srcT, IDF, cdf, p.L); break;
-    }
+    k_project_tc5<<<pgrid, 128, 0, st>>>(ctx, W, srcT, IDF, cdf, p.L);
     rc = check_launch("project(tcgen05)");
     if (rc) return rc;
     const int grid = p.n_tiles < max_ctas ? p.n_tiles : max_ctas;
@@ -560,17 +581,16 @@ int launch_fwd_tc5(const void* x, const float* ctx, const float* W, float* srcT,
 }
 
 template <typename T, int IDF>
-int dispatch_nq(const void* x, const float* ctx, const float* W, float* srcT, int cdf, const Tc5FwdParams& p, int dtype,
-                cudaStream_t st) {
+int dispatch_nq(const void* x, const Tc5FwdParams& p, int dtype, cudaStream_t st) {
     switch ((p.L + 3) / 4) {
-        case 1: return launch_fwd_tc5<T, IDF, 1>(x, ctx, W, srcT, cdf, p, dtype, st);
-        case 2: return launch_fwd_tc5<T, IDF, 2>(x, ctx, W, srcT, cdf, p, dtype, st);
-        case 3: return launch_fwd_tc5<T, IDF, 3>(x, ctx, W, srcT, cdf, p, dtype, st);
-        case 4: return launch_fwd_tc5<T, IDF, 4>(x, ctx, W, srcT, cdf, p, dtype, st);
-        case 5: return launch_fwd_tc5<T, IDF, 5>(x, ctx, W, srcT, cdf, p, dtype, st);
-        case 6: return launch_fwd_tc5<T, IDF, 6>(x, ctx, W, srcT, cdf, p, dtype, st);
-        case 7: return launch_fwd_tc5<T, IDF, 7>(x, ctx, W, srcT, cdf, p, dtype, st);
-        case 8: return launch_fwd_tc5<T, IDF, 8>(x, ctx, W, srcT, cdf, p, dtype, st);
+        case 1: return launch_fwd_tc5<T, IDF, 1>(x, p, dtype, st);
+        case 2: return launch_fwd_tc5<T, IDF, 2>(x, p, dtype, st);
+        case 3: return launch_fwd_tc5<T, IDF, 3>(x, p, dtype, st);
+        case 4: return launch_fwd_tc5<T, IDF, 4>(x, p, dtype, st);
+        case 5: return launch_fwd_tc5<T, IDF, 5>(x, p, dtype, st);
+        case 6: return launch_fwd_tc5<T, IDF, 6>(x, p, dtype, st);
+        case 7: return launch_fwd_tc5<T, IDF, 7>(x, p, dtype, st);
+        case 8: return launch_fwd_tc5<T, IDF, 8>(x, p, dtype, st);
         default: return -1;
     }
 }
@@ -581,6 +601,7 @@ bool tc5_supports(const AttnShape& s) {
     if (s.idf != 32 && s.idf != 48 && s.idf != 64) return false;
     if (s.L < 1 || s.L > 32) return false;
     if (s.Q % tc5::TQ != 0) return false;
+    if (s.cdf % 16 != 0) return false;                  // k_project_tc5 splits the reduction over 4 warps, float4 loads
     if (s.B > 4096 || (unsigned long long)s.B * s.Q >= (1ull << 31)) return false;
     return true;
 }
@@ -588,19 +609,19 @@ bool tc5_supports(const AttnShape& s) {
 int tc5_attn_fwd(const void* x, const float* ctx, const float* W, const uint8_t* mask, void* c_code, void* attn,
                  float* srcT, uint32_t* mask_bits, const AttnShape& s, cudaStream_t st) {
     Tc5FwdParams p{};
-    p.srcT = srcT; p.mask = mask; p.c_code = c_code; p.attn = attn; p.mask_bits = mask_bits;
+    p.srcT = srcT; p.ctx = ctx; p.W = W; p.cdf = s.cdf; p.mask = mask; p.c_code = c_code; p.attn = attn; p.mask_bits = mask_bits;
     p.B = s.B; p.L = s.L; p.Q = s.Q; p.mask_mode = s.mask_mode;
     p.tiles_per_sample = s.Q / tc5::TQ;
     p.n_tiles = s.B * p.tiles_per_sample;
     int rc = -1;
     if (s.dtype == SBA_F32) {
-        if (s.idf == 32) rc = dispatch_nq<float, 32>(x, ctx, W, srcT, s.cdf, p, s.dtype, st);
-        else if (s.idf == 48) rc = dispatch_nq<float, 48>(x, ctx, W, srcT, s.cdf, p, s.dtype, st);
-        else if (s.idf == 64) rc = dispatch_nq<float, 64>(x, ctx, W, srcT, s.cdf, p, s.dtype, st);
+        if (s.idf == 32) rc = dispatch_nq<float, 32>(x, p, s.dtype, st);
+        else if (s.idf == 48) rc = dispatch_nq<float, 48>(x, p, s.dtype, st);
+        else if (s.idf == 64) rc = dispatch_nq<float, 64>(x, p, s.dtype, st);
     } else {
-        if (s.idf == 32) rc = dispatch_nq<__nv_bfloat16, 32>(x, ctx, W, srcT, s.cdf, p, s.dtype, st);
-        else if (s.idf == 48) rc = dispatch_nq<__nv_bfloat16, 48>(x, ctx, W, srcT, s.cdf, p, s.dtype, st);
-        else if (s.idf == 64) rc = dispatch_nq<__nv_bfloat16, 64>(x, ctx, W, srcT, s.cdf, p, s.dtype, st);
+        if (s.idf == 32) rc = dispatch_nq<__nv_bfloat16, 32>(x, p, s.dtype, st);
+        else if (s.idf == 48) rc = dispatch_nq<__nv_bfloat16, 48>(x, p, s.dtype, st);
+        else if (s.idf == 64) rc = dispatch_nq<__nv_bfloat16, 64>(x, p, s.dtype, st);
     }
     if (rc == -1) {
         set_error("attn_fwd(tcgen05): unsupported shape idf=%d L=%d", s.idf, s.L);

@@ -33,6 +33,11 @@ bool tc5_supports(const AttnShape& s);
 int tc5_attn_fwd(const void* x, const float* ctx, const float* W, const uint8_t* mask, void* c_code, void* attn,
                  float* srcT, uint32_t* mask_bits, const AttnShape& s, cudaStream_t st);
 
+bool tc5_bwd_supports(const AttnShape& s);     // bf16 tensors for now; fp32 backward stays on the mma.sync family
+// dSrc holds B*idf*L floats followed by B+1 scratch words, like mma_attn_bwd
+int tc5_attn_bwd(const void* x, const float* ctx, const float* W, const float* srcT, const uint8_t* mask, const void* g_c,
+                 const void* g_attn, void* dX, float* dSrc, float* dW, float* dCtx, const AttnShape& s, cudaStream_t st);
+
 // words_loss.cu - fused DAMSM region-word similarity (kernel c) and its backward
 size_t words_bwd_workspace_bytes(int B_img, int B_cap, int nef, int R, int Lw);
 int words_sim_fwd(const float* img, const float* words, const int* cap_lens, float* sim, float* att_diag, float* wc_out,
