@@ -17,10 +17,11 @@
 //                                              its diagonal blocks are g.P and x.dS)
 //   consumers: dX row of the pixel -> staged -> TMA box store.
 // When the tile range leaves a sample the consumers add the two diagonal blocks of the TMEM
-// accumulator into dSrc[b] with fp32 atomics, and the last CTA to do so for that sample forms
-// dW += dSrc[b] . ctx[b]^T and dCtx[b] = W^T . dSrc[b] while the others keep streaming.
-// dSrc / dW / the per-sample counters are zeroed by a small kernel in front (programmatic
-// dependent launch: this kernel only waits for it before its first atomic).
+// accumulator into dSrc[b] with fp32 atomics.  dSrc / dW are zeroed by a small kernel in front
+// (programmatic dependent launch: this kernel only waits for it before its first atomic), and
+// dW = sum_b dSrc[b] . ctx[b]^T, dCtx[b] = W^T . dSrc[b] are formed by a small kernel behind it
+// (attn_bwd_post; also a programmatic dependent): doing that per sample inside this kernel puts
+// 64-way contended atomics on dW right at the end of the stream.
 #include <cstdlib>
 
 #include "kernels.h"
@@ -39,10 +40,10 @@ struct Tc5BwdParams {
     const float* W;       // [idf, cdf]    (epilogue, dCtx only)
     float* dW;            // [idf, cdf]    nullable
     float* dCtx;          // [B, cdf, L]   nullable
-    uint32_t* cnt;        // [B] per-sample completion counters (zeroed by k_zero_tc5)
     int B, L, Q, cdf, mask_mode;
     int tiles_per_sample;
     int n_tiles;
+    long long* trace;     // development aid (SBA_TC5_TRACE): per-phase clock64 stamps of CTA 0, else NULL
 };
 
 constexpr int pow2_cols(int n) { return n <= 32 ? 32 : n <= 64 ? 64 : n <= 128 ? 128 : n <= 256 ? 256 : 512; }
@@ -91,6 +92,60 @@ __global__ void __launch_bounds__(256) k_zero_tc5(float* __restrict__ a, size_t 
         for (size_t i = i0; i < nb; i += step) b[i] = 0.f;
 }
 
+// dW += sum_{b in group} dSrc[b] . ctx[b]^T for a [idf x 8] slice, dCtx[b] = W^T . dSrc[b]; a programmatic
+// dependent of the streaming kernel (griddepcontrol.wait = that grid is complete and flushed).
+//   blocks [0, n_dw)          : (8 input channels c, one of 16 sample groups); thread = (i, c); the groups
+//                               meet in fp32 atomics on dW (16-way contention, dW zeroed by k_zero_tc5)
+//   blocks [n_dw, n_dw + B)   : dCtx of one sample (only when words need a gradient)
+__global__ void __launch_bounds__(256) k_bwd_post_tc5(const float* __restrict__ dSrc, const float* __restrict__ ctx,
+                                                      const float* __restrict__ W, float* __restrict__ dW,
+                                                      float* __restrict__ dCtx, int B, int idf, int cdf, int L, int n_dw) {
+    extern __shared__ float sm[];
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    const int tid = threadIdx.x;
+    if ((int)blockIdx.x < n_dw) {
+        float* ds = sm;                  // [idf][L]
+        float* cs = sm + idf * L;        // [8][L]
+        const int cg = blockIdx.x >> 4, grp = blockIdx.x & 15;
+        const int c0 = cg * 8, nc = cdf - c0 < 8 ? cdf - c0 : 8;
+        const int b_lo = (B * grp) >> 4, b_hi = (B * (grp + 1)) >> 4;
+        const int per = (idf * 8 + blockDim.x - 1) / blockDim.x;     // outputs per thread (1 for idf <= 32)
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int b = b_lo; b < b_hi; ++b) {
+            __syncthreads();
+            for (int o = tid; o < idf * L; o += blockDim.x) ds[o] = __ldcg(dSrc + (size_t)b * idf * L + o);
+            for (int o = tid; o < nc * L; o += blockDim.x) cs[o] = __ldg(ctx + ((size_t)b * cdf + c0) * L + o);
+            __syncthreads();
+            for (int k = 0; k < per && k < 4; ++k) {
+                const int ic = tid + k * blockDim.x;
+                if (ic < idf * 8) {
+                    const int i = ic >> 3, c = ic & 7;
+                    if (c < nc) {
+                        float a = acc[k];
+                        for (int l = 0; l < L; ++l) a = fmaf(ds[i * L + l], cs[c * L + l], a);
+                        acc[k] = a;
+                    }
+                }
+            }
+        }
+        for (int k = 0; k < per && k < 4; ++k) {
+            const int ic = tid + k * blockDim.x;
+            if (ic < idf * 8 && (ic & 7) < nc) atomicAdd(dW + (size_t)(ic >> 3) * cdf + c0 + (ic & 7), acc[k]);
+        }
+    } else {
+        float* ds = sm;                  // [idf][L]
+        const int b = blockIdx.x - n_dw;
+        for (int o = tid; o < idf * L; o += blockDim.x) ds[o] = __ldcg(dSrc + (size_t)b * idf * L + o);
+        __syncthreads();
+        for (int o = tid; o < cdf * L; o += blockDim.x) {
+            const int c = o / L, l = o - c * L;
+            float a = 0.f;
+            for (int i = 0; i < idf; ++i) a = fmaf(__ldg(W + (size_t)i * cdf + c), ds[i * L + l], a);
+            dCtx[(size_t)b * cdf * L + o] = a;
+        }
+    }
+}
+
 __device__ __forceinline__ void warp_arrive(uint32_t bar, int lane) {
     __syncwarp();
     if (lane == 0) mbar_arrive(bar);
@@ -122,10 +177,14 @@ __global__ void __launch_bounds__(kThreads, Tc5BwdCfg<IDF, NQ>::CTAS_PER_SM > 3 
     __shared__ __align__(8) unsigned long long bar_x_full[NST], bar_x_empty[NST], bar_s_full, bar_ds_ready, bar_c_full,
         bar_dx_free, bar_b_ready;
     __shared__ uint32_t tmem_base_s;
-    __shared__ int fin_s;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int L = p.L, Q = p.Q, TPS = p.tiles_per_sample;
+    if (p.trace != nullptr && tid == 0) {
+        unsigned long long gt;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
+        p.trace[256 + 2 * blockIdx.x] = (long long)gt;
+    }
 
     if (tid == 0) {
 #pragma unroll
@@ -158,7 +217,7 @@ __global__ void __launch_bounds__(kThreads, Tc5BwdCfg<IDF, NQ>::CTAS_PER_SM > 3 
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = tmem_base_s;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, tmem_base_s, 0);     // provably warp-uniform
 
     const int w_begin = (int)(((long long)blockIdx.x * p.n_tiles) / gridDim.x);
     const int w_end = (int)(((long long)(blockIdx.x + 1) * p.n_tiles) / gridDim.x);
@@ -167,70 +226,84 @@ __global__ void __launch_bounds__(kThreads, Tc5BwdCfg<IDF, NQ>::CTAS_PER_SM > 3 
 
     if (warp == kProducerWarp) {
         // --------------------------------- TMA producer -----------------------------------------
-        if (lane == 0) {
-            int b = b0, t = t0;
-            for (int j = 0; j < n_local; ++j) {
-                const int stage = j % NST;
-                if (j >= NST) mbar_wait(smem_u32(&bar_x_empty[stage]), (uint32_t)((j / NST) - 1) & 1u);
-                const uint32_t full = smem_u32(&bar_x_full[stage]);
+        // (the whole warp runs the loop; one elected lane issues - see elect_one())
+        int b = b0, t = t0;
+        for (int j = 0; j < n_local; ++j) {
+            const int stage = j % NST;
+            if (j >= NST) mbar_wait(smem_u32(&bar_x_empty[stage]), (uint32_t)((j / NST) - 1) & 1u);
+            const uint32_t full = smem_u32(&bar_x_full[stage]);
+            const uint32_t dst = s_st + stage * C::STAGE_BYTES;
+            if (elect_one()) {
                 mbar_expect_tx(full, (uint32_t)C::STAGE_BYTES);
-                const uint32_t dst = s_st + stage * C::STAGE_BYTES;
 #pragma unroll
                 for (int bx = 0; bx < C::NBOX; ++bx) {
                     tma_load_2d(dst + (2 * bx) * C::BOX_BYTES, &tm_g, t * TQ + bx * C::BOX_PX, b * IDF, full);
                     tma_load_2d(dst + (2 * bx + 1) * C::BOX_BYTES, &tm_x, t * TQ + bx * C::BOX_PX, b * IDF, full);
                 }
-                if (++t == TPS) { t = 0; ++b; }
             }
+            __syncwarp();
+            if (++t == TPS) { t = 0; ++b; }
         }
     } else if (warp == kMmaWarp) {
         // --------------------------------- MMA issuer -------------------------------------------
-        if (lane == 0) {
-            int t = t0;
-            uint32_t nb = 0;
-            bool first_of_sample = true;
-            for (int j = 0; j < n_local; ++j) {
-                const int stage = j % NST;
-                const uint32_t st = s_st + stage * C::STAGE_BYTES;
-                if (first_of_sample) {
-                    mbar_wait(smem_u32(&bar_b_ready), nb & 1u);     // operands of this sample are in place
-                    ++nb;
-                }
-                if (j > 0) mbar_wait(smem_u32(&bar_dx_free), (uint32_t)(j - 1) & 1u);   // dX(j-1) has left the S columns
-                mbar_wait(smem_u32(&bar_x_full[stage]), (uint32_t)(j / NST) & 1u);
-                tc_fence_after();
-                // MMA1: S = x^T . B1, dP = g^T . B1  (tiles are MN-major A operands: 64-px blocks 2 boxes apart)
-#pragma unroll
-                for (int ks = 0; ks < C::KS1; ++ks) {
-                    const uint64_t db = smem_desc(s_b1 + ks * 256, 128, C::KCH1 * 128, kSwizzleNone);
-                    const uint64_t dax = smem_desc(st + C::BOX_BYTES + ks * 2048, 2 * C::BOX_BYTES, 1024, kSwizzle128B);
-                    const uint64_t dag = smem_desc(st + ks * 2048, 2 * C::BOX_BYTES, 1024, kSwizzle128B);
-                    umma_ss<false>(tmem_base + C::COL_S, dax, db, C::IDESC1, ks > 0 ? 1u : 0u);
-                    umma_ss<false>(tmem_base + C::COL_DP, dag, db, C::IDESC1, ks > 0 ? 1u : 0u);
-                }
-                umma_commit(smem_u32(&bar_s_full));
-
-                mbar_wait(smem_u32(&bar_ds_ready), (uint32_t)j & 1u);
-                tc_fence_after();
-                // MMA2a: dX = dS . B2  (A = dS rows of PB, MN-major: pixel blocks PB_KBLOCK apart)
-#pragma unroll
-                for (int ks = 0; ks < C::KS2; ++ks) {
-                    const uint64_t da = smem_desc(s_pb + (RP + 16 * ks) * 128, C::PB_KBLOCK, 1024, kSwizzle128B);
-                    const uint64_t db = smem_desc(s_b2 + ks * 256, 128, C::KCH2 * 128, kSwizzleNone);
-                    umma_ss<false>(tmem_base + C::COL_DX, da, db, C::IDESC2, ks > 0 ? 1u : 0u);
-                }
-                // MMA2b: acc (+)= [g ; x] . [P | dS]  (both K-major, K = pixels: 16 per step, 4 steps per 64-px block)
-#pragma unroll
-                for (int ks = 0; ks < C::KS3; ++ks) {
-                    const uint64_t da = smem_desc(st + (ks >> 2) * 2 * C::BOX_BYTES + (ks & 3) * 32, 16, 1024, kSwizzle128B);
-                    const uint64_t db = smem_desc(s_pb + (ks >> 2) * C::PB_KBLOCK + (ks & 3) * 32, 16, 1024, kSwizzle128B);
-                    umma_ss<false>(tmem_base + C::COL_ACC, da, db, C::IDESC3, (ks > 0 || !first_of_sample) ? 1u : 0u);
-                }
-                umma_commit(smem_u32(&bar_x_empty[stage]));
-                umma_commit(smem_u32(&bar_c_full));
-                first_of_sample = false;
-                if (++t == TPS) { t = 0; first_of_sample = true; }
+        // (the whole warp runs the loop; one elected lane issues - see elect_one())
+        // descriptor halves (tc5_common.cuh)
+        constexpr uint32_t kTileMnHi = desc_hi(1024, kSwizzle128B), kKHi = desc_hi(1024, kSwizzle128B);
+        constexpr uint32_t kBHi1 = desc_hi(C::KCH1 * 128, kSwizzleNone), kBHi2 = desc_hi(C::KCH2 * 128, kSwizzleNone);
+        const uint32_t tg_lo = desc_lo(s_st, 2 * C::BOX_BYTES), tx_lo = desc_lo(s_st + C::BOX_BYTES, 2 * C::BOX_BYTES);
+        const uint32_t tk_lo = desc_lo(s_st, 16);                                  // [g ; x] as one K-major operand
+        const uint32_t pbA_lo = desc_lo(s_pb + RP * 128, C::PB_KBLOCK), pbB_lo = desc_lo(s_pb, 16);
+        const uint32_t b1_lo = desc_lo(s_b1, 128), b2_lo = desc_lo(s_b2, 128);
+        int t = t0;
+        uint32_t nb = 0;
+        bool first_of_sample = true;
+        for (int j = 0; j < n_local; ++j) {
+            const int stage = j % NST;
+            if (first_of_sample) {
+                mbar_wait(smem_u32(&bar_b_ready), nb & 1u);     // operands of this sample are in place
+                ++nb;
             }
+            if (j > 0) mbar_wait(smem_u32(&bar_dx_free), (uint32_t)(j - 1) & 1u);   // dX(j-1) has left the S columns
+            mbar_wait(smem_u32(&bar_x_full[stage]), (uint32_t)(j / NST) & 1u);
+            tc_fence_after();
+            const bool tr = p.trace != nullptr && blockIdx.x == 0 && j < 16 && lane == 0;
+            if (tr) p.trace[j * 16 + 8] = clock64();
+            // MMA1: S = x^T . B1, dP = g^T . B1  (tiles are MN-major A operands: 64-px blocks 2 boxes apart)
+            const uint32_t st_lo = (uint32_t)(stage * (C::STAGE_BYTES >> 4));
+            if (elect_one()) {
+#pragma unroll
+            for (int ks = 0; ks < C::KS1; ++ks) {
+                const uint32_t ka = (uint32_t)(ks * 128), kb = (uint32_t)(ks * 16);
+                umma_ss<false>(tmem_base + C::COL_S, tx_lo + st_lo + ka, kTileMnHi, b1_lo + kb, kBHi1, C::IDESC1, ks > 0 ? 1u : 0u);
+                umma_ss<false>(tmem_base + C::COL_DP, tg_lo + st_lo + ka, kTileMnHi, b1_lo + kb, kBHi1, C::IDESC1, ks > 0 ? 1u : 0u);
+            }
+            umma_commit(smem_u32(&bar_s_full));
+            }
+            __syncwarp();
+            if (tr) p.trace[j * 16 + 9] = clock64();
+
+            mbar_wait(smem_u32(&bar_ds_ready), (uint32_t)j & 1u);
+            tc_fence_after();
+            if (tr) p.trace[j * 16 + 10] = clock64();
+            if (elect_one()) {
+            // MMA2a: dX = dS . B2  (A = dS rows of PB, MN-major: pixel blocks PB_KBLOCK apart)
+#pragma unroll
+            for (int ks = 0; ks < C::KS2; ++ks)
+                umma_ss<false>(tmem_base + C::COL_DX, pbA_lo + (uint32_t)(ks * 128), kTileMnHi, b2_lo + (uint32_t)(ks * 16),
+                               kBHi2, C::IDESC2, ks > 0 ? 1u : 0u);
+            // MMA2b: acc (+)= [g ; x] . [P | dS]  (both K-major, K = pixels: 16 per step, 4 steps per 64-px block)
+#pragma unroll
+            for (int ks = 0; ks < C::KS3; ++ks)
+                umma_ss<false>(tmem_base + C::COL_ACC, tk_lo + st_lo + (uint32_t)((ks >> 2) * (2 * C::BOX_BYTES >> 4) + (ks & 3) * 2),
+                               kKHi, pbB_lo + (uint32_t)((ks >> 2) * (C::PB_KBLOCK >> 4) + (ks & 3) * 2), kKHi, C::IDESC3,
+                               (ks > 0 || !first_of_sample) ? 1u : 0u);
+            umma_commit(smem_u32(&bar_x_empty[stage]));
+            umma_commit(smem_u32(&bar_c_full));
+            }
+            __syncwarp();
+            if (tr) p.trace[j * 16 + 11] = clock64();
+            first_of_sample = false;
+            if (++t == TPS) { t = 0; first_of_sample = true; }
         }
     } else {
         // --------------------------------- consumers: thread = pixel ----------------------------
@@ -250,11 +323,11 @@ __global__ void __launch_bounds__(kThreads, Tc5BwdCfg<IDF, NQ>::CTAS_PER_SM > 3 
         const uint32_t pb_col = (uint32_t)(px & 63) * 2;
         bool waited_zero = false;
 
-        // Add this CTA's share of dSrc[bb] (the diagonal blocks of the TMEM accumulator) to global memory;
-        // the last CTA of the sample forms dW / dCtx.  Called by all consumer warps together.
+        // Add this CTA's share of dSrc[bb] (the diagonal blocks of the TMEM accumulator) to global memory.
+        // Called by all consumer warps together once every MMA of the sample has completed.
         auto finish_sample = [&](int bb) {
             if (!waited_zero) {
-                asm volatile("griddepcontrol.wait;" ::: "memory");      // k_zero_tc5 has cleared dSrc / dW / counters
+                asm volatile("griddepcontrol.wait;" ::: "memory");      // k_zero_tc5 has cleared dSrc / dW
                 waited_zero = true;
             }
             // accumulator row r of this lane: M = 64 -> lanes 0..15 of each quarter hold rows 16*cw + lane
@@ -262,74 +335,19 @@ __global__ void __launch_bounds__(kThreads, Tc5BwdCfg<IDF, NQ>::CTAS_PER_SM > 3 
             const bool valid = (C::MD == 64 ? lane < 16 : true) && row < 2 * IDF;
             const bool is_x = row >= IDF;
             const int ch = is_x ? row - IDF : row;
-            uint32_t av[LP];
-            tc_fence_after();
             // column block: g rows take the P columns [0, LP), x rows the dS columns [RP, RP + LP)
-            {
-                uint32_t a0[LP], a1[LP];
-                tmem_ld<LP>(tl + C::COL_ACC, a0);
-                tmem_ld<LP>(tl + C::COL_ACC + RP, a1);
-                tmem_wait_ld();
-#pragma unroll
-                for (int l = 0; l < LP; ++l) av[l] = is_x ? a1[l] : a0[l];
-            }
+            uint32_t a0[LP], a1[LP];
+            tc_fence_after();
+            tmem_ld<LP>(tl + C::COL_ACC, a0);
+            tmem_ld<LP>(tl + C::COL_ACC + RP, a1);
+            tmem_wait_ld();
+            tc_fence_before();
             if (valid) {
                 float* db = p.dSrc + ((size_t)bb * IDF + ch) * L;
 #pragma unroll
                 for (int l = 0; l < LP; ++l)
-                    if (l < L) atomicAdd(db + l, __uint_as_float(av[l]));
+                    if (l < L) atomicAdd(db + l, __uint_as_float(is_x ? a1[l] : a0[l]));
             }
-            tc_fence_before();
-            __threadfence();
-            mma::named_bar_sync(1, kConsumers);
-            if (ct == 0) {
-                const long long G = gridDim.x, N = p.n_tiles;
-                const int k0 = (int)((((long long)bb * TPS + 1) * G - 1) / N);
-                const int k1 = (int)((((long long)(bb + 1) * TPS) * G - 1) / N);
-                const uint32_t old = atomicAdd(p.cnt + bb, 1u);
-                fin_s = (old + 1u == (uint32_t)(k1 - k0 + 1)) ? 1 : 0;
-            }
-            mma::named_bar_sync(1, kConsumers);
-            if (fin_s == 0 || (p.dW == nullptr && p.dCtx == nullptr)) return;
-            __threadfence();
-            if (lane == 0) bulk_wait_read<0>();         // the dX staging doubles as the dSrc[bb] buffer
-            mma::named_bar_sync(1, kConsumers);
-            float* ds = reinterpret_cast<float*>(g_out);             // [IDF][L]
-            const float* dsg = p.dSrc + (size_t)bb * IDF * L;
-            for (int o = ct; o < IDF * L; o += kConsumers) ds[o] = __ldcg(dsg + o);
-            mma::named_bar_sync(1, kConsumers);
-            const float* cb = p.ctx + (size_t)bb * p.cdf * L;
-            for (int cc = ct; cc < p.cdf; cc += kConsumers) {
-                if (p.dW != nullptr) {
-                    float cv[LP];
-#pragma unroll
-                    for (int l = 0; l < LP; ++l) cv[l] = (l < L) ? __ldg(cb + (size_t)cc * L + l) : 0.f;
-                    for (int i = 0; i < IDF; ++i) {
-                        float acc = 0.f;
-#pragma unroll
-                        for (int l = 0; l < LP; ++l)
-                            if (l < L) acc = fmaf(ds[i * L + l], cv[l], acc);
-                        atomicAdd(p.dW + (size_t)i * p.cdf + cc, acc);
-                    }
-                }
-                if (p.dCtx != nullptr) {
-                    float acc[LP];
-#pragma unroll
-                    for (int l = 0; l < LP; ++l) acc[l] = 0.f;
-                    for (int i = 0; i < IDF; ++i) {
-                        const float wv = __ldg(p.W + (size_t)i * p.cdf + cc);
-#pragma unroll
-                        for (int l = 0; l < LP; ++l)
-                            if (l < L) acc[l] = fmaf(wv, ds[i * L + l], acc[l]);
-                    }
-                    float* dc = p.dCtx + ((size_t)bb * p.cdf + cc) * L;
-#pragma unroll
-                    for (int l = 0; l < LP; ++l)
-                        if (l < L) dc[l] = acc[l];
-                }
-            }
-            fence_proxy_async();
-            mma::named_bar_sync(1, kConsumers);      // ds goes back to being the dX staging
         };
 
         for (int j = 0; j < n_local; ++j) {
@@ -347,6 +365,8 @@ __global__ void __launch_bounds__(kThreads, Tc5BwdCfg<IDF, NQ>::CTAS_PER_SM > 3 
                 fence_proxy_async();
                 warp_arrive(smem_u32(&bar_b_ready), lane);
             }
+            const bool tr = p.trace != nullptr && blockIdx.x == 0 && ct == 0 && j < 16;
+            if (tr) p.trace[j * 16 + 0] = clock64();
             const int q = t * TQ + px;
             float ga[HAS_GA ? LP : 1];
             if constexpr (HAS_GA) {
@@ -358,10 +378,12 @@ __global__ void __launch_bounds__(kThreads, Tc5BwdCfg<IDF, NQ>::CTAS_PER_SM > 3 
             // ---- S and dP rows of this pixel ---------------------------------------------------------
             mbar_wait(smem_u32(&bar_s_full), (uint32_t)j & 1u);
             tc_fence_after();
+            if (tr) p.trace[j * 16 + 1] = clock64();
             uint32_t sr[LP], dr[LP];
             tmem_ld<LP>(tl + C::COL_S, sr);
             tmem_ld<LP>(tl + C::COL_DP, dr);
             tmem_wait_ld();
+            if (tr) p.trace[j * 16 + 2] = clock64();
 
             // ---- P = masked softmax over words (recomputed; GlobalAttention.py:104-109) ---------------
             uint32_t mb = pad_bits;
@@ -398,13 +420,16 @@ __global__ void __launch_bounds__(kThreads, Tc5BwdCfg<IDF, NQ>::CTAS_PER_SM > 3 
                 *reinterpret_cast<__nv_bfloat16*>(pb_px + l * 128 + (pb_col ^ ((l & 7) << 4))) = __float2bfloat16_rn(s[l]);
                 *reinterpret_cast<__nv_bfloat16*>(pb_px + (RP + l) * 128 + (pb_col ^ ((l & 7) << 4))) = __float2bfloat16_rn(ds);
             }
+            if (tr) p.trace[j * 16 + 3] = clock64();
             fence_proxy_async();
             tc_fence_before();
             warp_arrive(smem_u32(&bar_ds_ready), lane);
+            if (tr) p.trace[j * 16 + 4] = clock64();
 
             // ---- dX row of this pixel: staged [channel][32 px] per warp, one TMA box store ---------------
             mbar_wait(smem_u32(&bar_c_full), (uint32_t)j & 1u);
             tc_fence_after();
+            if (tr) p.trace[j * 16 + 5] = clock64();
             if (lane == 0) bulk_wait_read<0>();        // the previous dX store has finished reading the staging
             __syncwarp();
 #pragma unroll
@@ -417,12 +442,14 @@ __global__ void __launch_bounds__(kThreads, Tc5BwdCfg<IDF, NQ>::CTAS_PER_SM > 3 
             }
             tc_fence_before();
             warp_arrive(smem_u32(&bar_dx_free), lane);
+            if (tr) p.trace[j * 16 + 6] = clock64();
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) {
                 tma_store_2d(&tm_dx, t * TQ + cw * 32, b * IDF, so);
                 bulk_commit();
             }
+            if (tr) p.trace[j * 16 + 7] = clock64();
 
             if (++t == TPS) { t = 0; ++b; }
             cap += step_mod;
@@ -437,6 +464,11 @@ __global__ void __launch_bounds__(kThreads, Tc5BwdCfg<IDF, NQ>::CTAS_PER_SM > 3 
     if (warp == kMmaWarp) {
         tc_fence_after();
         tmem_dealloc(tmem_base, C::TMEM_COLS);
+    }
+    if (p.trace != nullptr && tid == 0) {
+        unsigned long long gt;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
+        p.trace[256 + 2 * blockIdx.x + 1] = (long long)gt;
     }
 }
 
@@ -488,14 +520,44 @@ int launch_bwd_tc5(const void* x, const void* g, void* dX, const Tc5BwdParams& p
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tm_x, tm_g, tm_dx, p);
+    cfg.numAttrs = getenv("SBA_TC5_NO_PDL") ? 0 : 1;
+    Tc5BwdParams pk = p;
+    static long long* trace_buf = nullptr;
+    if (getenv("SBA_TC5_TRACE")) {
+        if (!trace_buf) cudaMalloc(&trace_buf, 4096 * sizeof(long long));
+        cudaMemsetAsync(trace_buf, 0, 4096 * sizeof(long long), st);
+        pk.trace = trace_buf;
+    }
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tm_x, tm_g, tm_dx, pk);
     if (e != cudaSuccess) {
         set_error("attn_bwd(tcgen05): launch: %s", cudaGetErrorString(e));
         return SBA_ERR_CUDA;
     }
+    if (pk.trace) {
+        static long long h[4096];
+        cudaStreamSynchronize(st);
+        cudaMemcpy(h, trace_buf, sizeof(h), cudaMemcpyDeviceToHost);
+        {
+            long long t0 = h[256];
+            for (int k = 0; k < grid && k < 1900; ++k) if (h[256 + 2 * k] < t0) t0 = h[256 + 2 * k];
+            fprintf(stderr, "CTA start/end (ns since the first start), every 37th CTA:\n");
+            for (int k = 0; k < grid && k < 1900; k += 37)
+                fprintf(stderr, "  cta %4d: %7lld .. %7lld\n", k, h[256 + 2 * k] - t0, h[256 + 2 * k + 1] - t0);
+        }
+        const char* names[12] = {"top", "s_full", "ld_S", "math+PB", "ds_rdy", "c_full", "dX_stg", "store", "M:x_full", "M:mma1", "M:ds_rdy", "M:mma2"};
+        fprintf(stderr, "tile");
+        for (int k = 0; k < 12; ++k) fprintf(stderr, " %9s", names[k]);
+        fprintf(stderr, "   (cycles since the first stamp)\n");
+        for (int j = 0; j < 16 && h[j * 16] != 0; ++j) {
+            fprintf(stderr, "%4d", j);
+            for (int k = 0; k < 12; ++k) fprintf(stderr, " %9lld", h[j * 16 + k] - h[0]);
+            fprintf(stderr, "\n");
+        }
+    }
     add_launches(2);
-    return check_launch("attn_bwd(tcgen05)");
+    rc = check_launch("attn_bwd(tcgen05)");
+    if (rc) return rc;
+    return attn_bwd_post(p.dSrc, p.ctx, p.W, p.dW, p.dCtx, p.B, IDF, p.cdf, p.L, st);
 }
 
 template <int IDF, bool HAS_GA>
@@ -520,13 +582,36 @@ int dispatch_ga(const void* x, const void* g, void* dX, const Tc5BwdParams& p, c
 
 }  // namespace
 
+int attn_bwd_post(const float* dSrc, const float* ctx, const float* W, float* dW, float* dCtx, int B, int idf, int cdf,
+                  int L, cudaStream_t st) {
+    if (dW == nullptr && dCtx == nullptr) return SBA_OK;
+    const int n_dw = dW != nullptr ? 16 * ((cdf + 7) / 8) : 0;
+    const int grid = n_dw + (dCtx != nullptr ? B : 0);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(256);
+    cfg.dynamicSmemBytes = (size_t)(idf + 8) * L * sizeof(float);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, k_bwd_post_tc5, dSrc, ctx, W, dW, dCtx, B, idf, cdf, L, n_dw);
+    if (e != cudaSuccess) {
+        set_error("attn_bwd(post): launch: %s", cudaGetErrorString(e));
+        return SBA_ERR_CUDA;
+    }
+    add_launches(1);
+    return check_launch("attn_bwd(post)");
+}
+
 bool tc5_bwd_supports(const AttnShape& s) { return tc5_supports(s) && s.dtype == SBA_BF16; }
 
 int tc5_attn_bwd(const void* x, const float* ctx, const float* W, const float* srcT, const uint8_t* mask, const void* g_c,
                  const void* g_attn, void* dX, float* dSrc, float* dW, float* dCtx, const AttnShape& s, cudaStream_t st) {
     Tc5BwdParams p{};
     p.srcT = srcT; p.mask = mask; p.ga = g_attn; p.dSrc = dSrc; p.ctx = ctx; p.W = W; p.dW = dW; p.dCtx = dCtx;
-    p.cnt = reinterpret_cast<uint32_t*>(dSrc + (size_t)s.B * s.idf * s.L);
     p.B = s.B; p.L = s.L; p.Q = s.Q; p.cdf = s.cdf; p.mask_mode = s.mask_mode;
     p.tiles_per_sample = s.Q / tc5::TQ;
     p.n_tiles = s.B * p.tiles_per_sample;

@@ -249,7 +249,7 @@ __global__ void __launch_bounds__(kThreads, Tc5FwdCfg<T, IDF, NQ>::CTAS_PER_SM)
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = tmem_base_s;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, tmem_base_s, 0);     // provably warp-uniform
 
     const int w_begin = (int)(((long long)blockIdx.x * p.n_tiles) / gridDim.x);
     const int w_end = (int)(((long long)(blockIdx.x + 1) * p.n_tiles) / gridDim.x);
@@ -258,88 +258,96 @@ __global__ void __launch_bounds__(kThreads, Tc5FwdCfg<T, IDF, NQ>::CTAS_PER_SM)
 
     if (warp == kProducerWarp) {
         // --------------------------------- TMA producer -----------------------------------------
-        if (lane == 0) {
-            int b = b0, t = t0;
-            for (int j = 0; j < n_local; ++j) {
-                const int stage = j % NST;
-                if (j >= NST) mbar_wait(smem_u32(&bar_x_empty[stage]), (uint32_t)((j / NST) - 1) & 1u);
-                const uint32_t full = smem_u32(&bar_x_full[stage]);
+        // (the whole warp runs the loop; one elected lane issues - see elect_one())
+        int b = b0, t = t0;
+        for (int j = 0; j < n_local; ++j) {
+            const int stage = j % NST;
+            if (j >= NST) mbar_wait(smem_u32(&bar_x_empty[stage]), (uint32_t)((j / NST) - 1) & 1u);
+            const uint32_t full = smem_u32(&bar_x_full[stage]);
+            const uint32_t dst = s_x + stage * C::STAGE_BYTES;
+            if (elect_one()) {
                 mbar_expect_tx(full, (uint32_t)C::STAGE_BYTES);
-                const uint32_t dst = s_x + stage * C::STAGE_BYTES;
 #pragma unroll
                 for (int bx = 0; bx < C::NBOX; ++bx)
                     tma_load_2d(dst + bx * C::BOX_BYTES, &tmx, t * TQ + bx * C::BOX_PX, b * IDF, full);
-                if (++t == TPS) { t = 0; ++b; }
             }
+            __syncwarp();
+            if (++t == TPS) { t = 0; ++b; }
         }
     } else if (warp == kMmaWarp) {
         // --------------------------------- MMA issuer -------------------------------------------
-        if (lane == 0) {
-            // MMA1(j): S[j & 1] = x_tile^T . B1   (3xTF32: hi.hi + hi.lo + lo.hi)
-            auto mma1 = [&](int j) {
-                const int stage = j % NST, buf = j & 1;
-                mbar_wait(smem_u32(&bar_x_full[stage]), (uint32_t)(j / NST) & 1u);
-                if constexpr (F32) mbar_wait(smem_u32(&bar_lo_ready), (uint32_t)j & 1u);
-                if (j >= 2) mbar_wait(smem_u32(&bar_s_free[buf]), (uint32_t)((j >> 1) - 1) & 1u);
-                tc_fence_after();
-                const uint32_t d = tmem_base + C::COL_S + 32 * buf;
-                const uint32_t a_hi = s_x + stage * C::STAGE_BYTES;
+        // (the whole warp runs the loop; one elected lane issues - see elect_one())
+        // descriptor halves (tc5_common.cuh): x tile / lo tile MN-major swizzled, B operands K-major plain
+        constexpr uint32_t kAHi = desc_hi(C::A_SBO, C::A_SWIZZLE);
+        constexpr uint32_t kBHi1 = desc_hi(C::KCH1 * 128, kSwizzleNone), kBHi2 = desc_hi(C::KCH2 * 128, kSwizzleNone);
+        const uint32_t a_lo0 = desc_lo(s_x, C::BOX_BYTES), alo_lo = desc_lo(s_lo, C::BOX_BYTES);
+        const uint32_t b1_lo = desc_lo(s_b1, 128), b2_lo = desc_lo(s_b2, 128);
+        // MMA1(j): S[j & 1] = x_tile^T . B1   (3xTF32: hi.hi + hi.lo + lo.hi)
+        auto mma1 = [&](int j) {
+            const int stage = j % NST, buf = j & 1;
+            mbar_wait(smem_u32(&bar_x_full[stage]), (uint32_t)(j / NST) & 1u);
+            if constexpr (F32) mbar_wait(smem_u32(&bar_lo_ready), (uint32_t)j & 1u);
+            if (j >= 2) mbar_wait(smem_u32(&bar_s_free[buf]), (uint32_t)((j >> 1) - 1) & 1u);
+            tc_fence_after();
+            const uint32_t d = tmem_base + C::COL_S + 32 * buf;
+            const uint32_t a_lo = a_lo0 + (uint32_t)(stage * (C::STAGE_BYTES >> 4));
+            if (elect_one()) {
 #pragma unroll
-                for (int ks = 0; ks < C::KS1; ++ks) {
-                    const uint64_t da = smem_desc(a_hi + ks * C::KSTEP_A, C::BOX_BYTES, C::A_SBO, C::A_SWIZZLE);
-                    const uint64_t db = smem_desc(s_b1 + ks * 256, 128, C::KCH1 * 128, kSwizzleNone);
-                    umma_ss<F32>(d, da, db, C::IDESC1, ks > 0 ? 1u : 0u);
-                    if constexpr (F32) {
-                        const uint64_t dal = smem_desc(s_lo + ks * C::KSTEP_A, C::BOX_BYTES, C::A_SBO, C::A_SWIZZLE);
-                        const uint64_t dbl = smem_desc(s_b1 + C::B1_BYTES + ks * 256, 128, C::KCH1 * 128, kSwizzleNone);
-                        umma_ss<F32>(d, da, dbl, C::IDESC1, 1u);
-                        umma_ss<F32>(d, dal, db, C::IDESC1, 1u);
-                    }
+            for (int ks = 0; ks < C::KS1; ++ks) {
+                const uint32_t ka = (uint32_t)(ks * (C::KSTEP_A >> 4)), kb = (uint32_t)(ks * 16);
+                umma_ss<F32>(d, a_lo + ka, kAHi, b1_lo + kb, kBHi1, C::IDESC1, ks > 0 ? 1u : 0u);
+                if constexpr (F32) {
+                    umma_ss<F32>(d, a_lo + ka, kAHi, b1_lo + (uint32_t)(C::B1_BYTES >> 4) + kb, kBHi1, C::IDESC1, 1u);
+                    umma_ss<F32>(d, alo_lo + ka, kAHi, b1_lo + kb, kBHi1, C::IDESC1, 1u);
                 }
-                umma_commit(smem_u32(&bar_x_empty[stage]));
-                umma_commit(smem_u32(&bar_s_full[buf]));
-            };
-            // MMA2(j): c = P . B2
-            auto mma2 = [&](int j) {
-                mbar_wait(smem_u32(&bar_p_ready), (uint32_t)j & 1u);
-                tc_fence_after();
-                const uint32_t d = tmem_base + C::COL_C;
+            }
+            umma_commit(smem_u32(&bar_x_empty[stage]));
+            umma_commit(smem_u32(&bar_s_full[buf]));
+            }
+            __syncwarp();
+        };
+        // MMA2(j): c = P . B2
+        auto mma2 = [&](int j) {
+            mbar_wait(smem_u32(&bar_p_ready), (uint32_t)j & 1u);
+            tc_fence_after();
+            const uint32_t d = tmem_base + C::COL_C;
+            if (elect_one()) {
 #pragma unroll
-                for (int ks = 0; ks < C::KS2; ++ks) {
-                    const uint32_t a = tmem_base + C::COL_P + ks * 8;        // 8 columns per k-step either way
-                    const uint64_t db = smem_desc(s_b2 + ks * 256, 128, C::KCH2 * 128, kSwizzleNone);
-                    umma_ts<F32>(d, a, db, C::IDESC2, ks > 0 ? 1u : 0u);
-                    if constexpr (F32) {
-                        const uint64_t dbl = smem_desc(s_b2 + C::B2_BYTES + ks * 256, 128, C::KCH2 * 128, kSwizzleNone);
-                        umma_ts<F32>(d, a, dbl, C::IDESC2, 1u);
-                        umma_ts<F32>(d, tmem_base + C::COL_PLO + ks * 8, db, C::IDESC2, 1u);
-                    }
+            for (int ks = 0; ks < C::KS2; ++ks) {
+                const uint32_t a = tmem_base + C::COL_P + ks * 8;        // 8 columns per k-step either way
+                const uint32_t kb = (uint32_t)(ks * 16);
+                umma_ts<F32>(d, a, b2_lo + kb, kBHi2, C::IDESC2, ks > 0 ? 1u : 0u);
+                if constexpr (F32) {
+                    umma_ts<F32>(d, a, b2_lo + (uint32_t)(C::B2_BYTES >> 4) + kb, kBHi2, C::IDESC2, 1u);
+                    umma_ts<F32>(d, tmem_base + C::COL_PLO + ks * 8, b2_lo + kb, kBHi2, C::IDESC2, 1u);
                 }
-                umma_commit(smem_u32(&bar_c_full));
-            };
-            int t = t0;
-            uint32_t nb = 0;
-            if (n_local > 0) {
-                mbar_wait(smem_u32(&bar_b_ready), nb & 1u);
+            }
+            umma_commit(smem_u32(&bar_c_full));
+            }
+            __syncwarp();
+        };
+        int t = t0;
+        uint32_t nb = 0;
+        if (n_local > 0) {
+            mbar_wait(smem_u32(&bar_b_ready), nb & 1u);
+            ++nb;
+            mma1(0);
+        }
+        for (int j = 0; j < n_local; ++j) {
+            const bool has_next = j + 1 < n_local;
+            const bool next_same = has_next && (t + 1 < TPS);
+            // bf16: S of the next tile is produced ahead of the softmax of this one; fp32: the lo tile of
+            // the next tile is written only after P of this one, so MMA2 goes first
+            if (!F32 && next_same) mma1(j + 1);
+            mma2(j);
+            if (has_next && !next_same) {
+                mbar_wait(smem_u32(&bar_b_ready), nb & 1u);     // operands of the next sample are in place
                 ++nb;
-                mma1(0);
+                mma1(j + 1);
+            } else if (F32 && next_same) {
+                mma1(j + 1);
             }
-            for (int j = 0; j < n_local; ++j) {
-                const bool has_next = j + 1 < n_local;
-                const bool next_same = has_next && (t + 1 < TPS);
-                // bf16: S of the next tile is produced ahead of the softmax of this one; fp32: the lo tile of
-                // the next tile is written only after P of this one, so MMA2 goes first
-                if (!F32 && next_same) mma1(j + 1);
-                mma2(j);
-                if (has_next && !next_same) {
-                    mbar_wait(smem_u32(&bar_b_ready), nb & 1u);     // operands of the next sample are in place
-                    ++nb;
-                    mma1(j + 1);
-                } else if (F32 && next_same) {
-                    mma1(j + 1);
-                }
-                if (++t == TPS) t = 0;
-            }
+            if (++t == TPS) t = 0;
         }
     } else {
         // --------------------------------- consumers: thread = pixel ----------------------------
@@ -570,7 +578,7 @@ int launch_fwd_tc5(const void* x, const Tc5FwdParams& p, int dtype, cudaStream_t
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = getenv("SBA_TC5_NO_PDL") ? 0 : 1;
     cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmx, tma_attn, tma_c, p);
     if (e != cudaSuccess) {
         set_error("attn_fwd(tcgen05): launch: %s", cudaGetErrorString(e));

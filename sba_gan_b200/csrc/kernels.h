@@ -33,6 +33,10 @@ bool tc5_supports(const AttnShape& s);
 int tc5_attn_fwd(const void* x, const float* ctx, const float* W, const uint8_t* mask, void* c_code, void* attn,
                  float* srcT, uint32_t* mask_bits, const AttnShape& s, cudaStream_t st);
 
+// dW (+)= sum_b dSrc[b] . ctx[b]^T (dW zeroed by the caller's launch sequence) and dCtx[b] = W^T . dSrc[b];
+// launched as a programmatic dependent of the kernel that produced dSrc
+int attn_bwd_post(const float* dSrc, const float* ctx, const float* W, float* dW, float* dCtx, int B, int idf, int cdf,
+                  int L, cudaStream_t st);
 bool tc5_bwd_supports(const AttnShape& s);     // bf16 tensors for now; fp32 backward stays on the mma.sync family
 // dSrc holds B*idf*L floats followed by B+1 scratch words, like mma_attn_bwd
 int tc5_attn_bwd(const void* x, const float* ctx, const float* W, const float* srcT, const uint8_t* mask, const void* g_c,

@@ -43,6 +43,16 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     } while (!done);
 }
 
+// One lane of a fully converged warp.  The producer / MMA warps run their loops warp-uniformly and
+// predicate only the issuing instructions on this, so that descriptors, TMEM addresses and
+// barrier addresses stay in uniform registers (a divergent `if (lane == 0)` region makes ptxas
+// wrap every UTCHMMA / UTMALDG in an elect-and-broadcast loop).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P1;\n\telect.sync _|P1, 0xffffffff;\n\tselp.u32 %0, 1, 0, P1;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
 // ---- TMA: 2-D tensor-map box load, completion on an mbarrier --------------------------------
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, uint32_t bar) {
     asm volatile(
@@ -156,7 +166,56 @@ constexpr uint32_t make_idesc(int fmt, int a_mn, int b_mn, int M, int N) {
            ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-// D[tmem] (+)= A[smem] . B[smem]^T ; one thread issues for the CTA
+// The issuing thread is a single dependent instruction stream, so descriptors are kept as two 32-bit
+// halves: the high half (stride offset, version, swizzle) is a compile-time constant per operand,
+// the low half (start address, leading offset) advances by a constant number of 16-byte units per
+// k-step - one integer add per MMA instead of rebuilding 64-bit descriptors.
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr, uint32_t lbo_bytes) {
+    return ((saddr & 0x3FFFFu) >> 4) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
+}
+constexpr uint32_t desc_hi(uint32_t sbo_bytes, uint32_t swizzle) {
+    return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | (swizzle << 29);
+}
+template <bool TF32>
+__device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                        uint32_t idesc, uint32_t accumulate) {
+    if constexpr (TF32) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %6, 0;\n\t"
+            "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, p;\n\t}" ::"r"(d_tmem),
+            "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+            : "memory");
+    } else {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %6, 0;\n\t"
+            "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(d_tmem),
+            "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+            : "memory");
+    }
+}
+template <bool TF32>
+__device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                        uint32_t accumulate) {
+    if constexpr (TF32) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t.reg .b64 db;\n\tsetp.ne.b32 p, %5, 0;\n\t"
+            "mov.b64 db, {%2, %3};\n\t"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], db, %4, p;\n\t}" ::"r"(d_tmem),
+            "r"(a_tmem), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+            : "memory");
+    } else {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t.reg .b64 db;\n\tsetp.ne.b32 p, %5, 0;\n\t"
+            "mov.b64 db, {%2, %3};\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n\t}" ::"r"(d_tmem),
+            "r"(a_tmem), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+            : "memory");
+    }
+}
+
+// D[tmem] (+)= A[smem] . B[smem]^T ; one thread issues for the CTA (64-bit descriptor form)
 template <bool TF32>
 __device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
     if constexpr (TF32) {
