@@ -132,28 +132,22 @@ def run_ours(args, rank, world, device):
             st[0].requires_grad_(True)
 
     ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
-    call_events = {(w, hw): [] for w in ("fwd", "bwd") for hw in STAGES}
 
-    def step(k, record=False):
-        """fwd+bwd of both attention stages through the public module."""
+    def step(k):
+        """fwd+bwd of both attention stages through the public module.  The gradients are taken with
+        autograd.grad: in the generator x is an activation, not a leaf, so there is no .grad accumulation
+        pass over it.  Returns the conv_context weight gradients (what the DDP bucket would carry)."""
+        dws = []
         for m, (x, gc, ctx, mask), hw in zip(mods, sets[k % nsets], STAGES):
             m.applyMask(mask)
-            if record:
-                e0, e1, e2, e3 = ev(), ev(), ev(), ev()
-                e0.record()
             c_code, _att = m(x, ctx)
-            if record:
-                e1.record()
-                e2.record()
-            c_code.backward(gc)
-            if record:
-                e3.record()
-                call_events[("fwd", hw)].append((e0, e1))
-                call_events[("bwd", hw)].append((e2, e3))
+            _dx, dw = torch.autograd.grad(c_code, [x, m.conv_context.weight], gc)
+            dws.append(dw)
+        return dws
 
-    def exchange():
+    def exchange(dws):
         if world > 1:
-            hs = [dist.all_reduce(m.conv_context.weight.grad, async_op=True) for m in mods]
+            hs = [dist.all_reduce(t, async_op=True) for t in dws]
             for h in hs:
                 h.wait()
 
@@ -165,34 +159,27 @@ def run_ours(args, rank, world, device):
     # warm-up (eager), then capture one CUDA graph per rotating buffer set: the step is a fixed
     # sequence of launches, so replaying it removes the Python/launch latency between kernels.
     for k in range(max(args.warmup, 3)):
-        step(k)
-        exchange()
+        exchange(step(k))
     barrier()
     graphs = []
     if not args.no_graph:
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            for k in range(nsets):
-                step(k)                            # grads now exist as static tensors
-        torch.cuda.current_stream().wait_stream(side)
-        torch.cuda.synchronize()
         for k in range(nsets):
             g = torch.cuda.CUDAGraph()
             F.launch_counter["n"] = 0
             with torch.cuda.graph(g):
-                step(k)
-            graphs.append((g, F.launch_counter["n"]))
-        for g, _ in graphs:
+                dws = step(k)
+            graphs.append((g, F.launch_counter["n"], dws))
+        for g, _, _ in graphs:
             g.replay()
         barrier()
 
     def run_step(k):
         if graphs:
-            graphs[k % nsets][0].replay()
+            g, _, dws = graphs[k % nsets]
+            g.replay()
         else:
-            step(k)
-        exchange()
+            dws = step(k)
+        exchange(dws)
 
     sampler = ClockSampler(torch.cuda.current_device())
     sampler.start()
@@ -217,24 +204,73 @@ def run_ours(args, rank, world, device):
     px_step = B_PER_GPU * sum(hw * hw for hw in STAGES) * world
     value = px_step / (ms * 1e-3)
 
-    # per-call device times (eager, events around each ABI call; a GPU-side spin keeps the queue
-    # ahead of the host so the events bracket kernels, not Python) -> roofline of the dominant kernel
-    for k in range(min(args.steps, 20)):
-        torch.cuda._sleep(3_000_000)
-        step(k, record=True)
-    torch.cuda.synchronize()
+    # per-call device times -> roofline of the dominant kernel: for each of the four ABI calls of a step, a
+    # CUDA graph of `reps` calls over the rotating buffer sets, bracketed by events on the capture stream
     calls = {}
-    for (w, hw), evs in call_events.items():
-        t = statistics.mean(a.elapsed_time(b) for a, b in evs) * 1e-3
-        nbytes = algorithmic_bytes(B_PER_GPU * hw * hw, es, w)
-        calls[f"{w}_{hw}"] = {"us": round(t * 1e6, 2), "gbs": round(nbytes / t / 1e9, 1), "bytes": nbytes}
+    reps = 12
+    lib = _abi.load()
+    dcode = _abi.SBA_BF16 if args.dtype == "bf16" else _abi.SBA_F32
+    algo = F._ALGOS[args.algo]
+    for mi, hw in enumerate(STAGES):
+        Q = hw * hw
+        w32 = mods[mi].conv_context.weight.detach().reshape(IDF, CDF).float().contiguous()
+        bufs = []
+        for s in range(nsets):
+            x, gc, ctx, mask = sets[s][mi]
+            bufs.append(dict(x=x.detach(), gc=gc, ctx=ctx.float().contiguous(), mask=mask.to(torch.uint8).contiguous(),
+                             c=torch.empty_like(x), a=torch.empty(B_PER_GPU, L, hw, hw, dtype=dtype, device=device),
+                             dx=torch.empty_like(x), srcT=torch.empty(B_PER_GPU, IDF, L, device=device),
+                             scr=torch.empty(3 * B_PER_GPU, dtype=torch.int32, device=device),
+                             dsrc=torch.empty(B_PER_GPU * IDF * L + B_PER_GPU + 1, device=device),
+                             dw=torch.empty(IDF, CDF, device=device)))
+
+        def fwd_call(s, st):
+            b = bufs[s % nsets]
+            _abi.check(lib.sba_attn_fwd(b["x"].data_ptr(), b["ctx"].data_ptr(), w32.data_ptr(), b["mask"].data_ptr(),
+                                        b["c"].data_ptr(), b["a"].data_ptr(), b["srcT"].data_ptr(), b["scr"].data_ptr(),
+                                        B_PER_GPU, IDF, CDF, L, Q, dcode, 0, algo, st), "sba_attn_fwd")
+
+        def bwd_call(s, st):
+            b = bufs[s % nsets]
+            _abi.check(lib.sba_attn_bwd(b["x"].data_ptr(), b["ctx"].data_ptr(), w32.data_ptr(), b["mask"].data_ptr(),
+                                        b["srcT"].data_ptr(), b["scr"].data_ptr(), b["gc"].data_ptr(), None,
+                                        b["dx"].data_ptr(), b["dsrc"].data_ptr(), b["dw"].data_ptr(), None,
+                                        B_PER_GPU, IDF, CDF, L, Q, dcode, 0, algo, st), "sba_attn_bwd")
+
+        cur = torch.cuda.current_stream().cuda_stream
+        for s in range(nsets):
+            fwd_call(s, cur)
+            bwd_call(s, cur)
+        torch.cuda.synchronize()
+        for name, fn in (("fwd", fwd_call), ("bwd", bwd_call)):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                st = torch.cuda.current_stream().cuda_stream
+                for s in range(reps):
+                    fn(s, st)
+            g.replay()
+            torch.cuda.synchronize()
+            e0, e1 = ev(), ev()
+            e0.record()
+            g.replay()
+            e1.record()
+            torch.cuda.synchronize()
+            t = e0.elapsed_time(e1) * 1e-3 / reps
+            nbytes = algorithmic_bytes(B_PER_GPU * hw * hw, es, name)
+            calls[f"{name}_{hw}"] = {"us": round(t * 1e6, 2), "gbs": round(nbytes / t / 1e9, 1), "bytes": nbytes}
+        del bufs
     dom = max(calls, key=lambda k: calls[k]["us"])
     peaks, peak_kind = load_peaks()
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get(f"{args.dtype}_{dom}")
     roofline = {
         "bound": "hbm", "kernel": f"sba_attn_{dom.split('_')[0]} @{dom.split('_')[1]}x{dom.split('_')[1]}",
         "achieved": calls[dom]["gbs"], "peak": peaks["hbm_gbs"], "unit": "GB/s",
         "frac": round(calls[dom]["gbs"] / peaks["hbm_gbs"], 4), "peak_source": f"{peak_kind} (MEASURED_PEAKS.json hbm_gbs)",
-        "traffic": None, "algorithmic_bytes_per_launch": calls[dom]["bytes"],
+        "traffic": traffic, "algorithmic_bytes_per_launch": calls[dom]["bytes"],
         "step_frac": round(sum(c["bytes"] for c in calls.values()) / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"], 4),
         "calls": calls,
     }

@@ -21,7 +21,7 @@
 // (one conflict-free LDS.64 per B operand).  bf16 tensors: single bf16 MMAs, sourceT
 // fragments register resident.
 //
-// dW / dContext are formed from dSrc by the small epilogue kernels in attn_simt.cu.
+// dW / dContext are formed from the complete dSrc by attn_bwd_post (attn_tc5_bwd.cu).
 #include "kernels.h"
 #include "mma_common.cuh"
 
@@ -142,16 +142,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_attn_bwd_mma(const BwdParams p)
             mb_s[cap] = bits;
         }
     }
-    // CTA 0 zeroes dW and then raises the flag the per-sample finishers wait on before their atomics
-    if (blockIdx.x == 0 && p.dW != nullptr) {
-        for (int o = tid; o < IDF * p.cdf; o += kThreads) p.dW[o] = 0.f;
-        __threadfence();
-    }
     __syncthreads();
-    if (blockIdx.x == 0 && tid == 0) {
-        __threadfence();
-        atomicExch(p.cnt + p.B, 1u);
-    }
 
     const int w_begin = (int)(((long long)blockIdx.x * p.n_tiles) / gridDim.x);
     const int w_end = (int)(((long long)(blockIdx.x + 1) * p.n_tiles) / gridDim.x);
@@ -206,64 +197,16 @@ __global__ void __launch_bounds__(kThreads, 2) k_attn_bwd_mma(const BwdParams p)
                     }
             }
     };
-    // Per-sample epilogue, fused behind the dSrc reduction: the LAST CTA to flush its share of
-    // sample bb (completion counter == number of CTAs whose tile range touches bb) forms
-    //   dW     += dSrc[bb] . ctx[bb]^T     (conv_context weight grad; atomics over samples)
-    //   dCtx[bb] = W^T . dSrc[bb]          (conv_context input grad)
-    // while the other CTAs keep streaming.  All eight consumer warps call this together.
+    // dSrc[bb] gets this CTA's share once its tile range leaves the sample; dW / dCtx are formed from the
+    // complete dSrc by attn_bwd_post (a programmatic dependent of this kernel): doing that here, per sample,
+    // puts 64-way contended atomics on dW right at the end of the stream.
+    bool waited_zero = false;
     auto finish_sample = [&](int bb) {
+        if (!waited_zero) {
+            asm volatile("griddepcontrol.wait;" ::: "memory");      // the zero-fill grid in front has cleared dSrc / dW
+            waited_zero = true;
+        }
         flush_dsrc(bb);
-        __threadfence();
-        named_bar_sync(1, kConsumers);
-        if (tid == 0) {
-            const long long G = gridDim.x, N = p.n_tiles;
-            const int k0 = (int)((((long long)bb * TPS + 1) * G - 1) / N);
-            const int k1 = (int)((((long long)(bb + 1) * TPS) * G - 1) / N);
-            const uint32_t old = atomicAdd(p.cnt + bb, 1u);
-            fin_s = (old + 1u == (uint32_t)(k1 - k0 + 1)) ? 1 : 0;
-        }
-        named_bar_sync(1, kConsumers);
-        if (fin_s == 0 || (p.dW == nullptr && p.dCtx == nullptr)) return;
-        __threadfence();
-        float* ds = reinterpret_cast<float*>(tab);                 // [IDF][L]; the fragment table is dead here
-        const float* db = p.dSrc + (size_t)bb * IDF * L;
-        for (int o = tid; o < IDF * L; o += kConsumers) ds[o] = __ldcg(db + o);
-        if (p.dW != nullptr) {
-            if (lane == 0) while (ld_acquire(p.cnt + p.B) == 0u) __nanosleep(32);
-            __syncwarp();
-        }
-        named_bar_sync(1, kConsumers);
-        const float* cb = p.ctx + (size_t)bb * p.cdf * L;
-        for (int cc = tid; cc < p.cdf; cc += kConsumers) {
-            if (p.dW != nullptr) {
-                float cv[NT * 8];
-#pragma unroll
-                for (int l = 0; l < NT * 8; ++l) cv[l] = (l < L) ? __ldg(cb + (size_t)cc * L + l) : 0.f;
-                for (int i = 0; i < IDF; ++i) {
-                    float acc = 0.f;
-#pragma unroll
-                    for (int l = 0; l < NT * 8; ++l)
-                        if (l < L) acc = fmaf(ds[i * L + l], cv[l], acc);
-                    atomicAdd(p.dW + (size_t)i * p.cdf + cc, acc);
-                }
-            }
-            if (p.dCtx != nullptr) {
-                float acc[NT * 8];
-#pragma unroll
-                for (int l = 0; l < NT * 8; ++l) acc[l] = 0.f;
-                for (int i = 0; i < IDF; ++i) {
-                    const float wv = __ldg(p.W + (size_t)i * p.cdf + cc);
-#pragma unroll
-                    for (int l = 0; l < NT * 8; ++l)
-                        if (l < L) acc[l] = fmaf(wv, ds[i * L + l], acc[l]);
-                }
-                float* dc = p.dCtx + ((size_t)bb * p.cdf + cc) * L;
-#pragma unroll
-                for (int l = 0; l < NT * 8; ++l)
-                    if (l < L) dc[l] = acc[l];
-            }
-        }
-        named_bar_sync(1, kConsumers);      // ds is re-used (fragment table / next epilogue)
     };
     // B-operand fragment fb of split sp (0 = hi, 1 = lo)
     auto frag = [&](int sp, int fb) -> uint2 {
@@ -676,15 +619,28 @@ int launch_bwd_mma(const BwdParams& p0, cudaStream_t st) {
         return SBA_ERR_UNSUPPORTED;
     }
     p.nst = nst;
-    cudaError_t e = cudaMemsetAsync(p.dSrc, 0, ((size_t)p.B * IDF * p.L + p.B + 1) * sizeof(float), st);
+    int rc = attn_bwd_zero(p.dSrc, (size_t)p.B * IDF * p.L + p.B + 1, p.dW, p.dW ? (size_t)IDF * p.cdf : 0, st);
+    if (rc) return rc;
+    const int grid = p.n_tiles < max_ctas ? p.n_tiles : max_ctas;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = kSmemCap;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, p);
     if (e != cudaSuccess) {
-        set_error("attn_bwd(mma): memset: %s", cudaGetErrorString(e));
+        set_error("attn_bwd(mma): launch: %s", cudaGetErrorString(e));
         return SBA_ERR_CUDA;
     }
-    const int grid = p.n_tiles < max_ctas ? p.n_tiles : max_ctas;
-    kern<<<grid, kThreads, kSmemCap, st>>>(p);
     add_launches(1);
-    return check_launch("attn_bwd(mma)");
+    rc = check_launch("attn_bwd(mma)");
+    if (rc) return rc;
+    return attn_bwd_post(p.dSrc, p.ctx, p.W, p.dW, p.dCtx, p.B, IDF, p.cdf, p.L, st);
 }
 
 template <typename T, int IDF, bool HAS_GA>

@@ -507,8 +507,7 @@ int launch_bwd_tc5(const void* x, const void* g, void* dX, const Tc5BwdParams& p
     if (!rc) rc = make_tile_map(&tm_dx, dX, SBA_BF16, p.B * IDF, p.Q, IDF, 32, false);
     if (rc) return rc;
     const size_t n_src = (size_t)p.B * IDF * p.L + p.B + 1;       // dSrc and the counter words behind it
-    k_zero_tc5<<<64, 256, 0, st>>>(p.dSrc, n_src, p.dW, p.dW ? (size_t)IDF * p.cdf : 0);
-    rc = check_launch("zero(tcgen05)");
+    rc = attn_bwd_zero(p.dSrc, n_src, p.dW, p.dW ? (size_t)IDF * p.cdf : 0, st);
     if (rc) return rc;
     const int grid = p.n_tiles < max_ctas ? p.n_tiles : max_ctas;
     cudaLaunchConfig_t cfg = {};
@@ -554,7 +553,7 @@ int launch_bwd_tc5(const void* x, const void* g, void* dX, const Tc5BwdParams& p
             fprintf(stderr, "\n");
         }
     }
-    add_launches(2);
+    add_launches(1);
     rc = check_launch("attn_bwd(tcgen05)");
     if (rc) return rc;
     return attn_bwd_post(p.dSrc, p.ctx, p.W, p.dW, p.dCtx, p.B, IDF, p.cdf, p.L, st);
@@ -581,6 +580,12 @@ int dispatch_ga(const void* x, const void* g, void* dX, const Tc5BwdParams& p, c
 }
 
 }  // namespace
+
+int attn_bwd_zero(float* dSrc, size_t n_src, float* dW, size_t n_dw, cudaStream_t st) {
+    k_zero_tc5<<<64, 256, 0, st>>>(dSrc, n_src, dW, n_dw);
+    add_launches(1);
+    return check_launch("attn_bwd(zero)");
+}
 
 int attn_bwd_post(const float* dSrc, const float* ctx, const float* W, float* dW, float* dCtx, int B, int idf, int cdf,
                   int L, cudaStream_t st) {

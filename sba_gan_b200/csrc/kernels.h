@@ -35,6 +35,8 @@ int tc5_attn_fwd(const void* x, const float* ctx, const float* W, const uint8_t*
 
 // dW (+)= sum_b dSrc[b] . ctx[b]^T (dW zeroed by the caller's launch sequence) and dCtx[b] = W^T . dSrc[b];
 // launched as a programmatic dependent of the kernel that produced dSrc
+// zero-fill grid in front of a backward kernel (which waits for it with griddepcontrol.wait before its first atomic)
+int attn_bwd_zero(float* dSrc, size_t n_src, float* dW, size_t n_dw, cudaStream_t st);
 int attn_bwd_post(const float* dSrc, const float* ctx, const float* W, float* dW, float* dCtx, int B, int idf, int cdf,
                   int L, cudaStream_t st);
 bool tc5_bwd_supports(const AttnShape& s);     // bf16 tensors for now; fp32 backward stays on the mma.sync family

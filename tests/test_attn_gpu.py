@@ -18,12 +18,21 @@ pytestmark = pytest.mark.gpu
 TOL_FWD_F32 = 1e-5
 TOL_GRAD_F32 = 1e-4
 TOL_BF16 = 2e-2
-ALGOS = ["simt", "mma"]
+ALGOS = ["simt", "mma", "tc5"]
 
 
 def _mma_ok(idf, L, Q, B=1):
     """shapes the tensor-core family covers (sba::mma_supports); others must be refused."""
     return idf in (32, 48) and 9 <= L <= 32 and Q % 128 == 0
+
+
+def _tc5_ok(idf, L, Q, cdf=256):
+    """shapes the tcgen05 family covers (sba::tc5_supports); others must be refused."""
+    return idf in (32, 48, 64) and 1 <= L <= 32 and Q % 128 == 0 and cdf % 16 == 0
+
+
+def _covered(algo, idf, L, Q):
+    return {"mma": _mma_ok, "tc5": _tc5_ok}.get(algo, lambda *a: True)(idf, L, Q)
 
 
 def _module(idf, cdf, weight, dtype=torch.float32, algo="auto", mask_mode="reference"):
@@ -63,8 +72,8 @@ def _sub(name, t):
 @pytest.mark.parametrize("name", list(ATTN_CASES))
 def test_matches_reference_golden(golden_dir, name, algo):
     B, idf, cdf, L, ih, iw, seed, masked, with_ga = ATTN_CASES[name]
-    if algo == "mma" and not _mma_ok(idf, L, ih * iw):
-        pytest.skip("shape not covered by the tensor-core family")
+    if not _covered(algo, idf, L, ih * iw):
+        pytest.skip("shape not covered by this kernel family")
     g = np.load(os.path.join(golden_dir, f"{name}_f32.npz"))
     d = synth_attention_inputs(B, idf, cdf, L, ih, iw, seed=seed, with_g_attn=with_ga)
     out = _run(d, masked, algo)
@@ -99,8 +108,8 @@ SWEEP = [
 @pytest.mark.parametrize("spec", SWEEP)
 def test_shape_sweep_vs_oracle(spec, algo):
     B, idf, L, ih, iw, masked, mask_mode, with_ga = spec
-    if algo == "mma" and not _mma_ok(idf, L, ih * iw):
-        pytest.skip("shape not covered by the tensor-core family")
+    if not _covered(algo, idf, L, ih * iw):
+        pytest.skip("shape not covered by this kernel family")
     d = synth_attention_inputs(B, idf, 256, L, ih, iw, seed=100 + B + idf + L, with_g_attn=with_ga, min_len=1)
     out = _run(d, masked, algo, mask_mode=mask_mode)
     d64 = {k: (v.double() if v.is_floating_point() else v) for k, v in d.items()}
@@ -143,8 +152,8 @@ def test_bf16_io(spec, algo):
     """bf16 tensors, fp32 arithmetic.  Oracle = fp32 reference maths on the bf16-rounded
     inputs (SURVEY.md §8 parity note); tolerance 2e-2."""
     B, idf, L, ih, iw, masked = spec
-    if algo == "mma" and not _mma_ok(idf, L, ih * iw):
-        pytest.skip("shape not covered by the tensor-core family")
+    if not _covered(algo, idf, L, ih * iw):
+        pytest.skip("shape not covered by this kernel family")
     d = synth_attention_inputs(B, idf, 256, L, ih, iw, seed=7, with_g_attn=True)
     out = _run(d, masked, algo, dtype=torch.bfloat16)
     r = {k: (v.to(torch.bfloat16).double() if v.is_floating_point() else v) for k, v in d.items()}
@@ -188,12 +197,13 @@ def test_sticky_mask_and_eval_mode():
     assert c1.shape == (4, 32, 8, 8) and a1.shape == (4, 18, 8, 8)
 
 
-def test_mma_refuses_uncovered_shapes():
+@pytest.mark.parametrize("algo", ["mma", "tc5"])
+def test_tensor_core_families_refuse_uncovered_shapes(algo):
     from sba_gan_b200 import word_region_attention
     x = torch.zeros(2, 32, 4, 4, device="cuda")
     w = torch.zeros(32, 256, 1, 1, device="cuda")
     with pytest.raises(RuntimeError, match="does not cover"):
-        word_region_attention(x, torch.zeros(2, 256, 12, device="cuda"), w, algo="mma")
+        word_region_attention(x, torch.zeros(2, 256, 12, device="cuda"), w, algo=algo)
 
 
 def test_error_behaviour():
