@@ -104,27 +104,31 @@ __global__ void __launch_bounds__(256) k_bwd_post_tc5(const float* __restrict__ 
     asm volatile("griddepcontrol.wait;" ::: "memory");
     const int tid = threadIdx.x;
     if ((int)blockIdx.x < n_dw) {
-        float* ds = sm;                  // [idf][L]
-        float* cs = sm + idf * L;        // [8][L]
+        // up to 4 samples are staged per round (one memory round trip each): [4][idf][L] then [4][8][L]
+        float* ds = sm;
+        float* cs = sm + 4 * idf * L;
         const int cg = blockIdx.x >> 4, grp = blockIdx.x & 15;
         const int c0 = cg * 8, nc = cdf - c0 < 8 ? cdf - c0 : 8;
         const int b_lo = (B * grp) >> 4, b_hi = (B * (grp + 1)) >> 4;
         const int per = (idf * 8 + blockDim.x - 1) / blockDim.x;     // outputs per thread (1 for idf <= 32)
         float acc[4] = {0.f, 0.f, 0.f, 0.f};
-        for (int b = b_lo; b < b_hi; ++b) {
+        for (int bb = b_lo; bb < b_hi; bb += 4) {
+            const int nb = b_hi - bb < 4 ? b_hi - bb : 4;
             __syncthreads();
-            for (int o = tid; o < idf * L; o += blockDim.x) ds[o] = __ldcg(dSrc + (size_t)b * idf * L + o);
-            for (int o = tid; o < nc * L; o += blockDim.x) cs[o] = __ldg(ctx + ((size_t)b * cdf + c0) * L + o);
+            for (int o = tid; o < nb * idf * L; o += blockDim.x) ds[o] = __ldcg(dSrc + (size_t)bb * idf * L + o);
+            for (int o = tid; o < nb * nc * L; o += blockDim.x) {
+                const int s = o / (nc * L), r = o - s * (nc * L);
+                cs[s * 8 * L + r] = __ldg(ctx + ((size_t)(bb + s) * cdf + c0) * L + r);
+            }
             __syncthreads();
             for (int k = 0; k < per && k < 4; ++k) {
                 const int ic = tid + k * blockDim.x;
-                if (ic < idf * 8) {
+                if (ic < idf * 8 && (ic & 7) < nc) {
                     const int i = ic >> 3, c = ic & 7;
-                    if (c < nc) {
-                        float a = acc[k];
-                        for (int l = 0; l < L; ++l) a = fmaf(ds[i * L + l], cs[c * L + l], a);
-                        acc[k] = a;
-                    }
+                    float a = acc[k];
+                    for (int s = 0; s < nb; ++s)
+                        for (int l = 0; l < L; ++l) a = fmaf(ds[(s * idf + i) * L + l], cs[(s * 8 + c) * L + l], a);
+                    acc[k] = a;
                 }
             }
         }
@@ -595,7 +599,7 @@ int attn_bwd_post(const float* dSrc, const float* ctx, const float* W, float* dW
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(256);
-    cfg.dynamicSmemBytes = (size_t)(idf + 8) * L * sizeof(float);
+    cfg.dynamicSmemBytes = (size_t)4 * (idf + 8) * L * sizeof(float);
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;

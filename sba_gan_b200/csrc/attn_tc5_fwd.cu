@@ -145,22 +145,33 @@ __global__ void __launch_bounds__(128) k_project_tc5(const float* __restrict__ c
     for (int sub = 0; sub < kq; sub += 64) {
         const int kc = kq - sub < 64 ? kq - sub : 64;  // multiple of 4
         const int c0 = cbeg + sub;
+        // one memory round trip: this lane's share of the W slice and its 64 ctx values are all requested
+        // before anything is consumed
+        float4 wq[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int o = lane + 32 * r;
+            const int row = o / (kc / 4), c4 = o - row * (kc / 4);
+            wq[r] = (o < 8 * (kc / 4)) ? __ldg(reinterpret_cast<const float4*>(W + (size_t)(i0 + row) * cdf + c0) + c4)
+                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        float v[64];
+#pragma unroll
+        for (int c = 0; c < 64; ++c) v[c] = (c < kc) ? __ldg(cb + (size_t)(c0 + c) * L) : 0.f;
         __syncwarp();
-        for (int o = lane; o < 8 * (kc / 4); o += 32) {
-            const int r = o / (kc / 4), c4 = o - r * (kc / 4);
-            reinterpret_cast<float4*>(&w_s[warp][r][0])[c4] =
-                __ldg(reinterpret_cast<const float4*>(W + (size_t)(i0 + r) * cdf + c0) + c4);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int o = lane + 32 * r;
+            const int row = o / (kc / 4), c4 = o - row * (kc / 4);
+            if (o < 8 * (kc / 4)) reinterpret_cast<float4*>(&w_s[warp][row][0])[c4] = wq[r];
         }
         __syncwarp();
-        for (int h = 0; h < kc; h += 32) {
-            float v[32];
 #pragma unroll
-            for (int c = 0; c < 32; ++c) v[c] = (h + c < kc) ? __ldg(cb + (size_t)(c0 + h + c) * L) : 0.f;
-#pragma unroll
-            for (int c = 0; c < 32; c += 4) {
+        for (int c = 0; c < 64; c += 4) {
+            if (c < kc) {
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
-                    const float4 w4 = *reinterpret_cast<const float4*>(&w_s[warp][k][(h + c) & 63]);
+                    const float4 w4 = *reinterpret_cast<const float4*>(&w_s[warp][k][c]);
                     acc[k] = fmaf(w4.x, v[c], acc[k]);
                     acc[k] = fmaf(w4.y, v[c + 1], acc[k]);
                     acc[k] = fmaf(w4.z, v[c + 2], acc[k]);
