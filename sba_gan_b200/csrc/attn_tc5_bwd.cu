@@ -71,7 +71,7 @@ struct Tc5BwdCfg {
     static constexpr int MD = 2 * IDF <= 64 ? 64 : 128;         // M of the dSrc MMA
     static constexpr int COL_S = 0, COL_DP = 32, COL_DX = 0 /* aliases S */, COL_ACC = 64;
     static constexpr int TMEM_COLS = pow2_cols((IDF > 64 ? IDF : 64) + ND);
-    static constexpr int OUT_WARP_BYTES = IDF * 32 * ES;        // per-warp dX staging [channel][32 px]
+    static constexpr int OUT_WARP_BYTES = 16 * 32 * ES;         // per-warp dX staging [16 channels][32 px]
     static constexpr int SMEM_BYTES = NST * STAGE_BYTES + PB_BYTES + B1_BYTES + B2_BYTES + 4 * OUT_WARP_BYTES;
     static constexpr uint32_t IDESC1 = make_idesc(1, 1, 0, TQ, NS);      // A = tile, MN-major
     static constexpr uint32_t IDESC2 = make_idesc(1, 1, 0, TQ, IDF);     // A = dS rows of PB, MN-major
@@ -79,7 +79,6 @@ struct Tc5BwdCfg {
     static constexpr int CTAS_PER_SM = 512 / TMEM_COLS;
     static_assert(IDF % 16 == 0 && 2 * IDF <= 128, "idf must be a multiple of 16, at most 64");
     static_assert(LP <= 32 && IDF <= 64, "at most 32 words");
-    static_assert(4 * OUT_WARP_BYTES >= IDF * 32 * 4, "dX staging doubles as the epilogue's dSrc[b] buffer");
 };
 
 // zero dSrc, the per-sample counters and dW; the streaming kernel waits for this grid only before its
@@ -156,7 +155,7 @@ __device__ __forceinline__ void warp_arrive(uint32_t bar, int lane) {
 }
 
 template <int IDF, int NQ, bool HAS_GA>
-__global__ void __launch_bounds__(kThreads, Tc5BwdCfg<IDF, NQ>::CTAS_PER_SM > 3 ? 3 : Tc5BwdCfg<IDF, NQ>::CTAS_PER_SM)
+__global__ void __launch_bounds__(kThreads, Tc5BwdCfg<IDF, NQ>::CTAS_PER_SM)
     k_attn_bwd_tc5(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_g,
                    const __grid_constant__ CUtensorMap tm_dx, const Tc5BwdParams p) {
     using C = Tc5BwdCfg<IDF, NQ>;
@@ -164,9 +163,10 @@ __global__ void __launch_bounds__(kThreads, Tc5BwdCfg<IDF, NQ>::CTAS_PER_SM > 3 
     constexpr int LP = C::LP, RP = C::RP, NST = C::NST;
     constexpr float kLog2e = 1.4426950408889634f;
 
-    extern __shared__ unsigned char smem_raw[];
-    const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    unsigned char* sgen = smem_raw + (sbase - smem_u32(smem_raw));
+    // no static shared memory in this kernel: the dynamic segment starts 1024-byte aligned (swizzle atoms)
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    const uint32_t sbase = smem_u32(smem_raw);
+    unsigned char* sgen = smem_raw;
     const uint32_t s_st = sbase;                                  // [NST] staged g / x tiles
     const uint32_t s_pb = s_st + NST * C::STAGE_BYTES;            // PB: [64-px block][row][128 B]
     const uint32_t s_b1 = s_pb + C::PB_BYTES;                     // sourceT, rows = words
@@ -178,9 +178,15 @@ __global__ void __launch_bounds__(kThreads, Tc5BwdCfg<IDF, NQ>::CTAS_PER_SM > 3 
     unsigned char* g_out = g_b2 + C::B2_BYTES;
     uint32_t* mb_s = reinterpret_cast<uint32_t*>(g_out + 4 * C::OUT_WARP_BYTES);   // [B] caption mask words
 
-    __shared__ __align__(8) unsigned long long bar_x_full[NST], bar_x_empty[NST], bar_s_full, bar_ds_ready, bar_c_full,
-        bar_dx_free, bar_b_ready;
-    __shared__ uint32_t tmem_base_s;
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(mb_s + ((p.B + 1) & ~1));
+    unsigned long long* bar_x_full = bars;
+    unsigned long long* bar_x_empty = bars + NST;
+    unsigned long long& bar_s_full = bars[2 * NST];
+    unsigned long long& bar_ds_ready = bars[2 * NST + 1];
+    unsigned long long& bar_c_full = bars[2 * NST + 2];
+    unsigned long long& bar_dx_free = bars[2 * NST + 3];
+    unsigned long long& bar_b_ready = bars[2 * NST + 4];
+    uint32_t& tmem_base_s = *reinterpret_cast<uint32_t*>(bars + 2 * NST + 5);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int L = p.L, Q = p.Q, TPS = p.tiles_per_sample;
@@ -189,8 +195,10 @@ __global__ void __launch_bounds__(kThreads, Tc5BwdCfg<IDF, NQ>::CTAS_PER_SM > 3 
         asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
         p.trace[256 + 2 * blockIdx.x] = (long long)gt;
     }
+    if (p.trace != nullptr && blockIdx.x == 0 && tid == 64) p.trace[240] = clock64();
 
     if (tid == 0) {
+        if (sbase & 1023u) __trap();
 #pragma unroll
         for (int s = 0; s < NST; ++s) {
             mbar_init(smem_u32(&bar_x_full[s]), 1);
@@ -222,6 +230,7 @@ __global__ void __launch_bounds__(kThreads, Tc5BwdCfg<IDF, NQ>::CTAS_PER_SM > 3 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, tmem_base_s, 0);     // provably warp-uniform
+    if (p.trace != nullptr && blockIdx.x == 0 && tid == 64) p.trace[241] = clock64();
 
     const int w_begin = (int)(((long long)blockIdx.x * p.n_tiles) / gridDim.x);
     const int w_end = (int)(((long long)(blockIdx.x + 1) * p.n_tiles) / gridDim.x);
@@ -360,14 +369,31 @@ __global__ void __launch_bounds__(kThreads, Tc5BwdCfg<IDF, NQ>::CTAS_PER_SM > 3 
                 cur_b = b;
                 // ---- operands of sample b: B1[word][channel] = B2[channel][word] = srcT ----
                 const float* sb = p.srcT + (size_t)b * IDF * L;
-                for (int o = ct; o < IDF * L; o += kConsumers) {
-                    const int ch = o / L, l = o - ch * L;
-                    const __nv_bfloat16 v = __float2bfloat16_rn(__ldg(sb + o));
-                    *reinterpret_cast<__nv_bfloat16*>(g_b1 + kmajor_off<2>(l, ch, C::KCH1)) = v;
-                    *reinterpret_cast<__nv_bfloat16*>(g_b2 + kmajor_off<2>(ch, l, C::KCH2)) = v;
-                }
+                // thread -> (channel ct / 4 [+ 32 g], words (ct % 4) + 4 k): all loads of a thread are issued
+                // before the first is consumed (one L2 round trip), and no division by the runtime L
+                constexpr int NG = IDF / 32 + (IDF % 32 != 0), NK = LP / 4;
+                float sv[NG][NK];
+#pragma unroll
+                for (int g = 0; g < NG; ++g)
+#pragma unroll
+                    for (int k = 0; k < NK; ++k) {
+                        const int ch = (ct >> 2) + 32 * g, l = (ct & 3) + 4 * k;
+                        sv[g][k] = (ch < IDF && l < L) ? __ldg(sb + ch * L + l) : 0.f;
+                    }
+#pragma unroll
+                for (int g = 0; g < NG; ++g)
+#pragma unroll
+                    for (int k = 0; k < NK; ++k) {
+                        const int ch = (ct >> 2) + 32 * g, l = (ct & 3) + 4 * k;
+                        if (ch < IDF && l < L) {
+                            const __nv_bfloat16 v = __float2bfloat16_rn(sv[g][k]);
+                            *reinterpret_cast<__nv_bfloat16*>(g_b1 + kmajor_off<2>(l, ch, C::KCH1)) = v;
+                            *reinterpret_cast<__nv_bfloat16*>(g_b2 + kmajor_off<2>(ch, l, C::KCH2)) = v;
+                        }
+                    }
                 fence_proxy_async();
                 warp_arrive(smem_u32(&bar_b_ready), lane);
+                if (p.trace != nullptr && blockIdx.x == 0 && ct == 0 && j == 0) p.trace[242] = clock64();
             }
             const bool tr = p.trace != nullptr && blockIdx.x == 0 && ct == 0 && j < 16;
             if (tr) p.trace[j * 16 + 0] = clock64();
@@ -434,24 +460,26 @@ __global__ void __launch_bounds__(kThreads, Tc5BwdCfg<IDF, NQ>::CTAS_PER_SM > 3 
             mbar_wait(smem_u32(&bar_c_full), (uint32_t)j & 1u);
             tc_fence_after();
             if (tr) p.trace[j * 16 + 5] = clock64();
-            if (lane == 0) bulk_wait_read<0>();        // the previous dX store has finished reading the staging
-            __syncwarp();
 #pragma unroll
             for (int h = 0; h < IDF / 16; ++h) {
                 uint32_t cr[16];
                 tmem_ld<16>(tl + C::COL_DX + 16 * h, cr);
                 tmem_wait_ld();
+                if (h == IDF / 16 - 1) {
+                    tc_fence_before();
+                    warp_arrive(smem_u32(&bar_dx_free), lane);
+                    if (tr) p.trace[j * 16 + 6] = clock64();
+                }
+                if (lane == 0) bulk_wait_read<0>();    // the previous box store has finished reading the staging
+                __syncwarp();
 #pragma unroll
-                for (int i = 0; i < 16; ++i) go[(16 * h + i) * 32] = __float2bfloat16_rn(__uint_as_float(cr[i]));
-            }
-            tc_fence_before();
-            warp_arrive(smem_u32(&bar_dx_free), lane);
-            if (tr) p.trace[j * 16 + 6] = clock64();
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) {
-                tma_store_2d(&tm_dx, t * TQ + cw * 32, b * IDF, so);
-                bulk_commit();
+                for (int i = 0; i < 16; ++i) go[i * 32] = __float2bfloat16_rn(__uint_as_float(cr[i]));
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) {
+                    tma_store_2d(&tm_dx, t * TQ + cw * 32, b * IDF + 16 * h, so);
+                    bulk_commit();
+                }
             }
             if (tr) p.trace[j * 16 + 7] = clock64();
 
@@ -480,7 +508,7 @@ template <int IDF, int NQ, bool HAS_GA>
 int launch_bwd_tc5(const void* x, const void* g, void* dX, const Tc5BwdParams& p, cudaStream_t st) {
     using C = Tc5BwdCfg<IDF, NQ>;
     auto kern = k_attn_bwd_tc5<IDF, NQ, HAS_GA>;
-    const size_t smem = (size_t)C::SMEM_BYTES + (size_t)p.B * 4 + 1024 + 16;
+    const size_t smem = (size_t)C::SMEM_BYTES + (size_t)((p.B + 1) & ~1) * 4 + (2 * C::NST + 6) * 8;
     static int sms = 0;
     static size_t smem_set = 0;
     if (smem > 220 * 1024) {
@@ -501,14 +529,13 @@ int launch_bwd_tc5(const void* x, const void* g, void* dX, const Tc5BwdParams& p
     }
     int per_sm = (int)((227 * 1024) / (smem_set + 1024));
     if (per_sm > C::CTAS_PER_SM) per_sm = C::CTAS_PER_SM;
-    if (per_sm > 3) per_sm = 3;
     if (per_sm < 1) per_sm = 1;
     if (getenv("SBA_TC5_CTAS_PER_SM")) per_sm = atoi(getenv("SBA_TC5_CTAS_PER_SM"));
     const int max_ctas = sms * per_sm;
     CUtensorMap tm_x, tm_g, tm_dx;
     int rc = make_tile_map(&tm_x, x, SBA_BF16, p.B * IDF, p.Q, IDF, 64, true);
     if (!rc) rc = make_tile_map(&tm_g, g, SBA_BF16, p.B * IDF, p.Q, IDF, 64, true);
-    if (!rc) rc = make_tile_map(&tm_dx, dX, SBA_BF16, p.B * IDF, p.Q, IDF, 32, false);
+    if (!rc) rc = make_tile_map(&tm_dx, dX, SBA_BF16, p.B * IDF, p.Q, 16, 32, false);
     if (rc) return rc;
     const size_t n_src = (size_t)p.B * IDF * p.L + p.B + 1;       // dSrc and the counter words behind it
     rc = attn_bwd_zero(p.dSrc, n_src, p.dW, p.dW ? (size_t)IDF * p.cdf : 0, st);
@@ -548,6 +575,8 @@ int launch_bwd_tc5(const void* x, const void* g, void* dX, const Tc5BwdParams& p
                 fprintf(stderr, "  cta %4d: %7lld .. %7lld\n", k, h[256 + 2 * k] - t0, h[256 + 2 * k + 1] - t0);
         }
         const char* names[12] = {"top", "s_full", "ld_S", "math+PB", "ds_rdy", "c_full", "dX_stg", "store", "M:x_full", "M:mma1", "M:ds_rdy", "M:mma2"};
+        fprintf(stderr, "CTA 0: entry %lld, prologue done +%lld, B operands built +%lld, first tile top +%lld (cycles)\n", 0LL,
+                h[241] - h[240], h[242] - h[240], h[0] - h[240]);
         fprintf(stderr, "tile");
         for (int k = 0; k < 12; ++k) fprintf(stderr, " %9s", names[k]);
         fprintf(stderr, "   (cycles since the first stamp)\n");

@@ -404,21 +404,37 @@ __global__ void __launch_bounds__(kThreads, Tc5FwdCfg<T, IDF, NQ>::CTAS_PER_SM)
                 // (every MMA that read the previous sample's operands has completed: c_full of tile j-1)
                 cur_b = b;
                 const float* sb = p.srcT + (size_t)b * IDF * L;
-                for (int o = ct; o < IDF * L; o += kConsumers) {
-                    const int ch = o / L, l = o - ch * L;
-                    const float v = __ldcg(sb + o), v1 = v * kLog2e;
-                    const uint32_t o1 = kmajor_off<ES>(l, ch, C::KCH1), o2 = kmajor_off<ES>(ch, l, C::KCH2);
-                    if constexpr (F32) {
-                        const float h1 = tf32_rna(v1), h2 = tf32_rna(v);
-                        *reinterpret_cast<float*>(g_b1 + o1) = h1;
-                        *reinterpret_cast<float*>(g_b1 + C::B1_BYTES + o1) = tf32_rna(v1 - h1);
-                        *reinterpret_cast<float*>(g_b2 + o2) = h2;
-                        *reinterpret_cast<float*>(g_b2 + C::B2_BYTES + o2) = tf32_rna(v - h2);
-                    } else {
-                        *reinterpret_cast<__nv_bfloat16*>(g_b1 + o1) = __float2bfloat16_rn(v1);
-                        *reinterpret_cast<__nv_bfloat16*>(g_b2 + o2) = __float2bfloat16_rn(v);
+                // thread -> (channel ct / 4 [+ 32 g], words (ct % 4) + 4 k): all loads of a thread are issued
+                // before the first is consumed (one L2 round trip), and no division by the runtime L
+                constexpr int NG = IDF / 32 + (IDF % 32 != 0), NK = LP / 4;
+                float sv[NG][NK];
+#pragma unroll
+                for (int g = 0; g < NG; ++g)
+#pragma unroll
+                    for (int k = 0; k < NK; ++k) {
+                        const int ch = (ct >> 2) + 32 * g, l = (ct & 3) + 4 * k;
+                        sv[g][k] = (ch < IDF && l < L) ? __ldcg(sb + ch * L + l) : 0.f;
                     }
-                }
+#pragma unroll
+                for (int g = 0; g < NG; ++g)
+#pragma unroll
+                    for (int k = 0; k < NK; ++k) {
+                        const int ch = (ct >> 2) + 32 * g, l = (ct & 3) + 4 * k;
+                        if (ch < IDF && l < L) {
+                            const float v = sv[g][k], v1 = v * kLog2e;
+                            const uint32_t o1 = kmajor_off<ES>(l, ch, C::KCH1), o2 = kmajor_off<ES>(ch, l, C::KCH2);
+                            if constexpr (F32) {
+                                const float h1 = tf32_rna(v1), h2 = tf32_rna(v);
+                                *reinterpret_cast<float*>(g_b1 + o1) = h1;
+                                *reinterpret_cast<float*>(g_b1 + C::B1_BYTES + o1) = tf32_rna(v1 - h1);
+                                *reinterpret_cast<float*>(g_b2 + o2) = h2;
+                                *reinterpret_cast<float*>(g_b2 + C::B2_BYTES + o2) = tf32_rna(v - h2);
+                            } else {
+                                *reinterpret_cast<__nv_bfloat16*>(g_b1 + o1) = __float2bfloat16_rn(v1);
+                                *reinterpret_cast<__nv_bfloat16*>(g_b2 + o2) = __float2bfloat16_rn(v);
+                            }
+                        }
+                    }
                 fence_proxy_async();
                 warp_arrive(smem_u32(&bar_b_ready), lane);
             }
