@@ -31,6 +31,26 @@ namespace sba {
 namespace {
 using namespace tc5;
 
+// development aid (SBA_TC5_TIMELINE): globaltimer stamps of the kernels of consecutive backward calls
+__device__ unsigned long long g_timeline[16 * 8];
+__device__ __forceinline__ unsigned long long gtime() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ void tl_min(int slot) { if (slot >= 0) atomicMin(&g_timeline[slot], gtime()); }
+__device__ __forceinline__ void tl_max(int slot) { if (slot >= 0) atomicMax(&g_timeline[slot], gtime()); }
+
+// development aid: SBA_TC5_TIMELINE=1 stamps the kernels of calls 20..35 and prints them at call 36
+static int g_tl_call = 0;
+static int timeline_slot() {
+    static const bool on = getenv("SBA_TC5_TIMELINE") != nullptr;
+    if (!on) return -1;
+    const int c = g_tl_call - 20;
+    return (c >= 0 && c < 16) ? c * 8 : -1;
+}
+
+
 struct Tc5BwdParams {
     const float* srcT;
     const uint8_t* mask;
@@ -44,6 +64,7 @@ struct Tc5BwdParams {
     int tiles_per_sample;
     int n_tiles;
     long long* trace;     // development aid (SBA_TC5_TRACE): per-phase clock64 stamps of CTA 0, else NULL
+    int tl;               // development aid (SBA_TC5_TIMELINE): slot base in g_timeline, else -1
 };
 
 constexpr int pow2_cols(int n) { return n <= 32 ? 32 : n <= 64 ? 64 : n <= 128 ? 128 : n <= 256 ? 256 : 512; }
@@ -66,13 +87,14 @@ struct Tc5BwdCfg {
     static constexpr int KCH1 = IDF * ES / 16, KCH2 = K2 * ES / 16;
     static constexpr int B1_BYTES = NS * IDF * ES, B2_BYTES = IDF * K2 * ES;
     static constexpr int PB_KBLOCK = NR * 128;                  // bytes of one 64-pixel block of PB
-    static constexpr int PB_BYTES = NBOX * PB_KBLOCK;
-    static constexpr int NST = 2;
+    static constexpr int PB_BYTES = NBOX * PB_KBLOCK;           // one PB buffer; two of them alternate (software pipeline)
+    static constexpr int NST = 3;
     static constexpr int MD = 2 * IDF <= 64 ? 64 : 128;         // M of the dSrc MMA
-    static constexpr int COL_S = 0, COL_DP = 32, COL_DX = 0 /* aliases S */, COL_ACC = 64;
-    static constexpr int TMEM_COLS = pow2_cols((IDF > 64 ? IDF : 64) + ND);
-    static constexpr int OUT_WARP_BYTES = 16 * 32 * ES;         // per-warp dX staging [16 channels][32 px]
-    static constexpr int SMEM_BYTES = NST * STAGE_BYTES + PB_BYTES + B1_BYTES + B2_BYTES + 4 * OUT_WARP_BYTES;
+    // TMEM columns: two {S, dP} buffers (tile parity), dX, the dSrc accumulator
+    static constexpr int COL_S = 0, COL_DP = 32, COL_BUF = 64, COL_DX = 128, COL_ACC = 128 + IDF;
+    static constexpr int TMEM_COLS = pow2_cols(COL_ACC + ND);
+    static constexpr int OUT_WARP_BYTES = IDF * 32 * ES;        // per-warp dX staging [channel][32 px]
+    static constexpr int SMEM_BYTES = NST * STAGE_BYTES + 2 * PB_BYTES + B1_BYTES + B2_BYTES + 4 * OUT_WARP_BYTES;
     static constexpr uint32_t IDESC1 = make_idesc(1, 1, 0, TQ, NS);      // A = tile, MN-major
     static constexpr uint32_t IDESC2 = make_idesc(1, 1, 0, TQ, IDF);     // A = dS rows of PB, MN-major
     static constexpr uint32_t IDESC3 = make_idesc(1, 0, 0, MD, ND);      // A = [g ; x], B = PB, both K-major
@@ -83,70 +105,124 @@ struct Tc5BwdCfg {
 
 // zero dSrc, the per-sample counters and dW; the streaming kernel waits for this grid only before its
 // first atomic (griddepcontrol.wait), so the fill overlaps its prologue and first tiles
-__global__ void __launch_bounds__(256) k_zero_tc5(float* __restrict__ a, size_t na, float* __restrict__ b, size_t nb) {
+__global__ void __launch_bounds__(256) k_zero_tc5(float* __restrict__ a, size_t na, float* __restrict__ b, size_t nb, int tl) {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (threadIdx.x == 0) tl_min(tl);
     const size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x, step = (size_t)gridDim.x * blockDim.x;
     for (size_t i = i0; i < na; i += step) a[i] = 0.f;
     if (b != nullptr)
         for (size_t i = i0; i < nb; i += step) b[i] = 0.f;
+    if (threadIdx.x == 0) tl_max(tl < 0 ? tl : tl + 1);
 }
 
-// dW += sum_{b in group} dSrc[b] . ctx[b]^T for a [idf x 8] slice, dCtx[b] = W^T . dSrc[b]; a programmatic
+// dW += sum_{b in group} dSrc[b] . ctx[b]^T for a [idf x 32] slice, dCtx[b] = W^T . dSrc[b]; a programmatic
 // dependent of the streaming kernel (griddepcontrol.wait = that grid is complete and flushed).
-//   blocks [0, n_dw)          : (8 input channels c, one of 16 sample groups); thread = (i, c); the groups
-//                               meet in fp32 atomics on dW (16-way contention, dW zeroed by k_zero_tc5)
+//   blocks [0, n_dw)          : (32 input channels c, one of 64 sample groups).  The K = (sample, word) axis
+//                               of up to 4 samples is staged flat - ds [idf][K], cs [K][32 c] - so the inner
+//                               loop is branch-free: one broadcast LDS + one LDS.128 per 4 FMAs per thread
+//                               (thread = channel i x 4 channels c).  The 64 groups meet in fp32 atomics on
+//                               dW (dW zeroed by k_zero_tc5); many small blocks hide each other's latency.
 //   blocks [n_dw, n_dw + B)   : dCtx of one sample (only when words need a gradient)
+constexpr int kPostCS = 36;        // row stride (floats) of cs: 16-byte aligned rows, 4-bank skew
+constexpr int kPostDS = 132;       // row stride (floats) of ds: K <= 128, 4-bank skew between channels
+template <int IDF>
 __global__ void __launch_bounds__(256) k_bwd_post_tc5(const float* __restrict__ dSrc, const float* __restrict__ ctx,
                                                       const float* __restrict__ W, float* __restrict__ dW,
-                                                      float* __restrict__ dCtx, int B, int idf, int cdf, int L, int n_dw) {
-    extern __shared__ float sm[];
+                                                      float* __restrict__ dCtx, int B, int cdf, int L, int n_dw, int tl) {
+    extern __shared__ __align__(16) float sm[];
+    constexpr bool HI = IDF > 32;          // a thread owns channel i0 and, for idf > 32, i0 + 32
+    if (threadIdx.x == 0) tl_min(tl < 0 ? tl : tl + 6);
     asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (threadIdx.x == 0) tl_min(tl < 0 ? tl : tl + 4);
     const int tid = threadIdx.x;
     if ((int)blockIdx.x < n_dw) {
-        // up to 4 samples are staged per round (one memory round trip each): [4][idf][L] then [4][8][L]
-        float* ds = sm;
-        float* cs = sm + 4 * idf * L;
-        const int cg = blockIdx.x >> 4, grp = blockIdx.x & 15;
-        const int c0 = cg * 8, nc = cdf - c0 < 8 ? cdf - c0 : 8;
-        const int b_lo = (B * grp) >> 4, b_hi = (B * (grp + 1)) >> 4;
-        const int per = (idf * 8 + blockDim.x - 1) / blockDim.x;     // outputs per thread (1 for idf <= 32)
-        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        float* cs = sm;                          // [K <= 128][kPostCS]
+        float* ds = sm + 128 * kPostCS;          // [64][kPostDS]
+        const int cg = blockIdx.x >> 6, grp = blockIdx.x & 63;
+        const int c0 = cg * 32, nc = cdf - c0 < 32 ? cdf - c0 : 32;
+        const int b_lo = (B * grp) >> 6, b_hi = (B * (grp + 1)) >> 6;
+        const int i0 = tid >> 3, cq = (tid & 7) * 4;
+        const int row = tid >> 1, half = tid & 1;          // staging: thread = half a row of L words
+        float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
         for (int bb = b_lo; bb < b_hi; bb += 4) {
             const int nb = b_hi - bb < 4 ? b_hi - bb : 4;
+            const int K = nb * L;
             __syncthreads();
-            for (int o = tid; o < nb * idf * L; o += blockDim.x) ds[o] = __ldcg(dSrc + (size_t)bb * idf * L + o);
-            for (int o = tid; o < nb * nc * L; o += blockDim.x) {
-                const int s = o / (nc * L), r = o - s * (nc * L);
-                cs[s * 8 * L + r] = __ldg(ctx + ((size_t)(bb + s) * cdf + c0) * L + r);
+            // all loads of the round are issued before the first store (one memory round trip):
+            //   dSrc rows (sample s, channel i) - up to 4 x 64 = 256 rows, two passes of 128 rows
+            //   ctx rows  (sample s, channel c) - 4 x 32 = 128 rows
+            float dv[2][16], cv[16];
+#pragma unroll
+            for (int ps = 0; ps < (HI ? 2 : 1); ++ps) {
+                const int r = row + 128 * ps, sidx = r / IDF, i = r - sidx * IDF;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int l = half * 16 + j;
+                    dv[ps][j] = (sidx < nb && l < L) ? __ldcg(dSrc + ((size_t)(bb + sidx) * IDF + i) * L + l) : 0.f;
+                }
+            }
+            {
+                const int sidx = row >> 5, c = row & 31;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int l = half * 16 + j;
+                    cv[j] = (sidx < nb && c < nc && l < L) ? __ldg(ctx + ((size_t)(bb + sidx) * cdf + c0 + c) * L + l) : 0.f;
+                }
+            }
+#pragma unroll
+            for (int ps = 0; ps < (HI ? 2 : 1); ++ps) {
+                const int r = row + 128 * ps, sidx = r / IDF, i = r - sidx * IDF;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int l = half * 16 + j;
+                    if (sidx < nb && l < L) ds[i * kPostDS + sidx * L + l] = dv[ps][j];
+                }
+            }
+            {
+                const int sidx = row >> 5, c = row & 31;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int l = half * 16 + j;
+                    if (sidx < nb && l < L) cs[(sidx * L + l) * kPostCS + c] = cv[j];
+                }
             }
             __syncthreads();
-            for (int k = 0; k < per && k < 4; ++k) {
-                const int ic = tid + k * blockDim.x;
-                if (ic < idf * 8 && (ic & 7) < nc) {
-                    const int i = ic >> 3, c = ic & 7;
-                    float a = acc[k];
-                    for (int s = 0; s < nb; ++s)
-                        for (int l = 0; l < L; ++l) a = fmaf(ds[(s * idf + i) * L + l], cs[(s * 8 + c) * L + l], a);
-                    acc[k] = a;
+            const float* d0p = ds + i0 * kPostDS;
+            const float* ccol = cs + cq;
+#pragma unroll 8
+            for (int k = 0; k < K; ++k) {
+                const float4 c4 = *reinterpret_cast<const float4*>(ccol + k * kPostCS);
+                const float d0 = d0p[k];
+                acc[0][0] = fmaf(d0, c4.x, acc[0][0]); acc[0][1] = fmaf(d0, c4.y, acc[0][1]);
+                acc[0][2] = fmaf(d0, c4.z, acc[0][2]); acc[0][3] = fmaf(d0, c4.w, acc[0][3]);
+                if constexpr (HI) {
+                    const float d1 = d0p[32 * kPostDS + k];       // rows >= IDF are never staged; results discarded
+                    acc[1][0] = fmaf(d1, c4.x, acc[1][0]); acc[1][1] = fmaf(d1, c4.y, acc[1][1]);
+                    acc[1][2] = fmaf(d1, c4.z, acc[1][2]); acc[1][3] = fmaf(d1, c4.w, acc[1][3]);
                 }
             }
         }
-        for (int k = 0; k < per && k < 4; ++k) {
-            const int ic = tid + k * blockDim.x;
-            if (ic < idf * 8 && (ic & 7) < nc) atomicAdd(dW + (size_t)(ic >> 3) * cdf + c0 + (ic & 7), acc[k]);
+#pragma unroll
+        for (int h = 0; h < (HI ? 2 : 1); ++h) {
+            const int i = i0 + 32 * h;
+            if (i < IDF)
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (cq + k < nc) atomicAdd(dW + (size_t)i * cdf + c0 + cq + k, acc[h][k]);
         }
     } else {
         float* ds = sm;                  // [idf][L]
         const int b = blockIdx.x - n_dw;
-        for (int o = tid; o < idf * L; o += blockDim.x) ds[o] = __ldcg(dSrc + (size_t)b * idf * L + o);
+        for (int o = tid; o < IDF * L; o += blockDim.x) ds[o] = __ldcg(dSrc + (size_t)b * IDF * L + o);
         __syncthreads();
         for (int o = tid; o < cdf * L; o += blockDim.x) {
             const int c = o / L, l = o - c * L;
             float a = 0.f;
-            for (int i = 0; i < idf; ++i) a = fmaf(__ldg(W + (size_t)i * cdf + c), ds[i * L + l], a);
+            for (int i = 0; i < IDF; ++i) a = fmaf(__ldg(W + (size_t)i * cdf + c), ds[i * L + l], a);
             dCtx[(size_t)b * cdf * L + o] = a;
         }
     }
+    if (threadIdx.x == 0) tl_max(tl < 0 ? tl : tl + 5);
 }
 
 __device__ __forceinline__ void warp_arrive(uint32_t bar, int lane) {
@@ -169,11 +245,11 @@ __global__ void __launch_bounds__(kThreads, Tc5BwdCfg<IDF, NQ>::CTAS_PER_SM)
     unsigned char* sgen = smem_raw;
     const uint32_t s_st = sbase;                                  // [NST] staged g / x tiles
     const uint32_t s_pb = s_st + NST * C::STAGE_BYTES;            // PB: [64-px block][row][128 B]
-    const uint32_t s_b1 = s_pb + C::PB_BYTES;                     // sourceT, rows = words
+    const uint32_t s_b1 = s_pb + 2 * C::PB_BYTES;                 // sourceT, rows = words
     const uint32_t s_b2 = s_b1 + C::B1_BYTES;                     // sourceT, rows = channels
     const uint32_t s_out = s_b2 + C::B2_BYTES;                    // [4 warps] dX staging
     unsigned char* g_pb = sgen + NST * C::STAGE_BYTES;
-    unsigned char* g_b1 = g_pb + C::PB_BYTES;
+    unsigned char* g_b1 = g_pb + 2 * C::PB_BYTES;
     unsigned char* g_b2 = g_b1 + C::B1_BYTES;
     unsigned char* g_out = g_b2 + C::B2_BYTES;
     uint32_t* mb_s = reinterpret_cast<uint32_t*>(g_out + 4 * C::OUT_WARP_BYTES);   // [B] caption mask words
@@ -181,15 +257,20 @@ __global__ void __launch_bounds__(kThreads, Tc5BwdCfg<IDF, NQ>::CTAS_PER_SM)
     unsigned long long* bars = reinterpret_cast<unsigned long long*>(mb_s + ((p.B + 1) & ~1));
     unsigned long long* bar_x_full = bars;
     unsigned long long* bar_x_empty = bars + NST;
-    unsigned long long& bar_s_full = bars[2 * NST];
-    unsigned long long& bar_ds_ready = bars[2 * NST + 1];
-    unsigned long long& bar_c_full = bars[2 * NST + 2];
-    unsigned long long& bar_dx_free = bars[2 * NST + 3];
-    unsigned long long& bar_b_ready = bars[2 * NST + 4];
-    uint32_t& tmem_base_s = *reinterpret_cast<uint32_t*>(bars + 2 * NST + 5);
+    unsigned long long* bar_s_full = bars + 2 * NST;          // [2] by tile parity
+    unsigned long long* bar_s_free = bars + 2 * NST + 2;      // [2]
+    unsigned long long& bar_ds_ready = bars[2 * NST + 4];
+    unsigned long long& bar_c_full = bars[2 * NST + 5];
+    unsigned long long& bar_dx_free = bars[2 * NST + 6];
+    unsigned long long& bar_b_ready = bars[2 * NST + 7];
+    uint32_t& tmem_base_s = *reinterpret_cast<uint32_t*>(bars + 2 * NST + 8);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int L = p.L, Q = p.Q, TPS = p.tiles_per_sample;
+    // let the post kernel's blocks become resident wherever there is room; they park in griddepcontrol.wait
+    // until this grid has completed, which takes its launch latency off the critical path
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (tid == 0) tl_min(p.tl < 0 ? p.tl : p.tl + 2);
     if (p.trace != nullptr && tid == 0) {
         unsigned long long gt;
         asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
@@ -204,7 +285,11 @@ __global__ void __launch_bounds__(kThreads, Tc5BwdCfg<IDF, NQ>::CTAS_PER_SM)
             mbar_init(smem_u32(&bar_x_full[s]), 1);
             mbar_init(smem_u32(&bar_x_empty[s]), 1);
         }
-        mbar_init(smem_u32(&bar_s_full), 1);
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(smem_u32(&bar_s_full[s]), 1);
+            mbar_init(smem_u32(&bar_s_free[s]), 4);
+        }
         mbar_init(smem_u32(&bar_ds_ready), 4);
         mbar_init(smem_u32(&bar_c_full), 1);
         mbar_init(smem_u32(&bar_dx_free), 4);
@@ -223,7 +308,7 @@ __global__ void __launch_bounds__(kThreads, Tc5BwdCfg<IDF, NQ>::CTAS_PER_SM)
         }
     }
     // zero PB and the B operand buffers once: padding rows / words are never written again
-    for (int o = tid; o < (C::PB_BYTES + C::B1_BYTES + C::B2_BYTES) / 16; o += kThreads)
+    for (int o = tid; o < (2 * C::PB_BYTES + C::B1_BYTES + C::B2_BYTES) / 16; o += kThreads)
         reinterpret_cast<uint4*>(g_pb)[o] = make_uint4(0u, 0u, 0u, 0u);
     fence_proxy_async();
     tc_fence_before();
@@ -267,56 +352,75 @@ __global__ void __launch_bounds__(kThreads, Tc5BwdCfg<IDF, NQ>::CTAS_PER_SM)
         const uint32_t tk_lo = desc_lo(s_st, 16);                                  // [g ; x] as one K-major operand
         const uint32_t pbA_lo = desc_lo(s_pb + RP * 128, C::PB_KBLOCK), pbB_lo = desc_lo(s_pb, 16);
         const uint32_t b1_lo = desc_lo(s_b1, 128), b2_lo = desc_lo(s_b2, 128);
+        // MMA1(j): S, dP of tile j into the {S, dP} buffer of its parity
+        auto mma1 = [&](int j) {
+            const int stage = j % NST, buf = j & 1;
+            mbar_wait(smem_u32(&bar_x_full[stage]), (uint32_t)(j / NST) & 1u);
+            if (j >= 2) mbar_wait(smem_u32(&bar_s_free[buf]), (uint32_t)((j >> 1) - 1) & 1u);
+            tc_fence_after();
+            const uint32_t st_lo = (uint32_t)(stage * (C::STAGE_BYTES >> 4));
+            const uint32_t dS_ = tmem_base + C::COL_BUF * buf + C::COL_S, dP_ = tmem_base + C::COL_BUF * buf + C::COL_DP;
+            if (elect_one()) {
+#pragma unroll
+                for (int ks = 0; ks < C::KS1; ++ks) {
+                    const uint32_t ka = (uint32_t)(ks * 128), kb = (uint32_t)(ks * 16);
+                    umma_ss<false>(dS_, tx_lo + st_lo + ka, kTileMnHi, b1_lo + kb, kBHi1, C::IDESC1, ks > 0 ? 1u : 0u);
+                    umma_ss<false>(dP_, tg_lo + st_lo + ka, kTileMnHi, b1_lo + kb, kBHi1, C::IDESC1, ks > 0 ? 1u : 0u);
+                }
+                umma_commit(smem_u32(&bar_s_full[buf]));
+            }
+            __syncwarp();
+        };
+        // MMA2(j): dX = dS . B2 and acc (+)= [g ; x] . [P | dS] from PB[j & 1]
+        auto mma2 = [&](int j, bool first_of_sample) {
+            const int stage = j % NST;
+            mbar_wait(smem_u32(&bar_ds_ready), (uint32_t)j & 1u);
+            if (j > 0) mbar_wait(smem_u32(&bar_dx_free), (uint32_t)(j - 1) & 1u);      // dX(j-1) is in registers
+            tc_fence_after();
+            const uint32_t st_lo = (uint32_t)(stage * (C::STAGE_BYTES >> 4));
+            const uint32_t pb_off = (uint32_t)((j & 1) * (C::PB_BYTES >> 4));
+            if (elect_one()) {
+                // (A = dS rows of PB, MN-major: pixel blocks PB_KBLOCK apart)
+#pragma unroll
+                for (int ks = 0; ks < C::KS2; ++ks)
+                    umma_ss<false>(tmem_base + C::COL_DX, pbA_lo + pb_off + (uint32_t)(ks * 128), kTileMnHi,
+                                   b2_lo + (uint32_t)(ks * 16), kBHi2, C::IDESC2, ks > 0 ? 1u : 0u);
+                // (both K-major, K = pixels: 16 per step, 4 steps per 64-px block)
+#pragma unroll
+                for (int ks = 0; ks < C::KS3; ++ks)
+                    umma_ss<false>(tmem_base + C::COL_ACC,
+                                   tk_lo + st_lo + (uint32_t)((ks >> 2) * (2 * C::BOX_BYTES >> 4) + (ks & 3) * 2), kKHi,
+                                   pbB_lo + pb_off + (uint32_t)((ks >> 2) * (C::PB_KBLOCK >> 4) + (ks & 3) * 2), kKHi,
+                                   C::IDESC3, (ks > 0 || !first_of_sample) ? 1u : 0u);
+                umma_commit(smem_u32(&bar_x_empty[stage]));
+                umma_commit(smem_u32(&bar_c_full));
+            }
+            __syncwarp();
+        };
+        // Software pipeline: S/dP of tile j+1 are produced BEFORE the second-stage MMAs of tile j, so the
+        // consumers' softmax of tile j+1 overlaps MMA2(j).  At a sample boundary the pipeline drains: the
+        // operands of the next sample are rebuilt only after every MMA of this one has completed.
         int t = t0;
         uint32_t nb = 0;
+        if (n_local > 0) {
+            mbar_wait(smem_u32(&bar_b_ready), nb & 1u);
+            ++nb;
+            mma1(0);
+        }
         bool first_of_sample = true;
         for (int j = 0; j < n_local; ++j) {
-            const int stage = j % NST;
-            if (first_of_sample) {
-                mbar_wait(smem_u32(&bar_b_ready), nb & 1u);     // operands of this sample are in place
-                ++nb;
-            }
-            if (j > 0) mbar_wait(smem_u32(&bar_dx_free), (uint32_t)(j - 1) & 1u);   // dX(j-1) has left the S columns
-            mbar_wait(smem_u32(&bar_x_full[stage]), (uint32_t)(j / NST) & 1u);
-            tc_fence_after();
-            const bool tr = p.trace != nullptr && blockIdx.x == 0 && j < 16 && lane == 0;
-            if (tr) p.trace[j * 16 + 8] = clock64();
-            // MMA1: S = x^T . B1, dP = g^T . B1  (tiles are MN-major A operands: 64-px blocks 2 boxes apart)
-            const uint32_t st_lo = (uint32_t)(stage * (C::STAGE_BYTES >> 4));
-            if (elect_one()) {
-#pragma unroll
-            for (int ks = 0; ks < C::KS1; ++ks) {
-                const uint32_t ka = (uint32_t)(ks * 128), kb = (uint32_t)(ks * 16);
-                umma_ss<false>(tmem_base + C::COL_S, tx_lo + st_lo + ka, kTileMnHi, b1_lo + kb, kBHi1, C::IDESC1, ks > 0 ? 1u : 0u);
-                umma_ss<false>(tmem_base + C::COL_DP, tg_lo + st_lo + ka, kTileMnHi, b1_lo + kb, kBHi1, C::IDESC1, ks > 0 ? 1u : 0u);
-            }
-            umma_commit(smem_u32(&bar_s_full));
-            }
-            __syncwarp();
-            if (tr) p.trace[j * 16 + 9] = clock64();
-
-            mbar_wait(smem_u32(&bar_ds_ready), (uint32_t)j & 1u);
-            tc_fence_after();
-            if (tr) p.trace[j * 16 + 10] = clock64();
-            if (elect_one()) {
-            // MMA2a: dX = dS . B2  (A = dS rows of PB, MN-major: pixel blocks PB_KBLOCK apart)
-#pragma unroll
-            for (int ks = 0; ks < C::KS2; ++ks)
-                umma_ss<false>(tmem_base + C::COL_DX, pbA_lo + (uint32_t)(ks * 128), kTileMnHi, b2_lo + (uint32_t)(ks * 16),
-                               kBHi2, C::IDESC2, ks > 0 ? 1u : 0u);
-            // MMA2b: acc (+)= [g ; x] . [P | dS]  (both K-major, K = pixels: 16 per step, 4 steps per 64-px block)
-#pragma unroll
-            for (int ks = 0; ks < C::KS3; ++ks)
-                umma_ss<false>(tmem_base + C::COL_ACC, tk_lo + st_lo + (uint32_t)((ks >> 2) * (2 * C::BOX_BYTES >> 4) + (ks & 3) * 2),
-                               kKHi, pbB_lo + (uint32_t)((ks >> 2) * (C::PB_KBLOCK >> 4) + (ks & 3) * 2), kKHi, C::IDESC3,
-                               (ks > 0 || !first_of_sample) ? 1u : 0u);
-            umma_commit(smem_u32(&bar_x_empty[stage]));
-            umma_commit(smem_u32(&bar_c_full));
-            }
-            __syncwarp();
-            if (tr) p.trace[j * 16 + 11] = clock64();
+            const bool has_next = j + 1 < n_local;
+            const bool next_same = has_next && (t + 1 < TPS);
+            if (next_same) mma1(j + 1);
+            mma2(j, first_of_sample);
             first_of_sample = false;
-            if (++t == TPS) { t = 0; first_of_sample = true; }
+            if (has_next && !next_same) {
+                mbar_wait(smem_u32(&bar_b_ready), nb & 1u);     // operands of the next sample are in place
+                ++nb;
+                mma1(j + 1);
+                first_of_sample = true;
+            }
+            if (++t == TPS) t = 0;
         }
     } else {
         // --------------------------------- consumers: thread = pixel ----------------------------
@@ -363,61 +467,59 @@ __global__ void __launch_bounds__(kThreads, Tc5BwdCfg<IDF, NQ>::CTAS_PER_SM)
             }
         };
 
-        for (int j = 0; j < n_local; ++j) {
-            if (b != cur_b) {
-                if (cur_b >= 0) finish_sample(cur_b);   // every MMA of the previous sample has completed (c_full)
-                cur_b = b;
-                // ---- operands of sample b: B1[word][channel] = B2[channel][word] = srcT ----
-                const float* sb = p.srcT + (size_t)b * IDF * L;
-                // thread -> (channel ct / 4 [+ 32 g], words (ct % 4) + 4 k): all loads of a thread are issued
-                // before the first is consumed (one L2 round trip), and no division by the runtime L
-                constexpr int NG = IDF / 32 + (IDF % 32 != 0), NK = LP / 4;
-                float sv[NG][NK];
+        // operands of sample bb: B1[word][channel] = B2[channel][word] = srcT (every MMA that read the
+        // previous sample's operands must have completed)
+        auto build_operands = [&](int bb) {
+            const float* sb = p.srcT + (size_t)bb * IDF * L;
+            // thread -> (channel ct / 4 [+ 32 g], words (ct % 4) + 4 k): all loads of a thread are issued
+            // before the first is consumed (one L2 round trip), and no division by the runtime L
+            constexpr int NG = IDF / 32 + (IDF % 32 != 0), NK = LP / 4;
+            float sv[NG][NK];
 #pragma unroll
-                for (int g = 0; g < NG; ++g)
+            for (int g = 0; g < NG; ++g)
 #pragma unroll
-                    for (int k = 0; k < NK; ++k) {
-                        const int ch = (ct >> 2) + 32 * g, l = (ct & 3) + 4 * k;
-                        sv[g][k] = (ch < IDF && l < L) ? __ldg(sb + ch * L + l) : 0.f;
+                for (int k = 0; k < NK; ++k) {
+                    const int ch = (ct >> 2) + 32 * g, l = (ct & 3) + 4 * k;
+                    sv[g][k] = (ch < IDF && l < L) ? __ldg(sb + ch * L + l) : 0.f;
+                }
+#pragma unroll
+            for (int g = 0; g < NG; ++g)
+#pragma unroll
+                for (int k = 0; k < NK; ++k) {
+                    const int ch = (ct >> 2) + 32 * g, l = (ct & 3) + 4 * k;
+                    if (ch < IDF && l < L) {
+                        const __nv_bfloat16 v = __float2bfloat16_rn(sv[g][k]);
+                        *reinterpret_cast<__nv_bfloat16*>(g_b1 + kmajor_off<2>(l, ch, C::KCH1)) = v;
+                        *reinterpret_cast<__nv_bfloat16*>(g_b2 + kmajor_off<2>(ch, l, C::KCH2)) = v;
                     }
-#pragma unroll
-                for (int g = 0; g < NG; ++g)
-#pragma unroll
-                    for (int k = 0; k < NK; ++k) {
-                        const int ch = (ct >> 2) + 32 * g, l = (ct & 3) + 4 * k;
-                        if (ch < IDF && l < L) {
-                            const __nv_bfloat16 v = __float2bfloat16_rn(sv[g][k]);
-                            *reinterpret_cast<__nv_bfloat16*>(g_b1 + kmajor_off<2>(l, ch, C::KCH1)) = v;
-                            *reinterpret_cast<__nv_bfloat16*>(g_b2 + kmajor_off<2>(ch, l, C::KCH2)) = v;
-                        }
-                    }
-                fence_proxy_async();
-                warp_arrive(smem_u32(&bar_b_ready), lane);
-                if (p.trace != nullptr && blockIdx.x == 0 && ct == 0 && j == 0) p.trace[242] = clock64();
-            }
-            const bool tr = p.trace != nullptr && blockIdx.x == 0 && ct == 0 && j < 16;
-            if (tr) p.trace[j * 16 + 0] = clock64();
-            const int q = t * TQ + px;
+                }
+            fence_proxy_async();
+            warp_arrive(smem_u32(&bar_b_ready), lane);
+        };
+
+        // First stage of tile j (sample bj, tile tj, caption index capj): S, dP -> P, dS -> PB[j & 1].
+        // The caller signals ds_ready once the dX columns are free as well.
+        auto math = [&](int j, int bj, int tj, uint32_t capj) {
+            const int buf = j & 1;
+            const int q = tj * TQ + px;
             float ga[HAS_GA ? LP : 1];
             if constexpr (HAS_GA) {
-                const T* gp = static_cast<const T*>(p.ga) + (size_t)b * L * Q + q;
+                const T* gp = static_cast<const T*>(p.ga) + (size_t)bj * L * Q + q;
 #pragma unroll
                 for (int l = 0; l < LP; ++l) ga[l] = (l < L) ? __bfloat162float(gp[(size_t)l * Q]) : 0.f;
             }
-
             // ---- S and dP rows of this pixel ---------------------------------------------------------
-            mbar_wait(smem_u32(&bar_s_full), (uint32_t)j & 1u);
+            mbar_wait(smem_u32(&bar_s_full[buf]), (uint32_t)(j >> 1) & 1u);
             tc_fence_after();
-            if (tr) p.trace[j * 16 + 1] = clock64();
             uint32_t sr[LP], dr[LP];
-            tmem_ld<LP>(tl + C::COL_S, sr);
-            tmem_ld<LP>(tl + C::COL_DP, dr);
+            tmem_ld<LP>(tl + C::COL_BUF * buf + C::COL_S, sr);
+            tmem_ld<LP>(tl + C::COL_BUF * buf + C::COL_DP, dr);
             tmem_wait_ld();
-            if (tr) p.trace[j * 16 + 2] = clock64();
-
+            tc_fence_before();
+            warp_arrive(smem_u32(&bar_s_free[buf]), lane);
             // ---- P = masked softmax over words (recomputed; GlobalAttention.py:104-109) ---------------
             uint32_t mb = pad_bits;
-            if (p.mask != nullptr) mb |= mb_s[p.mask_mode == SBA_MASK_PER_SAMPLE ? (uint32_t)b : cap];
+            if (p.mask != nullptr) mb |= mb_s[p.mask_mode == SBA_MASK_PER_SAMPLE ? (uint32_t)bj : capj];
             float s[LP];
             float m = -INFINITY;
 #pragma unroll
@@ -443,50 +545,71 @@ __global__ void __launch_bounds__(kThreads, Tc5BwdCfg<IDF, NQ>::CTAS_PER_SM)
                 if constexpr (HAS_GA) d[l] += ga[l];
                 dot = fmaf(s[l], d[l], dot);
             }
-            // ---- P and dS into PB: rows [0, LP) and [RP, RP + LP), bf16, swizzled ------------------------
+            // ---- P and dS into PB[buf]: rows [0, LP) and [RP, RP + LP), bf16, swizzled --------------------
+            unsigned char* pb = pb_px + buf * C::PB_BYTES;
 #pragma unroll
             for (int l = 0; l < LP; ++l) {
                 const float ds = s[l] * (d[l] - dot);
-                *reinterpret_cast<__nv_bfloat16*>(pb_px + l * 128 + (pb_col ^ ((l & 7) << 4))) = __float2bfloat16_rn(s[l]);
-                *reinterpret_cast<__nv_bfloat16*>(pb_px + (RP + l) * 128 + (pb_col ^ ((l & 7) << 4))) = __float2bfloat16_rn(ds);
+                *reinterpret_cast<__nv_bfloat16*>(pb + l * 128 + (pb_col ^ ((l & 7) << 4))) = __float2bfloat16_rn(s[l]);
+                *reinterpret_cast<__nv_bfloat16*>(pb + (RP + l) * 128 + (pb_col ^ ((l & 7) << 4))) = __float2bfloat16_rn(ds);
             }
-            if (tr) p.trace[j * 16 + 3] = clock64();
             fence_proxy_async();
-            tc_fence_before();
-            warp_arrive(smem_u32(&bar_ds_ready), lane);
-            if (tr) p.trace[j * 16 + 4] = clock64();
+        };
 
-            // ---- dX row of this pixel: staged [channel][32 px] per warp, one TMA box store ---------------
+        if (n_local > 0) {
+            build_operands(b);
+            cur_b = b;
+            math(0, b, t, cap);
+            warp_arrive(smem_u32(&bar_ds_ready), lane);
+        }
+        for (int j = 0; j < n_local; ++j) {
+            const bool tr = p.trace != nullptr && blockIdx.x == 0 && ct == 0 && j < 16;
+            if (tr) p.trace[j * 16 + 0] = clock64();
+            // coordinates of tile j + 1
+            int bn = b, tn = t + 1;
+            if (tn == TPS) { tn = 0; ++bn; }
+            uint32_t capn = cap + step_mod;
+            if (capn >= Bu) capn -= Bu;
+            const bool has_next = j + 1 < n_local, next_same = has_next && bn == b;
+
+            if (next_same) math(j + 1, bn, tn, capn);          // overlaps MMA2(j)
+            if (tr) p.trace[j * 16 + 3] = clock64();
+
+            // ---- dX row of this pixel into registers; then the dX columns / PB are free again ------------
             mbar_wait(smem_u32(&bar_c_full), (uint32_t)j & 1u);
             tc_fence_after();
             if (tr) p.trace[j * 16 + 5] = clock64();
+            uint32_t cr[IDF];
+            tmem_ld<IDF>(tl + C::COL_DX, cr);
+            tmem_wait_ld();
+            tc_fence_before();
+            warp_arrive(smem_u32(&bar_dx_free), lane);
+            if (next_same) warp_arrive(smem_u32(&bar_ds_ready), lane);
+            if (tr) p.trace[j * 16 + 6] = clock64();
+            // ---- staged [channel][32 px] per warp, one TMA box store --------------------------------------
+            if (lane == 0) bulk_wait_read<0>();        // the previous dX store has finished reading the staging
+            __syncwarp();
 #pragma unroll
-            for (int h = 0; h < IDF / 16; ++h) {
-                uint32_t cr[16];
-                tmem_ld<16>(tl + C::COL_DX + 16 * h, cr);
-                tmem_wait_ld();
-                if (h == IDF / 16 - 1) {
-                    tc_fence_before();
-                    warp_arrive(smem_u32(&bar_dx_free), lane);
-                    if (tr) p.trace[j * 16 + 6] = clock64();
-                }
-                if (lane == 0) bulk_wait_read<0>();    // the previous box store has finished reading the staging
-                __syncwarp();
-#pragma unroll
-                for (int i = 0; i < 16; ++i) go[i * 32] = __float2bfloat16_rn(__uint_as_float(cr[i]));
-                fence_proxy_async();
-                __syncwarp();
-                if (lane == 0) {
-                    tma_store_2d(&tm_dx, t * TQ + cw * 32, b * IDF + 16 * h, so);
-                    bulk_commit();
-                }
+            for (int i = 0; i < IDF; ++i) go[i * 32] = __float2bfloat16_rn(__uint_as_float(cr[i]));
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+                tma_store_2d(&tm_dx, t * TQ + cw * 32, b * IDF, so);
+                bulk_commit();
             }
             if (tr) p.trace[j * 16 + 7] = clock64();
 
-            if (++t == TPS) { t = 0; ++b; }
-            cap += step_mod;
-            if (cap >= Bu) cap -= Bu;
+            if (has_next && !next_same) {
+                // sample boundary: every MMA of sample b has completed (c_full(j)) - flush, rebuild, restart
+                finish_sample(b);
+                build_operands(bn);
+                cur_b = bn;
+                math(j + 1, bn, tn, capn);
+                warp_arrive(smem_u32(&bar_ds_ready), lane);
+            }
+            b = bn; t = tn; cap = capn;
         }
+        if (n_local > 0) cur_b = b - (t == 0 ? 1 : 0);      // sample of the last processed tile
         if (cur_b >= 0) finish_sample(cur_b);
         if (lane == 0) bulk_wait<0>();
         tc_fence_before();
@@ -502,13 +625,14 @@ __global__ void __launch_bounds__(kThreads, Tc5BwdCfg<IDF, NQ>::CTAS_PER_SM)
         asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
         p.trace[256 + 2 * blockIdx.x + 1] = (long long)gt;
     }
+    if (tid == 0) tl_max(p.tl < 0 ? p.tl : p.tl + 3);
 }
 
 template <int IDF, int NQ, bool HAS_GA>
 int launch_bwd_tc5(const void* x, const void* g, void* dX, const Tc5BwdParams& p, cudaStream_t st) {
     using C = Tc5BwdCfg<IDF, NQ>;
     auto kern = k_attn_bwd_tc5<IDF, NQ, HAS_GA>;
-    const size_t smem = (size_t)C::SMEM_BYTES + (size_t)((p.B + 1) & ~1) * 4 + (2 * C::NST + 6) * 8;
+    const size_t smem = (size_t)C::SMEM_BYTES + (size_t)((p.B + 1) & ~1) * 4 + (2 * C::NST + 9) * 8;
     static int sms = 0;
     static size_t smem_set = 0;
     if (smem > 220 * 1024) {
@@ -535,7 +659,7 @@ int launch_bwd_tc5(const void* x, const void* g, void* dX, const Tc5BwdParams& p
     CUtensorMap tm_x, tm_g, tm_dx;
     int rc = make_tile_map(&tm_x, x, SBA_BF16, p.B * IDF, p.Q, IDF, 64, true);
     if (!rc) rc = make_tile_map(&tm_g, g, SBA_BF16, p.B * IDF, p.Q, IDF, 64, true);
-    if (!rc) rc = make_tile_map(&tm_dx, dX, SBA_BF16, p.B * IDF, p.Q, 16, 32, false);
+    if (!rc) rc = make_tile_map(&tm_dx, dX, SBA_BF16, p.B * IDF, p.Q, IDF, 32, false);
     if (rc) return rc;
     const size_t n_src = (size_t)p.B * IDF * p.L + p.B + 1;       // dSrc and the counter words behind it
     rc = attn_bwd_zero(p.dSrc, n_src, p.dW, p.dW ? (size_t)IDF * p.cdf : 0, st);
@@ -552,6 +676,7 @@ int launch_bwd_tc5(const void* x, const void* g, void* dX, const Tc5BwdParams& p
     cfg.attrs = attr;
     cfg.numAttrs = getenv("SBA_TC5_NO_PDL") ? 0 : 1;
     Tc5BwdParams pk = p;
+    pk.tl = timeline_slot();
     static long long* trace_buf = nullptr;
     if (getenv("SBA_TC5_TRACE")) {
         if (!trace_buf) cudaMalloc(&trace_buf, 4096 * sizeof(long long));
@@ -615,7 +740,28 @@ int dispatch_ga(const void* x, const void* g, void* dX, const Tc5BwdParams& p, c
 }  // namespace
 
 int attn_bwd_zero(float* dSrc, size_t n_src, float* dW, size_t n_dw, cudaStream_t st) {
-    k_zero_tc5<<<64, 256, 0, st>>>(dSrc, n_src, dW, n_dw);
+    if (getenv("SBA_DBG_SKIP_ZERO")) return SBA_OK;
+    if (getenv("SBA_TC5_TIMELINE")) {
+        ++g_tl_call;
+        if (g_tl_call == 20) {
+            unsigned long long init[16 * 8];
+            for (int i = 0; i < 16 * 8; ++i) init[i] = (i % 8 == 0 || i % 8 == 2 || i % 8 == 4 || i % 8 == 6) ? ~0ull : 0ull;
+            cudaMemcpyToSymbol(g_timeline, init, sizeof(init));
+        }
+        if (g_tl_call == 37) {
+            unsigned long long h[16 * 8];
+            cudaDeviceSynchronize();
+            cudaMemcpyFromSymbol(h, g_timeline, sizeof(h));
+            fprintf(stderr, "call: zero start..end | main start..end | post entry, past wait..end   (us since zero start of the first call)\n");
+            for (int c = 0; c < 16; ++c) {
+                const unsigned long long* r = h + c * 8;
+                auto us = [&](unsigned long long v) { return (double)(long long)(v - h[0]) * 1e-3; };
+                fprintf(stderr, "%3d: %8.2f..%8.2f | %8.2f..%8.2f | %8.2f, %8.2f..%8.2f\n", c, us(r[0]), us(r[1]), us(r[2]), us(r[3]),
+                        us(r[6]), us(r[4]), us(r[5]));
+            }
+        }
+    }
+    k_zero_tc5<<<64, 256, 0, st>>>(dSrc, n_src, dW, n_dw, timeline_slot());
     add_launches(1);
     return check_launch("attn_bwd(zero)");
 }
@@ -623,19 +769,35 @@ int attn_bwd_zero(float* dSrc, size_t n_src, float* dW, size_t n_dw, cudaStream_
 int attn_bwd_post(const float* dSrc, const float* ctx, const float* W, float* dW, float* dCtx, int B, int idf, int cdf,
                   int L, cudaStream_t st) {
     if (dW == nullptr && dCtx == nullptr) return SBA_OK;
-    const int n_dw = dW != nullptr ? 16 * ((cdf + 7) / 8) : 0;
+    if (getenv("SBA_DBG_SKIP_POST")) return SBA_OK;
+    const int n_dw = dW != nullptr ? 64 * ((cdf + 31) / 32) : 0;
     const int grid = n_dw + (dCtx != nullptr ? B : 0);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(256);
-    cfg.dynamicSmemBytes = (size_t)4 * (idf + 8) * L * sizeof(float);
+    cfg.dynamicSmemBytes = (size_t)(128 * kPostCS + 64 * kPostDS) * sizeof(float);       // 52 KB: above the default limit
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(k_bwd_post_tc5<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.dynamicSmemBytes);
+        cudaFuncSetAttribute(k_bwd_post_tc5<48>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.dynamicSmemBytes);
+        cudaFuncSetAttribute(k_bwd_post_tc5<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.dynamicSmemBytes);
+        attr_set = true;
+    }
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, k_bwd_post_tc5, dSrc, ctx, W, dW, dCtx, B, idf, cdf, L, n_dw);
+    const int tl = timeline_slot();
+    cudaError_t e;
+    if (idf == 32) e = cudaLaunchKernelEx(&cfg, k_bwd_post_tc5<32>, dSrc, ctx, W, dW, dCtx, B, cdf, L, n_dw, tl);
+    else if (idf == 48) e = cudaLaunchKernelEx(&cfg, k_bwd_post_tc5<48>, dSrc, ctx, W, dW, dCtx, B, cdf, L, n_dw, tl);
+    else if (idf == 64) e = cudaLaunchKernelEx(&cfg, k_bwd_post_tc5<64>, dSrc, ctx, W, dW, dCtx, B, cdf, L, n_dw, tl);
+    else {
+        set_error("attn_bwd(post): idf=%d not covered", idf);
+        return SBA_ERR_UNSUPPORTED;
+    }
     if (e != cudaSuccess) {
         set_error("attn_bwd(post): launch: %s", cudaGetErrorString(e));
         return SBA_ERR_CUDA;

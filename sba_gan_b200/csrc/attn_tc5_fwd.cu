@@ -125,49 +125,50 @@ struct Tc5FwdCfg {
 
 // srcT = W . ctx (the bias-free 1x1 conv_context, GlobalAttention.py:95-97) as a small grid in
 // front of the streaming kernel, chained with programmatic dependent launch: block = (sample,
-// 8 output channels); warp = one quarter of the cdf reduction, lane = word.  Everything a warp
-// needs is requested up front (its W slice through warp-private shared memory, 32 ctx rows at
-// a time in registers), so the kernel lasts about two memory round trips.
-__global__ void __launch_bounds__(128) k_project_tc5(const float* __restrict__ ctx, const float* __restrict__ W,
+// 8 output channels); warp = one eighth of the cdf reduction, lane = word.  Everything a warp
+// needs is requested up front (its W slice through warp-private shared memory, up to 32 ctx rows
+// in registers), so the kernel lasts about one memory round trip plus 256 FMAs per lane.
+__global__ void __launch_bounds__(256) k_project_tc5(const float* __restrict__ ctx, const float* __restrict__ W,
                                                      float* __restrict__ srcT, int idf, int cdf, int L) {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    __shared__ __align__(16) float w_s[4][8][64];
-    __shared__ float red_s[4][8][32];
+    __shared__ __align__(16) float w_s[8][8][32];
+    __shared__ float red_s[8][8][32];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int rg = idf / 8;
     const int b = blockIdx.x / rg, i0 = (blockIdx.x - b * rg) * 8;
-    const int kq = cdf / 4, cbeg = warp * kq;          // this warp's slice of the reduction (cdf % 16 == 0)
+    const int kq = cdf / 8 / 4 * 4 + ((cdf / 8) % 4 ? 4 : 0);          // slice length, rounded up to a multiple of 4
+    const int cbeg = warp * kq;                                        // (cdf % 16 == 0: slices tile cdf, the last may be short)
+    const int cend = cbeg + kq < cdf ? cbeg + kq : cdf;
     const int lw = lane < L ? lane : L - 1;
     const float* cb = ctx + (size_t)b * cdf * L + lw;
     float acc[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) acc[k] = 0.f;
-    for (int sub = 0; sub < kq; sub += 64) {
-        const int kc = kq - sub < 64 ? kq - sub : 64;  // multiple of 4
-        const int c0 = cbeg + sub;
-        // one memory round trip: this lane's share of the W slice and its 64 ctx values are all requested
-        // before anything is consumed
-        float4 wq[4];
+    for (int c0 = cbeg; c0 < cend; c0 += 32) {
+        const int kc = cend - c0 < 32 ? cend - c0 : 32;               // multiple of 4
+        // one memory round trip: this lane's share of the W slice (8 rows x kc) and its ctx values are all
+        // requested before anything is consumed
+        float4 wq[2];
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
+        for (int r = 0; r < 2; ++r) {
             const int o = lane + 32 * r;
             const int row = o / (kc / 4), c4 = o - row * (kc / 4);
             wq[r] = (o < 8 * (kc / 4)) ? __ldg(reinterpret_cast<const float4*>(W + (size_t)(i0 + row) * cdf + c0) + c4)
                                        : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        float v[64];
+        float v[32];
 #pragma unroll
-        for (int c = 0; c < 64; ++c) v[c] = (c < kc) ? __ldg(cb + (size_t)(c0 + c) * L) : 0.f;
+        for (int c = 0; c < 32; ++c) v[c] = (c < kc) ? __ldg(cb + (size_t)(c0 + c) * L) : 0.f;
         __syncwarp();
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
+        for (int r = 0; r < 2; ++r) {
             const int o = lane + 32 * r;
             const int row = o / (kc / 4), c4 = o - row * (kc / 4);
             if (o < 8 * (kc / 4)) reinterpret_cast<float4*>(&w_s[warp][row][0])[c4] = wq[r];
         }
         __syncwarp();
 #pragma unroll
-        for (int c = 0; c < 64; c += 4) {
+        for (int c = 0; c < 32; c += 4) {
             if (c < kc) {
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
@@ -183,9 +184,14 @@ __global__ void __launch_bounds__(128) k_project_tc5(const float* __restrict__ c
 #pragma unroll
     for (int k = 0; k < 8; ++k) red_s[warp][k][lane] = acc[k];
     __syncthreads();
-    for (int o = tid; o < 8 * 32; o += 128) {
-        const int k = o >> 5, l = o & 31;
-        if (l < L) srcT[((size_t)b * idf + i0 + k) * L + l] = red_s[0][k][l] + red_s[1][k][l] + red_s[2][k][l] + red_s[3][k][l];
+    {
+        const int k = tid >> 5, l = tid & 31;
+        if (l < L) {
+            float a = 0.f;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) a += red_s[w][k][l];
+            srcT[((size_t)b * idf + i0 + k) * L + l] = a;
+        }
     }
 }
 
@@ -592,7 +598,7 @@ int launch_fwd_tc5(const void* x, const Tc5FwdParams& p, int dtype, cudaStream_t
     if (!rc) rc = make_tile_map(&tma_c, p.c_code, dtype, p.B * IDF, p.Q, IDF, 32, false);
     if (rc) return rc;
     const int pgrid = p.B * (IDF / 8);
-    k_project_tc5<<<pgrid, 128, 0, st>>>(ctx, W, srcT, IDF, cdf, p.L);
+    k_project_tc5<<<pgrid, 256, 0, st>>>(ctx, W, srcT, IDF, cdf, p.L);
     rc = check_launch("project(tcgen05)");
     if (rc) return rc;
     const int grid = p.n_tiles < max_ctas ? p.n_tiles : max_ctas;
