@@ -145,11 +145,22 @@ def run_ours(args, rank, world, device):
             dws.append(dw)
         return dws
 
+    pending = []
+
     def exchange(dws):
+        """All-reduce of the conv_context weight gradients, overlapped with the next step the way DDP
+        overlaps its buckets with backward: issued asynchronously behind this step's kernels, waited for
+        when the next exchange is issued (and at the end of the timed region)."""
         if world > 1:
-            hs = [dist.all_reduce(t, async_op=True) for t in dws]
-            for h in hs:
+            for h in pending:
                 h.wait()
+            pending.clear()
+            pending.extend(dist.all_reduce(t, async_op=True) for t in dws)
+
+    def drain():
+        for h in pending:
+            h.wait()
+        pending.clear()
 
     def barrier():
         if world > 1:
@@ -160,6 +171,7 @@ def run_ours(args, rank, world, device):
     # sequence of launches, so replaying it removes the Python/launch latency between kernels.
     for k in range(max(args.warmup, 3)):
         exchange(step(k))
+    drain()
     barrier()
     graphs = []
     if not args.no_graph:
@@ -191,6 +203,7 @@ def run_ours(args, rank, world, device):
     e_start.record()
     for k in range(args.steps):
         run_step(k)
+    drain()
     e_stop.record()
     barrier()
     t_wall1 = time.time()

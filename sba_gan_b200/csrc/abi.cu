@@ -125,7 +125,7 @@ int sba_attn_bwd(const void* x, const float* ctx, const float* W, const uint8_t*
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const bool can_mma = mma_supports(s) && aligned16(x) && aligned16(g_c);
     const bool can_tc5 = tc5_bwd_supports(s) && aligned16(x) && aligned16(g_c) && aligned16(dX);
-    if ((algo == SBA_ALGO_TCGEN05 || algo == SBA_ALGO_AUTO) && can_tc5) return tc5_attn_bwd(x, ctx, W, srcT, mask, g_c, g_attn, dX, dSrc, dW, dCtx, s, st);
+    if ((algo == SBA_ALGO_TCGEN05 || algo == SBA_ALGO_AUTO) && can_tc5) return tc5_attn_bwd(x, ctx, W, srcT, mask, mask_bits, g_c, g_attn, dX, dSrc, dW, dCtx, s, st);
     if (algo == SBA_ALGO_MMA && !can_mma) {
         set_error("sba_attn_bwd: SBA_ALGO_MMA does not cover idf=%d L=%d Q=%d cdf=%d B=%d (or x / g_c is not 16-byte aligned)", idf, L, Q, cdf, B);
         return SBA_ERR_UNSUPPORTED;

@@ -54,6 +54,7 @@ static int timeline_slot() {
 struct Tc5BwdParams {
     const float* srcT;
     const uint8_t* mask;
+    const uint32_t* mask_bits;   // [B] caption mask words written by the forward (scratch)
     const void* ga;       // [B, L, Q] nullable
     float* dSrc;          // [B, idf, L]
     const float* ctx;     // [B, cdf, L]   (epilogue)
@@ -252,9 +253,8 @@ __global__ void __launch_bounds__(kThreads, Tc5BwdCfg<IDF, NQ>::CTAS_PER_SM)
     unsigned char* g_b1 = g_pb + 2 * C::PB_BYTES;
     unsigned char* g_b2 = g_b1 + C::B1_BYTES;
     unsigned char* g_out = g_b2 + C::B2_BYTES;
-    uint32_t* mb_s = reinterpret_cast<uint32_t*>(g_out + 4 * C::OUT_WARP_BYTES);   // [B] caption mask words
 
-    unsigned long long* bars = reinterpret_cast<unsigned long long*>(mb_s + ((p.B + 1) & ~1));
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(g_out + 4 * C::OUT_WARP_BYTES);
     unsigned long long* bar_x_full = bars;
     unsigned long long* bar_x_empty = bars + NST;
     unsigned long long* bar_s_full = bars + 2 * NST;          // [2] by tile parity
@@ -278,6 +278,12 @@ __global__ void __launch_bounds__(kThreads, Tc5BwdCfg<IDF, NQ>::CTAS_PER_SM)
     }
     if (p.trace != nullptr && blockIdx.x == 0 && tid == 64) p.trace[240] = clock64();
 
+    const int w_begin = (int)(((long long)blockIdx.x * p.n_tiles) / gridDim.x);
+    const int w_end = (int)(((long long)(blockIdx.x + 1) * p.n_tiles) / gridDim.x);
+    const int n_local = w_end - w_begin;
+    const int b0 = w_begin / TPS, t0 = w_begin - b0 * TPS;
+    const int n_pre = n_local < NST ? n_local : NST;       // tiles whose loads thread 0 issues before the prologue
+
     if (tid == 0) {
         if (sbase & 1023u) __trap();
 #pragma unroll
@@ -295,18 +301,25 @@ __global__ void __launch_bounds__(kThreads, Tc5BwdCfg<IDF, NQ>::CTAS_PER_SM)
         mbar_init(smem_u32(&bar_dx_free), 4);
         mbar_init(smem_u32(&bar_b_ready), 4);
         fence_barrier_init();
-        prefetch_tensormap(&tm_x);
-        prefetch_tensormap(&tm_g);
+        // the first ring of g / x tiles is requested before the rest of the prologue (TMEM allocation, operand
+        // buffers) so that its DRAM latency runs under it
+        {
+            int b = b0, t = t0;
+            for (int j = 0; j < n_pre; ++j) {
+                const uint32_t full = smem_u32(&bar_x_full[j]);
+                mbar_expect_tx(full, (uint32_t)C::STAGE_BYTES);
+                const uint32_t dst = s_st + j * C::STAGE_BYTES;
+#pragma unroll
+                for (int bx = 0; bx < C::NBOX; ++bx) {
+                    tma_load_2d(dst + (2 * bx) * C::BOX_BYTES, &tm_g, t * TQ + bx * C::BOX_PX, b * IDF, full);
+                    tma_load_2d(dst + (2 * bx + 1) * C::BOX_BYTES, &tm_x, t * TQ + bx * C::BOX_PX, b * IDF, full);
+                }
+                if (++t == TPS) { t = 0; ++b; }
+            }
+        }
         prefetch_tensormap(&tm_dx);
     }
     if (warp == kMmaWarp) tmem_alloc(smem_u32(&tmem_base_s), C::TMEM_COLS);
-    if (p.mask != nullptr) {
-        for (int cap = tid; cap < p.B; cap += kThreads) {
-            uint32_t bits = 0;
-            for (int l = 0; l < L; ++l) bits |= (p.mask[(size_t)cap * L + l] ? 1u : 0u) << l;
-            mb_s[cap] = bits;
-        }
-    }
     // zero PB and the B operand buffers once: padding rows / words are never written again
     for (int o = tid; o < (2 * C::PB_BYTES + C::B1_BYTES + C::B2_BYTES) / 16; o += kThreads)
         reinterpret_cast<uint4*>(g_pb)[o] = make_uint4(0u, 0u, 0u, 0u);
@@ -317,18 +330,15 @@ __global__ void __launch_bounds__(kThreads, Tc5BwdCfg<IDF, NQ>::CTAS_PER_SM)
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, tmem_base_s, 0);     // provably warp-uniform
     if (p.trace != nullptr && blockIdx.x == 0 && tid == 64) p.trace[241] = clock64();
 
-    const int w_begin = (int)(((long long)blockIdx.x * p.n_tiles) / gridDim.x);
-    const int w_end = (int)(((long long)(blockIdx.x + 1) * p.n_tiles) / gridDim.x);
-    const int n_local = w_end - w_begin;
-    const int b0 = w_begin / TPS, t0 = w_begin - b0 * TPS;
 
     if (warp == kProducerWarp) {
         // --------------------------------- TMA producer -----------------------------------------
         // (the whole warp runs the loop; one elected lane issues - see elect_one())
-        int b = b0, t = t0;
-        for (int j = 0; j < n_local; ++j) {
+        int b = b0, t = t0 + n_pre;
+        while (t >= TPS) { t -= TPS; ++b; }
+        for (int j = n_pre; j < n_local; ++j) {
             const int stage = j % NST;
-            if (j >= NST) mbar_wait(smem_u32(&bar_x_empty[stage]), (uint32_t)((j / NST) - 1) & 1u);
+            mbar_wait(smem_u32(&bar_x_empty[stage]), (uint32_t)((j / NST) - 1) & 1u);
             const uint32_t full = smem_u32(&bar_x_full[stage]);
             const uint32_t dst = s_st + stage * C::STAGE_BYTES;
             if (elect_one()) {
@@ -519,7 +529,7 @@ __global__ void __launch_bounds__(kThreads, Tc5BwdCfg<IDF, NQ>::CTAS_PER_SM)
             warp_arrive(smem_u32(&bar_s_free[buf]), lane);
             // ---- P = masked softmax over words (recomputed; GlobalAttention.py:104-109) ---------------
             uint32_t mb = pad_bits;
-            if (p.mask != nullptr) mb |= mb_s[p.mask_mode == SBA_MASK_PER_SAMPLE ? (uint32_t)bj : capj];
+            if (p.mask != nullptr) mb |= __ldg(p.mask_bits + (p.mask_mode == SBA_MASK_PER_SAMPLE ? (uint32_t)bj : capj));
             float s[LP];
             float m = -INFINITY;
 #pragma unroll
@@ -632,7 +642,7 @@ template <int IDF, int NQ, bool HAS_GA>
 int launch_bwd_tc5(const void* x, const void* g, void* dX, const Tc5BwdParams& p, cudaStream_t st) {
     using C = Tc5BwdCfg<IDF, NQ>;
     auto kern = k_attn_bwd_tc5<IDF, NQ, HAS_GA>;
-    const size_t smem = (size_t)C::SMEM_BYTES + (size_t)((p.B + 1) & ~1) * 4 + (2 * C::NST + 9) * 8;
+    const size_t smem = (size_t)C::SMEM_BYTES + (2 * C::NST + 9) * 8;
     static int sms = 0;
     static size_t smem_set = 0;
     if (smem > 220 * 1024) {
@@ -808,10 +818,11 @@ int attn_bwd_post(const float* dSrc, const float* ctx, const float* W, float* dW
 
 bool tc5_bwd_supports(const AttnShape& s) { return tc5_supports(s) && s.dtype == SBA_BF16; }
 
-int tc5_attn_bwd(const void* x, const float* ctx, const float* W, const float* srcT, const uint8_t* mask, const void* g_c,
+int tc5_attn_bwd(const void* x, const float* ctx, const float* W, const float* srcT, const uint8_t* mask,
+                 const uint32_t* mask_bits, const void* g_c,
                  const void* g_attn, void* dX, float* dSrc, float* dW, float* dCtx, const AttnShape& s, cudaStream_t st) {
     Tc5BwdParams p{};
-    p.srcT = srcT; p.mask = mask; p.ga = g_attn; p.dSrc = dSrc; p.ctx = ctx; p.W = W; p.dW = dW; p.dCtx = dCtx;
+    p.srcT = srcT; p.mask = mask; p.mask_bits = mask_bits; p.ga = g_attn; p.dSrc = dSrc; p.ctx = ctx; p.W = W; p.dW = dW; p.dCtx = dCtx;
     p.B = s.B; p.L = s.L; p.Q = s.Q; p.cdf = s.cdf; p.mask_mode = s.mask_mode;
     p.tiles_per_sample = s.Q / tc5::TQ;
     p.n_tiles = s.B * p.tiles_per_sample;

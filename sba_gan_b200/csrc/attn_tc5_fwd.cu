@@ -129,8 +129,15 @@ struct Tc5FwdCfg {
 // needs is requested up front (its W slice through warp-private shared memory, up to 32 ctx rows
 // in registers), so the kernel lasts about one memory round trip plus 256 FMAs per lane.
 __global__ void __launch_bounds__(256) k_project_tc5(const float* __restrict__ ctx, const float* __restrict__ W,
-                                                     float* __restrict__ srcT, int idf, int cdf, int L) {
+                                                     float* __restrict__ srcT, const uint8_t* __restrict__ mask,
+                                                     uint32_t* __restrict__ mask_bits, int idf, int cdf, int L) {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    // caption padding mask -> one 32-bit word per caption (bit l = word l is padding), by the first block of each sample
+    if (mask != nullptr && blockIdx.x % (idf / 8) == 0 && threadIdx.x < 32) {
+        const int cap = blockIdx.x / (idf / 8);
+        const uint32_t bits = __ballot_sync(0xffffffffu, (int)threadIdx.x < L && mask[(size_t)cap * L + threadIdx.x] != 0);
+        if (threadIdx.x == 0) mask_bits[cap] = bits;
+    }
     __shared__ __align__(16) float w_s[8][8][32];
     __shared__ float red_s[8][8][32];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -222,7 +229,6 @@ __global__ void __launch_bounds__(kThreads, Tc5FwdCfg<T, IDF, NQ>::CTAS_PER_SM)
     unsigned char* g_b1 = g_lo + C::NLO * C::STAGE_BYTES;
     unsigned char* g_b2 = g_b1 + C::NSPLIT * C::B1_BYTES;
     unsigned char* g_out = g_b2 + C::NSPLIT * C::B2_BYTES;
-    uint32_t* mb_s = reinterpret_cast<uint32_t*>(g_out + 4 * C::OUT_WARP_BYTES);   // [B] caption mask words
 
     __shared__ __align__(8) unsigned long long bar_x_full[NST], bar_x_empty[NST], bar_s_full[2], bar_s_free[2], bar_lo_ready,
         bar_p_ready, bar_c_full, bar_b_ready;
@@ -230,6 +236,11 @@ __global__ void __launch_bounds__(kThreads, Tc5FwdCfg<T, IDF, NQ>::CTAS_PER_SM)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int L = p.L, TPS = p.tiles_per_sample;
+    const int w_begin = (int)(((long long)blockIdx.x * p.n_tiles) / gridDim.x);
+    const int w_end = (int)(((long long)(blockIdx.x + 1) * p.n_tiles) / gridDim.x);
+    const int n_local = w_end - w_begin;
+    const int b0 = w_begin / TPS, t0 = w_begin - b0 * TPS;
+    const int n_pre = n_local < NST ? n_local : NST;       // tiles whose loads thread 0 issues before the prologue
 
     if (tid == 0) {
 #pragma unroll
@@ -247,19 +258,23 @@ __global__ void __launch_bounds__(kThreads, Tc5FwdCfg<T, IDF, NQ>::CTAS_PER_SM)
         mbar_init(smem_u32(&bar_c_full), 1);
         mbar_init(smem_u32(&bar_b_ready), 4);
         fence_barrier_init();
-        prefetch_tensormap(&tmx);
+        // the first ring of x tiles is requested before the rest of the prologue (TMEM allocation, operand
+        // buffers) so that its DRAM latency runs under it; x does not depend on the projection grid
+        {
+            int b = b0, t = t0;
+            for (int j = 0; j < n_pre; ++j) {
+                const uint32_t full = smem_u32(&bar_x_full[j]);
+                mbar_expect_tx(full, (uint32_t)C::STAGE_BYTES);
+#pragma unroll
+                for (int bx = 0; bx < C::NBOX; ++bx)
+                    tma_load_2d(s_x + j * C::STAGE_BYTES + bx * C::BOX_BYTES, &tmx, t * TQ + bx * C::BOX_PX, b * IDF, full);
+                if (++t == TPS) { t = 0; ++b; }
+            }
+        }
         prefetch_tensormap(&tma_attn);
         prefetch_tensormap(&tma_c);
     }
     if (warp == kMmaWarp) tmem_alloc(smem_u32(&tmem_base_s), C::TMEM_COLS);
-    if (p.mask != nullptr) {
-        for (int cap = tid; cap < p.B; cap += kThreads) {
-            uint32_t bits = 0;
-            for (int l = 0; l < L; ++l) bits |= (p.mask[(size_t)cap * L + l] ? 1u : 0u) << l;
-            mb_s[cap] = bits;
-            if (blockIdx.x == 0) p.mask_bits[cap] = bits;
-        }
-    }
     // zero the B operand buffers once: the padding (words >= L) is never written again
     for (int o = tid; o < C::NSPLIT * (C::B1_BYTES + C::B2_BYTES) / 16; o += kThreads)
         reinterpret_cast<uint4*>(g_b1)[o] = make_uint4(0u, 0u, 0u, 0u);
@@ -268,18 +283,15 @@ __global__ void __launch_bounds__(kThreads, Tc5FwdCfg<T, IDF, NQ>::CTAS_PER_SM)
     tc_fence_after();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, tmem_base_s, 0);     // provably warp-uniform
 
-    const int w_begin = (int)(((long long)blockIdx.x * p.n_tiles) / gridDim.x);
-    const int w_end = (int)(((long long)(blockIdx.x + 1) * p.n_tiles) / gridDim.x);
-    const int n_local = w_end - w_begin;
-    const int b0 = w_begin / TPS, t0 = w_begin - b0 * TPS;
 
     if (warp == kProducerWarp) {
         // --------------------------------- TMA producer -----------------------------------------
         // (the whole warp runs the loop; one elected lane issues - see elect_one())
-        int b = b0, t = t0;
-        for (int j = 0; j < n_local; ++j) {
+        int b = b0, t = t0 + n_pre;
+        while (t >= TPS) { t -= TPS; ++b; }
+        for (int j = n_pre; j < n_local; ++j) {
             const int stage = j % NST;
-            if (j >= NST) mbar_wait(smem_u32(&bar_x_empty[stage]), (uint32_t)((j / NST) - 1) & 1u);
+            mbar_wait(smem_u32(&bar_x_empty[stage]), (uint32_t)((j / NST) - 1) & 1u);
             const uint32_t full = smem_u32(&bar_x_full[stage]);
             const uint32_t dst = s_x + stage * C::STAGE_BYTES;
             if (elect_one()) {
@@ -457,7 +469,7 @@ __global__ void __launch_bounds__(kThreads, Tc5FwdCfg<T, IDF, NQ>::CTAS_PER_SM)
 
             // ---- mask (GlobalAttention.py:104-108) + softmax over words (:109) -----------------------
             uint32_t mb = pad_bits;
-            if (p.mask != nullptr) mb |= mb_s[p.mask_mode == SBA_MASK_PER_SAMPLE ? (uint32_t)b : cap];
+            if (p.mask != nullptr) mb |= __ldg(p.mask_bits + (p.mask_mode == SBA_MASK_PER_SAMPLE ? (uint32_t)b : cap));
             float s[LP];
             float m = -INFINITY;
 #pragma unroll
@@ -565,7 +577,7 @@ int launch_fwd_tc5(const void* x, const Tc5FwdParams& p, int dtype, cudaStream_t
     const int cdf = p.cdf;
     using C = Tc5FwdCfg<T, IDF, NQ>;
     auto kern = k_attn_fwd_tc5<T, IDF, NQ>;
-    const size_t smem = (size_t)C::SMEM_BYTES + (size_t)p.B * 4 + 1024 + 16;
+    const size_t smem = (size_t)C::SMEM_BYTES + 1024 + 16;
     static int sms = 0;
     static size_t smem_set = 0;
     if (smem > 220 * 1024) {
@@ -598,7 +610,7 @@ int launch_fwd_tc5(const void* x, const Tc5FwdParams& p, int dtype, cudaStream_t
     if (!rc) rc = make_tile_map(&tma_c, p.c_code, dtype, p.B * IDF, p.Q, IDF, 32, false);
     if (rc) return rc;
     const int pgrid = p.B * (IDF / 8);
-    k_project_tc5<<<pgrid, 256, 0, st>>>(ctx, W, srcT, IDF, cdf, p.L);
+    k_project_tc5<<<pgrid, 256, 0, st>>>(ctx, W, srcT, p.mask, p.mask_bits, IDF, cdf, p.L);
     rc = check_launch("project(tcgen05)");
     if (rc) return rc;
     const int grid = p.n_tiles < max_ctas ? p.n_tiles : max_ctas;

@@ -41,7 +41,8 @@ int attn_bwd_post(const float* dSrc, const float* ctx, const float* W, float* dW
                   int L, cudaStream_t st);
 bool tc5_bwd_supports(const AttnShape& s);     // bf16 tensors for now; fp32 backward stays on the mma.sync family
 // dSrc holds B*idf*L floats followed by B+1 scratch words, like mma_attn_bwd
-int tc5_attn_bwd(const void* x, const float* ctx, const float* W, const float* srcT, const uint8_t* mask, const void* g_c,
+int tc5_attn_bwd(const void* x, const float* ctx, const float* W, const float* srcT, const uint8_t* mask,
+                 const uint32_t* mask_bits, const void* g_c,
                  const void* g_attn, void* dX, float* dSrc, float* dW, float* dCtx, const AttnShape& s, cudaStream_t st);
 
 // words_loss.cu - fused DAMSM region-word similarity (kernel c) and its backward
