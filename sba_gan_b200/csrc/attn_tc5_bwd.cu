@@ -684,7 +684,7 @@ int launch_bwd_tc5(const void* x, const void* g, void* dX, const Tc5BwdParams& p
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = getenv("SBA_TC5_NO_PDL") ? 0 : 1;
+    cfg.numAttrs = 1;
     Tc5BwdParams pk = p;
     pk.tl = timeline_slot();
     static long long* trace_buf = nullptr;
@@ -750,7 +750,6 @@ int dispatch_ga(const void* x, const void* g, void* dX, const Tc5BwdParams& p, c
 }  // namespace
 
 int attn_bwd_zero(float* dSrc, size_t n_src, float* dW, size_t n_dw, cudaStream_t st) {
-    if (getenv("SBA_DBG_SKIP_ZERO")) return SBA_OK;
     if (getenv("SBA_TC5_TIMELINE")) {
         ++g_tl_call;
         if (g_tl_call == 20) {
@@ -779,7 +778,6 @@ int attn_bwd_zero(float* dSrc, size_t n_src, float* dW, size_t n_dw, cudaStream_
 int attn_bwd_post(const float* dSrc, const float* ctx, const float* W, float* dW, float* dCtx, int B, int idf, int cdf,
                   int L, cudaStream_t st) {
     if (dW == nullptr && dCtx == nullptr) return SBA_OK;
-    if (getenv("SBA_DBG_SKIP_POST")) return SBA_OK;
     const int n_dw = dW != nullptr ? 64 * ((cdf + 31) / 32) : 0;
     const int grid = n_dw + (dCtx != nullptr ? B : 0);
     cudaLaunchConfig_t cfg = {};

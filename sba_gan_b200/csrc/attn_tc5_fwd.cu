@@ -623,7 +623,7 @@ int launch_fwd_tc5(const void* x, const Tc5FwdParams& p, int dtype, cudaStream_t
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = getenv("SBA_TC5_NO_PDL") ? 0 : 1;
+    cfg.numAttrs = 1;
     cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmx, tma_attn, tma_c, p);
     if (e != cudaSuccess) {
         set_error("attn_fwd(tcgen05): launch: %s", cudaGetErrorString(e));
