@@ -68,6 +68,10 @@ struct Tc5BwdParams {
     int tl;               // development aid (SBA_TC5_TIMELINE): slot base in g_timeline, else -1
 };
 
+// producer warp, MMA warp, 4 first-stage ("math") warps, 4 second-stage ("epilogue") warps
+constexpr int kBwdThreads = 64 + 128 + 128;
+constexpr int kFirstEpilogueWarp = 6;
+
 constexpr int pow2_cols(int n) { return n <= 32 ? 32 : n <= 64 ? 64 : n <= 128 ? 128 : n <= 256 ? 256 : 512; }
 
 template <int IDF, int NQ>
@@ -232,7 +236,7 @@ __device__ __forceinline__ void warp_arrive(uint32_t bar, int lane) {
 }
 
 template <int IDF, int NQ, bool HAS_GA>
-__global__ void __launch_bounds__(kThreads, Tc5BwdCfg<IDF, NQ>::CTAS_PER_SM)
+__global__ void __launch_bounds__(kBwdThreads, Tc5BwdCfg<IDF, NQ>::CTAS_PER_SM)
     k_attn_bwd_tc5(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_g,
                    const __grid_constant__ CUtensorMap tm_dx, const Tc5BwdParams p) {
     using C = Tc5BwdCfg<IDF, NQ>;
@@ -263,7 +267,9 @@ __global__ void __launch_bounds__(kThreads, Tc5BwdCfg<IDF, NQ>::CTAS_PER_SM)
     unsigned long long& bar_c_full = bars[2 * NST + 5];
     unsigned long long& bar_dx_free = bars[2 * NST + 6];
     unsigned long long& bar_b_ready = bars[2 * NST + 7];
-    uint32_t& tmem_base_s = *reinterpret_cast<uint32_t*>(bars + 2 * NST + 8);
+    unsigned long long* bar_pb_free = bars + 2 * NST + 8;     // [2] MMA2 of that parity has completed (PB, operands)
+    unsigned long long& bar_acc_free = bars[2 * NST + 10];    // the dSrc accumulator of a finished sample has been read
+    uint32_t& tmem_base_s = *reinterpret_cast<uint32_t*>(bars + 2 * NST + 11);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int L = p.L, Q = p.Q, TPS = p.tiles_per_sample;
@@ -296,6 +302,9 @@ __global__ void __launch_bounds__(kThreads, Tc5BwdCfg<IDF, NQ>::CTAS_PER_SM)
             mbar_init(smem_u32(&bar_s_full[s]), 1);
             mbar_init(smem_u32(&bar_s_free[s]), 4);
         }
+        mbar_init(smem_u32(&bar_pb_free[0]), 1);
+        mbar_init(smem_u32(&bar_pb_free[1]), 1);
+        mbar_init(smem_u32(&bar_acc_free), 4);
         mbar_init(smem_u32(&bar_ds_ready), 4);
         mbar_init(smem_u32(&bar_c_full), 1);
         mbar_init(smem_u32(&bar_dx_free), 4);
@@ -321,7 +330,7 @@ __global__ void __launch_bounds__(kThreads, Tc5BwdCfg<IDF, NQ>::CTAS_PER_SM)
     }
     if (warp == kMmaWarp) tmem_alloc(smem_u32(&tmem_base_s), C::TMEM_COLS);
     // zero PB and the B operand buffers once: padding rows / words are never written again
-    for (int o = tid; o < (2 * C::PB_BYTES + C::B1_BYTES + C::B2_BYTES) / 16; o += kThreads)
+    for (int o = tid; o < (2 * C::PB_BYTES + C::B1_BYTES + C::B2_BYTES) / 16; o += kBwdThreads)
         reinterpret_cast<uint4*>(g_pb)[o] = make_uint4(0u, 0u, 0u, 0u);
     fence_proxy_async();
     tc_fence_before();
@@ -382,10 +391,15 @@ __global__ void __launch_bounds__(kThreads, Tc5BwdCfg<IDF, NQ>::CTAS_PER_SM)
             __syncwarp();
         };
         // MMA2(j): dX = dS . B2 and acc (+)= [g ; x] . [P | dS] from PB[j & 1]
+        uint32_t n_flush = 0;        // accumulator hand-backs waited for so far
         auto mma2 = [&](int j, bool first_of_sample) {
             const int stage = j % NST;
             mbar_wait(smem_u32(&bar_ds_ready), (uint32_t)j & 1u);
             if (j > 0) mbar_wait(smem_u32(&bar_dx_free), (uint32_t)(j - 1) & 1u);      // dX(j-1) is in registers
+            if (first_of_sample && j > 0) {                                            // the previous sample's accumulator
+                mbar_wait(smem_u32(&bar_acc_free), n_flush & 1u);                      // has been read out
+                ++n_flush;
+            }
             tc_fence_after();
             const uint32_t st_lo = (uint32_t)(stage * (C::STAGE_BYTES >> 4));
             const uint32_t pb_off = (uint32_t)((j & 1) * (C::PB_BYTES >> 4));
@@ -403,6 +417,7 @@ __global__ void __launch_bounds__(kThreads, Tc5BwdCfg<IDF, NQ>::CTAS_PER_SM)
                                    pbB_lo + pb_off + (uint32_t)((ks >> 2) * (C::PB_KBLOCK >> 4) + (ks & 3) * 2), kKHi,
                                    C::IDESC3, (ks > 0 || !first_of_sample) ? 1u : 0u);
                 umma_commit(smem_u32(&bar_x_empty[stage]));
+                umma_commit(smem_u32(&bar_pb_free[j & 1]));
                 umma_commit(smem_u32(&bar_c_full));
             }
             __syncwarp();
@@ -432,8 +447,10 @@ __global__ void __launch_bounds__(kThreads, Tc5BwdCfg<IDF, NQ>::CTAS_PER_SM)
             }
             if (++t == TPS) t = 0;
         }
-    } else {
-        // --------------------------------- consumers: thread = pixel ----------------------------
+    } else if (warp < kFirstEpilogueWarp) {
+        // --------------------------------- first-stage warps: thread = pixel --------------------
+        // S, dP -> P, dS -> PB.  They run ahead of the second stage by up to one tile (two {S, dP} buffers,
+        // two PB buffers) and rebuild the operands at sample boundaries.
         const int ct = tid - 64;
         const int cw = warp & 3;
         const int px = cw * 32 + lane;
@@ -441,86 +458,61 @@ __global__ void __launch_bounds__(kThreads, Tc5BwdCfg<IDF, NQ>::CTAS_PER_SM)
         const uint32_t pad_bits = (L < 32) ? ~((1u << L) - 1u) : 0u;
         const uint32_t Bu = (uint32_t)p.B;
         const uint32_t step_mod = (uint32_t)TQ % Bu;
+        // reference mask order: pixel n = b*Q + q uses caption n mod B (GlobalAttention.py:104-108)
         uint32_t cap = (uint32_t)(((unsigned long long)w_begin * TQ + px) % Bu);
         int b = b0, t = t0, cur_b = -1;
-        const uint32_t so = s_out + cw * C::OUT_WARP_BYTES;
-        T* go = reinterpret_cast<T*>(g_out + cw * C::OUT_WARP_BYTES) + lane;
         // PB element (row n, this pixel): block (px / 64), row n, 16-byte chunks XOR-swizzled with n & 7
         unsigned char* pb_px = g_pb + (px >> 6) * C::PB_KBLOCK;
         const uint32_t pb_col = (uint32_t)(px & 63) * 2;
-        bool waited_zero = false;
 
-        // Add this CTA's share of dSrc[bb] (the diagonal blocks of the TMEM accumulator) to global memory.
-        // Called by all consumer warps together once every MMA of the sample has completed.
-        auto finish_sample = [&](int bb) {
-            if (!waited_zero) {
-                asm volatile("griddepcontrol.wait;" ::: "memory");      // k_zero_tc5 has cleared dSrc / dW
-                waited_zero = true;
-            }
-            // accumulator row r of this lane: M = 64 -> lanes 0..15 of each quarter hold rows 16*cw + lane
-            const int row = C::MD == 64 ? 16 * cw + lane : 32 * cw + lane;
-            const bool valid = (C::MD == 64 ? lane < 16 : true) && row < 2 * IDF;
-            const bool is_x = row >= IDF;
-            const int ch = is_x ? row - IDF : row;
-            // column block: g rows take the P columns [0, LP), x rows the dS columns [RP, RP + LP)
-            uint32_t a0[LP], a1[LP];
-            tc_fence_after();
-            tmem_ld<LP>(tl + C::COL_ACC, a0);
-            tmem_ld<LP>(tl + C::COL_ACC + RP, a1);
-            tmem_wait_ld();
-            tc_fence_before();
-            if (valid) {
-                float* db = p.dSrc + ((size_t)bb * IDF + ch) * L;
-#pragma unroll
-                for (int l = 0; l < LP; ++l)
-                    if (l < L) atomicAdd(db + l, __uint_as_float(is_x ? a1[l] : a0[l]));
-            }
-        };
-
-        // operands of sample bb: B1[word][channel] = B2[channel][word] = srcT (every MMA that read the
-        // previous sample's operands must have completed)
-        auto build_operands = [&](int bb) {
-            const float* sb = p.srcT + (size_t)bb * IDF * L;
-            // thread -> (channel ct / 4 [+ 32 g], words (ct % 4) + 4 k): all loads of a thread are issued
-            // before the first is consumed (one L2 round trip), and no division by the runtime L
-            constexpr int NG = IDF / 32 + (IDF % 32 != 0), NK = LP / 4;
-            float sv[NG][NK];
-#pragma unroll
-            for (int g = 0; g < NG; ++g)
-#pragma unroll
-                for (int k = 0; k < NK; ++k) {
-                    const int ch = (ct >> 2) + 32 * g, l = (ct & 3) + 4 * k;
-                    sv[g][k] = (ch < IDF && l < L) ? __ldg(sb + ch * L + l) : 0.f;
-                }
-#pragma unroll
-            for (int g = 0; g < NG; ++g)
-#pragma unroll
-                for (int k = 0; k < NK; ++k) {
-                    const int ch = (ct >> 2) + 32 * g, l = (ct & 3) + 4 * k;
-                    if (ch < IDF && l < L) {
-                        const __nv_bfloat16 v = __float2bfloat16_rn(sv[g][k]);
-                        *reinterpret_cast<__nv_bfloat16*>(g_b1 + kmajor_off<2>(l, ch, C::KCH1)) = v;
-                        *reinterpret_cast<__nv_bfloat16*>(g_b2 + kmajor_off<2>(ch, l, C::KCH2)) = v;
-                    }
-                }
-            fence_proxy_async();
-            warp_arrive(smem_u32(&bar_b_ready), lane);
-        };
-
-        // First stage of tile j (sample bj, tile tj, caption index capj): S, dP -> P, dS -> PB[j & 1].
-        // The caller signals ds_ready once the dX columns are free as well.
-        auto math = [&](int j, int bj, int tj, uint32_t capj) {
+        for (int j = 0; j < n_local; ++j) {
             const int buf = j & 1;
-            const int q = tj * TQ + px;
+            if (b != cur_b) {
+                // ---- operands of sample b: B1[word][channel] = B2[channel][word] = srcT -----------------
+                // every MMA that read the previous sample's operands has completed: MMA2(j - 1)
+                if (j > 0) mbar_wait(smem_u32(&bar_pb_free[(j - 1) & 1]), (uint32_t)((j - 1) >> 1) & 1u);
+                cur_b = b;
+                const float* sb = p.srcT + (size_t)b * IDF * L;
+                // thread -> (channel ct / 4 [+ 32 g], words (ct % 4) + 4 k): all loads of a thread are issued
+                // before the first is consumed (one L2 round trip), and no division by the runtime L
+                constexpr int NG = IDF / 32 + (IDF % 32 != 0), NK = LP / 4;
+                float sv[NG][NK];
+#pragma unroll
+                for (int g = 0; g < NG; ++g)
+#pragma unroll
+                    for (int k = 0; k < NK; ++k) {
+                        const int ch = (ct >> 2) + 32 * g, l = (ct & 3) + 4 * k;
+                        sv[g][k] = (ch < IDF && l < L) ? __ldg(sb + ch * L + l) : 0.f;
+                    }
+#pragma unroll
+                for (int g = 0; g < NG; ++g)
+#pragma unroll
+                    for (int k = 0; k < NK; ++k) {
+                        const int ch = (ct >> 2) + 32 * g, l = (ct & 3) + 4 * k;
+                        if (ch < IDF && l < L) {
+                            const __nv_bfloat16 v = __float2bfloat16_rn(sv[g][k]);
+                            *reinterpret_cast<__nv_bfloat16*>(g_b1 + kmajor_off<2>(l, ch, C::KCH1)) = v;
+                            *reinterpret_cast<__nv_bfloat16*>(g_b2 + kmajor_off<2>(ch, l, C::KCH2)) = v;
+                        }
+                    }
+                fence_proxy_async();
+                warp_arrive(smem_u32(&bar_b_ready), lane);
+            }
+            const bool tr = p.trace != nullptr && blockIdx.x == 0 && ct == 0 && j < 16;
+            if (tr) p.trace[j * 16 + 0] = clock64();
+            const int q = t * TQ + px;
+            uint32_t mb = pad_bits;
+            if (p.mask != nullptr) mb |= __ldg(p.mask_bits + (p.mask_mode == SBA_MASK_PER_SAMPLE ? (uint32_t)b : cap));
             float ga[HAS_GA ? LP : 1];
             if constexpr (HAS_GA) {
-                const T* gp = static_cast<const T*>(p.ga) + (size_t)bj * L * Q + q;
+                const T* gp = static_cast<const T*>(p.ga) + (size_t)b * L * Q + q;
 #pragma unroll
                 for (int l = 0; l < LP; ++l) ga[l] = (l < L) ? __bfloat162float(gp[(size_t)l * Q]) : 0.f;
             }
             // ---- S and dP rows of this pixel ---------------------------------------------------------
             mbar_wait(smem_u32(&bar_s_full[buf]), (uint32_t)(j >> 1) & 1u);
             tc_fence_after();
+            if (tr) p.trace[j * 16 + 1] = clock64();
             uint32_t sr[LP], dr[LP];
             tmem_ld<LP>(tl + C::COL_BUF * buf + C::COL_S, sr);
             tmem_ld<LP>(tl + C::COL_BUF * buf + C::COL_DP, dr);
@@ -528,8 +520,6 @@ __global__ void __launch_bounds__(kThreads, Tc5BwdCfg<IDF, NQ>::CTAS_PER_SM)
             tc_fence_before();
             warp_arrive(smem_u32(&bar_s_free[buf]), lane);
             // ---- P = masked softmax over words (recomputed; GlobalAttention.py:104-109) ---------------
-            uint32_t mb = pad_bits;
-            if (p.mask != nullptr) mb |= __ldg(p.mask_bits + (p.mask_mode == SBA_MASK_PER_SAMPLE ? (uint32_t)bj : capj));
             float s[LP];
             float m = -INFINITY;
 #pragma unroll
@@ -556,6 +546,7 @@ __global__ void __launch_bounds__(kThreads, Tc5BwdCfg<IDF, NQ>::CTAS_PER_SM)
                 dot = fmaf(s[l], d[l], dot);
             }
             // ---- P and dS into PB[buf]: rows [0, LP) and [RP, RP + LP), bf16, swizzled --------------------
+            if (j >= 2) mbar_wait(smem_u32(&bar_pb_free[buf]), (uint32_t)((j >> 1) - 1) & 1u);    // MMA2(j - 2) is done with it
             unsigned char* pb = pb_px + buf * C::PB_BYTES;
 #pragma unroll
             for (int l = 0; l < LP; ++l) {
@@ -564,28 +555,25 @@ __global__ void __launch_bounds__(kThreads, Tc5BwdCfg<IDF, NQ>::CTAS_PER_SM)
                 *reinterpret_cast<__nv_bfloat16*>(pb + (RP + l) * 128 + (pb_col ^ ((l & 7) << 4))) = __float2bfloat16_rn(ds);
             }
             fence_proxy_async();
-        };
-
-        if (n_local > 0) {
-            build_operands(b);
-            cur_b = b;
-            math(0, b, t, cap);
             warp_arrive(smem_u32(&bar_ds_ready), lane);
-        }
-        for (int j = 0; j < n_local; ++j) {
-            const bool tr = p.trace != nullptr && blockIdx.x == 0 && ct == 0 && j < 16;
-            if (tr) p.trace[j * 16 + 0] = clock64();
-            // coordinates of tile j + 1
-            int bn = b, tn = t + 1;
-            if (tn == TPS) { tn = 0; ++bn; }
-            uint32_t capn = cap + step_mod;
-            if (capn >= Bu) capn -= Bu;
-            const bool has_next = j + 1 < n_local, next_same = has_next && bn == b;
-
-            if (next_same) math(j + 1, bn, tn, capn);          // overlaps MMA2(j)
             if (tr) p.trace[j * 16 + 3] = clock64();
 
-            // ---- dX row of this pixel into registers; then the dX columns / PB are free again ------------
+            if (++t == TPS) { t = 0; ++b; }
+            cap += step_mod;
+            if (cap >= Bu) cap -= Bu;
+        }
+    } else {
+        // --------------------------------- second-stage warps: thread = pixel -------------------
+        // dX row of the pixel -> staged [channel][32 px] per warp -> one TMA box store; at the end of a sample
+        // the diagonal blocks of the TMEM accumulator are added to dSrc[b] with fp32 atomics.
+        const int cw = warp & 3;
+        const uint32_t tl = tmem_base + ((uint32_t)(cw * 32) << 16);
+        const uint32_t so = s_out + cw * C::OUT_WARP_BYTES;
+        T* go = reinterpret_cast<T*>(g_out + cw * C::OUT_WARP_BYTES) + lane;
+        int b = b0, t = t0;
+        bool waited_zero = false;
+        for (int j = 0; j < n_local; ++j) {
+            const bool tr = p.trace != nullptr && blockIdx.x == 0 && warp == kFirstEpilogueWarp && lane == 0 && j < 16;
             mbar_wait(smem_u32(&bar_c_full), (uint32_t)j & 1u);
             tc_fence_after();
             if (tr) p.trace[j * 16 + 5] = clock64();
@@ -594,9 +582,7 @@ __global__ void __launch_bounds__(kThreads, Tc5BwdCfg<IDF, NQ>::CTAS_PER_SM)
             tmem_wait_ld();
             tc_fence_before();
             warp_arrive(smem_u32(&bar_dx_free), lane);
-            if (next_same) warp_arrive(smem_u32(&bar_ds_ready), lane);
             if (tr) p.trace[j * 16 + 6] = clock64();
-            // ---- staged [channel][32 px] per warp, one TMA box store --------------------------------------
             if (lane == 0) bulk_wait_read<0>();        // the previous dX store has finished reading the staging
             __syncwarp();
 #pragma unroll
@@ -609,18 +595,35 @@ __global__ void __launch_bounds__(kThreads, Tc5BwdCfg<IDF, NQ>::CTAS_PER_SM)
             }
             if (tr) p.trace[j * 16 + 7] = clock64();
 
-            if (has_next && !next_same) {
-                // sample boundary: every MMA of sample b has completed (c_full(j)) - flush, rebuild, restart
-                finish_sample(b);
-                build_operands(bn);
-                cur_b = bn;
-                math(j + 1, bn, tn, capn);
-                warp_arrive(smem_u32(&bar_ds_ready), lane);
+            const bool last_of_sample = (t + 1 == TPS) || (j + 1 == n_local);
+            if (last_of_sample) {
+                // every MMA of sample b issued by this CTA has completed (c_full(j)): add its share of dSrc[b]
+                if (!waited_zero) {
+                    asm volatile("griddepcontrol.wait;" ::: "memory");      // k_zero_tc5 has cleared dSrc / dW
+                    waited_zero = true;
+                }
+                // accumulator row r of this lane: M = 64 -> lanes 0..15 of each quarter hold rows 16*cw + lane
+                const int row = C::MD == 64 ? 16 * cw + lane : 32 * cw + lane;
+                const bool valid = (C::MD == 64 ? lane < 16 : true) && row < 2 * IDF;
+                const bool is_x = row >= IDF;
+                const int ch = is_x ? row - IDF : row;
+                // column block: g rows take the P columns [0, LP), x rows the dS columns [RP, RP + LP)
+                uint32_t a0[LP], a1[LP];
+                tc_fence_after();
+                tmem_ld<LP>(tl + C::COL_ACC, a0);
+                tmem_ld<LP>(tl + C::COL_ACC + RP, a1);
+                tmem_wait_ld();
+                tc_fence_before();
+                if (j + 1 < n_local) warp_arrive(smem_u32(&bar_acc_free), lane);     // the next sample may overwrite it
+                if (valid) {
+                    float* db = p.dSrc + ((size_t)b * IDF + ch) * L;
+#pragma unroll
+                    for (int l = 0; l < LP; ++l)
+                        if (l < L) atomicAdd(db + l, __uint_as_float(is_x ? a1[l] : a0[l]));
+                }
             }
-            b = bn; t = tn; cap = capn;
+            if (++t == TPS) { t = 0; ++b; }
         }
-        if (n_local > 0) cur_b = b - (t == 0 ? 1 : 0);      // sample of the last processed tile
-        if (cur_b >= 0) finish_sample(cur_b);
         if (lane == 0) bulk_wait<0>();
         tc_fence_before();
     }
@@ -642,7 +645,7 @@ template <int IDF, int NQ, bool HAS_GA>
 int launch_bwd_tc5(const void* x, const void* g, void* dX, const Tc5BwdParams& p, cudaStream_t st) {
     using C = Tc5BwdCfg<IDF, NQ>;
     auto kern = k_attn_bwd_tc5<IDF, NQ, HAS_GA>;
-    const size_t smem = (size_t)C::SMEM_BYTES + (2 * C::NST + 9) * 8;
+    const size_t smem = (size_t)C::SMEM_BYTES + (2 * C::NST + 12) * 8;
     static int sms = 0;
     static size_t smem_set = 0;
     if (smem > 220 * 1024) {
@@ -677,7 +680,7 @@ int launch_bwd_tc5(const void* x, const void* g, void* dX, const Tc5BwdParams& p
     const int grid = p.n_tiles < max_ctas ? p.n_tiles : max_ctas;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(kThreads);
+    cfg.blockDim = dim3(kBwdThreads);
     cfg.dynamicSmemBytes = smem_set;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
