@@ -136,10 +136,8 @@ __global__ void __launch_bounds__(256) k_bwd_post_tc5(const float* __restrict__ 
                                                       float* __restrict__ dCtx, int B, int cdf, int L, int n_dw, int tl) {
     extern __shared__ __align__(16) float sm[];
     constexpr bool HI = IDF > 32;          // a thread owns channel i0 and, for idf > 32, i0 + 32
-    if (threadIdx.x == 0) tl_min(tl < 0 ? tl : tl + 6);
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-    if (threadIdx.x == 0) tl_min(tl < 0 ? tl : tl + 4);
     const int tid = threadIdx.x;
+    if (threadIdx.x == 0) tl_min(tl < 0 ? tl : tl + 6);
     if ((int)blockIdx.x < n_dw) {
         float* cs = sm;                          // [K <= 128][kPostCS]
         float* ds = sm + 128 * kPostCS;          // [64][kPostDS]
@@ -149,14 +147,35 @@ __global__ void __launch_bounds__(256) k_bwd_post_tc5(const float* __restrict__ 
         const int i0 = tid >> 3, cq = (tid & 7) * 4;
         const int row = tid >> 1, half = tid & 1;          // staging: thread = half a row of L words
         float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+        bool waited = false;
         for (int bb = b_lo; bb < b_hi; bb += 4) {
             const int nb = b_hi - bb < 4 ? b_hi - bb : 4;
             const int K = nb * L;
             __syncthreads();
-            // all loads of the round are issued before the first store (one memory round trip):
-            //   dSrc rows (sample s, channel i) - up to 4 x 64 = 256 rows, two passes of 128 rows
-            //   ctx rows  (sample s, channel c) - 4 x 32 = 128 rows
-            float dv[2][16], cv[16];
+            // ctx rows (sample s, channel c) - 4 x 32 = 128 rows - do not depend on the streaming kernel: they are
+            // staged BEFORE griddepcontrol.wait, while that grid is still running
+            {
+                const int sidx = row >> 5, c = row & 31;
+                float cv[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int l = half * 16 + j;
+                    cv[j] = (sidx < nb && c < nc && l < L) ? __ldg(ctx + ((size_t)(bb + sidx) * cdf + c0 + c) * L + l) : 0.f;
+                }
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int l = half * 16 + j;
+                    if (sidx < nb && l < L) cs[(sidx * L + l) * kPostCS + c] = cv[j];
+                }
+            }
+            if (!waited) {
+                asm volatile("griddepcontrol.wait;" ::: "memory");      // dSrc is complete and visible
+                if (threadIdx.x == 0) tl_min(tl < 0 ? tl : tl + 4);
+                waited = true;
+            }
+            // dSrc rows (sample s, channel i) - up to 4 x 64 = 256 rows, two passes of 128 rows; all loads of the
+            // round are issued before the first store (one memory round trip)
+            float dv[2][16];
 #pragma unroll
             for (int ps = 0; ps < (HI ? 2 : 1); ++ps) {
                 const int r = row + 128 * ps, sidx = r / IDF, i = r - sidx * IDF;
@@ -166,14 +185,6 @@ __global__ void __launch_bounds__(256) k_bwd_post_tc5(const float* __restrict__ 
                     dv[ps][j] = (sidx < nb && l < L) ? __ldcg(dSrc + ((size_t)(bb + sidx) * IDF + i) * L + l) : 0.f;
                 }
             }
-            {
-                const int sidx = row >> 5, c = row & 31;
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const int l = half * 16 + j;
-                    cv[j] = (sidx < nb && c < nc && l < L) ? __ldg(ctx + ((size_t)(bb + sidx) * cdf + c0 + c) * L + l) : 0.f;
-                }
-            }
 #pragma unroll
             for (int ps = 0; ps < (HI ? 2 : 1); ++ps) {
                 const int r = row + 128 * ps, sidx = r / IDF, i = r - sidx * IDF;
@@ -181,14 +192,6 @@ __global__ void __launch_bounds__(256) k_bwd_post_tc5(const float* __restrict__ 
                 for (int j = 0; j < 16; ++j) {
                     const int l = half * 16 + j;
                     if (sidx < nb && l < L) ds[i * kPostDS + sidx * L + l] = dv[ps][j];
-                }
-            }
-            {
-                const int sidx = row >> 5, c = row & 31;
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const int l = half * 16 + j;
-                    if (sidx < nb && l < L) cs[(sidx * L + l) * kPostCS + c] = cv[j];
                 }
             }
             __syncthreads();
@@ -207,6 +210,7 @@ __global__ void __launch_bounds__(256) k_bwd_post_tc5(const float* __restrict__ 
                 }
             }
         }
+        if (!waited) asm volatile("griddepcontrol.wait;" ::: "memory");     // (empty sample group) dW is zeroed upstream
 #pragma unroll
         for (int h = 0; h < (HI ? 2 : 1); ++h) {
             const int i = i0 + 32 * h;
@@ -216,6 +220,7 @@ __global__ void __launch_bounds__(256) k_bwd_post_tc5(const float* __restrict__ 
                     if (cq + k < nc) atomicAdd(dW + (size_t)i * cdf + c0 + cq + k, acc[h][k]);
         }
     } else {
+        asm volatile("griddepcontrol.wait;" ::: "memory");
         float* ds = sm;                  // [idf][L]
         const int b = blockIdx.x - n_dw;
         for (int o = tid; o < IDF * L; o += blockDim.x) ds[o] = __ldcg(dSrc + (size_t)b * IDF * L + o);
