@@ -147,7 +147,8 @@ def test_full_size_fp32(hw, algo):
 
 
 @pytest.mark.parametrize("algo", ALGOS)
-@pytest.mark.parametrize("spec", [(10, 32, 18, 64, 64, True), (3, 48, 12, 16, 16, False), (64, 32, 18, 64, 64, True)])
+@pytest.mark.parametrize("spec", [(10, 32, 18, 64, 64, True), (3, 48, 12, 16, 16, False), (64, 32, 18, 64, 64, True),
+                                  (2, 64, 32, 16, 16, True), (5, 32, 4, 16, 8, True), (130, 32, 20, 16, 8, True)])
 def test_bf16_io(spec, algo):
     """bf16 tensors, fp32 arithmetic.  Oracle = fp32 reference maths on the bf16-rounded
     inputs (SURVEY.md §8 parity note); tolerance 2e-2."""
