@@ -127,6 +127,8 @@ def run_ours(args, rank, world, device):
         mods.append(m)
     nsets = 3                                     # rotate buffers; one step already streams > L2 (126 MB)
     sets = [[make_inputs(hw, 1234 + rank + 17 * s + hw, dtype, device) for hw in STAGES] for s in range(nsets)]
+    for st_ in sets:                              # both generator stages attend over the SAME word features and mask
+        st_[1][2], st_[1][3] = st_[0][2], st_[0][3]    # (model_bert.py:580-588)
     for s in sets:
         for st in s:
             st[0].requires_grad_(True)

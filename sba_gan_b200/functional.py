@@ -2,6 +2,8 @@
 arithmetic is libsba_attn.so's.  Mirrors AttnGAN2/code/GlobalAttention.py:82-121."""
 from __future__ import annotations
 
+import weakref
+
 import torch
 
 from . import _abi
@@ -30,6 +32,23 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+# fp32 copy of the most recent word-feature tensor: both generator stages receive the SAME word_embs
+# (model_bert.py:580-588), so the second stage reuses the first stage's copy.  Keyed on the tensor
+# object (weak reference) and its version counter, never on a raw pointer.
+_ctx32_cache = {"ref": None, "version": -1, "value": None}
+
+
+def _context_fp32(context):
+    if context.dtype == torch.float32 and context.is_contiguous():
+        return context.detach()
+    c = _ctx32_cache
+    if c["ref"] is not None and c["ref"]() is context and c["version"] == context._version:
+        return c["value"]
+    value = context.detach().to(torch.float32).contiguous()
+    c["ref"], c["version"], c["value"] = weakref.ref(context), context._version, value
+    return value
+
+
 def attn_forward_raw(x, context, weight, mask_u8, mask_mode, algo):
     """x B x idf x ih x iw (fp32|bf16, contiguous), context B x cdf x L, weight idf x cdf.
     Returns (c_code, attn, srcT fp32, mask_bits|None)."""
@@ -37,7 +56,7 @@ def attn_forward_raw(x, context, weight, mask_u8, mask_mode, algo):
     B, idf, ih, iw = x.shape
     Q = ih * iw
     cdf, L = context.shape[1], context.shape[2]
-    ctx32 = context.detach().to(torch.float32).contiguous()
+    ctx32 = _context_fp32(context)
     w32 = weight.detach().reshape(idf, cdf).to(torch.float32).contiguous()
     c_code = torch.empty_like(x)
     attn = torch.empty((B, L, ih, iw), dtype=x.dtype, device=x.device)
@@ -114,5 +133,9 @@ def word_region_attention(x, context, weight, mask=None, mask_mode="reference", 
             # the reference would fail in masked_fill_ on the same mismatch (GlobalAttention.py:107-108)
             raise RuntimeError(f"word_region_attention: mask {tuple(mask.shape)} does not match "
                                f"batch {x.shape[0]} x sourceL {context.shape[2]}")
-        mask_u8 = mask.detach().to(device=x.device, dtype=torch.uint8).contiguous()
+        mask = mask.detach()
+        if mask.dtype == torch.bool and mask.device == x.device and mask.is_contiguous():
+            mask_u8 = mask.view(torch.uint8)                      # same bytes, no copy kernel
+        else:
+            mask_u8 = mask.to(device=x.device, dtype=torch.uint8).contiguous()
     return _WordRegionAttention.apply(x, context, weight, mask_u8, _MASK_MODES[mask_mode], _ALGOS[algo])
