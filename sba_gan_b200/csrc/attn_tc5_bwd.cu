@@ -111,6 +111,9 @@ struct Tc5BwdCfg {
 // zero dSrc, the per-sample counters and dW; the streaming kernel waits for this grid only before its
 // first atomic (griddepcontrol.wait), so the fill overlaps its prologue and first tiles
 __global__ void __launch_bounds__(256) k_zero_tc5(float* __restrict__ a, size_t na, float* __restrict__ b, size_t nb, int tl) {
+    // programmatic dependent of whatever precedes it (hides its launch latency); upstream work is complete
+    // before its own dependent - the streaming kernel, which reads x / g_c at once - may start
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (threadIdx.x == 0) tl_min(tl);
     const size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x, step = (size_t)gridDim.x * blockDim.x;
@@ -651,24 +654,31 @@ int launch_bwd_tc5(const void* x, const void* g, void* dX, const Tc5BwdParams& p
     using C = Tc5BwdCfg<IDF, NQ>;
     auto kern = k_attn_bwd_tc5<IDF, NQ, HAS_GA>;
     const size_t smem = (size_t)C::SMEM_BYTES + (2 * C::NST + 12) * 8;
-    static int sms = 0;
-    static size_t smem_set = 0;
-    if (smem > 220 * 1024) {
-        set_error("attn_bwd(tcgen05): %zu bytes of shared memory needed (B=%d)", smem, p.B);
+    // per device (a process may drive several): SM count, and whether this kernel's dynamic shared memory
+    // limit has been raised there (smem is a compile-time constant of the instantiation)
+    static int sms_of[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) {
+        set_error("%s(tcgen05): device index %d not supported", "attn_bwd", dev);
         return SBA_ERR_UNSUPPORTED;
     }
-    if (sms == 0 || smem > smem_set) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (smem > 220 * 1024) {
+        set_error("%s(tcgen05): %zu bytes of shared memory needed", "attn_bwd", smem);
+        return SBA_ERR_UNSUPPORTED;
+    }
+    if (sms_of[dev] == 0) {
+        int n = 0;
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess || sms < 1) {
-            set_error("attn_bwd(tcgen05): cudaFuncSetAttribute(%zu B): %s", smem, cudaGetErrorString(e));
-            sms = 0;
+        if (e != cudaSuccess || n < 1) {
+            set_error("%s(tcgen05): cudaFuncSetAttribute(%zu B): %s", "attn_bwd", smem, cudaGetErrorString(e));
             return SBA_ERR_CUDA;
         }
-        smem_set = smem;
+        sms_of[dev] = n;
     }
+    const int sms = sms_of[dev];
+    const size_t smem_set = smem;
     int per_sm = (int)((227 * 1024) / (smem_set + 1024));
     if (per_sm > C::CTAS_PER_SM) per_sm = C::CTAS_PER_SM;
     if (per_sm < 1) per_sm = 1;
@@ -778,7 +788,22 @@ int attn_bwd_zero(float* dSrc, size_t n_src, float* dW, size_t n_dw, cudaStream_
             }
         }
     }
-    k_zero_tc5<<<64, 256, 0, st>>>(dSrc, n_src, dW, n_dw, timeline_slot());
+    {
+        cudaLaunchConfig_t zc = {};
+        zc.gridDim = dim3(64);
+        zc.blockDim = dim3(256);
+        zc.stream = st;
+        cudaLaunchAttribute za[1];
+        za[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        za[0].val.programmaticStreamSerializationAllowed = 1;
+        zc.attrs = za;
+        zc.numAttrs = 1;
+        cudaError_t ze = cudaLaunchKernelEx(&zc, k_zero_tc5, dSrc, n_src, dW, n_dw, timeline_slot());
+        if (ze != cudaSuccess) {
+            set_error("attn_bwd(zero): launch: %s", cudaGetErrorString(ze));
+            return SBA_ERR_CUDA;
+        }
+    }
     add_launches(1);
     return check_launch("attn_bwd(zero)");
 }
@@ -792,7 +817,10 @@ int attn_bwd_post(const float* dSrc, const float* ctx, const float* W, float* dW
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(256);
     cfg.dynamicSmemBytes = (size_t)(128 * kPostCS + 64 * kPostDS) * sizeof(float);       // 52 KB: above the default limit
-    static bool attr_set = false;
+    static bool attr_set_of[64] = {false};
+    int pdev = 0;
+    cudaGetDevice(&pdev);
+    bool& attr_set = attr_set_of[pdev & 63];
     if (!attr_set) {
         cudaFuncSetAttribute(k_bwd_post_tc5<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.dynamicSmemBytes);
         cudaFuncSetAttribute(k_bwd_post_tc5<48>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.dynamicSmemBytes);

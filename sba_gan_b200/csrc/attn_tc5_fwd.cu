@@ -131,6 +131,10 @@ struct Tc5FwdCfg {
 __global__ void __launch_bounds__(256) k_project_tc5(const float* __restrict__ ctx, const float* __restrict__ W,
                                                      float* __restrict__ srcT, const uint8_t* __restrict__ mask,
                                                      uint32_t* __restrict__ mask_bits, int idf, int cdf, int L) {
+    // Launched as a programmatic dependent of whatever precedes it in the stream, which only hides its launch
+    // latency: it waits for that work to complete BEFORE it lets its own dependent (the streaming kernel,
+    // whose producer starts reading x at once) go, so nothing downstream can run ahead of upstream results.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     // caption padding mask -> one 32-bit word per caption (bit l = word l is padding), by the first block of each sample
     if (mask != nullptr && blockIdx.x % (idf / 8) == 0 && threadIdx.x < 32) {
@@ -578,24 +582,31 @@ int launch_fwd_tc5(const void* x, const Tc5FwdParams& p, int dtype, cudaStream_t
     using C = Tc5FwdCfg<T, IDF, NQ>;
     auto kern = k_attn_fwd_tc5<T, IDF, NQ>;
     const size_t smem = (size_t)C::SMEM_BYTES + 1024 + 16;
-    static int sms = 0;
-    static size_t smem_set = 0;
-    if (smem > 220 * 1024) {
-        set_error("attn_fwd(tcgen05): %zu bytes of shared memory needed (B=%d)", smem, p.B);
+    // per device (a process may drive several): SM count, and whether this kernel's dynamic shared memory
+    // limit has been raised there (smem is a compile-time constant of the instantiation)
+    static int sms_of[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) {
+        set_error("%s(tcgen05): device index %d not supported", "attn_fwd", dev);
         return SBA_ERR_UNSUPPORTED;
     }
-    if (sms == 0 || smem > smem_set) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (smem > 220 * 1024) {
+        set_error("%s(tcgen05): %zu bytes of shared memory needed", "attn_fwd", smem);
+        return SBA_ERR_UNSUPPORTED;
+    }
+    if (sms_of[dev] == 0) {
+        int n = 0;
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess || sms < 1) {
-            set_error("attn_fwd(tcgen05): cudaFuncSetAttribute(%zu B): %s", smem, cudaGetErrorString(e));
-            sms = 0;
+        if (e != cudaSuccess || n < 1) {
+            set_error("%s(tcgen05): cudaFuncSetAttribute(%zu B): %s", "attn_fwd", smem, cudaGetErrorString(e));
             return SBA_ERR_CUDA;
         }
-        smem_set = smem;
+        sms_of[dev] = n;
     }
+    const int sms = sms_of[dev];
+    const size_t smem_set = smem;
     // Resident CTAs per SM: the occupancy API answers 1 for kernels that allocate tensor memory, the
     // hardware co-schedules as many as registers, shared memory and the 512 TMEM columns allow.
     int per_sm = (int)((227 * 1024) / (smem_set + 1024));
@@ -610,7 +621,22 @@ int launch_fwd_tc5(const void* x, const Tc5FwdParams& p, int dtype, cudaStream_t
     if (!rc) rc = make_tile_map(&tma_c, p.c_code, dtype, p.B * IDF, p.Q, IDF, 32, false);
     if (rc) return rc;
     const int pgrid = p.B * (IDF / 8);
-    k_project_tc5<<<pgrid, 256, 0, st>>>(ctx, W, srcT, p.mask, p.mask_bits, IDF, cdf, p.L);
+    {
+        cudaLaunchConfig_t pc = {};
+        pc.gridDim = dim3(pgrid);
+        pc.blockDim = dim3(256);
+        pc.stream = st;
+        cudaLaunchAttribute pa[1];
+        pa[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        pa[0].val.programmaticStreamSerializationAllowed = 1;
+        pc.attrs = pa;
+        pc.numAttrs = 1;
+        cudaError_t pe = cudaLaunchKernelEx(&pc, k_project_tc5, ctx, W, srcT, p.mask, p.mask_bits, (int)IDF, cdf, p.L);
+        if (pe != cudaSuccess) {
+            set_error("project(tcgen05): launch: %s", cudaGetErrorString(pe));
+            return SBA_ERR_CUDA;
+        }
+    }
     rc = check_launch("project(tcgen05)");
     if (rc) return rc;
     const int grid = p.n_tiles < max_ctas ? p.n_tiles : max_ctas;
