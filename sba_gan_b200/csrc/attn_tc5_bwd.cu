@@ -1,27 +1,32 @@
 // Kernel (b): fused backward of GlobalAttentionGeneral on the 5th-generation tensor cores
-// (SBA_ALGO_TCGEN05, bf16 tensors).  Same skeleton as attn_tc5_fwd.cu: one persistent CTA =
-// 1 TMA producer warp + 1 MMA-issuing warp + 4 consumer warps (thread = pixel), contiguous
-// ranges of 128-pixel tiles.  Per tile (formulas: SURVEY.md §8a-4, oracle/attention.py):
-//   TMA      : the [idf x 128 px] tiles of g_c and x land interleaved box by box, so that the same
-//              bytes are (i) two MN-major A operands (pixels = M) and (ii) ONE K-major A operand
-//              [g ; x] with 2*idf rows (pixels = K).
-//   MMA1     : S  = x^T . sourceT      dP = g^T . sourceT                     (K = idf)
-//   consumers: P = masked softmax(S) (recomputed, not re-read from HBM)
-//              dS = P * (dP [+ g_attn] - sum_l P dP)
-//              P and dS are written (bf16, 128-byte swizzled rows [word][pixel]) into one
-//              shared-memory operand buffer PB.
-//   MMA2     : dX   = dS . sourceT^T          (A = the dS rows of PB, MN-major; K = words)
-//              dSrc += [g ; x] . [P | dS]     (A = the staged tiles, B = PB, K = 128 pixels;
-//                                              the accumulator stays in TMEM across all tiles of a
-//                                              sample: rows = g / x channels, columns = P / dS words;
-//                                              its diagonal blocks are g.P and x.dS)
-//   consumers: dX row of the pixel -> staged -> TMA box store.
-// When the tile range leaves a sample the consumers add the two diagonal blocks of the TMEM
-// accumulator into dSrc[b] with fp32 atomics.  dSrc / dW are zeroed by a small kernel in front
-// (programmatic dependent launch: this kernel only waits for it before its first atomic), and
-// dW = sum_b dSrc[b] . ctx[b]^T, dCtx[b] = W^T . dSrc[b] are formed by a small kernel behind it
-// (attn_bwd_post; also a programmatic dependent): doing that per sample inside this kernel puts
-// 64-way contended atomics on dW right at the end of the stream.
+// (SBA_ALGO_TCGEN05, bf16 tensors).  One persistent CTA (320 threads, 2 per SM) = 1 TMA producer
+// warp + 1 MMA-issuing warp + 4 first-stage warps + 4 second-stage warps (both stages thread = pixel,
+// each group covers the four TMEM lane quarters), contiguous ranges of 128-pixel tiles.  Per tile
+// (formulas: SURVEY.md §8a-4, oracle/attention.py):
+//   TMA         : the [idf x 128 px] tiles of g_c and x land interleaved box by box, so that the same
+//                 bytes are (i) two MN-major A operands (pixels = M) and (ii) ONE K-major A operand
+//                 [g ; x] with 2*idf rows (pixels = K).
+//   MMA1        : S  = x^T . sourceT      dP = g^T . sourceT                     (K = idf)
+//   first stage : P = masked softmax(S) (recomputed, not re-read from HBM)
+//                 dS = P * (dP [+ g_attn] - sum_l P dP)
+//                 P and dS are written (bf16, 128-byte swizzled rows [word][pixel]) into the
+//                 shared-memory operand buffer PB[tile parity].
+//   MMA2        : dX   = dS . sourceT^T          (A = the dS rows of PB, MN-major; K = words)
+//                 dSrc += [g ; x] . [P | dS]     (A = the staged tiles, B = PB, K = 128 pixels;
+//                                                 the accumulator stays in TMEM across all tiles of a
+//                                                 sample: rows = g / x channels, columns = P / dS words;
+//                                                 its diagonal blocks are g.P and x.dS)
+//   second stage: dX row of the pixel -> staged -> TMA box store; at the end of a sample the two
+//                 diagonal blocks of the TMEM accumulator are added to dSrc[b] with fp32 atomics.
+// Two {S, dP} TMEM buffers and two PB buffers form a software pipeline: MMA1(j+1) is issued before
+// MMA2(j), so the first stage of tile j+1 overlaps the tensor core and the second stage of tile j.
+// At a sample boundary the pipeline drains (the operands are rebuilt only after the last MMA of the
+// old sample has retired, the accumulator is handed back after it has been read).
+// dSrc / dW are zeroed by a small kernel in front (programmatic dependent launch: this kernel only
+// waits for it before its first atomic), and dW = sum_b dSrc[b] . ctx[b]^T, dCtx[b] = W^T . dSrc[b]
+// are formed by a small kernel behind it (attn_bwd_post; also a programmatic dependent, resident
+// early): doing that per sample inside this kernel stalls CTAs mid-stream and piles the whole
+// reduction up at the end of the stream.
 #include <cstdlib>
 
 #include "kernels.h"

@@ -9,8 +9,9 @@
 //              MMA2  c[128 x idf] = P . sourceT^T                     (A = P in TMEM, K = words)
 //              completion is signalled with tcgen05.commit on mbarriers.
 //   consumers: thread = pixel.  tcgen05.ld S row -> masked softmax over words in registers (no
-//              shuffles) -> attention map stored one pixel per lane (128 B per warp and word)
-//              -> P written back to TMEM as MMA2's A operand -> tcgen05.ld c row -> stored.
+//              shuffles) -> P written back to TMEM as MMA2's A operand -> attention map staged
+//              [word][32 px] per warp, one TMA box store -> tcgen05.ld c row -> staged, TMA box store.
+// S is double buffered in TMEM (MMA1 of the next tile runs ahead of the softmax of this one).
 // The B operands (sourceT of the current sample, both orientations, zero padded) are rebuilt in
 // shared memory by the consumers whenever the tile range enters a new sample.
 // bf16 tensors: single bf16 MMAs.  fp32 tensors: 3xTF32 - every operand is split into a tf32
