@@ -155,21 +155,3 @@ def func_attention(query, context, gamma1):
     _abi.check(rc, "sba_func_attention")
     launch_counter["n"] += _abi.last_launch_count()
     return wc.to(query.dtype), attn.reshape(B, T, ih, iw).to(query.dtype)
-
-
-def smoke_words_loss():
-    """Tiny words_loss forward+backward on cuda:0 against the CPU oracle (used by smoke())."""
-    import oracle
-    d = oracle.synth_words_loss_inputs(6, 256, 18, 17, 17, seed=5)
-    img = d["img_features"].cuda().requires_grad_(True)
-    words = d["words_emb"].cuda().requires_grad_(True)
-    l0, l1, maps = words_loss(img, words, d["labels"].cuda(), d["cap_lens"].cuda(), d["class_ids"], 6, 4.0, 5.0, 10.0)
-    (l0 + l1).backward()
-    torch.cuda.synchronize()
-    r0, r1, rmaps = oracle.words_loss(d["img_features"].double(), d["words_emb"].double(), d["labels"], d["cap_lens"],
-                                      d["class_ids"], 6, 4.0, 5.0, 10.0)
-    e0 = abs(l0.item() - r0.item()) / abs(r0.item())
-    e1 = abs(l1.item() - r1.item()) / abs(r1.item())
-    em = max(oracle.normalised_max_err(a.cpu(), b) for a, b in zip(maps, rmaps))
-    print(f"smoke words_loss errs: loss0 {e0:.2e} loss1 {e1:.2e} att_maps {em:.2e}")
-    assert e0 <= 1e-5 and e1 <= 1e-5 and em <= 1e-5, (e0, e1, em)

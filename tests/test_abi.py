@@ -28,15 +28,19 @@ def test_header_symbols_are_exported_and_bound():
 
 
 def test_no_oracle_import_in_product_path():
-    """The oracle is test infrastructure: nothing under sba_gan_b200/ may import it, except
-    smoke_words_loss which is the smoke checker itself."""
+    """The oracle is test infrastructure: nothing under sba_gan_b200/ (nor the measurement harness or the
+    tools) may import it; only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs do."""
     pkg = os.path.join(ROOT, "sba_gan_b200")
     for dirpath, _, files in os.walk(pkg):
         for f in files:
             if f.endswith(".py"):
                 src = open(os.path.join(dirpath, f)).read()
-                src = re.sub(r"def smoke_words_loss\(\):.*?(?=\ndef |\Z)", "", src, flags=re.S)
-                assert "oracle" not in src, f"{f} references the oracle outside the smoke checker"
+                assert "oracle" not in src, f"{f} references the oracle"
+    for sub in ("harness", "tools"):
+        for f in os.listdir(os.path.join(ROOT, sub)):
+            if f.endswith(".py"):
+                src = open(os.path.join(ROOT, sub, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src, f"{sub}/{f} imports the oracle"
 
 
 def test_module_surface_matches_reference():

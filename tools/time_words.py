@@ -3,14 +3,15 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from sba_gan_b200.losses import words_loss, words_similarity
-from oracle import synth_words_loss_inputs
 
 for B in (48, 256):
-    d = synth_words_loss_inputs(B, 256, 18, 17, 17, seed=1)
-    img = d["img_features"].cuda().requires_grad_(True)
-    words = d["words_emb"].cuda()
+    g = torch.Generator().manual_seed(1)        # synthetic CUB-shaped inputs
+    d = {"cap_lens": torch.sort(torch.randint(5, 19, (B,), generator=g), descending=True).values,
+         "class_ids": torch.randint(1, 201, (B,), generator=g).numpy()}
+    img = torch.randn(B, 256, 17, 17, generator=g).cuda().requires_grad_(True)
+    words = torch.tanh(torch.randn(B, 256, 18, generator=g)).cuda()
     lens = d["cap_lens"].cuda().int()
-    labels = d["labels"].cuda()
+    labels = torch.arange(B).cuda()
     Tbar = d["cap_lens"].float().mean().item()
     flops_f = 4.0 * B * B * 289 * Tbar * 256
 
