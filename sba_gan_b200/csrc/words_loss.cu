@@ -450,90 +450,138 @@ __global__ void __launch_bounds__(C::kThreads, 1) k_words(const WordsArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------
-// plain batched fp32 GEMM with two-level K addressing (for the gradient contractions)
+// batched fp32 GEMM with two-level K (and N) addressing for the gradient contractions
 //   A(m,k) = A + b*sA_batch + (k / kbA)*sA_kb + m*lda + (k % kbA)
 //   B(k,n) = transB ? B + b*sB_batch + (k / kbB)*sB_kb + n*ldb + (k % kbB)
 //                   : B + b*sB_batch + k*ldb + n
-//   C(m,n) = C + b*sC_batch + m*ldc + n      (+= when accumulate)
+//   C(m,n) = C + b*sC_batch + (n / nbC)*sC_nb + m*ldc + (n % nbC)      (+= when accumulate)
+// grid = (N tiles, M tiles, batch * splits); with splits > 1 every z-slice owns a K range and adds its
+// partial product with red.global.add (C must then hold the initial value; accumulate is implied).
+// 128 x BN tile, 256 threads, 8 x (BN/16) outputs per thread as 4-wide groups (LDS.128 operands),
+// shared tiles double-buffered, the next K tile's global loads in flight during the FMA block.
 // ---------------------------------------------------------------------------------------
 struct GemmArgs {
     const float* A; long long sA_batch, sA_kb; int kbA, lda;
     const float* B; long long sB_batch, sB_kb; int kbB, ldb, transB;
-    float* C; long long sC_batch; int ldc, accumulate;
-    int M, N, K;
+    float* C; long long sC_batch, sC_nb; int nbC, ldc, accumulate;
+    int M, N, K, splits;
 };
 
-template <int BM, int BN, int TM, int TN>
-__global__ void __launch_bounds__(256) k_gemm(const GemmArgs g) {
-    constexpr int BK = 16;
-    static_assert((BM / TM) * (BN / TN) == 256, "tile/thread mismatch");
-    __shared__ __align__(16) float As[BK][BM + 4];
-    __shared__ __align__(16) float Bs[BK][BN + 4];
+template <int BN>
+__global__ void __launch_bounds__(256, 2) k_gemm(const GemmArgs g) {
+    constexpr int BM = 128, BK = 16, TM = 8, TN = BN / 16, NV = TN / 4;
+    constexpr int LA = BM * BK / 256, LB = BN * BK / 256;
+    static_assert(TN % 4 == 0, "BN must be a multiple of 64");
+    __shared__ __align__(16) float As[2][BK][BM + 4];
+    __shared__ __align__(16) float Bs[2][BK][BN + 4];
     const int tid = threadIdx.x;
-    const int tx = tid % (BN / TN), ty = tid / (BN / TN);
-    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN, b = blockIdx.z;
+    const int tx = tid & 15, ty = tid >> 4;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    const int b = blockIdx.z / g.splits, z = blockIdx.z - b * g.splits;
+    const int kper = ceil_div(ceil_div(g.K, g.splits), BK) * BK;
+    const int kbeg = z * kper, kend = min(g.K, kbeg + kper);
     const float* A = g.A + (size_t)b * g.sA_batch;
     const float* B = g.B + (size_t)b * g.sB_batch;
+
+    // per-thread load slots: A element (am, ak) and B element (bn, bk) of the current K tile;
+    // the two-level K position (block, remainder) is advanced incrementally, no division per tile
+    const int ak = tid & (BK - 1), am = tid >> 4;                  // + 16 rows per slot
+    int a_kb = (kbeg + ak) / g.kbA, a_kr = (kbeg + ak) - a_kb * g.kbA;
+    const int bk_t = tid & (BK - 1), bn_t = tid >> 4;              // transB: k fastest
+    const int bn_n = tid % BN, bk_n = tid / BN;                    // non-trans: n fastest, + 256/BN k per slot
+    int b_kb = 0, b_kr = 0;
+    if (g.transB) { b_kb = (kbeg + bk_t) / g.kbB; b_kr = (kbeg + bk_t) - b_kb * g.kbB; }
+
+    float ra[LA], rb[LB];
+    auto gload = [&](int k0) {
+        const bool kok = k0 + ak < kend;
+        const float* ap = A + (size_t)a_kb * g.sA_kb + a_kr;
+#pragma unroll
+        for (int s = 0; s < LA; ++s) {
+            const int m = m0 + am + s * 16;
+            ra[s] = (kok && m < g.M) ? __ldg(ap + (size_t)m * g.lda) : 0.f;
+        }
+        a_kr += BK;
+        while (a_kr >= g.kbA) { a_kr -= g.kbA; ++a_kb; }
+        if (g.transB) {
+            const bool bok = k0 + bk_t < kend;
+            const float* bp = B + (size_t)b_kb * g.sB_kb + b_kr;
+#pragma unroll
+            for (int s = 0; s < LB; ++s) {
+                const int n = n0 + bn_t + s * 16;
+                rb[s] = (bok && n < g.N) ? __ldg(bp + (size_t)n * g.ldb) : 0.f;
+            }
+            b_kr += BK;
+            while (b_kr >= g.kbB) { b_kr -= g.kbB; ++b_kb; }
+        } else {
+            const int n = n0 + bn_n;
+#pragma unroll
+            for (int s = 0; s < LB; ++s) {
+                const int k = k0 + bk_n + s * (256 / BN);
+                rb[s] = (k < kend && n < g.N) ? __ldg(B + (size_t)k * g.ldb + n) : 0.f;
+            }
+        }
+    };
+    auto sstore = [&](int buf) {
+#pragma unroll
+        for (int s = 0; s < LA; ++s) As[buf][ak][am + s * 16] = ra[s];
+        if (g.transB) {
+#pragma unroll
+            for (int s = 0; s < LB; ++s) Bs[buf][bk_t][bn_t + s * 16] = rb[s];
+        } else {
+#pragma unroll
+            for (int s = 0; s < LB; ++s) Bs[buf][bk_n + s * (256 / BN)][bn_n] = rb[s];
+        }
+    };
+
     float acc[TM][TN];
 #pragma unroll
     for (int i = 0; i < TM; ++i)
 #pragma unroll
         for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
-    for (int k0 = 0; k0 < g.K; k0 += BK) {
-        for (int idx = tid; idx < BM * BK; idx += 256) {
-            const int m = idx / BK, kk = idx - m * BK;
-            const int k = k0 + kk;
-            float v = 0.f;
-            if (m0 + m < g.M && k < g.K) {
-                const int kb = k / g.kbA, kr = k - kb * g.kbA;
-                v = A[(size_t)kb * g.sA_kb + (size_t)(m0 + m) * g.lda + kr];
-            }
-            As[kk][m] = v;
-        }
-        if (g.transB) {
-            for (int idx = tid; idx < BN * BK; idx += 256) {
-                const int n = idx / BK, kk = idx - n * BK;
-                const int k = k0 + kk;
-                float v = 0.f;
-                if (n0 + n < g.N && k < g.K) {
-                    const int kb = k / g.kbB, kr = k - kb * g.kbB;
-                    v = B[(size_t)kb * g.sB_kb + (size_t)(n0 + n) * g.ldb + kr];
-                }
-                Bs[kk][n] = v;
-            }
-        } else {
-            for (int idx = tid; idx < BN * BK; idx += 256) {
-                const int kk = idx / BN, n = idx - kk * BN;
-                const int k = k0 + kk;
-                Bs[kk][n] = (n0 + n < g.N && k < g.K) ? B[(size_t)k * g.ldb + n0 + n] : 0.f;
-            }
-        }
+
+    if (kbeg < kend) {
+        gload(kbeg);
+        sstore(0);
         __syncthreads();
+        int buf = 0;
+        for (int k0 = kbeg; k0 < kend; k0 += BK) {
+            const bool more = k0 + BK < kend;
+            if (more) gload(k0 + BK);
 #pragma unroll
-        for (int kk = 0; kk < BK; ++kk) {
-            float av[TM], bv[TN];
+            for (int kk = 0; kk < BK; ++kk) {
+                float av[TM], bv[TN];
 #pragma unroll
-            for (int i = 0; i < TM; ++i) av[i] = As[kk][ty * TM + i];
+                for (int v = 0; v < 2; ++v)
+                    *reinterpret_cast<float4*>(&av[4 * v]) = *reinterpret_cast<const float4*>(&As[buf][kk][v * 64 + ty * 4]);
 #pragma unroll
-            for (int j = 0; j < TN; ++j) bv[j] = Bs[kk][tx * TN + j];
+                for (int v = 0; v < NV; ++v)
+                    *reinterpret_cast<float4*>(&bv[4 * v]) = *reinterpret_cast<const float4*>(&Bs[buf][kk][v * 64 + tx * 4]);
 #pragma unroll
-            for (int i = 0; i < TM; ++i)
+                for (int i = 0; i < TM; ++i)
 #pragma unroll
-                for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+                    for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+            }
+            if (more) {
+                sstore(buf ^ 1);
+                __syncthreads();
+                buf ^= 1;
+            }
         }
-        __syncthreads();
     }
     float* Cb = g.C + (size_t)b * g.sC_batch;
 #pragma unroll
     for (int i = 0; i < TM; ++i) {
-        const int m = m0 + ty * TM + i;
+        const int m = m0 + (i >> 2) * 64 + ty * 4 + (i & 3);
         if (m >= g.M) continue;
 #pragma unroll
         for (int j = 0; j < TN; ++j) {
-            const int n = n0 + tx * TN + j;
+            const int n = n0 + (j >> 2) * 64 + tx * 4 + (j & 3);
             if (n >= g.N) continue;
-            float* p = Cb + (size_t)m * g.ldc + n;
-            *p = g.accumulate ? *p + acc[i][j] : acc[i][j];
+            const int nb = n / g.nbC;
+            float* p = Cb + (size_t)nb * g.sC_nb + (size_t)m * g.ldc + (n - nb * g.nbC);
+            if (g.splits > 1) atomicAdd(p, acc[i][j]);
+            else *p = g.accumulate ? *p + acc[i][j] : acc[i][j];
         }
     }
 }
@@ -616,31 +664,38 @@ int words_sim_bwd(const float* img, const float* words, const int* cap_lens, con
     int rc = dispatch_words<true>(a, st);
     if (rc) return rc;
     const int KL = B_cap * Lw;
+    const int big = 0x7fffffff;
     // d_img[j] = W2 [nef x KL] . u_j [KL x R]  +  v_j [nef x KL] . a2_j [KL x R]
     GemmArgs g{};
     g.A = words; g.sA_batch = 0; g.sA_kb = (long long)nef * Lw; g.kbA = Lw; g.lda = Lw;
-    g.B = a.ws_u; g.sB_batch = (long long)KL * R; g.sB_kb = 0; g.kbB = 1; g.ldb = R; g.transB = 0;
-    g.C = d_img; g.sC_batch = (long long)nef * R; g.ldc = R; g.accumulate = 0;
-    g.M = nef; g.N = R; g.K = KL;
-    dim3 grid2(ceil_div(R, 64), ceil_div(nef, 64), B_img);
-    k_gemm<64, 64, 4, 4><<<grid2, 256, 0, st>>>(g);
-    g.A = a.ws_v; g.sA_batch = (long long)nef * KL; g.sA_kb = 0; g.kbA = KL; g.lda = KL;
+    g.B = a.ws_u; g.sB_batch = (long long)KL * R; g.sB_kb = 0; g.kbB = big; g.ldb = R; g.transB = 0;
+    g.C = d_img; g.sC_batch = (long long)nef * R; g.sC_nb = 0; g.nbC = big; g.ldc = R; g.accumulate = 0;
+    g.M = nef; g.N = R; g.K = KL; g.splits = 1;
+    dim3 grid2(ceil_div(R, 64), ceil_div(nef, 128), B_img);
+    k_gemm<64><<<grid2, 256, 0, st>>>(g);
+    g.A = a.ws_v; g.sA_batch = (long long)nef * KL; g.sA_kb = 0; g.kbA = big; g.lda = KL;
     g.B = a.ws_a2; g.accumulate = 1;
-    k_gemm<64, 64, 4, 4><<<grid2, 256, 0, st>>>(g);
+    k_gemm<64><<<grid2, 256, 0, st>>>(g);
     add_launches(2);
     rc = check_launch("words_sim_bwd(d_img gemm)");
     if (rc) return rc;
     if (d_words != nullptr) {
-        // d_words[i] = kappa_i W_i + sum_j X_j [nef x R] . u_ji^T [R x Lw]
+        // d_words[i][c][t] = kappa_i[t] W_i[c][t] + sum_{j,r} X_j[c][r] u_j[(i,t)][r]:
+        // one GEMM with M = nef, N = (i,t), K = (j,r), split over K so that the grid fills the GPU
         k_kappa_init<<<ceil_div(B_cap * nef * Lw, 256) < 1024 ? ceil_div(B_cap * nef * Lw, 256) : 1024, 256, 0, st>>>(
             words, a.kappa, d_words, B_cap, nef, Lw);
         GemmArgs h{};
         h.A = img; h.sA_batch = 0; h.sA_kb = (long long)nef * R; h.kbA = R; h.lda = R;
-        h.B = a.ws_u; h.sB_batch = (long long)Lw * R; h.sB_kb = (long long)KL * R; h.kbB = R; h.ldb = R; h.transB = 1;
-        h.C = d_words; h.sC_batch = (long long)nef * Lw; h.ldc = Lw; h.accumulate = 1;
-        h.M = nef; h.N = Lw; h.K = B_img * R;
-        dim3 grid3(ceil_div(Lw, 32), ceil_div(nef, 64), B_cap);
-        k_gemm<64, 32, 4, 2><<<grid3, 256, 0, st>>>(h);
+        h.B = a.ws_u; h.sB_batch = 0; h.sB_kb = (long long)KL * R; h.kbB = R; h.ldb = R; h.transB = 1;
+        h.C = d_words; h.sC_batch = 0; h.sC_nb = (long long)nef * Lw; h.nbC = Lw; h.ldc = Lw; h.accumulate = 1;
+        h.M = nef; h.N = KL; h.K = B_img * R;
+        const int tiles = ceil_div(KL, 128) * ceil_div(nef, 128);
+        int splits = ceil_div(2 * 148 * 2, tiles);                 // about two waves of 2 CTAs per SM
+        if (splits > B_img) splits = B_img;
+        if (splits < 1) splits = 1;
+        h.splits = splits;
+        dim3 grid3(ceil_div(KL, 128), ceil_div(nef, 128), splits);
+        k_gemm<128><<<grid3, 256, 0, st>>>(h);
         add_launches(2);
         rc = check_launch("words_sim_bwd(d_words gemm)");
         if (rc) return rc;
