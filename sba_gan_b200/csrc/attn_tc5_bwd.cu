@@ -276,13 +276,13 @@ __global__ void __launch_bounds__(kBwdThreads, Tc5BwdCfg<IDF, NQ>::CTAS_PER_SM)
     unsigned long long* bar_x_empty = bars + NST;
     unsigned long long* bar_s_full = bars + 2 * NST;          // [2] by tile parity
     unsigned long long* bar_s_free = bars + 2 * NST + 2;      // [2]
-    unsigned long long& bar_ds_ready = bars[2 * NST + 4];
+    unsigned long long* bar_ds_ready = bars + 2 * NST + 11;   // [2] by tile parity: the first-stage warps may be a tile apart
     unsigned long long& bar_c_full = bars[2 * NST + 5];
     unsigned long long& bar_dx_free = bars[2 * NST + 6];
     unsigned long long& bar_b_ready = bars[2 * NST + 7];
     unsigned long long* bar_pb_free = bars + 2 * NST + 8;     // [2] MMA2 of that parity has completed (PB, operands)
     unsigned long long& bar_acc_free = bars[2 * NST + 10];    // the dSrc accumulator of a finished sample has been read
-    uint32_t& tmem_base_s = *reinterpret_cast<uint32_t*>(bars + 2 * NST + 11);
+    uint32_t& tmem_base_s = *reinterpret_cast<uint32_t*>(bars + 2 * NST + 13);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int L = p.L, Q = p.Q, TPS = p.tiles_per_sample;
@@ -318,7 +318,8 @@ __global__ void __launch_bounds__(kBwdThreads, Tc5BwdCfg<IDF, NQ>::CTAS_PER_SM)
         mbar_init(smem_u32(&bar_pb_free[0]), 1);
         mbar_init(smem_u32(&bar_pb_free[1]), 1);
         mbar_init(smem_u32(&bar_acc_free), 4);
-        mbar_init(smem_u32(&bar_ds_ready), 4);
+        mbar_init(smem_u32(&bar_ds_ready[0]), 4);
+        mbar_init(smem_u32(&bar_ds_ready[1]), 4);
         mbar_init(smem_u32(&bar_c_full), 1);
         mbar_init(smem_u32(&bar_dx_free), 4);
         mbar_init(smem_u32(&bar_b_ready), 4);
@@ -407,7 +408,7 @@ __global__ void __launch_bounds__(kBwdThreads, Tc5BwdCfg<IDF, NQ>::CTAS_PER_SM)
         uint32_t n_flush = 0;        // accumulator hand-backs waited for so far
         auto mma2 = [&](int j, bool first_of_sample) {
             const int stage = j % NST;
-            mbar_wait(smem_u32(&bar_ds_ready), (uint32_t)j & 1u);
+            mbar_wait(smem_u32(&bar_ds_ready[j & 1]), (uint32_t)(j >> 1) & 1u);
             if (j > 0) mbar_wait(smem_u32(&bar_dx_free), (uint32_t)(j - 1) & 1u);      // dX(j-1) is in registers
             if (first_of_sample && j > 0) {                                            // the previous sample's accumulator
                 mbar_wait(smem_u32(&bar_acc_free), n_flush & 1u);                      // has been read out
@@ -568,7 +569,7 @@ __global__ void __launch_bounds__(kBwdThreads, Tc5BwdCfg<IDF, NQ>::CTAS_PER_SM)
                 *reinterpret_cast<__nv_bfloat16*>(pb + (RP + l) * 128 + (pb_col ^ ((l & 7) << 4))) = __float2bfloat16_rn(ds);
             }
             fence_proxy_async();
-            warp_arrive(smem_u32(&bar_ds_ready), lane);
+            warp_arrive(smem_u32(&bar_ds_ready[buf]), lane);
             if (tr) p.trace[j * 16 + 3] = clock64();
 
             if (++t == TPS) { t = 0; ++b; }
@@ -658,7 +659,7 @@ template <int IDF, int NQ, bool HAS_GA>
 int launch_bwd_tc5(const void* x, const void* g, void* dX, const Tc5BwdParams& p, cudaStream_t st) {
     using C = Tc5BwdCfg<IDF, NQ>;
     auto kern = k_attn_bwd_tc5<IDF, NQ, HAS_GA>;
-    const size_t smem = (size_t)C::SMEM_BYTES + (2 * C::NST + 12) * 8;
+    const size_t smem = (size_t)C::SMEM_BYTES + (2 * C::NST + 14) * 8;
     // per device (a process may drive several): SM count, and whether this kernel's dynamic shared memory
     // limit has been raised there (smem is a compile-time constant of the instantiation)
     static int sms_of[64] = {0};

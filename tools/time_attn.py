@@ -1,5 +1,6 @@
 """Quick device timing of the attention forward/backward ABI calls (development aid;
-bench.py is the contract).  Usage: python tools/time_attn.py [algo] [dtype]"""
+bench.py is the contract).  Usage: python tools/time_attn.py [algo] [dtype] [B,B,...]
+(the batch list is the bandwidth sweep of BASELINE.json configs[4]: 1024 / 8 GPUs = 128 per GPU)"""
 import sys
 import os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -11,9 +12,10 @@ algo = _ALGOS[sys.argv[1]] if len(sys.argv) > 1 else 0
 dt = torch.bfloat16 if len(sys.argv) > 2 and sys.argv[2] == "bf16" else torch.float32
 lib = _abi.load()
 dev = "cuda"
-B, idf, cdf, L = 64, 32, 256, 18
+idf, cdf, L = 32, 256, 18
 PEAK = 6553.6
-for hw in (64, 128):
+BS = [int(b) for b in sys.argv[3].split(",")] if len(sys.argv) > 3 else [64]
+for B, hw in [(b, h) for b in BS for h in (64, 128)]:
     Q = hw * hw
     nset = max(2, int(600e6 // (B * idf * Q * 4 * 5)) + 1)   # rotate > L2
     sets = []
@@ -63,11 +65,13 @@ for hw in (64, 128):
         gr.replay()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+        reps = int(os.environ.get("SBA_REPLAYS", "1"))      # > 1: sustained run (clock / power sampling)
         e0.record()
-        gr.replay()
+        for _ in range(reps):
+            gr.replay()
         e1.record()
         torch.cuda.synchronize()
-        return e0.elapsed_time(e1) / n * 1e-3
+        return e0.elapsed_time(e1) / (n * reps) * 1e-3
 
     es = 4 if dt == torch.float32 else 2
     tf = timeit(fwd)
@@ -75,6 +79,6 @@ for hw in (64, 128):
     px = B * Q
     bf = px * (2 * idf + L) * es
     bb = px * 3 * idf * es
-    print(f"{hw}x{hw} {dt} algo={algo}: fwd {tf*1e6:.1f} us {bf/tf/1e9:.0f} GB/s ({bf/tf/1e9/PEAK:.2%}) | "
+    print(f"B={B} {hw}x{hw} {dt} algo={algo}: fwd {tf*1e6:.1f} us {bf/tf/1e9:.0f} GB/s ({bf/tf/1e9/PEAK:.2%}) | "
           f"bwd {tb*1e6:.1f} us {bb/tb/1e9:.0f} GB/s ({bb/tb/1e9/PEAK:.2%}) | "
           f"fwd+bwd {px/(tf+tb)/1e9:.2f} Gpx/s {(bf+bb)/(tf+tb)/1e9:.0f} GB/s ({(bf+bb)/(tf+tb)/1e9/PEAK:.2%})", flush=True)
