@@ -80,6 +80,10 @@ struct Tc5FwdParams {
     int B, L, Q, mask_mode;
     int tiles_per_sample;
     int n_tiles;
+    uint32_t* sched;      // dynamic tile scheduler: chunk counter (scratch word, zeroed by k_project_tc5)
+    int static_tiles;     // tiles of the contiguous static share every CTA starts with (0: all tiles are dynamic)
+    int chunk;            // tiles per dynamic chunk
+    int dyn_first;        // first tile of the dynamic region = gridDim.x * static_tiles
 };
 
 constexpr int pow2_cols(int n) { return n <= 32 ? 32 : n <= 64 ? 64 : n <= 128 ? 128 : n <= 256 ? 256 : 512; }
@@ -131,12 +135,14 @@ struct Tc5FwdCfg {
 // in registers), so the kernel lasts about one memory round trip plus 256 FMAs per lane.
 __global__ void __launch_bounds__(256) k_project_tc5(const float* __restrict__ ctx, const float* __restrict__ W,
                                                      float* __restrict__ srcT, const uint8_t* __restrict__ mask,
-                                                     uint32_t* __restrict__ mask_bits, int idf, int cdf, int L) {
+                                                     uint32_t* __restrict__ mask_bits, uint32_t* __restrict__ sched, int idf,
+                                                     int cdf, int L) {
     // Launched as a programmatic dependent of whatever precedes it in the stream, which only hides its launch
     // latency: it waits for that work to complete BEFORE it lets its own dependent (the streaming kernel,
     // whose producer starts reading x at once) go, so nothing downstream can run ahead of upstream results.
     asm volatile("griddepcontrol.wait;" ::: "memory");
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (blockIdx.x == 0 && threadIdx.x == 0) *sched = 0u;        // chunk counter of the streaming kernel's tile scheduler
     // caption padding mask -> one 32-bit word per caption (bit l = word l is padding), by the first block of each sample
     if (mask != nullptr && blockIdx.x % (idf / 8) == 0 && threadIdx.x < 32) {
         const int cap = blockIdx.x / (idf / 8);
@@ -207,6 +213,62 @@ __global__ void __launch_bounds__(256) k_project_tc5(const float* __restrict__ c
     }
 }
 
+
+// ----------------------------------------------------------------------------------------------
+// Dynamic tile schedule.  SMs do not stream at the same rate once the memory system is saturated
+// (per-SM duration of an equal static share spreads by +-40 % on B200, grouped by TPC position),
+// so tiles are handed out in chunks: chunk blockIdx.x first, then gridDim.x + atomicAdd(counter).
+// The producer warp fetches chunk ids and publishes {first tile, count} entries through a small
+// shared-memory queue; the MMA warp and the consumer warps read every entry (count 0 = end).
+// ----------------------------------------------------------------------------------------------
+constexpr int kQueueDepth = 8;
+struct ChunkReader {
+    uint32_t full0, empty0;      // shared addresses of the queue barriers
+    const volatile int2* q;
+    int n;                       // next queue entry to read
+    int tps;                     // tiles per sample
+    int cnt, i;                  // tiles of the current chunk, position in it
+    int b, t;                    // sample and tile-in-sample of the current tile
+    int nfirst, ncnt, nb;        // next chunk (valid when have_next)
+    bool have_next;
+    __device__ __forceinline__ void fetch(int lane) {
+        const int slot = n & (kQueueDepth - 1);
+        mbar_wait(full0 + 8 * slot, (uint32_t)(n / kQueueDepth) & 1u);
+        nfirst = q[slot].x;
+        ncnt = q[slot].y;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty0 + 8 * slot);
+        ++n;
+        nb = nfirst / tps;       // the only division: once per chunk
+        have_next = true;
+    }
+    __device__ __forceinline__ void take() {
+        cnt = ncnt; i = 0; b = nb; t = nfirst - nb * tps; have_next = false;
+    }
+    __device__ __forceinline__ void init(uint32_t full, uint32_t empty, const int2* queue, int tiles_per_sample, int lane) {
+        full0 = full; empty0 = empty; q = queue; n = 0; tps = tiles_per_sample;
+        fetch(lane);
+        take();
+    }
+    __device__ __forceinline__ bool done() const { return cnt == 0; }
+    __device__ __forceinline__ bool chunk_start() const { return i == 0; }
+    // sample of the tile after this one, -1 if this is the CTA's last tile (may wait for the producer)
+    __device__ __forceinline__ int peek_sample(int lane) {
+        if (i + 1 < cnt) return t + 1 == tps ? b + 1 : b;
+        if (!have_next) fetch(lane);
+        return ncnt > 0 ? nb : -1;
+    }
+    __device__ __forceinline__ void advance(int lane) {
+        if (i + 1 < cnt) {
+            ++i;
+            if (++t == tps) { t = 0; ++b; }
+            return;
+        }
+        if (!have_next) fetch(lane);
+        take();
+    }
+};
+
 // one arrival per consumer warp: every lane orders its tcgen05 / shared-memory traffic first
 __device__ __forceinline__ void warp_arrive(uint32_t bar, int lane) {
     __syncwarp();
@@ -236,16 +298,18 @@ __global__ void __launch_bounds__(kThreads, Tc5FwdCfg<T, IDF, NQ>::CTAS_PER_SM)
     unsigned char* g_out = g_b2 + C::NSPLIT * C::B2_BYTES;
 
     __shared__ __align__(8) unsigned long long bar_x_full[NST], bar_x_empty[NST], bar_s_full[2], bar_s_free[2], bar_lo_ready,
-        bar_p_ready, bar_c_full, bar_b_ready;
+        bar_p_ready, bar_c_full, bar_b_ready, bar_q_full[kQueueDepth], bar_q_empty[kQueueDepth];
+    __shared__ int2 q_ent[kQueueDepth];
     __shared__ uint32_t tmem_base_s;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int L = p.L, TPS = p.tiles_per_sample;
-    const int w_begin = (int)(((long long)blockIdx.x * p.n_tiles) / gridDim.x);
-    const int w_end = (int)(((long long)(blockIdx.x + 1) * p.n_tiles) / gridDim.x);
-    const int n_local = w_end - w_begin;
+    const int CH = p.chunk, ST = p.static_tiles;
+    // first chunk: this CTA's static share, or (no static share) dynamic chunk blockIdx.x
+    const int w_begin = (int)blockIdx.x * (ST > 0 ? ST : CH);
+    const int cnt0 = ST > 0 ? ST : (p.n_tiles - w_begin < CH ? p.n_tiles - w_begin : CH);
     const int b0 = w_begin / TPS, t0 = w_begin - b0 * TPS;
-    const int n_pre = n_local < NST ? n_local : NST;       // tiles whose loads thread 0 issues before the prologue
+    const int n_pre = cnt0 < NST ? cnt0 : NST;              // tiles whose loads thread 0 issues before the prologue
 
     if (tid == 0) {
 #pragma unroll
@@ -262,6 +326,11 @@ __global__ void __launch_bounds__(kThreads, Tc5FwdCfg<T, IDF, NQ>::CTAS_PER_SM)
         mbar_init(smem_u32(&bar_p_ready), 4);
         mbar_init(smem_u32(&bar_c_full), 1);
         mbar_init(smem_u32(&bar_b_ready), 4);
+#pragma unroll
+        for (int s = 0; s < kQueueDepth; ++s) {
+            mbar_init(smem_u32(&bar_q_full[s]), 1);
+            mbar_init(smem_u32(&bar_q_empty[s]), 5);       // MMA warp + 4 consumer warps
+        }
         fence_barrier_init();
         // the first ring of x tiles is requested before the rest of the prologue (TMEM allocation, operand
         // buffers) so that its DRAM latency runs under it; x does not depend on the projection grid
@@ -292,21 +361,42 @@ __global__ void __launch_bounds__(kThreads, Tc5FwdCfg<T, IDF, NQ>::CTAS_PER_SM)
     if (warp == kProducerWarp) {
         // --------------------------------- TMA producer -----------------------------------------
         // (the whole warp runs the loop; one elected lane issues - see elect_one())
-        int b = b0, t = t0 + n_pre;
-        while (t >= TPS) { t -= TPS; ++b; }
-        for (int j = n_pre; j < n_local; ++j) {
-            const int stage = j % NST;
-            mbar_wait(smem_u32(&bar_x_empty[stage]), (uint32_t)((j / NST) - 1) & 1u);
-            const uint32_t full = smem_u32(&bar_x_full[stage]);
-            const uint32_t dst = s_x + stage * C::STAGE_BYTES;
-            if (elect_one()) {
-                mbar_expect_tx(full, (uint32_t)C::STAGE_BYTES);
-#pragma unroll
-                for (int bx = 0; bx < C::NBOX; ++bx)
-                    tma_load_2d(dst + bx * C::BOX_BYTES, &tmx, t * TQ + bx * C::BOX_PX, b * IDF, full);
+        int j = 0;                                             // tiles issued so far (ring position)
+        int first = w_begin, cnt = cnt0;
+        for (int n = 0;; ++n) {
+            const int slot = n & (kQueueDepth - 1);
+            if (n >= kQueueDepth) mbar_wait(smem_u32(&bar_q_empty[slot]), (uint32_t)((n / kQueueDepth) - 1) & 1u);
+            if (lane == 0) {
+                q_ent[slot] = make_int2(first, cnt);
+                mbar_arrive(smem_u32(&bar_q_full[slot]));          // release: the entry is visible to the readers
             }
             __syncwarp();
-            if (++t == TPS) { t = 0; ++b; }
+            if (cnt == 0) break;
+            int bq = first / TPS, t = first - bq * TPS;
+            for (int i = 0; i < cnt; ++i, ++j, ++t) {
+                if (t == TPS) { t = 0; ++bq; }
+                if (n == 0 && i < n_pre) continue;                 // issued by thread 0 before the prologue
+                const int stage = j % NST;
+                if (j >= NST) mbar_wait(smem_u32(&bar_x_empty[stage]), (uint32_t)((j / NST) - 1) & 1u);
+                const uint32_t full = smem_u32(&bar_x_full[stage]);
+                const uint32_t dst = s_x + stage * C::STAGE_BYTES;
+                if (elect_one()) {
+                    mbar_expect_tx(full, (uint32_t)C::STAGE_BYTES);
+#pragma unroll
+                    for (int bx = 0; bx < C::NBOX; ++bx)
+                        tma_load_2d(dst + bx * C::BOX_BYTES, &tmx, t * TQ + bx * C::BOX_PX, bq * IDF, full);
+                }
+                __syncwarp();
+            }
+            // next chunk: the counter was zeroed by k_project_tc5, complete once griddepcontrol.wait returns
+            if (n == 0) asm volatile("griddepcontrol.wait;" ::: "memory");
+            int next = 0;
+            if (lane == 0) next = (ST > 0 ? 0 : (int)gridDim.x) + (int)atomicAdd(p.sched, 1u);
+            next = __shfl_sync(0xffffffffu, next, 0);
+            // (64-bit: the counter keeps growing while the last CTAs drain)
+            const long long nf = (long long)p.dyn_first + (long long)next * CH;
+            first = nf < p.n_tiles ? (int)nf : p.n_tiles;
+            cnt = p.n_tiles - first < CH ? p.n_tiles - first : CH;
         }
     } else if (warp == kMmaWarp) {
         // --------------------------------- MMA issuer -------------------------------------------
@@ -360,16 +450,18 @@ __global__ void __launch_bounds__(kThreads, Tc5FwdCfg<T, IDF, NQ>::CTAS_PER_SM)
             }
             __syncwarp();
         };
-        int t = t0;
+        ChunkReader rd;
+        rd.init(smem_u32(&bar_q_full[0]), smem_u32(&bar_q_empty[0]), q_ent, TPS, lane);
         uint32_t nb = 0;
-        if (n_local > 0) {
+        if (!rd.done()) {
             mbar_wait(smem_u32(&bar_b_ready), nb & 1u);
             ++nb;
             mma1(0);
         }
-        for (int j = 0; j < n_local; ++j) {
-            const bool has_next = j + 1 < n_local;
-            const bool next_same = has_next && (t + 1 < TPS);
+        for (int j = 0; !rd.done(); ++j) {
+            const int bn = rd.peek_sample(lane);
+            const bool has_next = bn >= 0;
+            const bool next_same = bn == rd.b;
             // bf16: S of the next tile is produced ahead of the softmax of this one; fp32: the lo tile of
             // the next tile is written only after P of this one, so MMA2 goes first
             if (!F32 && next_same) mma1(j + 1);
@@ -381,7 +473,7 @@ __global__ void __launch_bounds__(kThreads, Tc5FwdCfg<T, IDF, NQ>::CTAS_PER_SM)
             } else if (F32 && next_same) {
                 mma1(j + 1);
             }
-            if (++t == TPS) t = 0;
+            rd.advance(lane);
         }
     } else {
         // --------------------------------- consumers: thread = pixel ----------------------------
@@ -393,8 +485,10 @@ __global__ void __launch_bounds__(kThreads, Tc5FwdCfg<T, IDF, NQ>::CTAS_PER_SM)
         const uint32_t Bu = (uint32_t)p.B;
         const uint32_t step_mod = (uint32_t)TQ % Bu;
         // reference mask order: pixel n = b*Q + q uses caption n mod B (GlobalAttention.py:104-108)
-        uint32_t cap = (uint32_t)(((unsigned long long)w_begin * TQ + px) % Bu);
-        int b = b0, t = t0, cur_b = -1;
+        uint32_t cap = 0;
+        int b = 0, t = 0, cur_b = -1;
+        ChunkReader rd;
+        rd.init(smem_u32(&bar_q_full[0]), smem_u32(&bar_q_empty[0]), q_ent, TPS, lane);
         // this warp's output staging: lane = pixel column
         const uint32_t so_a = s_out + cw * C::OUT_WARP_BYTES, so_c = so_a + C::OUT_A_BYTES;
         T* go_a = reinterpret_cast<T*>(g_out + cw * C::OUT_WARP_BYTES) + lane;
@@ -418,48 +512,58 @@ __global__ void __launch_bounds__(kThreads, Tc5FwdCfg<T, IDF, NQ>::CTAS_PER_SM)
             }
         };
 
-        asm volatile("griddepcontrol.wait;" ::: "memory");      // srcT of k_project_tc5 is complete and visible
-        if (n_local > 0) make_lo(0);
-
-        for (int j = 0; j < n_local; ++j) {
-            if (b != cur_b) {
-                // ---- operands of sample b: B1[word][channel] = log2e*srcT, B2[channel][word] = srcT ----
-                // (every MMA that read the previous sample's operands has completed: c_full of tile j-1)
-                cur_b = b;
-                const float* sb = p.srcT + (size_t)b * IDF * L;
-                // thread -> (channel ct / 4 [+ 32 g], words (ct % 4) + 4 k): all loads of a thread are issued
-                // before the first is consumed (one L2 round trip), and no division by the runtime L
-                constexpr int NG = IDF / 32 + (IDF % 32 != 0), NK = LP / 4;
-                float sv[NG][NK];
+        // operands of a sample: B1[word][channel] = log2e * srcT, B2[channel][word] = srcT.
+        // thread -> (channel ct / 4 [+ 32 g], words (ct % 4) + 4 k): all loads of a thread are issued before the first
+        // is consumed (one L2 round trip), and no division by the runtime L.  load_src may run while the MMAs of the
+        // previous sample are still in flight; store_ops only after they have completed (c_full of its last tile).
+        constexpr int NG = IDF / 32 + (IDF % 32 != 0), NK = LP / 4;
+        float sv[NG][NK];
+        auto load_src = [&](int bs) {
+            const float* sb = p.srcT + (size_t)bs * IDF * L;
 #pragma unroll
-                for (int g = 0; g < NG; ++g)
+            for (int g = 0; g < NG; ++g)
 #pragma unroll
-                    for (int k = 0; k < NK; ++k) {
-                        const int ch = (ct >> 2) + 32 * g, l = (ct & 3) + 4 * k;
-                        sv[g][k] = (ch < IDF && l < L) ? __ldcg(sb + ch * L + l) : 0.f;
-                    }
+                for (int k = 0; k < NK; ++k) {
+                    const int ch = (ct >> 2) + 32 * g, l = (ct & 3) + 4 * k;
+                    sv[g][k] = (ch < IDF && l < L) ? __ldcg(sb + ch * L + l) : 0.f;
+                }
+        };
+        auto store_ops = [&]() {
 #pragma unroll
-                for (int g = 0; g < NG; ++g)
+            for (int g = 0; g < NG; ++g)
 #pragma unroll
-                    for (int k = 0; k < NK; ++k) {
-                        const int ch = (ct >> 2) + 32 * g, l = (ct & 3) + 4 * k;
-                        if (ch < IDF && l < L) {
-                            const float v = sv[g][k], v1 = v * kLog2e;
-                            const uint32_t o1 = kmajor_off<ES>(l, ch, C::KCH1), o2 = kmajor_off<ES>(ch, l, C::KCH2);
-                            if constexpr (F32) {
-                                const float h1 = tf32_rna(v1), h2 = tf32_rna(v);
-                                *reinterpret_cast<float*>(g_b1 + o1) = h1;
-                                *reinterpret_cast<float*>(g_b1 + C::B1_BYTES + o1) = tf32_rna(v1 - h1);
-                                *reinterpret_cast<float*>(g_b2 + o2) = h2;
-                                *reinterpret_cast<float*>(g_b2 + C::B2_BYTES + o2) = tf32_rna(v - h2);
-                            } else {
-                                *reinterpret_cast<__nv_bfloat16*>(g_b1 + o1) = __float2bfloat16_rn(v1);
-                                *reinterpret_cast<__nv_bfloat16*>(g_b2 + o2) = __float2bfloat16_rn(v);
-                            }
+                for (int k = 0; k < NK; ++k) {
+                    const int ch = (ct >> 2) + 32 * g, l = (ct & 3) + 4 * k;
+                    if (ch < IDF && l < L) {
+                        const float v = sv[g][k], v1 = v * kLog2e;
+                        const uint32_t o1 = kmajor_off<ES>(l, ch, C::KCH1), o2 = kmajor_off<ES>(ch, l, C::KCH2);
+                        if constexpr (F32) {
+                            const float h1 = tf32_rna(v1), h2 = tf32_rna(v);
+                            *reinterpret_cast<float*>(g_b1 + o1) = h1;
+                            *reinterpret_cast<float*>(g_b1 + C::B1_BYTES + o1) = tf32_rna(v1 - h1);
+                            *reinterpret_cast<float*>(g_b2 + o2) = h2;
+                            *reinterpret_cast<float*>(g_b2 + C::B2_BYTES + o2) = tf32_rna(v - h2);
+                        } else {
+                            *reinterpret_cast<__nv_bfloat16*>(g_b1 + o1) = __float2bfloat16_rn(v1);
+                            *reinterpret_cast<__nv_bfloat16*>(g_b2 + o2) = __float2bfloat16_rn(v);
                         }
                     }
-                fence_proxy_async();
-                warp_arrive(smem_u32(&bar_b_ready), lane);
+                }
+            fence_proxy_async();
+            warp_arrive(smem_u32(&bar_b_ready), lane);
+        };
+
+        asm volatile("griddepcontrol.wait;" ::: "memory");      // srcT of k_project_tc5 is complete and visible
+        if (!rd.done()) make_lo(0);
+
+        for (int j = 0; !rd.done(); ++j) {
+            b = rd.b;
+            t = rd.t;
+            if (rd.chunk_start()) cap = (uint32_t)((((unsigned long long)b * TPS + t) * TQ + px) % Bu);
+            if (b != cur_b) {            // first tile of the CTA (later boundaries are prepared one tile ahead, below)
+                cur_b = b;
+                load_src(b);
+                store_ops();
             }
 
             // ---- S row of this pixel (already in the log2 domain) ---------------------------------
@@ -518,7 +622,13 @@ __global__ void __launch_bounds__(kThreads, Tc5FwdCfg<T, IDF, NQ>::CTAS_PER_SM)
             tc_fence_before();
             warp_arrive(smem_u32(&bar_p_ready), lane);
 
-            if (j + 1 < n_local) make_lo(j + 1);       // fp32: MMA1(j) has completed, the lo tile is free
+            const int bn = rd.peek_sample(lane);
+            if constexpr (F32) {
+                if (bn >= 0) make_lo(j + 1);               // MMA1(j) has completed, the lo tile is free
+            }
+            // sample boundary ahead: fetch the next sample's srcT now, under MMA2(j) and the attention-map store
+            const bool boundary = bn >= 0 && bn != b;
+            if (boundary) load_src(bn);
 
             // ---- attention map: staged [word][32 px] per warp, one TMA box store -------------------
             const int q0 = t * TQ + cw * 32;
@@ -539,6 +649,10 @@ __global__ void __launch_bounds__(kThreads, Tc5FwdCfg<T, IDF, NQ>::CTAS_PER_SM)
             // ---- c row of this pixel ---------------------------------------------------------------
             mbar_wait(smem_u32(&bar_c_full), (uint32_t)j & 1u);
             tc_fence_after();
+            if (boundary) {                            // every MMA of this sample has completed: swap the operands now,
+                cur_b = bn;                            // so that MMA1 of the next tile runs under this tile's epilogue
+                store_ops();
+            }
             if (lane == 0) bulk_wait_read<1>();        // the previous c store has finished reading its staging
             __syncwarp();
 #pragma unroll
@@ -559,7 +673,7 @@ __global__ void __launch_bounds__(kThreads, Tc5FwdCfg<T, IDF, NQ>::CTAS_PER_SM)
                 bulk_commit();
             }
 
-            if (++t == TPS) { t = 0; ++b; }
+            rd.advance(lane);
             cap += step_mod;
             if (cap >= Bu) cap -= Bu;
         }
@@ -575,7 +689,8 @@ __global__ void __launch_bounds__(kThreads, Tc5FwdCfg<T, IDF, NQ>::CTAS_PER_SM)
 }
 
 template <typename T, int IDF, int NQ>
-int launch_fwd_tc5(const void* x, const Tc5FwdParams& p, int dtype, cudaStream_t st) {
+int launch_fwd_tc5(const void* x, const Tc5FwdParams& p_in, int dtype, cudaStream_t st) {
+    Tc5FwdParams p = p_in;
     const float* ctx = p.ctx;
     const float* W = p.W;
     float* srcT = p.srcT;
@@ -615,6 +730,21 @@ int launch_fwd_tc5(const void* x, const Tc5FwdParams& p, int dtype, cudaStream_t
     if (per_sm < 1) per_sm = 1;
     if (getenv("SBA_TC5_CTAS_PER_SM")) per_sm = atoi(getenv("SBA_TC5_CTAS_PER_SM"));
     const int max_ctas = sms * per_sm;
+    // Tile schedule: every CTA starts with a contiguous static share (few sample switches), the rest is handed
+    // out dynamically in small chunks so that SMs that stream faster take more (per-SM rates differ by +-40 %).
+    int grid = p.n_tiles < max_ctas ? p.n_tiles : max_ctas;
+    {
+        // short streams (a few tiles per CTA): whole static shares, single leftover tiles go to whoever is first
+        int pct = p.n_tiles < 8 * grid ? 100 : 80, ch = p.n_tiles < 8 * grid ? 1 : 2;
+        if (getenv("SBA_TC5_STATIC")) pct = atoi(getenv("SBA_TC5_STATIC"));
+        if (getenv("SBA_TC5_CHUNK")) ch = atoi(getenv("SBA_TC5_CHUNK"));
+        if (pct < 0 || pct > 100) pct = 80;
+        if (ch < 1) ch = 1;
+        p.static_tiles = (int)((long long)p.n_tiles * pct / 100 / grid);
+        p.chunk = ch;
+        if (p.static_tiles == 0 && grid > (p.n_tiles + ch - 1) / ch) grid = (p.n_tiles + ch - 1) / ch;   // one first chunk each
+        p.dyn_first = grid * p.static_tiles;
+    }
     CUtensorMap tmx, tma_attn, tma_c;
     const int es = dtype == SBA_F32 ? 4 : 2;
     int rc = make_tile_map(&tmx, x, dtype, p.B * IDF, p.Q, IDF, 128 / es, true);
@@ -632,7 +762,7 @@ int launch_fwd_tc5(const void* x, const Tc5FwdParams& p, int dtype, cudaStream_t
         pa[0].val.programmaticStreamSerializationAllowed = 1;
         pc.attrs = pa;
         pc.numAttrs = 1;
-        cudaError_t pe = cudaLaunchKernelEx(&pc, k_project_tc5, ctx, W, srcT, p.mask, p.mask_bits, (int)IDF, cdf, p.L);
+        cudaError_t pe = cudaLaunchKernelEx(&pc, k_project_tc5, ctx, W, srcT, p.mask, p.mask_bits, p.sched, (int)IDF, cdf, p.L);
         if (pe != cudaSuccess) {
             set_error("project(tcgen05): launch: %s", cudaGetErrorString(pe));
             return SBA_ERR_CUDA;
@@ -640,7 +770,6 @@ int launch_fwd_tc5(const void* x, const Tc5FwdParams& p, int dtype, cudaStream_t
     }
     rc = check_launch("project(tcgen05)");
     if (rc) return rc;
-    const int grid = p.n_tiles < max_ctas ? p.n_tiles : max_ctas;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(kThreads);
@@ -693,6 +822,7 @@ int tc5_attn_fwd(const void* x, const float* ctx, const float* W, const uint8_t*
     p.B = s.B; p.L = s.L; p.Q = s.Q; p.mask_mode = s.mask_mode;
     p.tiles_per_sample = s.Q / tc5::TQ;
     p.n_tiles = s.B * p.tiles_per_sample;
+    p.sched = mask_bits + s.B;            // scratch holds 3B words: [0, B) mask words, [B] chunk counter
     int rc = -1;
     if (s.dtype == SBA_F32) {
         if (s.idf == 32) rc = dispatch_nq<float, 32>(x, p, s.dtype, st);
