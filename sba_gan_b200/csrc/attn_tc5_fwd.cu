@@ -214,61 +214,6 @@ __global__ void __launch_bounds__(256) k_project_tc5(const float* __restrict__ c
 }
 
 
-// ----------------------------------------------------------------------------------------------
-// Dynamic tile schedule.  SMs do not stream at the same rate once the memory system is saturated
-// (per-SM duration of an equal static share spreads by +-40 % on B200, grouped by TPC position),
-// so tiles are handed out in chunks: chunk blockIdx.x first, then gridDim.x + atomicAdd(counter).
-// The producer warp fetches chunk ids and publishes {first tile, count} entries through a small
-// shared-memory queue; the MMA warp and the consumer warps read every entry (count 0 = end).
-// ----------------------------------------------------------------------------------------------
-constexpr int kQueueDepth = 8;
-struct ChunkReader {
-    uint32_t full0, empty0;      // shared addresses of the queue barriers
-    const volatile int2* q;
-    int n;                       // next queue entry to read
-    int tps;                     // tiles per sample
-    int cnt, i;                  // tiles of the current chunk, position in it
-    int b, t;                    // sample and tile-in-sample of the current tile
-    int nfirst, ncnt, nb;        // next chunk (valid when have_next)
-    bool have_next;
-    __device__ __forceinline__ void fetch(int lane) {
-        const int slot = n & (kQueueDepth - 1);
-        mbar_wait(full0 + 8 * slot, (uint32_t)(n / kQueueDepth) & 1u);
-        nfirst = q[slot].x;
-        ncnt = q[slot].y;
-        __syncwarp();
-        if (lane == 0) mbar_arrive(empty0 + 8 * slot);
-        ++n;
-        nb = nfirst / tps;       // the only division: once per chunk
-        have_next = true;
-    }
-    __device__ __forceinline__ void take() {
-        cnt = ncnt; i = 0; b = nb; t = nfirst - nb * tps; have_next = false;
-    }
-    __device__ __forceinline__ void init(uint32_t full, uint32_t empty, const int2* queue, int tiles_per_sample, int lane) {
-        full0 = full; empty0 = empty; q = queue; n = 0; tps = tiles_per_sample;
-        fetch(lane);
-        take();
-    }
-    __device__ __forceinline__ bool done() const { return cnt == 0; }
-    __device__ __forceinline__ bool chunk_start() const { return i == 0; }
-    // sample of the tile after this one, -1 if this is the CTA's last tile (may wait for the producer)
-    __device__ __forceinline__ int peek_sample(int lane) {
-        if (i + 1 < cnt) return t + 1 == tps ? b + 1 : b;
-        if (!have_next) fetch(lane);
-        return ncnt > 0 ? nb : -1;
-    }
-    __device__ __forceinline__ void advance(int lane) {
-        if (i + 1 < cnt) {
-            ++i;
-            if (++t == tps) { t = 0; ++b; }
-            return;
-        }
-        if (!have_next) fetch(lane);
-        take();
-    }
-};
-
 // one arrival per consumer warp: every lane orders its tcgen05 / shared-memory traffic first
 __device__ __forceinline__ void warp_arrive(uint32_t bar, int lane) {
     __syncwarp();
