@@ -75,7 +75,8 @@ SBA_API int sba_last_launch_count(void);
  * attn     [B, L, Q]     dtype  out attention map
  * srcT     [B, idf, L]   fp32   out sourceT = W.ctx, kept for the backward
  * scratch  [3*B] uint32  scratch    [0,B): caption mask bit words (kept for the backward),
- *                                   [B,3B): free for the kernels of this launch
+ *                                   [B,3B): free for the kernels of this launch (word B is the
+ *                                   tile-schedule counter of the tcgen05 forward)
  */
 SBA_API int sba_attn_fwd(const void* x, const float* ctx, const float* W, const uint8_t* mask,
                  void* c_code, void* attn, float* srcT, uint32_t* scratch,

@@ -2,7 +2,8 @@
 // (SBA_ALGO_TCGEN05): TMA tensor loads -> tcgen05.mma -> TMEM -> one pixel per thread.
 //
 // One persistent CTA = 1 TMA producer warp + 1 MMA-issuing warp + 4 consumer warps, working
-// through a contiguous range of 128-pixel tiles:
+// through 128-pixel tiles: a contiguous static share first, then small chunks fetched from a
+// global counter (tc5_common.cuh: ChunkReader; SMs stream at different rates under load):
 //   producer : 2-D TMA box loads of the [idf x 128 px] tile of x (128-byte swizzled rows) into a
 //              shared-memory ring; the tile as it lands is the MN-major A operand of MMA1.
 //   MMA warp : MMA1  S[128 x 32]  = x_tile^T . (log2e * sourceT)      (K = idf)
@@ -13,7 +14,8 @@
 //              [word][32 px] per warp, one TMA box store -> tcgen05.ld c row -> staged, TMA box store.
 // S is double buffered in TMEM (MMA1 of the next tile runs ahead of the softmax of this one).
 // The B operands (sourceT of the current sample, both orientations, zero padded) are rebuilt in
-// shared memory by the consumers whenever the tile range enters a new sample.
+// shared memory by the consumers whenever the tile sequence enters a new sample (prepared one
+// tile ahead: srcT is fetched under MMA2, the swap follows c_full).
 // bf16 tensors: single bf16 MMAs.  fp32 tensors: 3xTF32 - every operand is split into a tf32
 // "hi" part and a residual "lo" part and multiplied as hi.hi + lo.hi + hi.lo (~2^-21 relative);
 // the hi part of x is the tile itself (the tensor core reads the top 19 bits), its lo part
