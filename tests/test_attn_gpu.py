@@ -101,6 +101,8 @@ SWEEP = [
     (5, 48, 20, 32, 16, True, "per_sample", False),    # default WORDS_NUM
     (2, 32, 9, 16, 16, False, "reference", True),      # smallest L of the tensor-core family
     (130, 32, 18, 16, 8, True, "reference", False),    # more samples than CTAs-per-sample logic assumes
+    (100, 32, 18, 60, 64, True, "reference", False),   # 30 tiles per sample (not a power of two), 3000 tiles: the
+                                                       # dynamic tail of the tcgen05 forward's tile schedule (fp32 grid)
 ]
 
 
@@ -148,7 +150,8 @@ def test_full_size_fp32(hw, algo):
 
 @pytest.mark.parametrize("algo", ALGOS)
 @pytest.mark.parametrize("spec", [(10, 32, 18, 64, 64, True), (3, 48, 12, 16, 16, False), (64, 32, 18, 64, 64, True),
-                                  (2, 64, 32, 16, 16, True), (5, 32, 4, 16, 8, True), (130, 32, 20, 16, 8, True)])
+                                  (2, 64, 32, 16, 16, True), (5, 32, 4, 16, 8, True), (130, 32, 20, 16, 8, True),
+                                  (160, 32, 18, 60, 64, True)])      # 4800 tiles of 30 per sample: dynamic tile schedule
 def test_bf16_io(spec, algo):
     """bf16 tensors, fp32 arithmetic.  Oracle = fp32 reference maths on the bf16-rounded
     inputs (SURVEY.md §8 parity note); tolerance 2e-2."""
