@@ -40,7 +40,9 @@ struct WL {
     static constexpr int A2T = NC * RP * TP;
     static constexpr int SCR = NC * WPC * 32;
     static constexpr int ALPHA = NC * 32;
-    static constexpr size_t kSmemBytes = (size_t)(XBUF + WBUF + A2T + SCR + ALPHA) * sizeof(float);
+    // x / w tiles double buffered where that fits in 220 KB (all but the 32-word variant)
+    static constexpr int NBUF = (size_t)(2 * XBUF + 2 * WBUF + A2T + SCR + ALPHA) * sizeof(float) <= 220 * 1024 ? 2 : 1;
+    static constexpr size_t kSmemBytes = (size_t)(NBUF * XBUF + NBUF * WBUF + A2T + SCR + ALPHA) * sizeof(float);
 };
 
 struct OpSum { __device__ __forceinline__ float operator()(float a, float b) const { return a + b; } };
@@ -82,6 +84,17 @@ __device__ __forceinline__ void caption_allreduce(float (&v)[C::TP], float* scra
     __syncthreads();
 }
 
+
+// 4-byte asynchronous global -> shared copy (zero fill when !valid): the next image tile streams in while the
+// FMAs of the current one run
+__device__ __forceinline__ void cp_async4(float* dst, const float* src, bool valid) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
+    const int sz = valid ? 4 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 struct WordsArgs {
     const float* img;       // [B_img][nef][R]
     const float* words;     // [B_cap][nef][Lw]
@@ -100,34 +113,59 @@ struct WordsArgs {
     int fixed_T;
 };
 
-// streams one [KC x RP] channel-major tile of image j and one [KC x NC x TP] tile of the
-// (optionally alpha-scaled + v-shifted) words into shared memory
-template <class C, bool DWC>
-__device__ __forceinline__ void load_p1_tiles(const WordsArgs& a, int j, int cap0, int c0, const int* T_s,
-                                              const float* alpha_s, float* xbuf, float* wbuf, int tid) {
+// [KC x RP] channel-major tile of image j -> shared memory, asynchronously (cp.async, zero fill)
+template <class C>
+__device__ __forceinline__ void load_x_p1_async(const WordsArgs& a, int j, int c0, float* xbuf, int tid) {
     const float* xj = a.img + (size_t)j * a.nef * a.R;
     for (int idx = tid; idx < C::KC * C::RP; idx += C::kThreads) {
         const int kk = idx / C::RP, r = idx - kk * C::RP;
         const int c = c0 + kk;
-        xbuf[idx] = (c < a.nef && r < a.R) ? __ldg(xj + (size_t)c * a.R + r) : 0.f;
-    }
-    for (int idx = tid; idx < C::KC * C::NC * C::TP; idx += C::kThreads) {
-        const int kk = idx / (C::NC * C::TP);
-        const int rem = idx - kk * (C::NC * C::TP);
-        const int cp = rem / C::TP, t = rem - cp * C::TP;
-        const int c = c0 + kk;
-        const int ii = a.paired ? j : cap0 + cp;
-        float val = 0.f;
-        if (c < a.nef && t < T_s[cp]) {
-            val = __ldg(a.words + ((size_t)ii * a.nef + c) * a.Lw + t);
-            if (DWC) {
-                // dwc[c,t] = alpha_t W[c,t] + v[c,t]; v was written by this CTA before the barrier
-                val = alpha_s[cp * 32 + t] * val + a.ws_v[(((size_t)j * a.nef + c) * a.B_cap + ii) * a.Lw + t];
-            }
-        }
-        wbuf[idx] = val;
+        const bool ok = c < a.nef && r < a.R;
+        cp_async4(xbuf + idx, ok ? xj + (size_t)c * a.R + r : xj, ok);
     }
 }
+// [KC x NC x TP] tile of the (optionally alpha-scaled + v-shifted) words: loaded into registers, stored later
+template <class C>
+struct WTile {
+    static constexpr int N = (C::KC * C::NC * C::TP + C::kThreads - 1) / C::kThreads;
+    float v[N];
+};
+template <class C, bool DWC>
+__device__ __forceinline__ void load_w_regs(const WordsArgs& a, int j, int cap0, int c0, const int* T_s, const float* alpha_s,
+                                            WTile<C>& w, int tid) {
+#pragma unroll
+    for (int s = 0; s < WTile<C>::N; ++s) {
+        const int idx = tid + s * C::kThreads;
+        float val = 0.f;
+        if (idx < C::KC * C::NC * C::TP) {
+            const int kk = idx / (C::NC * C::TP);
+            const int rem = idx - kk * (C::NC * C::TP);
+            const int cp = rem / C::TP, t = rem - cp * C::TP;
+            const int c = c0 + kk;
+            const int ii = a.paired ? j : cap0 + cp;
+            if (c < a.nef && t < T_s[cp]) {
+                val = __ldg(a.words + ((size_t)ii * a.nef + c) * a.Lw + t);
+                if (DWC) {
+                    // dwc[c,t] = alpha_t W[c,t] + v[c,t]; v was written by this CTA before the barrier
+                    val = alpha_s[cp * 32 + t] * val + a.ws_v[(((size_t)j * a.nef + c) * a.B_cap + ii) * a.Lw + t];
+                }
+            }
+        }
+        w.v[s] = val;
+    }
+}
+template <class C>
+__device__ __forceinline__ void store_w_regs(const WTile<C>& w, float* wbuf, int tid) {
+#pragma unroll
+    for (int s = 0; s < WTile<C>::N; ++s) {
+        const int idx = tid + s * C::kThreads;
+        if (idx < C::KC * C::NC * C::TP) wbuf[idx] = w.v[s];
+    }
+}
+// P1 / P3 contraction over all channels: acc[q][t] = sum_c X[c, r0+q] * Wc[c, cap, t], tiles double buffered
+template <class C, bool DWC, bool STAGE>
+__device__ __forceinline__ void p1_all(const WordsArgs& a, int j, int cap0, const int* T_s, const float* alpha_s, float* xbuf,
+                                       float* wbuf, int r0, int cap, int tid, float (&acc)[C::RT][C::TP]);
 
 // acc[a][t] += sum over the chunk's channels of X[c, r0+a] * Wc[c, cap, t]
 template <class C>
@@ -155,13 +193,58 @@ __device__ __forceinline__ void p1_chunk(const float* xbuf, const float* wbuf, i
     }
 }
 
+template <class C, bool DWC, bool STAGE>
+__device__ __forceinline__ void p1_all(const WordsArgs& a, int j, int cap0, const int* T_s, const float* alpha_s, float* xbuf,
+                                       float* wbuf, int r0, int cap, int tid, float (&acc)[C::RT][C::TP]) {
+    WTile<C> w;
+    __syncthreads();                      // the tile buffers are free (and, DWC: ws_v / alpha_s writes are visible)
+    load_x_p1_async<C>(a, j, 0, xbuf, tid);
+    cp_async_commit();
+    load_w_regs<C, DWC>(a, j, cap0, 0, T_s, alpha_s, w, tid);
+    store_w_regs<C>(w, wbuf, tid);
+    cp_async_wait_all();
+    __syncthreads();
+    int buf = 0;
+    for (int c0 = 0; c0 < a.nef; c0 += C::KC) {
+        const bool more = c0 + C::KC < a.nef;
+        if constexpr (C::NBUF == 2) {
+            if (more) {
+                load_x_p1_async<C>(a, j, c0 + C::KC, xbuf + (buf ^ 1) * C::XBUF, tid);
+                cp_async_commit();
+                load_w_regs<C, DWC>(a, j, cap0, c0 + C::KC, T_s, alpha_s, w, tid);
+                // the backward kernel runs at the register limit: its small word tile is stored at once instead of being
+                // held across the FMA block (one exposed L2 round trip per chunk; the image tile stays asynchronous)
+                if (!STAGE) store_w_regs<C>(w, wbuf + (buf ^ 1) * C::WBUF, tid);
+            }
+            p1_chunk<C>(xbuf + buf * C::XBUF, wbuf + buf * C::WBUF, r0, cap, acc);
+            if (more) {
+                if (STAGE) store_w_regs<C>(w, wbuf + (buf ^ 1) * C::WBUF, tid);
+                cp_async_wait_all();
+            }
+            __syncthreads();
+            buf ^= 1;
+        } else {                                  // single buffers: load the next tile after the FMAs of this one
+            p1_chunk<C>(xbuf, wbuf, r0, cap, acc);
+            __syncthreads();
+            if (more) {
+                load_x_p1_async<C>(a, j, c0 + C::KC, xbuf, tid);
+                cp_async_commit();
+                load_w_regs<C, DWC>(a, j, cap0, c0 + C::KC, T_s, alpha_s, w, tid);
+                store_w_regs<C>(w, wbuf, tid);
+                cp_async_wait_all();
+                __syncthreads();
+            }
+        }
+    }
+}
+
 template <class C, bool BWD>
 __global__ void __launch_bounds__(C::kThreads, 1) k_words(const WordsArgs a) {
     constexpr int TP = C::TP, RT = C::RT, TPC = C::TPC, NC = C::NC, RP = C::RP, CPT = C::CPT;
     extern __shared__ __align__(16) float smem[];
-    float* xbuf = smem;
-    float* wbuf = xbuf + C::XBUF;
-    float* a2t = wbuf + C::WBUF;     // [NC][RP][TP]
+    float* xbuf = smem;                       // [NBUF][XBUF]
+    float* wbuf = xbuf + C::NBUF * C::XBUF;   // [NBUF][WBUF]
+    float* a2t = wbuf + C::NBUF * C::WBUF;    // [NC][RP][TP]
     float* scratch = a2t + C::A2T;   // [NC][WPC][32]
     float* alpha_s = scratch + C::SCR;  // [NC][32]
     __shared__ int T_s[NC];
@@ -189,12 +272,7 @@ __global__ void __launch_bounds__(C::kThreads, 1) k_words(const WordsArgs a) {
     for (int q = 0; q < RT; ++q)
 #pragma unroll
         for (int t = 0; t < TP; ++t) s[q][t] = 0.f;
-    for (int c0 = 0; c0 < a.nef; c0 += C::KC) {
-        __syncthreads();
-        load_p1_tiles<C, false>(a, j, cap0, c0, T_s, alpha_s, xbuf, wbuf, tid);
-        __syncthreads();
-        p1_chunk<C>(xbuf, wbuf, r0, cap, s);
-    }
+    p1_all<C, false, !BWD>(a, j, cap0, T_s, alpha_s, xbuf, wbuf, r0, cap, tid, s);
 
     // ---- a1 = softmax over words (GlobalAttention.py:50-51), thread local ----------------
 #pragma unroll
@@ -286,20 +364,31 @@ __global__ void __launch_bounds__(C::kThreads, 1) k_words(const WordsArgs a) {
     {
         const float* xj = a.img + (size_t)j * a.nef * a.R;
         const int warp = tid >> 5;
+        auto load_x_p2_async = [&](int rc0, float* xb) {
+            const int r = rc0 + lane;
+            for (int c = warp; c < a.nef; c += C::kWarps)
+                cp_async4(xb + lane * C::XT_STRIDE + c, r < a.R ? xj + (size_t)c * a.R + r : xj, r < a.R);
+        };
+        __syncthreads();                  // P1's last tile has been consumed
+        load_x_p2_async(0, xbuf);
+        cp_async_commit();
+        cp_async_wait_all();
+        __syncthreads();
+        int buf = 0;
         for (int rc0 = 0; rc0 < a.R; rc0 += C::RC) {
-            __syncthreads();
-            for (int c = warp; c < a.nef; c += C::kWarps) {
-                const int r = rc0 + lane;
-                xbuf[lane * C::XT_STRIDE + c] = (r < a.R) ? __ldg(xj + (size_t)c * a.R + r) : 0.f;
+            const bool more = rc0 + C::RC < a.R;
+            if (C::NBUF == 2 && more) {
+                load_x_p2_async(rc0 + C::RC, xbuf + (buf ^ 1) * C::XBUF);
+                cp_async_commit();
             }
-            __syncthreads();
+            const float* xb = xbuf + buf * C::XBUF;
 #pragma unroll 2
             for (int rr = 0; rr < C::RC; ++rr) {
                 float xv[CPT];
 #pragma unroll
                 for (int k = 0; k < CPT; ++k) {
                     const int ch = tc + k * TPC;
-                    xv[k] = (ch < a.nef) ? xbuf[rr * C::XT_STRIDE + ch] : 0.f;
+                    xv[k] = (ch < a.nef) ? xb[rr * C::XT_STRIDE + ch] : 0.f;
                 }
                 const float2* a2 = reinterpret_cast<const float2*>(a2t + ((size_t)cap * RP + rc0 + rr) * TP);
 #pragma unroll
@@ -310,6 +399,19 @@ __global__ void __launch_bounds__(C::kThreads, 1) k_words(const WordsArgs a) {
                         wc[k][2 * t2] = fmaf(xv[k], w.x, wc[k][2 * t2]);
                         wc[k][2 * t2 + 1] = fmaf(xv[k], w.y, wc[k][2 * t2 + 1]);
                     }
+                }
+            }
+            if constexpr (C::NBUF == 2) {
+                if (more) cp_async_wait_all();
+                __syncthreads();
+                buf ^= 1;
+            } else {
+                __syncthreads();
+                if (more) {
+                    load_x_p2_async(rc0 + C::RC, xbuf);
+                    cp_async_commit();
+                    cp_async_wait_all();
+                    __syncthreads();
                 }
             }
         }
@@ -406,12 +508,7 @@ __global__ void __launch_bounds__(C::kThreads, 1) k_words(const WordsArgs a) {
         for (int q = 0; q < RT; ++q)
 #pragma unroll
             for (int t = 0; t < TP; ++t) s[q][t] = 0.f;
-        for (int c0 = 0; c0 < a.nef; c0 += C::KC) {
-            __syncthreads();   // also orders the ws_v / alpha_s writes above before the reads below
-            load_p1_tiles<C, true>(a, j, cap0, c0, T_s, alpha_s, xbuf, wbuf, tid);
-            __syncthreads();
-            p1_chunk<C>(xbuf, wbuf, r0, cap, s);
-        }
+        p1_all<C, true, false>(a, j, cap0, T_s, alpha_s, xbuf, wbuf, r0, cap, tid, s);   // (its first barrier orders the ws_v / alpha_s writes)
         // softmax-over-regions backward: dz = a2 * (da2 - sum_r a2 da2)
         float dotr[TP];
 #pragma unroll
