@@ -8,7 +8,8 @@
 //   P2  wc[c,t]  = sum_r X[c,r] a2[t,r]                (thread = 4 channels x all words)
 //       cos_t    = <W_t, wc_t> / max(|W_t||wc_t|, eps); sim = gamma3 log sum_t exp(gamma2 cos_t)
 // with the image tile streamed through shared memory twice (channel-major for P1,
-// region-major for P2).  The backward (template BWD) recomputes the above, then
+// region-major for P2) by cp.async into double buffers, the next slice landing under the FMAs of
+// the current one.  The backward (template BWD) recomputes the above, then
 //   P3  da2[r,t] = sum_c X[c,r] dwc[c,t],  softmax backward twice -> ds
 // and materialises per-pair  u = ds + alpha a2,  a2,  v = beta wc  in HBM so that the two
 // dense gradient contractions become plain batched GEMMs (k_gemm below):
