@@ -54,17 +54,40 @@ __device__ __forceinline__ bool elect_one() {
 }
 
 // ---- TMA: 2-D tensor-map box load, completion on an mbarrier --------------------------------
+// L2 eviction-priority hint for streaming tensors (read once / written once): evict_first keeps them from
+// displacing each other's dirty lines.  Compile-time switch for A/B measurements.
+#ifndef SBA_TC5_L2_HINTS
+#define SBA_TC5_L2_HINTS 0
+#endif
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, uint32_t bar) {
+#if SBA_TC5_L2_HINTS & 1
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;"
+        ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(bar), "l"(l2_policy_evict_first())
+        : "memory");
+#else
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
         ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(bar)
         : "memory");
+#endif
 }
 // shared -> global box store (bulk async-group completion)
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, int c0, int c1, uint32_t src) {
+#if SBA_TC5_L2_HINTS & 2
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%1, %2}], [%3], %4;" ::"l"(tm),
+                 "r"(c0), "r"(c1), "r"(src), "l"(l2_policy_evict_first())
+                 : "memory");
+#else
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(tm), "r"(c0), "r"(c1),
                  "r"(src)
                  : "memory");
+#endif
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // all but the N most recent bulk groups of this thread have finished READING shared memory
