@@ -145,6 +145,7 @@ __global__ void __launch_bounds__(256) k_bwd_post_tc5(const float* __restrict__ 
     extern __shared__ __align__(16) float sm[];
     constexpr bool HI = IDF > 32;          // a thread owns channel i0 and, for idf > 32, i0 + 32
     const int tid = threadIdx.x;
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");      // (the head kernel of the next call, see above)
     if (threadIdx.x == 0) tl_min(tl < 0 ? tl : tl + 6);
     if ((int)blockIdx.x < n_dw) {
         float* cs = sm;                          // [K <= 128][kPostCS]

@@ -251,6 +251,9 @@ __global__ void __launch_bounds__(kThreads, Tc5FwdCfg<T, IDF, NQ>::CTAS_PER_SM)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int L = p.L, TPS = p.tiles_per_sample;
+    // a programmatic dependent behind this grid (the head kernel of the next call) may become resident now; it
+    // parks in griddepcontrol.wait until this grid has completed, which takes its launch latency off the stream
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int CH = p.chunk, ST = p.static_tiles;
     // first chunk: this CTA's static share, or (no static share) dynamic chunk blockIdx.x
     const int w_begin = (int)blockIdx.x * (ST > 0 ? ST : CH);
