@@ -359,9 +359,11 @@ def run_reference(args):
         x, gc, ctx, mask = make_inputs(hw, 1234 + hw, torch.float32, "cpu")
         w = torch.nn.init.orthogonal_(torch.empty(IDF, CDF), 1.0)
         inputs.append((x, gc, ctx, mask, w))
-    for _ in range(max(1, min(args.warmup, 2))):
+    # K and W as asked (a step is ~0.1 s on the box's host cores), bounded so that the run stays within minutes
+    warmup = max(1, min(args.warmup, 50))
+    for _ in range(warmup):
         reference_step_cpu(inputs, n_threads)
-    steps = max(1, min(args.steps, 10))
+    steps = max(1, min(args.steps, 500))
     ts = []
     for _ in range(steps):
         t0 = time.perf_counter()
@@ -373,7 +375,7 @@ def run_reference(args):
     sample = f"{steps} full steps (B=64, 64x64 + 128x128 fwd+bwd) fp32, median"
     return {
         "impl": "reference", "metric": "word-attn fwd+bwd region-px/s", "value": value, "unit": "region-px/s",
-        "n_gpus": args.gpus, "steps": steps, "warmup": max(1, min(args.warmup, 2)), "ms_per_step": round(t * 1e3, 2),
+        "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": round(t * 1e3, 2),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "B_per_gpu": B_PER_GPU, "regions": [hw * hw for hw in STAGES],
                    "note": "reference CPU path = oracle port (torch CPU); the Python reference cannot travel to the GPU box"},
