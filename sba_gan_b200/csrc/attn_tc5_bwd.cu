@@ -730,6 +730,16 @@ int launch_bwd_tc5(const void* x, const void* g, void* dX, const Tc5BwdParams& p
         {
             long long t0 = h[256];
             for (int k = 0; k < grid && k < 1900; ++k) if (h[256 + 2 * k] < t0) t0 = h[256 + 2 * k];
+            {
+                double sum = 0; long long mx = 0, mn = 1LL << 62; int n = 0;
+                for (int k = 0; k < grid && k < 1900; ++k) {
+                    const long long d = h[256 + 2 * k + 1] - h[256 + 2 * k];
+                    sum += (double)d; ++n;
+                    if (d > mx) mx = d;
+                    if (d < mn) mn = d;
+                }
+                fprintf(stderr, "CTA lifetime over %d CTAs: min %lld mean %.0f max %lld ns\n", n, mn, sum / n, mx);
+            }
             fprintf(stderr, "CTA start/end (ns since the first start), every 37th CTA:\n");
             for (int k = 0; k < grid && k < 1900; k += 37)
                 fprintf(stderr, "  cta %4d: %7lld .. %7lld\n", k, h[256 + 2 * k] - t0, h[256 + 2 * k + 1] - t0);
