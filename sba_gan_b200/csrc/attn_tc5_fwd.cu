@@ -109,7 +109,13 @@ struct Tc5FwdCfg {
     static constexpr int B1_BYTES = NS * IDF * ES;
     static constexpr int B2_BYTES = IDF * K2 * ES;
     static constexpr int NSPLIT = F32 ? 2 : 1;
-    static constexpr int NST = F32 ? 3 : 4;                    // x ring depth
+#ifndef SBA_NST_BF16
+#define SBA_NST_BF16 3      // measured: 2 and 3 beat 4 by 2-7 % (smaller footprint; the ring never runs dry), 6 loses a CTA per SM
+#endif
+#ifndef SBA_NST_F32
+#define SBA_NST_F32 3
+#endif
+    static constexpr int NST = F32 ? SBA_NST_F32 : SBA_NST_BF16;   // x ring depth (compile-time switches for A/B measurements)
     static constexpr int NLO = F32 ? 1 : 0;                    // lo tile (fp32)
     static constexpr int PC = F32 ? K2 : K2 / 2;               // TMEM columns of one P operand
     static constexpr int COL_S = 0, COL_P = 64, COL_PLO = 96, COL_C = F32 ? 128 : 96;
