@@ -79,7 +79,7 @@ constexpr int kFirstEpilogueWarp = 6;
 
 constexpr int pow2_cols(int n) { return n <= 32 ? 32 : n <= 64 ? 64 : n <= 128 ? 128 : n <= 256 ? 256 : 512; }
 
-template <int IDF, int NQ>
+template <int IDF, int NQ, int NST_ = 3>
 struct Tc5BwdCfg {
     static constexpr int ES = 2;                                // bf16
     static constexpr int LP = 4 * NQ;                           // words held per thread
@@ -98,7 +98,7 @@ struct Tc5BwdCfg {
     static constexpr int B1_BYTES = NS * IDF * ES, B2_BYTES = IDF * K2 * ES;
     static constexpr int PB_KBLOCK = NR * 128;                  // bytes of one 64-pixel block of PB
     static constexpr int PB_BYTES = NBOX * PB_KBLOCK;           // one PB buffer; two of them alternate (software pipeline)
-    static constexpr int NST = 3;
+    static constexpr int NST = NST_;                            // g/x ring depth: 3, or 4 for long streams at idf 32 (measured +2-4 %)
     static constexpr int MD = 2 * IDF <= 64 ? 64 : 128;         // M of the dSrc MMA
     // TMEM columns: two {S, dP} buffers (tile parity), dX, the dSrc accumulator
     static constexpr int COL_S = 0, COL_DP = 32, COL_BUF = 64, COL_DX = 128, COL_ACC = 128 + IDF;
@@ -249,11 +249,11 @@ __device__ __forceinline__ void warp_arrive(uint32_t bar, int lane) {
     if (lane == 0) mbar_arrive(bar);
 }
 
-template <int IDF, int NQ, bool HAS_GA>
-__global__ void __launch_bounds__(kBwdThreads, Tc5BwdCfg<IDF, NQ>::CTAS_PER_SM)
+template <int IDF, int NQ, bool HAS_GA, int NST_>
+__global__ void __launch_bounds__(kBwdThreads, Tc5BwdCfg<IDF, NQ, NST_>::CTAS_PER_SM)
     k_attn_bwd_tc5(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_g,
                    const __grid_constant__ CUtensorMap tm_dx, const Tc5BwdParams p) {
-    using C = Tc5BwdCfg<IDF, NQ>;
+    using C = Tc5BwdCfg<IDF, NQ, NST_>;
     using T = __nv_bfloat16;
     constexpr int LP = C::LP, RP = C::RP, NST = C::NST;
     constexpr float kLog2e = 1.4426950408889634f;
@@ -656,10 +656,10 @@ __global__ void __launch_bounds__(kBwdThreads, Tc5BwdCfg<IDF, NQ>::CTAS_PER_SM)
     if (tid == 0) tl_max(p.tl < 0 ? p.tl : p.tl + 3);
 }
 
-template <int IDF, int NQ, bool HAS_GA>
+template <int IDF, int NQ, bool HAS_GA, int NST_>
 int launch_bwd_tc5(const void* x, const void* g, void* dX, const Tc5BwdParams& p, cudaStream_t st) {
-    using C = Tc5BwdCfg<IDF, NQ>;
-    auto kern = k_attn_bwd_tc5<IDF, NQ, HAS_GA>;
+    using C = Tc5BwdCfg<IDF, NQ, NST_>;
+    auto kern = k_attn_bwd_tc5<IDF, NQ, HAS_GA, NST_>;
     const size_t smem = (size_t)C::SMEM_BYTES + (2 * C::NST + 14) * 8;
     // per device (a process may drive several): SM count, and whether this kernel's dynamic shared memory
     // limit has been raised there (smem is a compile-time constant of the instantiation)
@@ -764,17 +764,22 @@ int launch_bwd_tc5(const void* x, const void* g, void* dX, const Tc5BwdParams& p
 
 template <int IDF, bool HAS_GA>
 int dispatch_nq(const void* x, const void* g, void* dX, const Tc5BwdParams& p, cudaStream_t st) {
+    // long streams at idf 32 (>= 16 tiles per CTA of a 2-per-SM grid, e.g. 128x128 at B >= 40) take the 4-deep ring:
+    // it still fits two CTAs per SM there and measured 2-4 % faster; short streams lose to its longer prologue
+    constexpr bool kDeep = IDF == 32;
+    const bool deep = kDeep && p.n_tiles >= 16 * 2 * 148;
+#define SBA_BWD_CASE(n)                                                                     \
+    case n:                                                                                 \
+        if constexpr (kDeep) {                                                              \
+            if (deep) return launch_bwd_tc5<IDF, n, HAS_GA, 4>(x, g, dX, p, st);            \
+        }                                                                                   \
+        return launch_bwd_tc5<IDF, n, HAS_GA, 3>(x, g, dX, p, st);
     switch ((p.L + 3) / 4) {
-        case 1: return launch_bwd_tc5<IDF, 1, HAS_GA>(x, g, dX, p, st);
-        case 2: return launch_bwd_tc5<IDF, 2, HAS_GA>(x, g, dX, p, st);
-        case 3: return launch_bwd_tc5<IDF, 3, HAS_GA>(x, g, dX, p, st);
-        case 4: return launch_bwd_tc5<IDF, 4, HAS_GA>(x, g, dX, p, st);
-        case 5: return launch_bwd_tc5<IDF, 5, HAS_GA>(x, g, dX, p, st);
-        case 6: return launch_bwd_tc5<IDF, 6, HAS_GA>(x, g, dX, p, st);
-        case 7: return launch_bwd_tc5<IDF, 7, HAS_GA>(x, g, dX, p, st);
-        case 8: return launch_bwd_tc5<IDF, 8, HAS_GA>(x, g, dX, p, st);
+        SBA_BWD_CASE(1) SBA_BWD_CASE(2) SBA_BWD_CASE(3) SBA_BWD_CASE(4)
+        SBA_BWD_CASE(5) SBA_BWD_CASE(6) SBA_BWD_CASE(7) SBA_BWD_CASE(8)
         default: return -1;
     }
+#undef SBA_BWD_CASE
 }
 
 template <int IDF>
