@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""bench.py - headline benchmark of the word-region attention hot path (BASELINE.json).
+"""bench.py - benchmark of the word-region attention hot path (BASELINE.json).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--dtype bf16|fp32]
 
@@ -10,16 +10,24 @@ step   : one G_NET training pass over the attention hot path at BASELINE configs
          (the attention map is discarded in training, trainer_bert.py:267).
 value  : inputs resident in HBM, CUDA events, max over ranks.
 e2e    : the same step through the public module (GlobalAttentionGeneral.forward + autograd)
-         with HOST buffers: pinned H2D of x / context / g_c and D2H of the weight gradients and
-         a scalar every step.
---impl reference: the reference's CPU path (oracle port, torch CPU fp32, all host threads).
-Multi-GPU (torchrun): batch-sharded, weak scaling; the only exchange is the all-reduce of the
-conv_context weight gradients (what the generator's DDP bucket would carry).
+         with HOST buffers: pinned H2D of x / context / g_c (prefetched on a copy stream, one step
+         ahead, as a training input pipeline would) and D2H of the weight gradients + a scalar.
+sub    : the rest of BASELINE.json's metric and configs, each a bounded measurement in the same run:
+         fp32 (the same step with fp32 tensors), sustained (>= 2 s of back-to-back steps, own clock sample),
+         gpu_eager_baseline (the reference's eager torch op sequence on the same GPU),
+         batch_sweep (configs[4]: 128 samples per GPU at 128x128), words_loss (configs[2]: B = 48 / 256,
+         row-sharded over the ranks when N > 1), gan_step (configs[3]: full G+D adversarial step,
+         imgs/s at N GPUs, fused hot path vs eager reference ops).
+--impl reference: the reference's own CPU implementation of the step (oracle/_ref when present, else
+         the oracle port), torch CPU fp32, all host threads.
+Multi-GPU (torchrun): batch-sharded, weak scaling; the only exchange of the headline step is ONE
+flattened all-reduce of the two conv_context weight gradients (what the generator's DDP bucket carries).
 """
 from __future__ import annotations
 
 import argparse
 import json
+import math
 import os
 import statistics
 import subprocess
@@ -35,6 +43,7 @@ import torch  # noqa: E402
 B_PER_GPU, IDF, CDF, L = 64, 32, 256, 18
 STAGES = (64, 128)
 WORKLOAD = "AttnGAN2 bird_style G_NET stage-2 (64x64) + stage-3 (128x128) word-region attention fwd+bwd, B=64/GPU, idf32 cdf256 L18"
+FFMA_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12      # CUDA-core fp32 ceiling of a B200: 74.4 TFLOP/s
 
 
 def load_peaks():
@@ -46,7 +55,7 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks line of B200_PROFILING.md, sampled during the timed region."""
+    """nvidia-smi clocks line of B200_PROFILING.md, sampled during a timed region."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -68,12 +77,8 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append((time.time(), line.strip()))
 
-    def stop(self, t0, t1):
-        if self.proc is None:
-            return None
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, mx, reasons = [], 0.0, set()
+    def window(self, t0, t1):
+        sm, mx, pw, reasons = [], 0.0, [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         rows = [r for t, r in self.rows if t0 - 0.05 <= t <= t1 + 0.15] or [r for _, r in self.rows[-3:]]
         for r in rows:
@@ -81,6 +86,7 @@ class ClockSampler:
             try:
                 sm.append(float(f[0]))
                 mx = max(mx, float(f[1]))
+                pw.append(float(f[2]))
             except (ValueError, IndexError):
                 continue
             for n, v in zip(names, f[3:7]):
@@ -88,16 +94,22 @@ class ClockSampler:
                     reasons.add(n)
         if not sm:
             return None
-        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": mx, "power_w": round(statistics.median(pw), 1) if pw else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+    def stop(self):
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
 
 
-def make_inputs(hw, seed, dtype, device, pin=False):
+def make_inputs(hw, seed, dtype, device, pin=False, batch=B_PER_GPU):
     """Synthetic CUB-shaped tensors of SURVEY.md §8(d) for one attention stage."""
     g = torch.Generator().manual_seed(seed)
-    x = torch.randn(B_PER_GPU, IDF, hw, hw, generator=g).to(dtype)
-    gc = torch.randn(B_PER_GPU, IDF, hw, hw, generator=g).to(dtype)
-    ctx = torch.tanh(torch.randn(B_PER_GPU, CDF, L, generator=g)).to(dtype)
-    lens = torch.sort(torch.randint(5, L + 1, (B_PER_GPU,), generator=g), descending=True).values
+    x = torch.randn(batch, IDF, hw, hw, generator=g).to(dtype)
+    gc = torch.randn(batch, IDF, hw, hw, generator=g).to(dtype)
+    ctx = torch.tanh(torch.randn(batch, CDF, L, generator=g)).to(dtype)
+    lens = torch.sort(torch.randint(5, L + 1, (batch,), generator=g), descending=True).values
     mask = torch.arange(L)[None, :] >= lens[:, None]
     if pin:
         return [t.pin_memory() for t in (x, gc, ctx)] + [mask]
@@ -110,147 +122,70 @@ def algorithmic_bytes(px, es, which):
     return px * per_px
 
 
-def run_ours(args, rank, world, device):
-    import torch.distributed as dist
-    from sba_gan_b200 import GlobalAttentionGeneral, _abi
-    from sba_gan_b200 import functional as F
-    _abi.load()                                   # fail loudly if the CUDA library is missing
-    dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
-    es = 2 if args.dtype == "bf16" else 4
-    torch.manual_seed(1234 + rank)
-    mods = []
-    for _ in STAGES:
-        m = GlobalAttentionGeneral(IDF, CDF)
-        torch.nn.init.orthogonal_(m.conv_context.weight.data, 1.0)      # miscc/utils.py:288-289
-        m = m.to(device)        # parameters stay fp32 (autocast-style mixed precision); activations are `dtype`
-        m.algo = args.algo
-        mods.append(m)
-    nsets = 3                                     # rotate buffers; one step already streams > L2 (126 MB)
-    sets = [[make_inputs(hw, 1234 + rank + 17 * s + hw, dtype, device) for hw in STAGES] for s in range(nsets)]
-    for st_ in sets:                              # both generator stages attend over the SAME word features and mask
-        st_[1][2], st_[1][3] = st_[0][2], st_[0][3]    # (model_bert.py:580-588)
-    for s in sets:
-        for st in s:
-            st[0].requires_grad_(True)
+def ev():
+    return torch.cuda.Event(enable_timing=True)
 
-    ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
 
-    def step(k):
-        """fwd+bwd of both attention stages through the public module.  The gradients are taken with
-        autograd.grad: in the generator x is an activation, not a leaf, so there is no .grad accumulation
-        pass over it.  Returns the conv_context weight gradients (what the DDP bucket would carry)."""
-        dws = []
-        for m, (x, gc, ctx, mask), hw in zip(mods, sets[k % nsets], STAGES):
-            m.applyMask(mask)
-            c_code, _att = m(x, ctx)
-            _dx, dw = torch.autograd.grad(c_code, [x, m.conv_context.weight], gc)
-            dws.append(dw)
-        return dws
+class Ctx:
+    """rank / world / device and the collective helpers every leg uses."""
 
-    pending = []
+    def __init__(self, rank, world, device):
+        self.rank, self.world, self.device = rank, world, device
 
-    def exchange(dws):
-        """All-reduce of the conv_context weight gradients, overlapped with the next step the way DDP
-        overlaps its buckets with backward: issued asynchronously behind this step's kernels, waited for
-        when the next exchange is issued (and at the end of the timed region)."""
-        if world > 1:
-            for h in pending:
-                h.wait()
-            pending.clear()
-            pending.extend(dist.all_reduce(t, async_op=True) for t in dws)
-
-    def drain():
-        for h in pending:
-            h.wait()
-        pending.clear()
-
-    def barrier():
-        if world > 1:
+    def barrier(self):
+        if self.world > 1:
+            import torch.distributed as dist
             dist.barrier()
         torch.cuda.synchronize()
 
-    # warm-up (eager), then capture one CUDA graph per rotating buffer set: the step is a fixed
-    # sequence of launches, so replaying it removes the Python/launch latency between kernels.
-    for k in range(max(args.warmup, 3)):
-        exchange(step(k))
-    drain()
-    barrier()
-    graphs = []
-    if not args.no_graph:
-        for k in range(nsets):
-            g = torch.cuda.CUDAGraph()
-            F.launch_counter["n"] = 0
-            with torch.cuda.graph(g):
-                dws = step(k)
-            graphs.append((g, F.launch_counter["n"], dws))
-        for g, _, _ in graphs:
-            g.replay()
-        barrier()
+    def max_over_ranks(self, v):
+        if self.world > 1:
+            import torch.distributed as dist
+            t = torch.tensor([v], device=self.device, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return t.item()
+        return v
 
-    def run_step(k):
-        if graphs:
-            g, _, dws = graphs[k % nsets]
-            g.replay()
-        else:
-            dws = step(k)
-        exchange(dws)
 
-    sampler = ClockSampler(torch.cuda.current_device())
-    sampler.start()
-    time.sleep(0.25)
-    F.launch_counter["n"] = 0
-    barrier()
-    t_wall0 = time.time()
-    e_start, e_stop = ev(), ev()
-    e_start.record()
-    for k in range(args.steps):
-        run_step(k)
-    drain()
-    e_stop.record()
-    barrier()
-    t_wall1 = time.time()
-    launches = sum(graphs[k % nsets][1] for k in range(args.steps)) if graphs else F.launch_counter["n"]
-    clocks = sampler.stop(t_wall0, t_wall1)
-    ms = e_start.elapsed_time(e_stop) / args.steps
-    if world > 1:
-        t = torch.tensor([ms], device=device)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = t.item()
-    px_step = B_PER_GPU * sum(hw * hw for hw in STAGES) * world
-    value = px_step / (ms * 1e-3)
-
-    # per-call device times -> roofline of the dominant kernel: for each of the four ABI calls of a step, a
-    # CUDA graph of `reps` calls over the rotating buffer sets, bracketed by events on the capture stream
-    calls = {}
-    reps = 12
+# ------------------------------------------------------------------------------------------------
+# per-call device times of the C-ABI calls -> roofline of the dominant call
+# ------------------------------------------------------------------------------------------------
+def time_abi_calls(cx, dtype, algo, batch, stages, nsets=3, reps=12):
+    """For each (fwd, bwd) x stage: a CUDA graph of `reps` back-to-back ABI calls over rotating buffer sets
+    (inputs larger than L2 in total), bracketed by events on the capture stream."""
+    from sba_gan_b200 import _abi
+    from sba_gan_b200 import functional as F
     lib = _abi.load()
-    dcode = _abi.SBA_BF16 if args.dtype == "bf16" else _abi.SBA_F32
-    algo = F._ALGOS[args.algo]
-    for mi, hw in enumerate(STAGES):
+    device = cx.device
+    es = 2 if dtype == torch.bfloat16 else 4
+    dcode = _abi.SBA_BF16 if dtype == torch.bfloat16 else _abi.SBA_F32
+    code = F._ALGOS[algo]
+    calls = {}
+    for hw in stages:
         Q = hw * hw
-        w32 = mods[mi].conv_context.weight.detach().reshape(IDF, CDF).float().contiguous()
+        w32 = torch.nn.init.orthogonal_(torch.empty(IDF, CDF), 1.0).to(device)
         bufs = []
         for s in range(nsets):
-            x, gc, ctx, mask = sets[s][mi]
-            bufs.append(dict(x=x.detach(), gc=gc, ctx=ctx.float().contiguous(), mask=mask.to(torch.uint8).contiguous(),
-                             c=torch.empty_like(x), a=torch.empty(B_PER_GPU, L, hw, hw, dtype=dtype, device=device),
-                             dx=torch.empty_like(x), srcT=torch.empty(B_PER_GPU, IDF, L, device=device),
-                             scr=torch.empty(3 * B_PER_GPU, dtype=torch.int32, device=device),
-                             dsrc=torch.empty(B_PER_GPU * IDF * L + B_PER_GPU + 1, device=device),
+            x, gc, ctx, mask = make_inputs(hw, 4321 + cx.rank + 17 * s + hw, dtype, device, batch=batch)
+            bufs.append(dict(x=x, gc=gc, ctx=ctx.float().contiguous(), mask=mask.to(torch.uint8).contiguous(),
+                             c=torch.empty_like(x), a=torch.empty(batch, L, hw, hw, dtype=dtype, device=device),
+                             dx=torch.empty_like(x), srcT=torch.empty(batch, IDF, L, device=device),
+                             scr=torch.empty(3 * batch, dtype=torch.int32, device=device),
+                             ws=torch.empty(lib.sba_attn_bwd_workspace_floats(batch, IDF, CDF, L), device=device),
                              dw=torch.empty(IDF, CDF, device=device)))
 
         def fwd_call(s, st):
             b = bufs[s % nsets]
             _abi.check(lib.sba_attn_fwd(b["x"].data_ptr(), b["ctx"].data_ptr(), w32.data_ptr(), b["mask"].data_ptr(),
                                         b["c"].data_ptr(), b["a"].data_ptr(), b["srcT"].data_ptr(), b["scr"].data_ptr(),
-                                        B_PER_GPU, IDF, CDF, L, Q, dcode, 0, algo, st), "sba_attn_fwd")
+                                        batch, IDF, CDF, L, Q, dcode, 0, code, st), "sba_attn_fwd")
 
         def bwd_call(s, st):
             b = bufs[s % nsets]
             _abi.check(lib.sba_attn_bwd(b["x"].data_ptr(), b["ctx"].data_ptr(), w32.data_ptr(), b["mask"].data_ptr(),
                                         b["srcT"].data_ptr(), b["scr"].data_ptr(), b["gc"].data_ptr(), None,
-                                        b["dx"].data_ptr(), b["dsrc"].data_ptr(), b["dw"].data_ptr(), None,
-                                        B_PER_GPU, IDF, CDF, L, Q, dcode, 0, algo, st), "sba_attn_bwd")
+                                        b["dx"].data_ptr(), b["ws"].data_ptr(), b["ws"].numel(), b["dw"].data_ptr(), None,
+                                        batch, IDF, CDF, L, Q, dcode, 0, code, st), "sba_attn_bwd")
 
         cur = torch.cuda.current_stream().cuda_stream
         for s in range(nsets):
@@ -265,121 +200,497 @@ def run_ours(args, rank, world, device):
                     fn(s, st)
             g.replay()
             torch.cuda.synchronize()
-            e0, e1 = ev(), ev()
-            e0.record()
-            g.replay()
-            e1.record()
-            torch.cuda.synchronize()
-            t = e0.elapsed_time(e1) * 1e-3 / reps
-            nbytes = algorithmic_bytes(B_PER_GPU * hw * hw, es, name)
-            calls[f"{name}_{hw}"] = {"us": round(t * 1e6, 2), "gbs": round(nbytes / t / 1e9, 1), "bytes": nbytes}
+            best = None
+            for _ in range(3):
+                e0, e1 = ev(), ev()
+                e0.record()
+                g.replay()
+                e1.record()
+                torch.cuda.synchronize()
+                t = e0.elapsed_time(e1) * 1e-3 / reps
+                best = t if best is None else min(best, t)
+            nbytes = algorithmic_bytes(batch * hw * hw, es, name)
+            calls[f"{name}_{hw}"] = {"us": round(best * 1e6, 2), "gbs": round(nbytes / best / 1e9, 1), "bytes": nbytes}
         del bufs
-    dom = max(calls, key=lambda k: calls[k]["us"])
+    return calls
+
+
+# ------------------------------------------------------------------------------------------------
+# the headline step: device-resident, through the public module, CUDA-graph replay
+# ------------------------------------------------------------------------------------------------
+class AttentionStep:
+    def __init__(self, cx, dtype, algo, att_cls=None, use_graph=True, nsets=3):
+        import torch.distributed as dist
+        from sba_gan_b200 import GlobalAttentionGeneral
+        from sba_gan_b200 import functional as F
+        self.cx, self.dist, self.F, self.nsets = cx, dist, F, nsets
+        device = cx.device
+        torch.manual_seed(1234 + cx.rank)
+        self.mods = []
+        for _ in STAGES:
+            m = (att_cls or GlobalAttentionGeneral)(IDF, CDF)
+            torch.nn.init.orthogonal_(m.conv_context.weight.data, 1.0)      # miscc/utils.py:288-289
+            m = m.to(device)        # parameters stay fp32 (autocast-style mixed precision); activations are `dtype`
+            if att_cls is None:
+                m.algo = algo
+            elif dtype != torch.float32:
+                m = m.to(dtype)     # the eager reference ops have no mixed-precision path: module and tensors in one dtype
+            self.mods.append(m)
+        self.sets = [[make_inputs(hw, 1234 + cx.rank + 17 * s + hw, dtype, device) for hw in STAGES] for s in range(nsets)]
+        for st_ in self.sets:                         # both generator stages attend over the SAME word features and mask
+            st_[1][2], st_[1][3] = st_[0][2], st_[0][3]    # (model_bert.py:580-588)
+        for s in self.sets:
+            for st in s:
+                st[0].requires_grad_(True)
+        self.pending = None
+        self.graphs = []
+        self.use_graph = use_graph
+
+    def step(self, k):
+        """fwd+bwd of both attention stages through the public module.  The gradients are taken with
+        autograd.grad: in the generator x is an activation, not a leaf, so there is no .grad accumulation
+        pass over it.  Returns the two conv_context weight gradients flattened into ONE buffer (what the
+        generator's DDP bucket would carry)."""
+        dws = []
+        for m, (x, gc, ctx, mask) in zip(self.mods, self.sets[k % self.nsets]):
+            m.applyMask(mask)
+            c_code, _att = m(x, ctx)
+            _dx, dw = torch.autograd.grad(c_code, [x, m.conv_context.weight], gc)
+            dws.append(dw.reshape(-1).float())
+        return torch.cat(dws)
+
+    def exchange(self, flat):
+        """ONE all-reduce of the flattened weight gradients per step, overlapped with the next step the way DDP
+        overlaps its buckets with backward: issued asynchronously behind this step's kernels, waited for when
+        the next exchange is issued (and at the end of the timed region)."""
+        if self.cx.world > 1:
+            self.drain()
+            self.pending = self.dist.all_reduce(flat, async_op=True)
+
+    def drain(self):
+        if self.pending is not None:
+            self.pending.wait()
+            self.pending = None
+
+    def prepare(self, warmup):
+        for k in range(max(warmup, 3)):
+            self.exchange(self.step(k))
+        self.drain()
+        self.cx.barrier()
+        if self.use_graph:
+            for k in range(self.nsets):
+                g = torch.cuda.CUDAGraph()
+                self.F.launch_counter["n"] = 0
+                with torch.cuda.graph(g):
+                    flat = self.step(k)
+                self.graphs.append((g, self.F.launch_counter["n"], flat))
+            for g, _, _ in self.graphs:
+                g.replay()
+            self.cx.barrier()
+
+    def run_step(self, k):
+        if self.graphs:
+            g, _, flat = self.graphs[k % self.nsets]
+            g.replay()
+        else:
+            flat = self.step(k)
+        self.exchange(flat)
+
+    def timed(self, steps):
+        """EXACTLY `steps` steps between barriers; returns (ms per step max over ranks, launches, wall window)."""
+        self.F.launch_counter["n"] = 0
+        self.cx.barrier()
+        t0 = time.time()
+        e0, e1 = ev(), ev()
+        e0.record()
+        for k in range(steps):
+            self.run_step(k)
+        self.drain()
+        e1.record()
+        self.cx.barrier()
+        t1 = time.time()
+        launches = sum(self.graphs[k % self.nsets][1] for k in range(steps)) if self.graphs else self.F.launch_counter["n"]
+        ms = self.cx.max_over_ranks(e0.elapsed_time(e1) / steps)
+        return ms, launches, (t0, t1)
+
+
+def px_per_step(world):
+    return B_PER_GPU * sum(hw * hw for hw in STAGES) * world
+
+
+def roofline_record(calls, ms, dtype_name):
     peaks, peak_kind = load_peaks()
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    if os.path.exists(tpath):
-        with open(tpath) as f:
-            traffic = json.load(f).get(f"{args.dtype}_{dom}")
-    roofline = {
+    dom = max(calls, key=lambda k: calls[k]["us"])
+    traffic, tsrc = None, None
+    for name in ("r02_traffic.json", "r01_traffic.json"):
+        tpath = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(tpath):
+            with open(tpath) as f:
+                traffic = json.load(f).get(f"{dtype_name}_{dom}")
+            tsrc = f"profiles/{name}: ncu --set full capture of this kernel (dram__bytes_read+write per launch), not measured in this run"
+            if traffic is not None:
+                break
+    return {
         "bound": "hbm", "kernel": f"sba_attn_{dom.split('_')[0]} @{dom.split('_')[1]}x{dom.split('_')[1]}",
         "achieved": calls[dom]["gbs"], "peak": peaks["hbm_gbs"], "unit": "GB/s",
         "frac": round(calls[dom]["gbs"] / peaks["hbm_gbs"], 4), "peak_source": f"{peak_kind} (MEASURED_PEAKS.json hbm_gbs)",
-        "traffic": traffic, "algorithmic_bytes_per_launch": calls[dom]["bytes"],
+        "traffic": traffic, "traffic_source": tsrc, "algorithmic_bytes_per_launch": calls[dom]["bytes"],
         "step_frac": round(sum(c["bytes"] for c in calls.values()) / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"], 4),
-        "calls": calls,
+        "calls": {k: dict(v, frac=round(v["gbs"] / peaks["hbm_gbs"], 4)) for k, v in calls.items()},
     }
 
-    # e2e: same step through the public module with HOST buffers (rank-local, all ranks run it)
-    host = [make_inputs(hw, 99 + rank + hw, dtype, device, pin=True) for hw in STAGES]
-    dev_bufs = [[torch.empty_like(t, device=device) for t in h[:3]] for h in host]
+
+# ------------------------------------------------------------------------------------------------
+# e2e: host buffers, copies inside the timed region (prefetched one step ahead on a copy stream)
+# ------------------------------------------------------------------------------------------------
+def run_e2e(cx, mods, dtype, steps):
+    device = cx.device
+    host = [make_inputs(hw, 99 + cx.rank + hw, dtype, device, pin=True) for hw in STAGES]
+    dev_sets = [[[torch.empty_like(t, device=device) for t in h[:3]] for h in host] for _ in range(2)]
+    masks = [h[3].to(device) for h in host]
     res_host = torch.empty(2 * IDF * CDF + 2, dtype=torch.float32).pin_memory()
     h2d = sum(t.numel() * t.element_size() for h in host for t in h[:3])
     d2h = res_host.numel() * 4
+    copy_stream = torch.cuda.Stream()
+    main = torch.cuda.current_stream()
+    copied = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
 
-    def e2e_step():
+    def prefetch(i):
+        """host -> device copy of step i's inputs on the copy stream (its buffers were last read by step i - 2)"""
+        s = i % 2
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[s])
+            for h, dbuf in zip(host, dev_sets[s]):
+                for src, dst in zip(h[:3], dbuf):
+                    dst.copy_(src, non_blocking=True)
+            copied[s].record(copy_stream)
+
+    def compute(i):
+        s = i % 2
+        main.wait_event(copied[s])
         outs = []
-        for m, h, dbuf, hw in zip(mods, host, dev_bufs, STAGES):
-            for src, dst in zip(h[:3], dbuf):
-                dst.copy_(src, non_blocking=True)
+        for m, dbuf, mask in zip(mods, dev_sets[s], masks):
             x = dbuf[0].requires_grad_(True)
-            x.grad = None
-            m.conv_context.weight.grad = None
-            m.applyMask(h[3].to(device, non_blocking=True))
+            m.applyMask(mask)
             c_code, _att = m(x, dbuf[2])
-            c_code.backward(dbuf[1])
-            outs += [m.conv_context.weight.grad.float().reshape(-1), x.grad.float().sum().reshape(1)]
+            dx, dw = torch.autograd.grad(c_code, [x, m.conv_context.weight], dbuf[1])
+            outs += [dw.float().reshape(-1), dx.float().sum().reshape(1)]
             dbuf[0] = x.detach()
+        consumed[s].record(main)
         res_host.copy_(torch.cat(outs), non_blocking=True)
-        torch.cuda.current_stream().synchronize()
 
-    for _ in range(3):
-        e2e_step()
-    barrier()
-    n_e2e = max(3, min(args.steps, 10))
+    def loop(n):
+        for ev_ in consumed:
+            ev_.record(main)
+        prefetch(0)
+        for i in range(n):
+            prefetch(i + 1)                 # next step's inputs travel while this step computes
+            compute(i)
+            main.synchronize()              # the step's result has been read on the host
+        torch.cuda.synchronize()
+
+    loop(3)
+    cx.barrier()
+    n = max(3, min(steps, 10))
     t0 = time.perf_counter()
-    for _ in range(n_e2e):
-        e2e_step()
-    barrier()
-    e2e_s = (time.perf_counter() - t0) / n_e2e
-    if world > 1:
-        t = torch.tensor([e2e_s], device=device)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = t.item()
-    e2e = {"value": px_step / e2e_s, "unit": "region-px/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-           "ms_per_step": round(e2e_s * 1e3, 3)}
+    loop(n)
+    cx.barrier()
+    # (n + 1 input sets are copied for n steps: the prefetch of the step after the last is inside the region)
+    e2e_s = cx.max_over_ranks((time.perf_counter() - t0) / n)
+
+    # the host->device ceiling of this box for the same buffers, nothing else running on this rank
+    def copy_only(m):
+        for i in range(m):
+            for h, dbuf in zip(host, dev_sets[i % 2]):
+                for src, dst in zip(h[:3], dbuf):
+                    dst.copy_(src, non_blocking=True)
+        torch.cuda.synchronize()
+    copy_only(2)
+    cx.barrier()
+    t0 = time.perf_counter()
+    copy_only(5)
+    cx.barrier()
+    copy_s = cx.max_over_ranks((time.perf_counter() - t0) / 5)
+    return {"value": px_per_step(cx.world) / e2e_s, "unit": "region-px/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+            "ms_per_step": round(e2e_s * 1e3, 3), "h2d_gbs_per_gpu": round(h2d / e2e_s / 1e9, 1),
+            "h2d_copy_only_ms": round(copy_s * 1e3, 3), "h2d_copy_only_gbs_per_gpu": round(h2d / copy_s / 1e9, 1),
+            "note": "inputs prefetched one step ahead on a copy stream; the step is bound by the host->device copy "
+                    "(h2d_copy_only_* = the same copies alone, all ranks at once)"}
+
+
+# ------------------------------------------------------------------------------------------------
+# sub-records
+# ------------------------------------------------------------------------------------------------
+def sub_sustained(cx, stepper, ms_hint, seconds=2.5):
+    """>= `seconds` of back-to-back steps with its own clock sample: clock / power behaviour under a training cadence."""
+    n = max(100, int(math.ceil(seconds / (ms_hint * 1e-3))))
+    sampler = ClockSampler(torch.cuda.current_device())
+    sampler.start()
+    time.sleep(0.2)
+    ms, _, (t0, t1) = stepper.timed(n)
+    sampler.stop()
+    return {"value": px_per_step(cx.world) / (ms * 1e-3), "unit": "region-px/s", "steps": n, "ms_per_step": round(ms, 4),
+            "seconds": round(t1 - t0, 2), "clocks": sampler.window(t0, t1)}
+
+
+def sub_eager_baseline(cx, dtype, steps):
+    """The reference's own op sequence (GlobalAttention.py:92-117) as stock torch / cuBLAS ops on the SAME GPU,
+    same step, same inputs: the bar SURVEY.md §2 sets for every new kernel."""
+    from harness.gan_step import EagerAttention
+    try:
+        st = AttentionStep(cx, dtype, "auto", att_cls=EagerAttention, use_graph=True)
+        st.prepare(3)
+        launch = "cuda-graph replay"
+    except Exception as e:  # capture of the eager sequence failed: time it eagerly
+        torch.cuda.synchronize()
+        st = AttentionStep(cx, dtype, "auto", att_cls=EagerAttention, use_graph=False)
+        st.prepare(3)
+        launch = f"eager ({type(e).__name__} under capture)"
+    ms, _, _ = st.timed(max(5, min(steps, 20)))
+    return {"value": px_per_step(cx.world) / (ms * 1e-3), "unit": "region-px/s", "ms_per_step": round(ms, 4), "launch": launch,
+            "what": "reference eager op sequence (transpose+bmm+masked_fill+softmax+transpose+bmm, autograd backward) on this GPU"}
+
+
+def sub_words_loss(cx):
+    """BASELINE configs[2]: DAMSM words_loss at B = 48 / 256 (17x17 regions, 18 words, gammas 4/5/10); with N > 1
+    ranks the B x B similarity is sharded by image rows (parallel.sharded_words_loss) - strong scaling of one op."""
+    from sba_gan_b200 import parallel
+    from sba_gan_b200.losses import words_loss, words_similarity
+    device, world, rank = cx.device, cx.world, cx.rank
+    out = {}
+    for B in (48, 256):
+        g = torch.Generator().manual_seed(1)
+        lens_c = torch.sort(torch.randint(5, 19, (B,), generator=g), descending=True).values
+        cls_c = torch.randint(1, 201, (B,), generator=g)
+        img_c = torch.randn(B, 256, 17, 17, generator=g)
+        words_c = torch.tanh(torch.randn(B, 256, 18, generator=g))
+        tbar = lens_c.float().mean().item()
+        flops_f = 4.0 * B * B * 289 * tbar * 256
+        rec = {"B": B, "mean_len": round(tbar, 2)}
+
+        def timeit(fn, n):
+            fn()
+            cx.barrier()
+            e0, e1 = ev(), ev()
+            e0.record()
+            for _ in range(n):
+                fn()
+            e1.record()
+            cx.barrier()
+            return cx.max_over_ranks(e0.elapsed_time(e1) / n)
+
+        if world == 1:
+            img = img_c.to(device).requires_grad_(True)
+            words, lens = words_c.to(device), lens_c.to(device).int()
+            labels, cls = torch.arange(B, device=device), cls_c.to(device)
+
+            def fwd():
+                with torch.no_grad():
+                    words_similarity(img, words, lens, 4.0, 5.0, 10.0)
+
+            def fb(wg=False):
+                w = words.detach().requires_grad_(wg)
+                l0, l1, _ = words_loss(img, w, labels, lens, cls, B, 4.0, 5.0, 10.0)
+                torch.autograd.grad(l0 + l1, [img, w] if wg else [img])
+
+            n = 20 if B <= 64 else 5
+            tf, tb, tw = timeit(fwd, n), timeit(fb, n), timeit(lambda: fb(True), n)
+            rec.update(fwd_ms=round(tf, 3), fwd_tflops=round(flops_f / (tf * 1e-3) / 1e12, 2),
+                       fwd_frac_of_ffma_ceiling=round(flops_f / (tf * 1e-3) / 1e12 / FFMA_TFLOPS, 3),
+                       fwd_bwd_img_ms=round(tb, 3), fwd_bwd_img_words_ms=round(tw, 3),
+                       pairs_per_s=round(B * B / (tb * 1e-3)))
+        else:
+            b = B // world
+            if b * world != B:
+                rec["skipped"] = f"B={B} not divisible by {world} ranks"
+                out[f"B{B}"] = rec
+                continue
+            sl = slice(rank * b, (rank + 1) * b)
+            img = img_c[sl].to(device).requires_grad_(True)
+            words, lens, cls = words_c[sl].to(device), lens_c[sl].to(device), cls_c[sl].to(device)
+
+            def fb():
+                s0, s1 = parallel.sharded_words_loss(img, words, lens, cls, 4.0, 5.0, 10.0)
+                torch.autograd.grad(s0 + s1, [img])
+
+            tb = timeit(fb, 20 if B <= 64 else 5)
+            rec.update(sharding=f"{world} ranks x {b} image rows, all-gather of word features and of sim rows (NCCL)",
+                       fwd_bwd_img_ms=round(tb, 3), pairs_per_s=round(B * B / (tb * 1e-3)))
+        out[f"B{B}"] = rec
+    out["flops_model"] = "fwd = 4*B^2*289*mean_len*256; ceiling = 74.4 TFLOP/s CUDA-core fp32 (148 SMs x 128 lanes x 2 x 1.965 GHz)"
+    return out
+
+
+def sub_gan_step(cx, steps=6, batch=20):
+    """BASELINE configs[3]: the full G+D adversarial step (harness/gan_step.py: trainer_bert.py:251-304 step body,
+    bird_style networks restated from scratch, synthetic data, random init), batch-sharded, manual flattened gradient
+    all-reduce per network; fused hot path vs the reference's eager ops for the same two operators."""
+    from harness.gan_step import Trainer
+    out = {"batch_per_gpu": batch, "global_batch": batch * cx.world, "steps": steps, "dtype": "fp32"}
+    for attention in ("fused", "eager"):
+        tr = Trainer(batch, cx.device, attention, cx.world, seed=1234 + cx.rank)
+        for _ in range(3):
+            tr.step()
+        cx.barrier()
+        e0, e1 = ev(), ev()
+        e0.record()
+        for _ in range(steps):
+            tr.step()
+        e1.record()
+        cx.barrier()
+        ms = cx.max_over_ranks(e0.elapsed_time(e1) / steps)
+        out[attention] = {"imgs_per_s": round(batch * cx.world / (ms * 1e-3), 1), "ms_per_step": round(ms, 2)}
+        del tr
+        torch.cuda.empty_cache()
+    out["speedup_fused_vs_eager"] = round(out["fused"]["imgs_per_s"] / out["eager"]["imgs_per_s"], 3)
+    return out
+
+
+def run_ours(args, cx):
+    from sba_gan_b200 import _abi
+    _abi.load()                                   # fail loudly if the CUDA library is missing
+    dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
+    world = cx.world
+    stepper = AttentionStep(cx, dtype, args.algo, use_graph=not args.no_graph)
+    stepper.prepare(args.warmup)
+    sampler = ClockSampler(torch.cuda.current_device())
+    sampler.start()
+    time.sleep(0.25)
+    ms, launches, (t0, t1) = stepper.timed(args.steps)
+    sampler.stop()
+    clocks = sampler.window(t0, t1)
+    value = px_per_step(world) / (ms * 1e-3)
+
+    calls = time_abi_calls(cx, dtype, args.algo, B_PER_GPU, STAGES)
+    roofline = roofline_record(calls, ms, args.dtype)
+    e2e = run_e2e(cx, stepper.mods, dtype, args.steps)
+
+    sub = {}
+    if not args.no_sub:
+        def leg(name, fn):
+            t_leg = time.time()
+            try:
+                sub[name] = fn()
+            except Exception as e:      # a failed side measurement must not take the headline line down
+                sub[name] = {"error": f"{type(e).__name__}: {e}"[:300]}
+                torch.cuda.synchronize()
+            if isinstance(sub[name], dict):
+                sub[name]["leg_seconds"] = round(time.time() - t_leg, 1)
+            cx.barrier()
+
+        leg("sustained", lambda: sub_sustained(cx, stepper, ms))
+        del stepper
+        torch.cuda.empty_cache()
+        other = torch.float32 if dtype == torch.bfloat16 else torch.bfloat16
+        oname = "fp32" if dtype == torch.bfloat16 else "bf16"
+
+        def other_dtype():
+            st = AttentionStep(cx, other, args.algo, use_graph=not args.no_graph)
+            st.prepare(3)
+            oms, _, _ = st.timed(args.steps)
+            del st
+            ocalls = time_abi_calls(cx, other, args.algo, B_PER_GPU, STAGES)
+            r = roofline_record(ocalls, oms, oname)
+            return {"value": px_per_step(world) / (oms * 1e-3), "unit": "region-px/s", "ms_per_step": round(oms, 4), "dtype": oname,
+                    "step_frac": r["step_frac"], "calls": r["calls"]}
+        leg(oname, other_dtype)
+        leg("gpu_eager_baseline", lambda: sub_eager_baseline(cx, dtype, args.steps))
+        leg("gpu_eager_baseline_fp32", lambda: sub_eager_baseline(cx, torch.float32, args.steps))
+
+        def sweep():
+            c = time_abi_calls(cx, dtype, args.algo, 128, (128,), nsets=2, reps=8)
+            peaks, _ = load_peaks()
+            t = (c["fwd_128"]["us"] + c["bwd_128"]["us"]) * 1e-6
+            by = c["fwd_128"]["bytes"] + c["bwd_128"]["bytes"]
+            return {"config": "BASELINE configs[4]: global batch 1024 over 8 GPUs = 128 per GPU, 128x128 regions", "B_per_gpu": 128,
+                    "global_batch": 128 * world, "fwd_us": c["fwd_128"]["us"], "bwd_us": c["bwd_128"]["us"],
+                    "region_px_per_s_per_gpu": round(128 * 128 * 128 / t), "hbm_frac": round(by / t / 1e9 / peaks["hbm_gbs"], 4)}
+        leg("batch_sweep", sweep)
+        leg("words_loss", lambda: sub_words_loss(cx))
+        leg("gan_step", lambda: sub_gan_step(cx))
 
     out = {
         "metric": "word-attn fwd+bwd region-px/s", "value": value, "unit": "region-px/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms, 4), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
         "config": {"workload": WORKLOAD, "B_per_gpu": B_PER_GPU, "regions": [hw * hw for hw in STAGES],
-                   "io_dtype": args.dtype, "param_dtype": "fp32", "accumulate": "fp32", "algo": args.algo, "launch": "eager" if args.no_graph else "cuda-graph replay", "mask": "ragged, reference mod-B order",
-                   "g_attn": None, "l2": "inputs larger than L2: one step streams %d MB per GPU over 3 rotating buffer sets" %
+                   "io_dtype": args.dtype, "param_dtype": "fp32", "accumulate": "fp32", "algo": args.algo,
+                   "launch": "eager" if args.no_graph else "cuda-graph replay", "mask": "ragged, reference mod-B order",
+                   "g_attn": None, "exchange": "one flattened 64 KB all-reduce of both conv_context weight gradients per step",
+                   "l2": "inputs larger than L2: one step streams %d MB per GPU over 3 rotating buffer sets" %
                    (sum(c["bytes"] for c in calls.values()) // 2 ** 20)},
-        "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "clocks": clocks,
+        "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "clocks": clocks, "sub": sub,
     }
     return out
 
 
-def reference_step_cpu(inputs, n_threads):
-    """The reference's CPU path for one step (oracle/cpu_path.py: the torch op sequence of
-    GlobalAttention.py:82-121 with autograd backward, torch CPU fp32)."""
-    from oracle.cpu_path import attn_fwd_bwd_autograd
-    for x, gc, ctx, mask, w in inputs:
-        c, _attn, dX, dW = attn_fwd_bwd_autograd(x, ctx, w, mask, gc)
-    return c, dX, dW
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the reference's own implementation (oracle/_ref) or, without it, the oracle port
+# ------------------------------------------------------------------------------------------------
+class CpuReference:
+    def __init__(self):
+        self.n_threads = os.cpu_count() or 1
+        torch.set_num_threads(self.n_threads)
+        self.kind, self.mods = "port", None
+        try:
+            from oracle.build_ref import load_ref
+            ref = load_ref()
+        except Exception:
+            ref = None
+        self.inputs = []
+        for hw in STAGES:
+            x, gc, ctx, mask = make_inputs(hw, 1234 + hw, torch.float32, "cpu")
+            w = torch.nn.init.orthogonal_(torch.empty(IDF, CDF, 1, 1), 1.0)
+            self.inputs.append((x, gc, ctx, mask, w))
+        if ref is not None:
+            self.kind = "reference"
+            self.mods = []
+            for (_x, _gc, _ctx, _mask, w) in self.inputs:
+                m = ref[0].GlobalAttentionGeneral(IDF, CDF)          # the unmodified reference module
+                with torch.no_grad():
+                    m.conv_context.weight.copy_(w)
+                self.mods.append(m)
+
+    def step(self):
+        if self.mods is not None:
+            for m, (x, gc, ctx, mask, _w) in zip(self.mods, self.inputs):
+                xr = x.detach().requires_grad_(True)
+                m.conv_context.weight.grad = None
+                m.applyMask(mask)
+                c, _attn = m(xr, ctx)
+                c.backward(gc)
+            return
+        from oracle.cpu_path import attn_fwd_bwd_autograd
+        for x, gc, ctx, mask, w in self.inputs:
+            attn_fwd_bwd_autograd(x, ctx, w, mask, gc)
+
+    def describe(self):
+        return ("unmodified reference GlobalAttentionGeneral (oracle/_ref, copied from AttnGAN2/code/GlobalAttention.py) + autograd"
+                if self.kind == "reference" else "oracle port of the reference op sequence (oracle/cpu_path.py)")
 
 
 def run_reference(args):
-    n_threads = os.cpu_count() or 1
-    torch.set_num_threads(n_threads)
-    inputs = []
-    for hw in STAGES:
-        x, gc, ctx, mask = make_inputs(hw, 1234 + hw, torch.float32, "cpu")
-        w = torch.nn.init.orthogonal_(torch.empty(IDF, CDF), 1.0)
-        inputs.append((x, gc, ctx, mask, w))
+    ref = CpuReference()
     # K and W as asked (a step is ~0.1 s on the box's host cores), bounded so that the run stays within minutes
     warmup = max(1, min(args.warmup, 50))
     for _ in range(warmup):
-        reference_step_cpu(inputs, n_threads)
+        ref.step()
     steps = max(1, min(args.steps, 500))
     ts = []
     for _ in range(steps):
         t0 = time.perf_counter()
-        reference_step_cpu(inputs, n_threads)
+        ref.step()
         ts.append(time.perf_counter() - t0)
     t = statistics.median(ts)
-    px = B_PER_GPU * sum(hw * hw for hw in STAGES)
-    value = px / t
+    value = px_per_step(1) / t
     sample = f"{steps} full steps (B=64, 64x64 + 128x128 fwd+bwd) fp32, median"
     return {
         "impl": "reference", "metric": "word-attn fwd+bwd region-px/s", "value": value, "unit": "region-px/s",
         "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": round(t * 1e3, 2),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "B_per_gpu": B_PER_GPU, "regions": [hw * hw for hw in STAGES],
-                   "note": "reference CPU path = oracle port (torch CPU); the Python reference cannot travel to the GPU box"},
-        "cpu_baseline": {"value": value, "unit": "region-px/s", "cores": n_threads, "kind": "port", "sample": sample},
+        "config": {"workload": WORKLOAD, "B_per_gpu": B_PER_GPU, "regions": [hw * hw for hw in STAGES], "note": ref.describe()},
+        "cpu_baseline": {"value": value, "unit": "region-px/s", "cores": ref.n_threads, "kind": ref.kind, "sample": sample},
         "e2e": {"value": value, "unit": "region-px/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -387,24 +698,18 @@ def run_reference(args):
 
 def cpu_baseline_leg():
     """Bounded CPU sample beside the GPU number (rank 0, N=1 only)."""
-    n_threads = os.cpu_count() or 1
-    torch.set_num_threads(n_threads)
-    inputs = []
-    for hw in STAGES:
-        x, gc, ctx, mask = make_inputs(hw, 1234 + hw, torch.float32, "cpu")
-        w = torch.nn.init.orthogonal_(torch.empty(IDF, CDF), 1.0)
-        inputs.append((x, gc, ctx, mask, w))
-    reference_step_cpu(inputs, n_threads)
+    ref = CpuReference()
+    ref.step()
     ts = []
     t_end = time.perf_counter() + 12.0
     while len(ts) < 3 or (time.perf_counter() < t_end and len(ts) < 30):
         t0 = time.perf_counter()
-        reference_step_cpu(inputs, n_threads)
+        ref.step()
         ts.append(time.perf_counter() - t0)
     t = statistics.median(ts)
-    px = B_PER_GPU * sum(hw * hw for hw in STAGES)
-    return {"value": px / t, "unit": "region-px/s", "cores": n_threads, "kind": "port",
-            "sample": f"{len(ts)} full steps of the same workload (fp32, torch CPU, {n_threads} threads), median {t*1e3:.0f} ms"}
+    return {"value": px_per_step(1) / t, "unit": "region-px/s", "cores": ref.n_threads, "kind": ref.kind,
+            "sample": f"{len(ts)} full steps of the same workload (fp32, torch CPU, {ref.n_threads} threads), median {t*1e3:.0f} ms; "
+                      + ref.describe()}
 
 
 def main():
@@ -414,8 +719,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
-    ap.add_argument("--algo", default="auto", choices=["auto", "simt", "mma"])
+    ap.add_argument("--algo", default="auto", choices=["auto", "simt", "mma", "tc5"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sub", action="store_true", help="headline only: skip the sub-records (fp32, sustained, words_loss, gan_step ...)")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of CUDA-graph replays")
     args = ap.parse_args()
 
@@ -435,7 +741,7 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=device)
-    out = run_ours(args, rank, world, device)
+    out = run_ours(args, Ctx(rank, world, device))
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline_leg()

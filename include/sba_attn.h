@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SBA_ABI_VERSION 3
+#define SBA_ABI_VERSION 4
 
 #if defined(__GNUC__)
 #define SBA_API __attribute__((visibility("default")))
@@ -83,6 +83,13 @@ SBA_API int sba_attn_fwd(const void* x, const float* ctx, const float* W, const 
                  int B, int idf, int cdf, int L, int Q,
                  int dtype, int mask_mode, int algo, void* stream);
 
+/* Kernel family that served the last successful sba_attn_fwd* / sba_attn_bwd* call on this thread
+ * (an SBA_ALGO_* value), and whether a concrete family covers a shape (which: 0 = forward,
+ * 1 = backward).  An explicit `algo` is honoured strictly: a family that does not cover the shape
+ * is refused with SBA_ERR_UNSUPPORTED, never silently replaced. */
+SBA_API int sba_last_algo(void);
+SBA_API int sba_attn_supported(int which, int algo, int B, int idf, int cdf, int L, int Q, int dtype);
+
 /* ---- autograd backward of the above ------------------------------
  * srcT     [B, idf, L] fp32         from the forward
  * scratch  [3*B] uint32             from the forward (mask words; ignored when mask == NULL)
@@ -90,17 +97,38 @@ SBA_API int sba_attn_fwd(const void* x, const float* ctx, const float* W, const 
  * g_attn   [B, L, Q]   dtype nullable grad of attn (NULL in GAN training: attn is discarded,
  *                                   trainer_bert.py:267)
  * dX       [B, idf, Q] dtype  out
- * dSrc     [B*idf*L + B + 1] fp32 out: grad of sourceT [B, idf, L] (also the reduction workspace),
- *                                   followed by B + 1 scratch words (per-sample completion counters)
+ * ws       [ws_floats] fp32         workspace of at least sba_attn_bwd_workspace_floats(B, idf, cdf, L)
+ *                                   floats, 16-byte aligned, contents undefined on entry (nothing needs
+ *                                   zeroing).  When dW or dCtx is requested its first B*idf*L floats
+ *                                   hold the gradient of sourceT [B, idf, L] on return.
  * dW       [idf, cdf]  fp32   out   nullable
  * dCtx     [B, cdf, L] fp32   out   nullable (words are detached in GAN training)
+ * The tcgen05 family accumulates in a fixed order: results are bit-identical run to run.
  */
+SBA_API size_t sba_attn_bwd_workspace_floats(int B, int idf, int cdf, int L);
 SBA_API int sba_attn_bwd(const void* x, const float* ctx, const float* W, const uint8_t* mask,
                  const float* srcT, const uint32_t* scratch,
                  const void* g_c, const void* g_attn,
-                 void* dX, float* dSrc, float* dW, float* dCtx,
+                 void* dX, float* ws, size_t ws_floats, float* dW, float* dCtx,
                  int B, int idf, int cdf, int L, int Q,
                  int dtype, int mask_mode, int algo, void* stream);
+
+/* ---- the caller's torch.cat((h_code, c_code), 1) folded into the attention ----------
+ * (NEXT_STAGE_G.forward, model_bert.py:459-461)
+ * sba_attn_fwd_into writes weightedContext into rows [c_row0, c_row0 + idf) of every sample of
+ * c_buf [B, c_rows, Q] (e.g. c_rows = 2*idf, c_row0 = idf: the second half of h_c_code) instead
+ * of a tensor of its own; sba_attn_bwd_from reads g_c from the same rows of g_buf [B, g_rows, Q]
+ * (the gradient of the concatenated buffer), so neither the concatenation nor its backward
+ * slice copy exists.  tcgen05 family only (shapes: sba_attn_supported(.., SBA_ALGO_TCGEN05, ..)).
+ */
+SBA_API int sba_attn_fwd_into(const void* x, const float* ctx, const float* W, const uint8_t* mask,
+                 void* c_buf, int c_rows, int c_row0, void* attn, float* srcT, uint32_t* scratch,
+                 int B, int idf, int cdf, int L, int Q, int dtype, int mask_mode, void* stream);
+SBA_API int sba_attn_bwd_from(const void* x, const float* ctx, const float* W, const uint8_t* mask,
+                 const float* srcT, const uint32_t* scratch,
+                 const void* g_buf, int g_rows, int g_row0, const void* g_attn,
+                 void* dX, float* ws, size_t ws_floats, float* dW, float* dCtx,
+                 int B, int idf, int cdf, int L, int Q, int dtype, int mask_mode, void* stream);
 
 /* ---- DAMSM region-word similarity: func_attention + cosine + LSE --------------------
  * (GlobalAttention.py:31-69, miscc/losses.py:11-17, 72-123)
@@ -135,6 +163,31 @@ SBA_API int sba_words_sim_bwd(const float* img, const float* words, const int32_
  * (batch element b of the query attends over batch element b of the context). */
 SBA_API int sba_func_attention(const float* query, const float* context, float* wc, float* attn,
                        int B, int nef, int T, int R, float gamma1, void* stream);
+
+/* ---- the B x B matching tail of words_loss and sent_loss -----------
+ * sba_match_ce_*: same-class masking + the two cross-entropies (miscc/losses.py:24-34, 53-59 and
+ * :73-76, 116-129).  Entry (i, j), i != j, counts as -inf when class_ids[i] == class_ids[j]
+ * (class_ids NULL: no masking); losses[0] = CE(scores, labels), losses[1] = CE(scores^T, labels),
+ * mean over B.  The mask is applied on the fly - nothing is built on the host, the -inf matrix
+ * is never written.
+ * scores    [B, B] fp32 (unmasked)      class_ids [B] int32 nullable      labels [B] int64
+ * losses    [2] fp32 out                lse [4*B] fp32 out: kept for the backward
+ * g         [2] fp32: upstream gradients of the two losses          d_scores [B, B] fp32 out
+ */
+SBA_API int sba_match_ce_fwd(const float* scores, const int32_t* class_ids, const int64_t* labels,
+                     float* losses, float* lse, int B, void* stream);
+SBA_API int sba_match_ce_bwd(const float* scores, const int32_t* class_ids, const int64_t* labels,
+                     const float* lse, const float* g, float* d_scores, int B, void* stream);
+
+/* sba_sent_scores_*: the score matrix of sent_loss (miscc/losses.py:42-49):
+ * scores[i, j] = gamma3 * <cnn_i, rnn_j> / max(|cnn_i| |rnn_j|, eps), and its gradient.
+ * cnn, rnn  [B, nef] fp32      scores [B, B] fp32 out      norms [2*B] fp32 out (kept for the backward)
+ */
+SBA_API int sba_sent_scores_fwd(const float* cnn, const float* rnn, float* scores, float* norms,
+                     int B, int nef, float gamma3, float eps, void* stream);
+SBA_API int sba_sent_scores_bwd(const float* cnn, const float* rnn, const float* norms, const float* scores,
+                     const float* d_scores, float* d_cnn, float* d_rnn,
+                     int B, int nef, float gamma3, float eps, void* stream);
 
 #ifdef __cplusplus
 }

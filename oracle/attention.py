@@ -169,6 +169,22 @@ def ce_tail(sim, labels, class_ids):
     return loss0, loss1, sim
 
 
+def sent_scores(cnn_code, rnn_code, gamma3=10.0, eps=1e-8):
+    """The B x B score matrix of sent_loss (losses.py:42-49) before class masking:
+    scores[i, j] = gamma3 * <cnn_i, rnn_j> / max(|cnn_i| |rnn_j|, eps)."""
+    n0 = cnn_code.norm(dim=1, keepdim=True)                     # :42
+    n1 = rnn_code.norm(dim=1, keepdim=True)                     # :43
+    scores = cnn_code @ rnn_code.t()                            # :45
+    return scores / (n0 @ n1.t()).clamp(min=eps) * gamma3       # :46-47
+
+
+def sent_loss(cnn_code, rnn_code, labels, class_ids, batch_size, eps=1e-8, gamma3=10.0):
+    """sent_loss (losses.py:20-59) with gamma3 explicit; returns (loss0, loss1)."""
+    scores = sent_scores(cnn_code[:batch_size], rnn_code[:batch_size], gamma3, eps)
+    loss0, loss1, _ = ce_tail(scores, labels, class_ids)        # :24-34, 51-59
+    return loss0, loss1
+
+
 def words_loss(img_features, words_emb, labels, cap_lens, class_ids, batch_size,
                gamma1=4.0, gamma2=5.0, gamma3=10.0, eps=1e-8):
     """words_loss (losses.py:62-132) with the gammas as explicit arguments

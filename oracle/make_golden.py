@@ -67,6 +67,33 @@ WL_CASES = {
 }
 
 
+SL_CASES = {
+    # name: (B, nef, seed, gamma3, use_class_ids)       sent_loss (losses.py:20-59)
+    "sl_b6": (6, 32, 41, 10.0, True),
+    "sl_b12_dupclass": (12, 256, 42, 10.0, True),
+    "sl_b5_noclass": (5, 64, 43, 5.0, False),
+}
+
+
+def synth_sent_inputs(B, nef, seed, dtype):
+    rs = np.random.RandomState(seed)
+    cnn = torch.from_numpy(rs.standard_normal((B, nef))).to(dtype)
+    rnn = torch.from_numpy(np.tanh(rs.standard_normal((B, nef)))).to(dtype)
+    cls = rs.randint(1, max(2, B // 2) + 1, size=B)
+    return cnn, rnn, cls
+
+
+def run_sent_loss(ref_losses, cfg, spec, dtype):
+    B, nef, seed, g3, use_cls = spec
+    cnn, rnn, cls = synth_sent_inputs(B, nef, seed, dtype)
+    cfg.TRAIN.SMOOTH.GAMMA3 = g3
+    a, b = cnn.clone().requires_grad_(True), rnn.clone().requires_grad_(True)
+    l0, l1 = ref_losses.sent_loss(a, b, torch.arange(B), cls if use_cls else None, B)
+    (l0 + 2.0 * l1).backward()              # different weights: the two gradients are told apart
+    return dict(loss0=l0.detach().numpy(), loss1=l1.detach().numpy(), d_cnn=a.grad.numpy(), d_rnn=b.grad.numpy(),
+                class_ids=cls, in_sum=np.concatenate([checksum(cnn), checksum(rnn)]))
+
+
 def checksum(t):
     t = t.double()
     return np.array([t.sum().item(), t.abs().sum().item()])
@@ -156,6 +183,8 @@ def main():
             rec = run_words_loss(ref_losses, cfg, name, spec, dtype)
             np.savez_compressed(os.path.join(outdir, f"{name}_{tag}.npz"), **rec)
         np.savez_compressed(os.path.join(outdir, f"func_attention_{tag}.npz"), **run_func_attention(ref_ga, dtype))
+        for name, spec in SL_CASES.items():
+            np.savez_compressed(os.path.join(outdir, f"{name}_{tag}.npz"), **run_sent_loss(ref_losses, cfg, spec, dtype))
     total = sum(os.path.getsize(os.path.join(outdir, f)) for f in os.listdir(outdir))
     print(f"wrote {len(os.listdir(outdir))} fixtures, {total / 1e6:.2f} MB, torch {torch.__version__}")
 

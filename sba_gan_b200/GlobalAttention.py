@@ -33,7 +33,8 @@ class GlobalAttentionGeneral(nn.Module):
     """
 
     mask_mode = "reference"
-    algo = "auto"
+    algo = "auto"        # kernel family of the forward ("auto" | "simt" | "mma" | "tc5"); explicit = strict
+    algo_bwd = None      # ... of the backward; None = the same as `algo`
 
     def __init__(self, idf, cdf):
         super().__init__()
@@ -48,4 +49,4 @@ class GlobalAttentionGeneral(nn.Module):
         """input: batch x idf x ih x iw (queryL = ih*iw); context: batch x cdf x sourceL
         returns (weightedContext batch x idf x ih x iw, attn batch x sourceL x ih x iw)."""
         return word_region_attention(input, context, self.conv_context.weight, self.mask,
-                                     mask_mode=self.mask_mode, algo=self.algo)
+                                     mask_mode=self.mask_mode, algo=self.algo, algo_bwd=self.algo_bwd)

@@ -12,9 +12,10 @@ import sys
 from . import _abi  # noqa: F401
 from .functional import word_region_attention  # noqa: F401
 from .GlobalAttention import GlobalAttentionGeneral, conv1x1  # noqa: F401
-from .losses import func_attention, words_loss  # noqa: F401
+from .losses import func_attention, match_cross_entropy, sent_loss, words_loss  # noqa: F401
 
-__all__ = ["GlobalAttentionGeneral", "conv1x1", "func_attention", "words_loss", "word_region_attention", "install"]
+__all__ = ["GlobalAttentionGeneral", "conv1x1", "func_attention", "words_loss", "sent_loss", "match_cross_entropy",
+           "word_region_attention", "install"]
 
 
 def install(patch_loaded: bool = True) -> None:
@@ -37,3 +38,5 @@ def install(patch_loaded: bool = True) -> None:
         m = sys.modules.get(name)
         if m is not None and hasattr(m, "words_loss"):
             m.words_loss = words_loss
+        if m is not None and hasattr(m, "sent_loss"):
+            m.sent_loss = sent_loss

@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_PKG, "lib", "libsba_attn.so")
 SBA_F32, SBA_BF16 = 0, 1
 SBA_MASK_REFERENCE, SBA_MASK_PER_SAMPLE = 0, 1
 SBA_ALGO_AUTO, SBA_ALGO_SIMT, SBA_ALGO_MMA, SBA_ALGO_TCGEN05 = 0, 1, 2, 3
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 # every symbol include/sba_attn.h declares: (restype, argtypes)
 SYMBOLS = {
@@ -21,11 +21,21 @@ SYMBOLS = {
     "sba_last_error": (c_char_p, []),
     "sba_last_launch_count": (c_int, []),
     "sba_attn_fwd": (c_int, [c_void_p] * 8 + [c_int] * 8 + [c_void_p]),
-    "sba_attn_bwd": (c_int, [c_void_p] * 12 + [c_int] * 8 + [c_void_p]),
+    "sba_last_algo": (c_int, []),
+    "sba_attn_supported": (c_int, [c_int] * 8),
+    "sba_attn_bwd_workspace_floats": (c_size_t, [c_int] * 4),
+    "sba_attn_bwd": (c_int, [c_void_p] * 10 + [c_size_t] + [c_void_p] * 2 + [c_int] * 8 + [c_void_p]),
+    "sba_attn_fwd_into": (c_int, [c_void_p] * 5 + [c_int] * 2 + [c_void_p] * 3 + [c_int] * 7 + [c_void_p]),
+    "sba_attn_bwd_from": (c_int, [c_void_p] * 7 + [c_int] * 2 + [c_void_p] * 3 + [c_size_t] + [c_void_p] * 2 + [c_int] * 7
+                          + [c_void_p]),
     "sba_words_sim_fwd": (c_int, [c_void_p] * 5 + [c_int] * 6 + [c_float] * 4 + [c_void_p]),
     "sba_words_sim_bwd_workspace_bytes": (c_size_t, [c_int] * 5),
     "sba_words_sim_bwd": (c_int, [c_void_p] * 7 + [c_int] * 6 + [c_float] * 4 + [c_void_p]),
     "sba_func_attention": (c_int, [c_void_p] * 4 + [c_int] * 4 + [c_float] + [c_void_p]),
+    "sba_match_ce_fwd": (c_int, [c_void_p] * 5 + [c_int] + [c_void_p]),
+    "sba_match_ce_bwd": (c_int, [c_void_p] * 6 + [c_int] + [c_void_p]),
+    "sba_sent_scores_fwd": (c_int, [c_void_p] * 4 + [c_int] * 2 + [c_float] * 2 + [c_void_p]),
+    "sba_sent_scores_bwd": (c_int, [c_void_p] * 7 + [c_int] * 2 + [c_float] * 2 + [c_void_p]),
 }
 
 _lib = None

@@ -11,7 +11,8 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB_DIR = os.path.join(PKG, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libsba_attn.so")
-SOURCES = ["abi.cu", "attn_simt.cu", "attn_mma_fwd.cu", "attn_mma_bwd.cu", "attn_tc5_fwd.cu", "attn_tc5_bwd.cu", "words_loss.cu"]
+SOURCES = ["abi.cu", "attn_simt.cu", "attn_mma_fwd.cu", "attn_mma_bwd.cu", "attn_bwd_post.cu", "attn_tc5_fwd.cu", "attn_tc5_bwd.cu",
+           "words_loss.cu", "match_loss.cu", "dev_aids.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr",
@@ -34,8 +35,12 @@ def _stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile every CUDA source into one shared library; returns its path."""
+def build(force: bool = False, verbose: bool = False, dev: bool = False) -> str:
+    """Compile every CUDA source into one shared library; returns its path.
+    dev=True adds -DSBA_DEV_AIDS (tuning knobs from the environment, kernel timeline: csrc/dev_aids.cu);
+    the product library is built without it."""
+    if dev:
+        force = True
     if not force and not _stale():
         return LIB_PATH
     os.makedirs(LIB_DIR, exist_ok=True)
@@ -44,7 +49,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     nvcc = _nvcc()
     for src in SOURCES:
         obj = os.path.join(LIB_DIR, src.replace(".cu", ".o"))
-        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc, *NVCC_FLAGS, *(["-DSBA_DEV_AIDS"] if dev else []), "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
@@ -64,4 +69,4 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, dev="--dev" in sys.argv))

@@ -11,6 +11,7 @@ namespace sba {
 namespace {
 thread_local char g_err[512] = "";
 thread_local int g_launches = 0;
+thread_local int g_algo = SBA_ALGO_AUTO;      // kernel family of the last attention call
 }  // namespace
 
 void set_error(const char* fmt, ...) {
@@ -44,8 +45,14 @@ int check_attn_shape(const char* fn, int B, int idf, int cdf, int L, int Q, int 
         set_error("%s: L=%d words exceeds the supported maximum of %d", fn, L, kMaxWords);
         return SBA_ERR_UNSUPPORTED;
     }
-    if (idf > 1024) {
-        set_error("%s: idf=%d exceeds the supported maximum of 1024", fn, idf);
+    // the CUDA-core family keeps sourceT (and, backward, a 32-pixel staging tile per channel) in shared memory:
+    // idf * 64 floats <= 64 KB; the word features of one sample (cdf * L floats) must fit as well
+    if (idf > 256) {
+        set_error("%s: idf=%d exceeds the supported maximum of 256", fn, idf);
+        return SBA_ERR_UNSUPPORTED;
+    }
+    if ((size_t)cdf * L * sizeof(float) > 200 * 1024) {
+        set_error("%s: cdf*L = %d context words per sample exceed the supported maximum of 51200", fn, cdf * L);
         return SBA_ERR_UNSUPPORTED;
     }
     if (dtype != SBA_F32 && dtype != SBA_BF16) {
@@ -78,67 +85,157 @@ int sba_abi_version(void) { return SBA_ABI_VERSION; }
 const char* sba_last_error(void) { return g_err; }
 int sba_last_launch_count(void) { return g_launches; }
 
-int sba_attn_fwd(const void* x, const float* ctx, const float* W, const uint8_t* mask, void* c_code, void* attn,
-                 float* srcT, uint32_t* mask_bits, int B, int idf, int cdf, int L, int Q, int dtype, int mask_mode,
-                 int algo, void* stream) {
+int sba_last_algo(void) { return g_algo; }
+
+// which == 0: forward, 1: backward.  1 when `algo` (a concrete family) covers the shape, else 0.
+int sba_attn_supported(int which, int algo, int B, int idf, int cdf, int L, int Q, int dtype) {
+    if (B <= 0 || idf <= 0 || idf > 256 || cdf <= 0 || L <= 0 || L > kMaxWords || Q <= 0) return 0;
+    if (dtype != SBA_F32 && dtype != SBA_BF16) return 0;
+    AttnShape s{B, idf, cdf, L, Q, dtype, SBA_MASK_REFERENCE};
+    switch (algo) {
+        case SBA_ALGO_SIMT: return 1;
+        case SBA_ALGO_MMA: return mma_supports(s) ? 1 : 0;
+        case SBA_ALGO_TCGEN05: return (which == 0 ? tc5_supports(s) : tc5_bwd_supports(s)) ? 1 : 0;
+        case SBA_ALGO_AUTO: return 1;
+        default: return 0;
+    }
+}
+
+size_t sba_attn_bwd_workspace_floats(int B, int idf, int cdf, int L) {
+    if (B <= 0 || idf <= 0 || cdf <= 0 || L <= 0) return 0;
+    return attn_bwd_workspace_floats(B, idf, cdf, L);
+}
+
+static int attn_fwd_impl(const void* x, const float* ctx, const float* W, const uint8_t* mask, void* c_code, void* attn,
+                         float* srcT, uint32_t* mask_bits, AttnShape s, int algo, void* stream, const char* fn) {
     g_launches = 0;
     g_err[0] = 0;
     if (!x || !ctx || !W || !c_code || !attn || !srcT || !mask_bits) {
-        set_error("sba_attn_fwd: null pointer argument");
+        set_error("%s: null pointer argument", fn);
         return SBA_ERR_ARG;
     }
-    int rc = check_attn_shape("sba_attn_fwd", B, idf, cdf, L, Q, dtype, mask_mode, algo);
+    int rc = check_attn_shape(fn, s.B, s.idf, s.cdf, s.L, s.Q, s.dtype, s.mask_mode, algo);
     if (rc) return rc;
-    AttnShape s{B, idf, cdf, L, Q, dtype, mask_mode};
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const bool can_mma = mma_supports(s) && aligned16(x);
+    const bool strided = s.c_rows > 0;          // c_code goes into a wider buffer: tensor-map stores only
+    const bool can_mma = !strided && mma_supports(s) && aligned16(x);
     const bool can_tc5 = tc5_supports(s) && aligned16(x) && aligned16(W) && aligned16(c_code) && aligned16(attn);
-    if (algo == SBA_ALGO_TCGEN05 || (algo == SBA_ALGO_AUTO && can_tc5)) {
+    if (algo == SBA_ALGO_TCGEN05 || (algo == SBA_ALGO_AUTO && can_tc5) || strided) {
         if (!can_tc5) {
-            set_error("sba_attn_fwd: SBA_ALGO_TCGEN05 does not cover idf=%d L=%d Q=%d B=%d (or x is not 16-byte aligned)", idf, L, Q, B);
+            set_error("%s: SBA_ALGO_TCGEN05 does not cover idf=%d L=%d Q=%d B=%d (or x is not 16-byte aligned)", fn, s.idf,
+                      s.L, s.Q, s.B);
             return SBA_ERR_UNSUPPORTED;
         }
+        g_algo = SBA_ALGO_TCGEN05;
         return tc5_attn_fwd(x, ctx, W, mask, c_code, attn, srcT, mask_bits, s, st);
     }
     if (algo == SBA_ALGO_MMA && !can_mma) {
-        set_error("sba_attn_fwd: SBA_ALGO_MMA does not cover idf=%d L=%d Q=%d cdf=%d B=%d (or x is not 16-byte aligned)", idf, L, Q, cdf, B);
+        set_error("%s: SBA_ALGO_MMA does not cover idf=%d L=%d Q=%d cdf=%d B=%d (or x is not 16-byte aligned)", fn, s.idf,
+                  s.L, s.Q, s.cdf, s.B);
         return SBA_ERR_UNSUPPORTED;
     }
-    if (algo != SBA_ALGO_SIMT && can_mma) return mma_attn_fwd(x, ctx, W, mask, c_code, attn, srcT, mask_bits, s, st);
+    if (algo != SBA_ALGO_SIMT && can_mma) {
+        g_algo = SBA_ALGO_MMA;
+        return mma_attn_fwd(x, ctx, W, mask, c_code, attn, srcT, mask_bits, s, st);
+    }
+    g_algo = SBA_ALGO_SIMT;
     rc = simt_project(ctx, W, mask, srcT, mask_bits, s, st);
     if (rc) return rc;
     return simt_attn_fwd(x, srcT, mask ? mask_bits : nullptr, c_code, attn, s, st);
 }
 
-int sba_attn_bwd(const void* x, const float* ctx, const float* W, const uint8_t* mask, const float* srcT,
-                 const uint32_t* mask_bits, const void* g_c, const void* g_attn, void* dX, float* dSrc, float* dW,
-                 float* dCtx, int B, int idf, int cdf, int L, int Q, int dtype, int mask_mode, int algo, void* stream) {
+static int attn_bwd_impl(const void* x, const float* ctx, const float* W, const uint8_t* mask, const float* srcT,
+                         const uint32_t* mask_bits, const void* g_c, const void* g_attn, void* dX, float* ws,
+                         size_t ws_floats, float* dW, float* dCtx, AttnShape s, int algo, void* stream, const char* fn) {
     g_launches = 0;
     g_err[0] = 0;
-    if (!x || !ctx || !W || !srcT || !g_c || !dX || !dSrc || (mask && !mask_bits)) {
-        set_error("sba_attn_bwd: null pointer argument");
+    if (!x || !ctx || !W || !srcT || !g_c || !dX || !ws || (mask && !mask_bits)) {
+        set_error("%s: null pointer argument", fn);
         return SBA_ERR_ARG;
     }
-    int rc = check_attn_shape("sba_attn_bwd", B, idf, cdf, L, Q, dtype, mask_mode, algo);
+    int rc = check_attn_shape(fn, s.B, s.idf, s.cdf, s.L, s.Q, s.dtype, s.mask_mode, algo);
     if (rc) return rc;
-    AttnShape s{B, idf, cdf, L, Q, dtype, mask_mode};
+    if (ws_floats < (size_t)s.B * s.idf * s.L + s.B + 1) {
+        set_error("%s: workspace of %zu floats is too small (sba_attn_bwd_workspace_floats)", fn, ws_floats);
+        return SBA_ERR_ARG;
+    }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const bool can_mma = mma_supports(s) && aligned16(x) && aligned16(g_c);
-    const bool can_tc5 = tc5_bwd_supports(s) && aligned16(x) && aligned16(g_c) && aligned16(dX);
-    if ((algo == SBA_ALGO_TCGEN05 || algo == SBA_ALGO_AUTO) && can_tc5) return tc5_attn_bwd(x, ctx, W, srcT, mask, mask_bits, g_c, g_attn, dX, dSrc, dW, dCtx, s, st);
+    const bool strided = s.c_rows > 0;          // g_c is a slice of a wider buffer: tensor-map loads only
+    const bool can_mma = !strided && mma_supports(s) && aligned16(x) && aligned16(g_c);
+    const bool can_tc5 = tc5_bwd_supports(s) && aligned16(x) && aligned16(g_c) && aligned16(dX) && aligned16(ws);
+    if (algo == SBA_ALGO_TCGEN05 || (algo == SBA_ALGO_AUTO && can_tc5) || strided) {
+        if (!can_tc5) {
+            set_error("%s: SBA_ALGO_TCGEN05 does not cover idf=%d L=%d Q=%d B=%d dtype=%d (bf16 tensors, 16-byte aligned)", fn,
+                      s.idf, s.L, s.Q, s.B, s.dtype);
+            return SBA_ERR_UNSUPPORTED;
+        }
+        g_algo = SBA_ALGO_TCGEN05;
+        return tc5_attn_bwd(x, ctx, W, srcT, mask, mask_bits, g_c, g_attn, dX, ws, ws_floats, dW, dCtx, s, st);
+    }
     if (algo == SBA_ALGO_MMA && !can_mma) {
-        set_error("sba_attn_bwd: SBA_ALGO_MMA does not cover idf=%d L=%d Q=%d cdf=%d B=%d (or x / g_c is not 16-byte aligned)", idf, L, Q, cdf, B);
+        set_error("%s: SBA_ALGO_MMA does not cover idf=%d L=%d Q=%d cdf=%d B=%d (or x / g_c is not 16-byte aligned)", fn,
+                  s.idf, s.L, s.Q, s.cdf, s.B);
         return SBA_ERR_UNSUPPORTED;
     }
-    if (algo != SBA_ALGO_SIMT && can_mma) return mma_attn_bwd(x, ctx, W, srcT, mask, g_c, g_attn, dX, dSrc, dW, dCtx, s, st);
-    cudaError_t e = cudaMemsetAsync(dSrc, 0, (size_t)B * idf * L * sizeof(float), st);
+    if (algo != SBA_ALGO_SIMT && can_mma) {
+        g_algo = SBA_ALGO_MMA;
+        return mma_attn_bwd(x, ctx, W, srcT, mask, g_c, g_attn, dX, ws, dW, dCtx, s, st);
+    }
+    g_algo = SBA_ALGO_SIMT;
+    cudaError_t e = cudaMemsetAsync(ws, 0, (size_t)s.B * s.idf * s.L * sizeof(float), st);
     if (e != cudaSuccess) {
-        set_error("sba_attn_bwd: memset: %s", cudaGetErrorString(e));
+        set_error("%s: memset: %s", fn, cudaGetErrorString(e));
         return SBA_ERR_CUDA;
     }
-    rc = simt_attn_bwd(x, srcT, mask ? mask_bits : nullptr, g_c, g_attn, dX, dSrc, s, st);
+    rc = simt_attn_bwd(x, srcT, mask ? mask_bits : nullptr, g_c, g_attn, dX, ws, s, st);
     if (rc) return rc;
-    return simt_attn_bwd_epilogue(ctx, W, dSrc, dW, dCtx, s, st);
+    return simt_attn_bwd_epilogue(ctx, W, ws, dW, dCtx, s, st);
+}
+
+int sba_attn_fwd(const void* x, const float* ctx, const float* W, const uint8_t* mask, void* c_code, void* attn,
+                 float* srcT, uint32_t* mask_bits, int B, int idf, int cdf, int L, int Q, int dtype, int mask_mode,
+                 int algo, void* stream) {
+    return attn_fwd_impl(x, ctx, W, mask, c_code, attn, srcT, mask_bits, AttnShape{B, idf, cdf, L, Q, dtype, mask_mode}, algo,
+                         stream, "sba_attn_fwd");
+}
+
+int sba_attn_bwd(const void* x, const float* ctx, const float* W, const uint8_t* mask, const float* srcT,
+                 const uint32_t* mask_bits, const void* g_c, const void* g_attn, void* dX, float* ws, size_t ws_floats,
+                 float* dW, float* dCtx, int B, int idf, int cdf, int L, int Q, int dtype, int mask_mode, int algo,
+                 void* stream) {
+    return attn_bwd_impl(x, ctx, W, mask, srcT, mask_bits, g_c, g_attn, dX, ws, ws_floats, dW, dCtx,
+                         AttnShape{B, idf, cdf, L, Q, dtype, mask_mode}, algo, stream, "sba_attn_bwd");
+}
+
+// NEXT_STAGE_G's torch.cat((h_code, c_code), 1) folded into the attention (model_bert.py:460-461): the forward
+// writes c_code into rows [c_row0, c_row0 + idf) of every sample of a [B, c_rows, Q] buffer, the backward reads
+// g_c from the same rows of the buffer's gradient.  tcgen05 family only (tensor-map addressing).
+int sba_attn_fwd_into(const void* x, const float* ctx, const float* W, const uint8_t* mask, void* c_buf, int c_rows,
+                      int c_row0, void* attn, float* srcT, uint32_t* mask_bits, int B, int idf, int cdf, int L, int Q,
+                      int dtype, int mask_mode, void* stream) {
+    if (c_rows < idf || c_row0 < 0 || c_row0 + idf > c_rows) {
+        set_error("sba_attn_fwd_into: rows [%d, %d) do not fit a %d-row buffer", c_row0, c_row0 + idf, c_rows);
+        return SBA_ERR_ARG;
+    }
+    AttnShape s{B, idf, cdf, L, Q, dtype, mask_mode};
+    s.c_rows = c_rows;
+    s.c_row0 = c_row0;
+    return attn_fwd_impl(x, ctx, W, mask, c_buf, attn, srcT, mask_bits, s, SBA_ALGO_TCGEN05, stream, "sba_attn_fwd_into");
+}
+
+int sba_attn_bwd_from(const void* x, const float* ctx, const float* W, const uint8_t* mask, const float* srcT,
+                      const uint32_t* mask_bits, const void* g_buf, int g_rows, int g_row0, const void* g_attn, void* dX,
+                      float* ws, size_t ws_floats, float* dW, float* dCtx, int B, int idf, int cdf, int L, int Q, int dtype,
+                      int mask_mode, void* stream) {
+    if (g_rows < idf || g_row0 < 0 || g_row0 + idf > g_rows) {
+        set_error("sba_attn_bwd_from: rows [%d, %d) do not fit a %d-row buffer", g_row0, g_row0 + idf, g_rows);
+        return SBA_ERR_ARG;
+    }
+    AttnShape s{B, idf, cdf, L, Q, dtype, mask_mode};
+    s.c_rows = g_rows;
+    s.c_row0 = g_row0;
+    return attn_bwd_impl(x, ctx, W, mask, srcT, mask_bits, g_buf, g_attn, dX, ws, ws_floats, dW, dCtx, s, SBA_ALGO_TCGEN05,
+                         stream, "sba_attn_bwd_from");
 }
 
 static int check_words_shape(const char* fn, int B_img, int B_cap, int nef, int R, int Lw) {
@@ -204,6 +301,53 @@ int sba_func_attention(const float* query, const float* context, float* wc, floa
     if (rc) return rc;
     return words_sim_fwd(context, query, nullptr, nullptr, attn, wc, B, B, 0, nef, R, T, gamma1, 1.f, 1.f, 1e-8f, 1,
                          static_cast<cudaStream_t>(stream));
+}
+
+int sba_match_ce_fwd(const float* scores, const int32_t* class_ids, const int64_t* labels, float* losses, float* lse, int B,
+                     void* stream) {
+    g_launches = 0;
+    g_err[0] = 0;
+    if (!scores || !labels || !losses || !lse || B <= 0) {
+        set_error("sba_match_ce_fwd: null pointer argument or B <= 0");
+        return SBA_ERR_ARG;
+    }
+    return match_ce_fwd(scores, class_ids, reinterpret_cast<const long long*>(labels), losses, lse, B,
+                        static_cast<cudaStream_t>(stream));
+}
+
+int sba_match_ce_bwd(const float* scores, const int32_t* class_ids, const int64_t* labels, const float* lse, const float* g,
+                     float* d_scores, int B, void* stream) {
+    g_launches = 0;
+    g_err[0] = 0;
+    if (!scores || !labels || !lse || !g || !d_scores || B <= 0) {
+        set_error("sba_match_ce_bwd: null pointer argument or B <= 0");
+        return SBA_ERR_ARG;
+    }
+    return match_ce_bwd(scores, class_ids, reinterpret_cast<const long long*>(labels), lse, g, d_scores, B,
+                        static_cast<cudaStream_t>(stream));
+}
+
+int sba_sent_scores_fwd(const float* cnn, const float* rnn, float* scores, float* norms, int B, int nef, float gamma3,
+                        float eps, void* stream) {
+    g_launches = 0;
+    g_err[0] = 0;
+    if (!cnn || !rnn || !scores || !norms || B <= 0 || nef <= 0) {
+        set_error("sba_sent_scores_fwd: null pointer argument or non-positive size");
+        return SBA_ERR_ARG;
+    }
+    return sent_scores_fwd(cnn, rnn, scores, norms, B, nef, gamma3, eps, static_cast<cudaStream_t>(stream));
+}
+
+int sba_sent_scores_bwd(const float* cnn, const float* rnn, const float* norms, const float* scores, const float* d_scores,
+                        float* d_cnn, float* d_rnn, int B, int nef, float gamma3, float eps, void* stream) {
+    g_launches = 0;
+    g_err[0] = 0;
+    if (!cnn || !rnn || !norms || !scores || !d_scores || !d_cnn || !d_rnn || B <= 0 || nef <= 0) {
+        set_error("sba_sent_scores_bwd: null pointer argument or non-positive size");
+        return SBA_ERR_ARG;
+    }
+    return sent_scores_bwd(cnn, rnn, norms, scores, d_scores, d_cnn, d_rnn, B, nef, gamma3, eps,
+                           static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -342,15 +342,22 @@ int launch_fwd(const void* x, const float* srcT, const uint32_t* mb, void* c, vo
 template <typename T, int LP, int PX>
 int launch_bwd(const void* x, const float* srcT, const uint32_t* mb, const void* g, const void* ga, void* dX,
                float* dSrc, const AttnShape& s, cudaStream_t st) {
-    const size_t smem = (size_t)s.idf * (LP + 32) * sizeof(float);
+    const size_t smem = (size_t)s.idf * (LP + 32) * sizeof(float);      // <= 64 KB for idf <= 256 (check_attn_shape)
     dim3 grid(ceil_div(s.Q, kThreads * PX), s.B);
+    if (smem > 48 * 1024) {
+        cudaError_t e = ga != nullptr
+            ? cudaFuncSetAttribute(k_attn_bwd<T, LP, PX, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+            : cudaFuncSetAttribute(k_attn_bwd<T, LP, PX, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) {
+            set_error("attn_bwd(simt): %zu bytes of shared memory: %s", smem, cudaGetErrorString(e));
+            return SBA_ERR_UNSUPPORTED;
+        }
+    }
     if (ga != nullptr) {
-        if (smem > 48 * 1024) cudaFuncSetAttribute(k_attn_bwd<T, LP, PX, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         k_attn_bwd<T, LP, PX, true><<<grid, kThreads, smem, st>>>(
             static_cast<const T*>(x), srcT, mb, static_cast<const T*>(g), static_cast<const T*>(ga),
             static_cast<T*>(dX), dSrc, s.B, s.idf, s.L, s.Q, s.mask_mode);
     } else {
-        if (smem > 48 * 1024) cudaFuncSetAttribute(k_attn_bwd<T, LP, PX, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         k_attn_bwd<T, LP, PX, false><<<grid, kThreads, smem, st>>>(
             static_cast<const T*>(x), srcT, mb, static_cast<const T*>(g), nullptr, static_cast<T*>(dX), dSrc, s.B,
             s.idf, s.L, s.Q, s.mask_mode);

@@ -16,19 +16,20 @@
 //                                                 the accumulator stays in TMEM across all tiles of a
 //                                                 sample: rows = g / x channels, columns = P / dS words;
 //                                                 its diagonal blocks are g.P and x.dS)
-//   second stage: dX row of the pixel -> staged -> TMA box store; at the end of a sample the two
-//                 diagonal blocks of the TMEM accumulator are added to dSrc[b] with fp32 atomics.
+//   second stage: dX row of the pixel -> staged -> TMA box store; when the CTA leaves a sample, the two
+//                 diagonal blocks of the TMEM accumulator are added (g.P + x.dS, through shared memory)
+//                 and stored to this CTA's PARTIAL SLOT of the sample: slot = CTA index + sample index
+//                 (unique because the CTAs' tile ranges are contiguous and ordered).
 // Two {S, dP} TMEM buffers and two PB buffers form a software pipeline: MMA1(j+1) is issued before
 // MMA2(j), so the first stage of tile j+1 overlaps the tensor core and the second stage of tile j.
 // At a sample boundary the pipeline drains (the operands are rebuilt only after the last MMA of the
 // old sample has retired, the accumulator is handed back after it has been read).
-// dSrc / dW are zeroed by a small kernel in front (programmatic dependent launch: this kernel only
-// waits for it before its first atomic), and dW = sum_b dSrc[b] . ctx[b]^T, dCtx[b] = W^T . dSrc[b]
-// are formed by a small kernel behind it (attn_bwd_post; also a programmatic dependent, resident
-// early): doing that per sample inside this kernel stalls CTAs mid-stream and piles the whole
-// reduction up at the end of the stream.
-#include <cstdlib>
-
+// A small kernel behind it (k_bwd_finish_tc5, a programmatic dependent that is resident early) adds the
+// slots of every sample in a FIXED order -> dSrc[b], forms dW = sum_b dSrc[b] . ctx[b]^T over 16 sample
+// groups whose partial products the last-arriving block of each column slice adds in group order, and
+// dCtx[b] = W^T . dSrc[b].  Nothing is zero-filled and nothing is accumulated with atomics: the whole
+// backward is two kernels and bit-reproducible run to run (data-parallel replicas stay identical).
+#include "host_util.h"
 #include "kernels.h"
 #include "tc5_common.cuh"
 
@@ -36,41 +37,19 @@ namespace sba {
 namespace {
 using namespace tc5;
 
-// development aid (SBA_TC5_TIMELINE): globaltimer stamps of the kernels of consecutive backward calls
-__device__ unsigned long long g_timeline[16 * 8];
-__device__ __forceinline__ unsigned long long gtime() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-    return t;
-}
-__device__ __forceinline__ void tl_min(int slot) { if (slot >= 0) atomicMin(&g_timeline[slot], gtime()); }
-__device__ __forceinline__ void tl_max(int slot) { if (slot >= 0) atomicMax(&g_timeline[slot], gtime()); }
-
-// development aid: SBA_TC5_TIMELINE=1 stamps the kernels of calls 20..35 and prints them at call 36
-static int g_tl_call = 0;
-static int timeline_slot() {
-    static const bool on = getenv("SBA_TC5_TIMELINE") != nullptr;
-    if (!on) return -1;
-    const int c = g_tl_call - 20;
-    return (c >= 0 && c < 16) ? c * 8 : -1;
-}
-
-
 struct Tc5BwdParams {
     const float* srcT;
     const uint8_t* mask;
     const uint32_t* mask_bits;   // [B] caption mask words written by the forward (scratch)
     const void* ga;       // [B, L, Q] nullable
-    float* dSrc;          // [B, idf, L]
-    const float* ctx;     // [B, cdf, L]   (epilogue)
-    const float* W;       // [idf, cdf]    (epilogue, dCtx only)
-    float* dW;            // [idf, cdf]    nullable
-    float* dCtx;          // [B, cdf, L]   nullable
-    int B, L, Q, cdf, mask_mode;
+    float* part;          // [n_ctas + B][idf][LP] partial dSrc sums: slot = CTA index + sample index
+    uint32_t* counters;   // completion counters of the finish kernel, zeroed here by CTA 0
+    int n_counters;
+    int B, L, Q, mask_mode;
+    int g_rows, g_row0;   // g_c lives in rows [g_row0, g_row0 + idf) of a [B, g_rows, Q] buffer
     int tiles_per_sample;
     int n_tiles;
-    long long* trace;     // development aid (SBA_TC5_TRACE): per-phase clock64 stamps of CTA 0, else NULL
-    int tl;               // development aid (SBA_TC5_TIMELINE): slot base in g_timeline, else -1
+    unsigned long long* tl;   // development timeline stamps (tc5_common.cuh), NULL in the product library
 };
 
 // producer warp, MMA warp, 4 first-stage ("math") warps, 4 second-stage ("epilogue") warps
@@ -104,7 +83,9 @@ struct Tc5BwdCfg {
     static constexpr int COL_S = 0, COL_DP = 32, COL_BUF = 64, COL_DX = 128, COL_ACC = 128 + IDF;
     static constexpr int TMEM_COLS = pow2_cols(COL_ACC + ND);
     static constexpr int OUT_WARP_BYTES = IDF * 32 * ES;        // per-warp dX staging [channel][32 px]
-    static constexpr int SMEM_BYTES = NST * STAGE_BYTES + 2 * PB_BYTES + B1_BYTES + B2_BYTES + 4 * OUT_WARP_BYTES;
+    static constexpr int XCHG_BYTES = IDF * LP * 4;             // x.dS block on its way to the g.P rows (sample flush)
+    static constexpr int SMEM_BYTES =
+        NST * STAGE_BYTES + 2 * PB_BYTES + B1_BYTES + B2_BYTES + 4 * OUT_WARP_BYTES + XCHG_BYTES;
     static constexpr uint32_t IDESC1 = make_idesc(1, 1, 0, TQ, NS);      // A = tile, MN-major
     static constexpr uint32_t IDESC2 = make_idesc(1, 1, 0, TQ, IDF);     // A = dS rows of PB, MN-major
     static constexpr uint32_t IDESC3 = make_idesc(1, 0, 0, MD, ND);      // A = [g ; x], B = PB, both K-major
@@ -113,135 +94,177 @@ struct Tc5BwdCfg {
     static_assert(LP <= 32 && IDF <= 64, "at most 32 words");
 };
 
-// zero dSrc, the per-sample counters and dW; the streaming kernel waits for this grid only before its
-// first atomic (griddepcontrol.wait), so the fill overlaps its prologue and first tiles
-__global__ void __launch_bounds__(256) k_zero_tc5(float* __restrict__ a, size_t na, float* __restrict__ b, size_t nb, int tl) {
-    // programmatic dependent of whatever precedes it (hides its launch latency); upstream work is complete
-    // before its own dependent - the streaming kernel, which reads x / g_c at once - may start
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    if (threadIdx.x == 0) tl_min(tl);
-    const size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x, step = (size_t)gridDim.x * blockDim.x;
-    for (size_t i = i0; i < na; i += step) a[i] = 0.f;
-    if (b != nullptr)
-        for (size_t i = i0; i < nb; i += step) b[i] = 0.f;
-    if (threadIdx.x == 0) tl_max(tl < 0 ? tl : tl + 1);
+// ------------------------------------------------------------------------------------------------
+// Finish kernel: dSrc[b] = sum of the sample's partial slots (fixed order), dW, dCtx.
+//   blocks [0, n_dw)        : (sample group grp, slice of 4 output channels i).  Per round of up to `nb` samples
+//                             (K = nb * L <= 96 rows of the flattened (sample, word) axis) the block stages
+//                             cs [K][256 c] = ctx^T of those samples - BEFORE griddepcontrol.wait, i.e. while the
+//                             streaming kernel is still running - and, after it, ds [K][4] = the slot sums of its
+//                             4 channels: one batch of up to 8 independent 16-byte loads per thread (one L2 round
+//                             trip).  Thread = input channel c: dW[i0..i0+3][c] += sum_k ds[k][.] cs[k][c], one
+//                             conflict-free LDS + one broadcast LDS.128 per 4 FMAs.  The group's partial goes to
+//                             dwp[grp]; the block that arrives last at its channel slice's counter adds the
+//                             `groups` partials in group order (again one batch of loads) and writes dW.
+//   blocks [n_dw, n_dw + B) : dCtx of one sample (only when words need a gradient)
+// After the grid dependency the critical path is: slot loads -> FMAs -> partial store + counter -> partial loads.
+// ------------------------------------------------------------------------------------------------
+struct Tc5FinishParams {
+    const float* part;    // [n_ctas + B][idf][LP]
+    const float* ctx;     // [B, cdf, L]
+    const float* W;       // [idf, cdf]   (dCtx only)
+    float* dSrc;          // [B, idf, L] out
+    float* dW;            // [idf, cdf] out, nullable
+    float* dCtx;          // [B, cdf, L] out, nullable
+    float* dwp;           // [groups][idf][cdf] group partials of dW
+    uint32_t* counters;   // [1 + idf/4], zeroed by the streaming kernel
+    int B, cdf, L, LP;
+    int tiles_per_sample, n_tiles, n_ctas;    // tile -> CTA map of the streaming kernel
+    int groups, nb, n_dw;                     // sample groups, samples per round, number of dW blocks
+    unsigned long long* tl;
+};
+
+// CTA k of the streaming kernel owns tiles [floor(k n / G), floor((k + 1) n / G)): the CTA that owns tile t
+__device__ __forceinline__ int tile_owner(int t, int n_tiles, int n_ctas) {
+    return (int)((((long long)t + 1) * n_ctas - 1) / n_tiles);
 }
 
-// dW += sum_{b in group} dSrc[b] . ctx[b]^T for a [idf x 32] slice, dCtx[b] = W^T . dSrc[b]; a programmatic
-// dependent of the streaming kernel (griddepcontrol.wait = that grid is complete and flushed).
-//   blocks [0, n_dw)          : (32 input channels c, one of 64 sample groups).  The K = (sample, word) axis
-//                               of up to 4 samples is staged flat - ds [idf][K], cs [K][32 c] - so the inner
-//                               loop is branch-free: one broadcast LDS + one LDS.128 per 4 FMAs per thread
-//                               (thread = channel i x 4 channels c).  The 64 groups meet in fp32 atomics on
-//                               dW (dW zeroed by k_zero_tc5); many small blocks hide each other's latency.
-//   blocks [n_dw, n_dw + B)   : dCtx of one sample (only when words need a gradient)
-constexpr int kPostCS = 36;        // row stride (floats) of cs: 16-byte aligned rows, 4-bank skew
-constexpr int kPostDS = 132;       // row stride (floats) of ds: K <= 128, 4-bank skew between channels
+constexpr int kFinK = 96;          // rows of the flattened (sample, word) axis per round
+constexpr int kFinC = 256;         // input channels per pass = threads per block
+constexpr int kFinSlots = 8;       // slots loaded in one batch (more: a second batch)
+constexpr int kFinGroups = 16;     // at most this many sample groups (partials added by the last block)
 template <int IDF>
-__global__ void __launch_bounds__(256) k_bwd_post_tc5(const float* __restrict__ dSrc, const float* __restrict__ ctx,
-                                                      const float* __restrict__ W, float* __restrict__ dW,
-                                                      float* __restrict__ dCtx, int B, int cdf, int L, int n_dw, int tl) {
+__global__ void __launch_bounds__(kFinC) k_bwd_finish_tc5(const Tc5FinishParams p) {
     extern __shared__ __align__(16) float sm[];
-    constexpr bool HI = IDF > 32;          // a thread owns channel i0 and, for idf > 32, i0 + 32
+    __shared__ int s_last;
     const int tid = threadIdx.x;
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");      // (the head kernel of the next call, see above)
-    if (threadIdx.x == 0) tl_min(tl < 0 ? tl : tl + 6);
-    if ((int)blockIdx.x < n_dw) {
-        float* cs = sm;                          // [K <= 128][kPostCS]
-        float* ds = sm + 128 * kPostCS;          // [64][kPostDS]
-        const int cg = blockIdx.x >> 6, grp = blockIdx.x & 63;
-        const int c0 = cg * 32, nc = cdf - c0 < 32 ? cdf - c0 : 32;
-        const int b_lo = (B * grp) >> 6, b_hi = (B * (grp + 1)) >> 6;
-        const int i0 = tid >> 3, cq = (tid & 7) * 4;
-        const int row = tid >> 1, half = tid & 1;          // staging: thread = half a row of L words
-        float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+    const int B = p.B, cdf = p.cdf, L = p.L, LP = p.LP, TPS = p.tiles_per_sample;
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");      // (the head kernel of the next call)
+    if ((int)blockIdx.x < p.n_dw) {
+        float* cs = sm;                          // [kFinK][kFinC]
+        float* ds = sm + kFinK * kFinC;          // [kFinK][4]
+        constexpr int NSL = IDF / 4;             // channel slices
+        const int grp = blockIdx.x / NSL, sl = blockIdx.x - grp * NSL;
+        const int i0 = sl * 4;
+        const int b_lo = (int)(((long long)B * grp) / p.groups), b_hi = (int)(((long long)B * (grp + 1)) / p.groups);
+        const int LP4 = LP >> 2;
         bool waited = false;
-        for (int bb = b_lo; bb < b_hi; bb += 4) {
-            const int nb = b_hi - bb < 4 ? b_hi - bb : 4;
-            const int K = nb * L;
-            __syncthreads();
-            // ctx rows (sample s, channel c) - 4 x 32 = 128 rows - do not depend on the streaming kernel: they are
-            // staged BEFORE griddepcontrol.wait, while that grid is still running
-            {
-                const int sidx = row >> 5, c = row & 31;
-                float cv[16];
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const int l = half * 16 + j;
-                    cv[j] = (sidx < nb && c < nc && l < L) ? __ldg(ctx + ((size_t)(bb + sidx) * cdf + c0 + c) * L + l) : 0.f;
+        for (int cc = 0; cc < cdf; cc += kFinC) {            // (cdf <= 256: one pass)
+            const int c = cc + tid;
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int bb = b_lo; bb < b_hi; bb += p.nb) {
+                const int nb = b_hi - bb < p.nb ? b_hi - bb : p.nb;
+                const int K = nb * L;
+                __syncthreads();
+                // cs[k = (s, l)][c] = ctx[bb + s][c][l]: independent of the streaming kernel.  Thread = channel c
+                // reads its nb rows of L contiguous words; consecutive threads write consecutive shared words.
+                if (c < cdf) {
+                    for (int sidx = 0; sidx < nb; ++sidx) {
+                        const float* row = p.ctx + ((size_t)(bb + sidx) * cdf + c) * L;
+                        for (int l = 0; l < L; ++l) cs[(sidx * L + l) * kFinC + tid] = __ldg(row + l);
+                    }
                 }
+                // slot sums of (sample s, channel i0 + r, words 4q..4q+3): nb * 4 * LP4 items, <= 160
+                const int items = nb * 4 * LP4;
+                const bool mine = tid < items;
+                int sidx = 0, r = 0, q = 0, k_lo = 0, k_hi = -1;
+                if (mine) {
+                    sidx = tid / (4 * LP4);
+                    const int rem = tid - sidx * 4 * LP4;
+                    r = rem / LP4;
+                    q = rem - r * LP4;
+                    k_lo = tile_owner((bb + sidx) * TPS, p.n_tiles, p.n_ctas);
+                    k_hi = tile_owner((bb + sidx + 1) * TPS - 1, p.n_tiles, p.n_ctas);
+                }
+                if (!waited) {
+                    asm volatile("griddepcontrol.wait;" ::: "memory");      // every slot is complete and visible
+                    if (tid == 0) SBA_TL(p.tl, 4);
+                    waited = true;
+                }
+                if (mine) {
+                    const int b = bb + sidx;
+                    const float* base = p.part + ((size_t)b * IDF + i0 + r) * LP + 4 * q;      // slot (k + b): + k * IDF * LP
+                    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+                    for (int k0 = k_lo; k0 <= k_hi; k0 += kFinSlots) {
+                        float4 v[kFinSlots];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const int l = half * 16 + j;
-                    if (sidx < nb && l < L) cs[(sidx * L + l) * kPostCS + c] = cv[j];
+                        for (int u = 0; u < kFinSlots; ++u)
+                            v[u] = (k0 + u <= k_hi) ? __ldcg(reinterpret_cast<const float4*>(base + (size_t)(k0 + u + b) * IDF * LP))
+                                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                        for (int u = 0; u < kFinSlots; ++u) { a.x += v[u].x; a.y += v[u].y; a.z += v[u].z; a.w += v[u].w; }
+                    }
+                    const float av[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int l = 4 * q + e;
+                        if (l < L) {
+                            ds[(sidx * L + l) * 4 + r] = av[e];
+                            if (cc == 0) p.dSrc[((size_t)b * IDF + i0 + r) * L + l] = av[e];
+                        }
+                    }
+                }
+                __syncthreads();
+#pragma unroll 8
+                for (int k = 0; k < K; ++k) {
+                    const float cv = cs[k * kFinC + tid];
+                    const float4 d4 = *reinterpret_cast<const float4*>(ds + 4 * k);
+                    acc[0] = fmaf(d4.x, cv, acc[0]); acc[1] = fmaf(d4.y, cv, acc[1]);
+                    acc[2] = fmaf(d4.z, cv, acc[2]); acc[3] = fmaf(d4.w, cv, acc[3]);
                 }
             }
             if (!waited) {
-                asm volatile("griddepcontrol.wait;" ::: "memory");      // dSrc is complete and visible
-                if (threadIdx.x == 0) tl_min(tl < 0 ? tl : tl + 4);
+                asm volatile("griddepcontrol.wait;" ::: "memory");     // (empty sample group) counters zeroed upstream
                 waited = true;
             }
-            // dSrc rows (sample s, channel i) - up to 4 x 64 = 256 rows, two passes of 128 rows; all loads of the
-            // round are issued before the first store (one memory round trip)
-            float dv[2][16];
+            // group partial -> dwp[grp][i][c]
+            if (c < cdf) {
 #pragma unroll
-            for (int ps = 0; ps < (HI ? 2 : 1); ++ps) {
-                const int r = row + 128 * ps, sidx = r / IDF, i = r - sidx * IDF;
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const int l = half * 16 + j;
-                    dv[ps][j] = (sidx < nb && l < L) ? __ldcg(dSrc + ((size_t)(bb + sidx) * IDF + i) * L + l) : 0.f;
-                }
-            }
-#pragma unroll
-            for (int ps = 0; ps < (HI ? 2 : 1); ++ps) {
-                const int r = row + 128 * ps, sidx = r / IDF, i = r - sidx * IDF;
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const int l = half * 16 + j;
-                    if (sidx < nb && l < L) ds[i * kPostDS + sidx * L + l] = dv[ps][j];
-                }
-            }
-            __syncthreads();
-            const float* d0p = ds + i0 * kPostDS;
-            const float* ccol = cs + cq;
-#pragma unroll 8
-            for (int k = 0; k < K; ++k) {
-                const float4 c4 = *reinterpret_cast<const float4*>(ccol + k * kPostCS);
-                const float d0 = d0p[k];
-                acc[0][0] = fmaf(d0, c4.x, acc[0][0]); acc[0][1] = fmaf(d0, c4.y, acc[0][1]);
-                acc[0][2] = fmaf(d0, c4.z, acc[0][2]); acc[0][3] = fmaf(d0, c4.w, acc[0][3]);
-                if constexpr (HI) {
-                    const float d1 = d0p[32 * kPostDS + k];       // rows >= IDF are never staged; results discarded
-                    acc[1][0] = fmaf(d1, c4.x, acc[1][0]); acc[1][1] = fmaf(d1, c4.y, acc[1][1]);
-                    acc[1][2] = fmaf(d1, c4.z, acc[1][2]); acc[1][3] = fmaf(d1, c4.w, acc[1][3]);
-                }
+                for (int r = 0; r < 4; ++r) p.dwp[((size_t)grp * IDF + i0 + r) * cdf + c] = acc[r];
             }
         }
-        if (!waited) asm volatile("griddepcontrol.wait;" ::: "memory");     // (empty sample group) dW is zeroed upstream
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) s_last = (atomicAdd(p.counters + 1 + sl, 1u) == (uint32_t)(p.groups - 1));
+        __syncthreads();
+        if (s_last) {                       // every group's partial of this channel slice is complete: add in group order
+            __threadfence();
+            for (int o = tid; o < cdf; o += kFinC) {             // 4 rows x cdf outputs, a float4 column-quad per (row, 4 c)
 #pragma unroll
-        for (int h = 0; h < (HI ? 2 : 1); ++h) {
-            const int i = i0 + 32 * h;
-            if (i < IDF)
+                for (int r = 0; r < 4; ++r) {
+                    float v[kFinGroups];
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    if (cq + k < nc) atomicAdd(dW + (size_t)i * cdf + c0 + cq + k, acc[h][k]);
+                    for (int g = 0; g < kFinGroups; ++g)
+                        v[g] = g < p.groups ? __ldcg(p.dwp + ((size_t)g * IDF + i0 + r) * cdf + o) : 0.f;
+                    float a = 0.f;
+#pragma unroll
+                    for (int g = 0; g < kFinGroups; ++g) a += v[g];
+                    p.dW[(size_t)(i0 + r) * cdf + o] = a;
+                }
+            }
         }
     } else {
-        asm volatile("griddepcontrol.wait;" ::: "memory");
         float* ds = sm;                  // [idf][L]
-        const int b = blockIdx.x - n_dw;
-        for (int o = tid; o < IDF * L; o += blockDim.x) ds[o] = __ldcg(dSrc + (size_t)b * IDF * L + o);
+        const int b = blockIdx.x - p.n_dw;
+        const int k_lo = tile_owner(b * TPS, p.n_tiles, p.n_ctas), k_hi = tile_owner((b + 1) * TPS - 1, p.n_tiles, p.n_ctas);
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        for (int o = tid; o < IDF * LP; o += blockDim.x) {
+            const int i = o / LP, l = o - i * LP;
+            float a = 0.f;
+            for (int k = k_lo; k <= k_hi; ++k) a += __ldcg(p.part + ((size_t)(k + b) * IDF + i) * LP + l);
+            if (l < L) {
+                ds[i * L + l] = a;
+                if (p.n_dw == 0) p.dSrc[((size_t)b * IDF + i) * L + l] = a;
+            }
+        }
         __syncthreads();
         for (int o = tid; o < cdf * L; o += blockDim.x) {
             const int c = o / L, l = o - c * L;
             float a = 0.f;
-            for (int i = 0; i < IDF; ++i) a = fmaf(__ldg(W + (size_t)i * cdf + c), ds[i * L + l], a);
-            dCtx[(size_t)b * cdf * L + o] = a;
+            for (int i = 0; i < IDF; ++i) a = fmaf(__ldg(p.W + (size_t)i * cdf + c), ds[i * L + l], a);
+            p.dCtx[(size_t)b * cdf * L + o] = a;
         }
     }
-    if (threadIdx.x == 0) tl_max(tl < 0 ? tl : tl + 5);
+    if (tid == 0) SBA_TL(p.tl, 5);
 }
 
 __device__ __forceinline__ void warp_arrive(uint32_t bar, int lane) {
@@ -271,8 +294,9 @@ __global__ void __launch_bounds__(kBwdThreads, Tc5BwdCfg<IDF, NQ, NST_>::CTAS_PE
     unsigned char* g_b1 = g_pb + 2 * C::PB_BYTES;
     unsigned char* g_b2 = g_b1 + C::B1_BYTES;
     unsigned char* g_out = g_b2 + C::B2_BYTES;
+    float* g_xchg = reinterpret_cast<float*>(g_out + 4 * C::OUT_WARP_BYTES);      // [idf][LP] sample flush exchange
 
-    unsigned long long* bars = reinterpret_cast<unsigned long long*>(g_out + 4 * C::OUT_WARP_BYTES);
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(g_out + 4 * C::OUT_WARP_BYTES + C::XCHG_BYTES);
     unsigned long long* bar_x_full = bars;
     unsigned long long* bar_x_empty = bars + NST;
     unsigned long long* bar_s_full = bars + 2 * NST;          // [2] by tile parity
@@ -287,16 +311,10 @@ __global__ void __launch_bounds__(kBwdThreads, Tc5BwdCfg<IDF, NQ, NST_>::CTAS_PE
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int L = p.L, Q = p.Q, TPS = p.tiles_per_sample;
-    // let the post kernel's blocks become resident wherever there is room; they park in griddepcontrol.wait
+    // let the finish kernel's blocks become resident wherever there is room; they park in griddepcontrol.wait
     // until this grid has completed, which takes its launch latency off the critical path
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    if (tid == 0) tl_min(p.tl < 0 ? p.tl : p.tl + 2);
-    if (p.trace != nullptr && tid == 0) {
-        unsigned long long gt;
-        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
-        p.trace[256 + 2 * blockIdx.x] = (long long)gt;
-    }
-    if (p.trace != nullptr && blockIdx.x == 0 && tid == 64) p.trace[240] = clock64();
+    if (tid == 0) SBA_TL(p.tl, 2);
 
     const int w_begin = (int)(((long long)blockIdx.x * p.n_tiles) / gridDim.x);
     const int w_end = (int)(((long long)(blockIdx.x + 1) * p.n_tiles) / gridDim.x);
@@ -325,6 +343,12 @@ __global__ void __launch_bounds__(kBwdThreads, Tc5BwdCfg<IDF, NQ, NST_>::CTAS_PE
         mbar_init(smem_u32(&bar_dx_free), 4);
         mbar_init(smem_u32(&bar_b_ready), 4);
         fence_barrier_init();
+        // This kernel heads the call's launch chain (programmatic dependent of whatever precedes it in the stream):
+        // everything above ran under the predecessor's tail; nothing of the caller's memory is touched before this.
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        SBA_TL(p.tl, 6);
+        if (blockIdx.x == 0)
+            for (int c = 0; c < p.n_counters; ++c) p.counters[c] = 0u;      // the finish kernel's completion counters
         // the first ring of g / x tiles is requested before the rest of the prologue (TMEM allocation, operand
         // buffers) so that its DRAM latency runs under it
         {
@@ -335,7 +359,7 @@ __global__ void __launch_bounds__(kBwdThreads, Tc5BwdCfg<IDF, NQ, NST_>::CTAS_PE
                 const uint32_t dst = s_st + j * C::STAGE_BYTES;
 #pragma unroll
                 for (int bx = 0; bx < C::NBOX; ++bx) {
-                    tma_load_2d(dst + (2 * bx) * C::BOX_BYTES, &tm_g, t * TQ + bx * C::BOX_PX, b * IDF, full);
+                    tma_load_2d(dst + (2 * bx) * C::BOX_BYTES, &tm_g, t * TQ + bx * C::BOX_PX, b * p.g_rows + p.g_row0, full);
                     tma_load_2d(dst + (2 * bx + 1) * C::BOX_BYTES, &tm_x, t * TQ + bx * C::BOX_PX, b * IDF, full);
                 }
                 if (++t == TPS) { t = 0; ++b; }
@@ -352,7 +376,7 @@ __global__ void __launch_bounds__(kBwdThreads, Tc5BwdCfg<IDF, NQ, NST_>::CTAS_PE
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, tmem_base_s, 0);     // provably warp-uniform
-    if (p.trace != nullptr && blockIdx.x == 0 && tid == 64) p.trace[241] = clock64();
+    asm volatile("griddepcontrol.wait;" ::: "memory");      // (thread 0 already passed it: returns at once)
 
 
     if (warp == kProducerWarp) {
@@ -369,7 +393,7 @@ __global__ void __launch_bounds__(kBwdThreads, Tc5BwdCfg<IDF, NQ, NST_>::CTAS_PE
                 mbar_expect_tx(full, (uint32_t)C::STAGE_BYTES);
 #pragma unroll
                 for (int bx = 0; bx < C::NBOX; ++bx) {
-                    tma_load_2d(dst + (2 * bx) * C::BOX_BYTES, &tm_g, t * TQ + bx * C::BOX_PX, b * IDF, full);
+                    tma_load_2d(dst + (2 * bx) * C::BOX_BYTES, &tm_g, t * TQ + bx * C::BOX_PX, b * p.g_rows + p.g_row0, full);
                     tma_load_2d(dst + (2 * bx + 1) * C::BOX_BYTES, &tm_x, t * TQ + bx * C::BOX_PX, b * IDF, full);
                 }
             }
@@ -497,7 +521,7 @@ __global__ void __launch_bounds__(kBwdThreads, Tc5BwdCfg<IDF, NQ, NST_>::CTAS_PE
 #pragma unroll
                     for (int k = 0; k < NK; ++k) {
                         const int ch = (ct >> 2) + 32 * g, l = (ct & 3) + 4 * k;
-                        sv[g][k] = (ch < IDF && l < L) ? __ldg(sb + ch * L + l) : 0.f;
+                        sv[g][k] = (ch < IDF && l < L) ? __ldcg(sb + ch * L + l) : 0.f;
                     }
 #pragma unroll
                 for (int g = 0; g < NG; ++g)
@@ -513,11 +537,9 @@ __global__ void __launch_bounds__(kBwdThreads, Tc5BwdCfg<IDF, NQ, NST_>::CTAS_PE
                 fence_proxy_async();
                 warp_arrive(smem_u32(&bar_b_ready), lane);
             }
-            const bool tr = p.trace != nullptr && blockIdx.x == 0 && ct == 0 && j < 16;
-            if (tr) p.trace[j * 16 + 0] = clock64();
             const int q = t * TQ + px;
             uint32_t mb = pad_bits;
-            if (p.mask != nullptr) mb |= __ldg(p.mask_bits + (p.mask_mode == SBA_MASK_PER_SAMPLE ? (uint32_t)b : cap));
+            if (p.mask != nullptr) mb |= __ldcg(p.mask_bits + (p.mask_mode == SBA_MASK_PER_SAMPLE ? (uint32_t)b : cap));
             float ga[HAS_GA ? LP : 1];
             if constexpr (HAS_GA) {
                 const T* gp = static_cast<const T*>(p.ga) + (size_t)b * L * Q + q;
@@ -527,7 +549,6 @@ __global__ void __launch_bounds__(kBwdThreads, Tc5BwdCfg<IDF, NQ, NST_>::CTAS_PE
             // ---- S and dP rows of this pixel ---------------------------------------------------------
             mbar_wait(smem_u32(&bar_s_full[buf]), (uint32_t)(j >> 1) & 1u);
             tc_fence_after();
-            if (tr) p.trace[j * 16 + 1] = clock64();
             uint32_t sr[LP], dr[LP];
             tmem_ld<LP>(tl + C::COL_BUF * buf + C::COL_S, sr);
             tmem_ld<LP>(tl + C::COL_BUF * buf + C::COL_DP, dr);
@@ -571,7 +592,6 @@ __global__ void __launch_bounds__(kBwdThreads, Tc5BwdCfg<IDF, NQ, NST_>::CTAS_PE
             }
             fence_proxy_async();
             warp_arrive(smem_u32(&bar_ds_ready[buf]), lane);
-            if (tr) p.trace[j * 16 + 3] = clock64();
 
             if (++t == TPS) { t = 0; ++b; }
             cap += step_mod;
@@ -579,25 +599,21 @@ __global__ void __launch_bounds__(kBwdThreads, Tc5BwdCfg<IDF, NQ, NST_>::CTAS_PE
         }
     } else {
         // --------------------------------- second-stage warps: thread = pixel -------------------
-        // dX row of the pixel -> staged [channel][32 px] per warp -> one TMA box store; at the end of a sample
-        // the diagonal blocks of the TMEM accumulator are added to dSrc[b] with fp32 atomics.
+        // dX row of the pixel -> staged [channel][32 px] per warp -> one TMA box store; when the CTA leaves a sample
+        // the diagonal blocks of the TMEM accumulator are added and stored to the (CTA, sample) partial slot.
         const int cw = warp & 3;
         const uint32_t tl = tmem_base + ((uint32_t)(cw * 32) << 16);
         const uint32_t so = s_out + cw * C::OUT_WARP_BYTES;
         T* go = reinterpret_cast<T*>(g_out + cw * C::OUT_WARP_BYTES) + lane;
         int b = b0, t = t0;
-        bool waited_zero = false;
         for (int j = 0; j < n_local; ++j) {
-            const bool tr = p.trace != nullptr && blockIdx.x == 0 && warp == kFirstEpilogueWarp && lane == 0 && j < 16;
             mbar_wait(smem_u32(&bar_c_full), (uint32_t)j & 1u);
             tc_fence_after();
-            if (tr) p.trace[j * 16 + 5] = clock64();
             uint32_t cr[IDF];
             tmem_ld<IDF>(tl + C::COL_DX, cr);
             tmem_wait_ld();
             tc_fence_before();
             warp_arrive(smem_u32(&bar_dx_free), lane);
-            if (tr) p.trace[j * 16 + 6] = clock64();
             if (lane == 0) bulk_wait_read<0>();        // the previous dX store has finished reading the staging
             __syncwarp();
 #pragma unroll
@@ -608,15 +624,10 @@ __global__ void __launch_bounds__(kBwdThreads, Tc5BwdCfg<IDF, NQ, NST_>::CTAS_PE
                 tma_store_2d(&tm_dx, t * TQ + cw * 32, b * IDF, so);
                 bulk_commit();
             }
-            if (tr) p.trace[j * 16 + 7] = clock64();
 
             const bool last_of_sample = (t + 1 == TPS) || (j + 1 == n_local);
             if (last_of_sample) {
-                // every MMA of sample b issued by this CTA has completed (c_full(j)): add its share of dSrc[b]
-                if (!waited_zero) {
-                    asm volatile("griddepcontrol.wait;" ::: "memory");      // k_zero_tc5 has cleared dSrc / dW
-                    waited_zero = true;
-                }
+                // every MMA of sample b issued by this CTA has completed (c_full(j)): flush its share of dSrc[b].
                 // accumulator row r of this lane: M = 64 -> lanes 0..15 of each quarter hold rows 16*cw + lane
                 const int row = C::MD == 64 ? 16 * cw + lane : 32 * cw + lane;
                 const bool valid = (C::MD == 64 ? lane < 16 : true) && row < 2 * IDF;
@@ -630,15 +641,29 @@ __global__ void __launch_bounds__(kBwdThreads, Tc5BwdCfg<IDF, NQ, NST_>::CTAS_PE
                 tmem_wait_ld();
                 tc_fence_before();
                 if (j + 1 < n_local) warp_arrive(smem_u32(&bar_acc_free), lane);     // the next sample may overwrite it
-                if (valid) {
-                    float* db = p.dSrc + ((size_t)b * IDF + ch) * L;
+                // dSrc[b][ch] share = (g.P)[ch] + (x.dS)[ch]: the x rows travel through shared memory to the lanes
+                // that hold the g rows, which add (always in this order) and store the slot row
+                mma::named_bar_sync(1, 128);                   // the previous flush's readers are done
+                float* xs = g_xchg + ch * LP;
+                if (valid && is_x) {
 #pragma unroll
-                    for (int l = 0; l < LP; ++l)
-                        if (l < L) atomicAdd(db + l, __uint_as_float(is_x ? a1[l] : a0[l]));
+                    for (int q = 0; q < LP / 4; ++q)
+                        reinterpret_cast<uint4*>(xs)[q] = make_uint4(a1[4 * q], a1[4 * q + 1], a1[4 * q + 2], a1[4 * q + 3]);
+                }
+                mma::named_bar_sync(1, 128);
+                if (valid && !is_x) {
+                    float4* out = reinterpret_cast<float4*>(p.part + ((size_t)(blockIdx.x + b) * IDF + ch) * LP);
+#pragma unroll
+                    for (int q = 0; q < LP / 4; ++q) {
+                        const float4 xv = reinterpret_cast<const float4*>(xs)[q];
+                        out[q] = make_float4(__uint_as_float(a0[4 * q]) + xv.x, __uint_as_float(a0[4 * q + 1]) + xv.y,
+                                             __uint_as_float(a0[4 * q + 2]) + xv.z, __uint_as_float(a0[4 * q + 3]) + xv.w);
+                    }
                 }
             }
             if (++t == TPS) { t = 0; ++b; }
         }
+        if (warp == kFirstEpilogueWarp && lane == 0) SBA_TL(p.tl, 7);
         if (lane == 0) bulk_wait<0>();
         tc_fence_before();
     }
@@ -648,122 +673,91 @@ __global__ void __launch_bounds__(kBwdThreads, Tc5BwdCfg<IDF, NQ, NST_>::CTAS_PE
         tc_fence_after();
         tmem_dealloc(tmem_base, C::TMEM_COLS);
     }
-    if (p.trace != nullptr && tid == 0) {
-        unsigned long long gt;
-        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
-        p.trace[256 + 2 * blockIdx.x + 1] = (long long)gt;
-    }
-    if (tid == 0) tl_max(p.tl < 0 ? p.tl : p.tl + 3);
+    if (tid == 0) SBA_TL(p.tl, 3);
+}
+
+// workspace layout behind the B*idf*L + B + 1 words the other kernel families use (sizes in floats)
+struct Tc5BwdWs {
+    size_t part, dwp, counters, total;
+    int slots, groups, nb, lp, n_counters;
+};
+Tc5BwdWs tc5_bwd_ws(int B, int idf, int cdf, int L, int sms) {
+    Tc5BwdWs w{};
+    w.lp = (L + 3) / 4 * 4;
+    w.slots = 2 * sms + B;                                   // at most two CTAs per SM (TMEM), slot = CTA + sample
+    w.nb = kFinK / L < 4 ? kFinK / L : 4;                    // samples per round of the finish kernel (L <= 32: >= 3)
+    w.groups = (B + w.nb - 1) / w.nb < kFinGroups ? (B + w.nb - 1) / w.nb : kFinGroups;
+    w.n_counters = 1 + idf / 4;
+    const size_t head = ((size_t)B * idf * L + B + 1 + 3) / 4 * 4;
+    w.part = head;
+    w.dwp = w.part + (size_t)w.slots * idf * w.lp;
+    w.counters = w.dwp + ((size_t)w.groups * idf * cdf + 3) / 4 * 4;
+    w.total = w.counters + (size_t)(w.n_counters + 3) / 4 * 4;
+    return w;
 }
 
 template <int IDF, int NQ, bool HAS_GA, int NST_>
-int launch_bwd_tc5(const void* x, const void* g, void* dX, const Tc5BwdParams& p, cudaStream_t st) {
+int launch_bwd_tc5(const void* x, const void* g, void* dX, const Tc5BwdParams& p_in, const Tc5FinishParams& f_in,
+                   cudaStream_t st) {
     using C = Tc5BwdCfg<IDF, NQ, NST_>;
     auto kern = k_attn_bwd_tc5<IDF, NQ, HAS_GA, NST_>;
-    const size_t smem = (size_t)C::SMEM_BYTES + (2 * C::NST + 14) * 8;
-    // per device (a process may drive several): SM count, and whether this kernel's dynamic shared memory
-    // limit has been raised there (smem is a compile-time constant of the instantiation)
-    static int sms_of[64] = {0};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev < 0 || dev >= 64) {
-        set_error("%s(tcgen05): device index %d not supported", "attn_bwd", dev);
-        return SBA_ERR_UNSUPPORTED;
-    }
-    if (smem > 220 * 1024) {
-        set_error("%s(tcgen05): %zu bytes of shared memory needed", "attn_bwd", smem);
-        return SBA_ERR_UNSUPPORTED;
-    }
-    if (sms_of[dev] == 0) {
-        int n = 0;
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess || n < 1) {
-            set_error("%s(tcgen05): cudaFuncSetAttribute(%zu B): %s", "attn_bwd", smem, cudaGetErrorString(e));
-            return SBA_ERR_CUDA;
-        }
-        sms_of[dev] = n;
-    }
-    const int sms = sms_of[dev];
-    const size_t smem_set = smem;
-    int per_sm = (int)((227 * 1024) / (smem_set + 1024));
+    constexpr size_t smem = (size_t)C::SMEM_BYTES + (2 * C::NST + 14) * 8;
+    static_assert(smem <= 220 * 1024, "shared memory budget of the tcgen05 backward exceeded");
+    int dev = 0, sms = 0;
+    int rc = current_device(&dev, &sms, "attn_bwd(tcgen05)");
+    if (rc) return rc;
+    static std::atomic<unsigned long long> smem_done{0};
+    rc = ensure_dynamic_smem(kern, smem, dev, smem_done, "attn_bwd(tcgen05)");
+    if (rc) return rc;
+    int per_sm = (int)((227 * 1024) / (smem + 1024));
     if (per_sm > C::CTAS_PER_SM) per_sm = C::CTAS_PER_SM;
+    if (per_sm > 2) per_sm = 2;                              // the slot workspace is sized for two CTAs per SM
     if (per_sm < 1) per_sm = 1;
-    if (getenv("SBA_TC5_CTAS_PER_SM")) per_sm = atoi(getenv("SBA_TC5_CTAS_PER_SM"));
+#ifdef SBA_DEV_AIDS
+    if (dev_tuning().ctas_per_sm > 0 && dev_tuning().ctas_per_sm < per_sm) per_sm = dev_tuning().ctas_per_sm;
+#endif
     const int max_ctas = sms * per_sm;
+    Tc5BwdParams p = p_in;
+    Tc5FinishParams f = f_in;
     CUtensorMap tm_x, tm_g, tm_dx;
-    int rc = make_tile_map(&tm_x, x, SBA_BF16, p.B * IDF, p.Q, IDF, 64, true);
-    if (!rc) rc = make_tile_map(&tm_g, g, SBA_BF16, p.B * IDF, p.Q, IDF, 64, true);
+    rc = make_tile_map(&tm_x, x, SBA_BF16, p.B * IDF, p.Q, IDF, 64, true);
+    if (!rc) rc = make_tile_map(&tm_g, g, SBA_BF16, p.B * p.g_rows, p.Q, IDF, 64, true);
     if (!rc) rc = make_tile_map(&tm_dx, dX, SBA_BF16, p.B * IDF, p.Q, IDF, 32, false);
     if (rc) return rc;
-    const size_t n_src = (size_t)p.B * IDF * p.L + p.B + 1;       // dSrc and the counter words behind it
-    rc = attn_bwd_zero(p.dSrc, n_src, p.dW, p.dW ? (size_t)IDF * p.cdf : 0, st);
-    if (rc) return rc;
     const int grid = p.n_tiles < max_ctas ? p.n_tiles : max_ctas;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(kBwdThreads);
-    cfg.dynamicSmemBytes = smem_set;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    Tc5BwdParams pk = p;
-    pk.tl = timeline_slot();
-    static long long* trace_buf = nullptr;
-    if (getenv("SBA_TC5_TRACE")) {
-        if (!trace_buf) cudaMalloc(&trace_buf, 4096 * sizeof(long long));
-        cudaMemsetAsync(trace_buf, 0, 4096 * sizeof(long long), st);
-        pk.trace = trace_buf;
-    }
-    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tm_x, tm_g, tm_dx, pk);
-    if (e != cudaSuccess) {
-        set_error("attn_bwd(tcgen05): launch: %s", cudaGetErrorString(e));
-        return SBA_ERR_CUDA;
-    }
-    if (pk.trace) {
-        static long long h[4096];
-        cudaStreamSynchronize(st);
-        cudaMemcpy(h, trace_buf, sizeof(h), cudaMemcpyDeviceToHost);
-        {
-            long long t0 = h[256];
-            for (int k = 0; k < grid && k < 1900; ++k) if (h[256 + 2 * k] < t0) t0 = h[256 + 2 * k];
-            {
-                double sum = 0; long long mx = 0, mn = 1LL << 62; int n = 0;
-                for (int k = 0; k < grid && k < 1900; ++k) {
-                    const long long d = h[256 + 2 * k + 1] - h[256 + 2 * k];
-                    sum += (double)d; ++n;
-                    if (d > mx) mx = d;
-                    if (d < mn) mn = d;
-                }
-                fprintf(stderr, "CTA lifetime over %d CTAs: min %lld mean %.0f max %lld ns\n", n, mn, sum / n, mx);
-            }
-            fprintf(stderr, "CTA start/end (ns since the first start), every 37th CTA:\n");
-            for (int k = 0; k < grid && k < 1900; k += 37)
-                fprintf(stderr, "  cta %4d: %7lld .. %7lld\n", k, h[256 + 2 * k] - t0, h[256 + 2 * k + 1] - t0);
-        }
-        const char* names[12] = {"top", "s_full", "ld_S", "math+PB", "ds_rdy", "c_full", "dX_stg", "store", "M:x_full", "M:mma1", "M:ds_rdy", "M:mma2"};
-        fprintf(stderr, "CTA 0: entry %lld, prologue done +%lld, B operands built +%lld, first tile top +%lld (cycles)\n", 0LL,
-                h[241] - h[240], h[242] - h[240], h[0] - h[240]);
-        fprintf(stderr, "tile");
-        for (int k = 0; k < 12; ++k) fprintf(stderr, " %9s", names[k]);
-        fprintf(stderr, "   (cycles since the first stamp)\n");
-        for (int j = 0; j < 16 && h[j * 16] != 0; ++j) {
-            fprintf(stderr, "%4d", j);
-            for (int k = 0; k < 12; ++k) fprintf(stderr, " %9lld", h[j * 16 + k] - h[0]);
-            fprintf(stderr, "\n");
+    p.tl = f.tl = SBA_TL_SLOT();
+    {
+        PdlLaunch ml(dim3(grid), dim3(kBwdThreads), smem, st);
+        cudaError_t e = cudaLaunchKernelEx(&ml.cfg, kern, tm_x, tm_g, tm_dx, p);
+        if (e != cudaSuccess) {
+            set_error("attn_bwd(tcgen05): launch: %s", cudaGetErrorString(e));
+            return SBA_ERR_CUDA;
         }
     }
     add_launches(1);
     rc = check_launch("attn_bwd(tcgen05)");
     if (rc) return rc;
-    return attn_bwd_post(p.dSrc, p.ctx, p.W, p.dW, p.dCtx, p.B, IDF, p.cdf, p.L, st);
+    // finish kernel: slots -> dSrc, dW, dCtx
+    f.n_ctas = grid;
+    f.n_dw = f.dW != nullptr ? f.groups * (IDF / 4) : 0;
+    const int fgrid = f.n_dw + (f.dCtx != nullptr ? f.B : 0);
+    if (fgrid == 0) return SBA_OK;
+    constexpr size_t fsmem = (size_t)(kFinK * kFinC + kFinK * 4) * sizeof(float);           // 97.5 KB
+    static std::atomic<unsigned long long> fsmem_done{0};
+    rc = ensure_dynamic_smem(k_bwd_finish_tc5<IDF>, fsmem, dev, fsmem_done, "attn_bwd(finish)");
+    if (rc) return rc;
+    PdlLaunch fl(dim3(fgrid), dim3(kFinC), fsmem, st);
+    cudaError_t e = cudaLaunchKernelEx(&fl.cfg, k_bwd_finish_tc5<IDF>, f);
+    if (e != cudaSuccess) {
+        set_error("attn_bwd(finish): launch: %s", cudaGetErrorString(e));
+        return SBA_ERR_CUDA;
+    }
+    add_launches(1);
+    return check_launch("attn_bwd(finish)");
 }
 
 template <int IDF, bool HAS_GA>
-int dispatch_nq(const void* x, const void* g, void* dX, const Tc5BwdParams& p, cudaStream_t st) {
+int dispatch_nq(const void* x, const void* g, void* dX, const Tc5BwdParams& p, const Tc5FinishParams& f, cudaStream_t st) {
     // long streams at idf 32 (>= 16 tiles per CTA of a 2-per-SM grid, e.g. 128x128 at B >= 40) take the 4-deep ring:
     // it still fits two CTAs per SM there and measured 2-4 % faster; short streams lose to its longer prologue
     constexpr bool kDeep = IDF == 32;
@@ -771,9 +765,9 @@ int dispatch_nq(const void* x, const void* g, void* dX, const Tc5BwdParams& p, c
 #define SBA_BWD_CASE(n)                                                                     \
     case n:                                                                                 \
         if constexpr (kDeep) {                                                              \
-            if (deep) return launch_bwd_tc5<IDF, n, HAS_GA, 4>(x, g, dX, p, st);            \
+            if (deep) return launch_bwd_tc5<IDF, n, HAS_GA, 4>(x, g, dX, p, f, st);         \
         }                                                                                   \
-        return launch_bwd_tc5<IDF, n, HAS_GA, 3>(x, g, dX, p, st);
+        return launch_bwd_tc5<IDF, n, HAS_GA, 3>(x, g, dX, p, f, st);
     switch ((p.L + 3) / 4) {
         SBA_BWD_CASE(1) SBA_BWD_CASE(2) SBA_BWD_CASE(3) SBA_BWD_CASE(4)
         SBA_BWD_CASE(5) SBA_BWD_CASE(6) SBA_BWD_CASE(7) SBA_BWD_CASE(8)
@@ -783,109 +777,51 @@ int dispatch_nq(const void* x, const void* g, void* dX, const Tc5BwdParams& p, c
 }
 
 template <int IDF>
-int dispatch_ga(const void* x, const void* g, void* dX, const Tc5BwdParams& p, cudaStream_t st) {
-    return p.ga != nullptr ? dispatch_nq<IDF, true>(x, g, dX, p, st) : dispatch_nq<IDF, false>(x, g, dX, p, st);
+int dispatch_ga(const void* x, const void* g, void* dX, const Tc5BwdParams& p, const Tc5FinishParams& f, cudaStream_t st) {
+    return p.ga != nullptr ? dispatch_nq<IDF, true>(x, g, dX, p, f, st) : dispatch_nq<IDF, false>(x, g, dX, p, f, st);
 }
 
 }  // namespace
 
-int attn_bwd_zero(float* dSrc, size_t n_src, float* dW, size_t n_dw, cudaStream_t st) {
-    if (getenv("SBA_TC5_TIMELINE")) {
-        ++g_tl_call;
-        if (g_tl_call == 20) {
-            unsigned long long init[16 * 8];
-            for (int i = 0; i < 16 * 8; ++i) init[i] = (i % 8 == 0 || i % 8 == 2 || i % 8 == 4 || i % 8 == 6) ? ~0ull : 0ull;
-            cudaMemcpyToSymbol(g_timeline, init, sizeof(init));
-        }
-        if (g_tl_call == 37) {
-            unsigned long long h[16 * 8];
-            cudaDeviceSynchronize();
-            cudaMemcpyFromSymbol(h, g_timeline, sizeof(h));
-            fprintf(stderr, "call: zero start..end | main start..end | post entry, past wait..end   (us since zero start of the first call)\n");
-            for (int c = 0; c < 16; ++c) {
-                const unsigned long long* r = h + c * 8;
-                auto us = [&](unsigned long long v) { return (double)(long long)(v - h[0]) * 1e-3; };
-                fprintf(stderr, "%3d: %8.2f..%8.2f | %8.2f..%8.2f | %8.2f, %8.2f..%8.2f\n", c, us(r[0]), us(r[1]), us(r[2]), us(r[3]),
-                        us(r[6]), us(r[4]), us(r[5]));
-            }
-        }
-    }
-    {
-        cudaLaunchConfig_t zc = {};
-        zc.gridDim = dim3(64);
-        zc.blockDim = dim3(256);
-        zc.stream = st;
-        cudaLaunchAttribute za[1];
-        za[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        za[0].val.programmaticStreamSerializationAllowed = 1;
-        zc.attrs = za;
-        zc.numAttrs = 1;
-        cudaError_t ze = cudaLaunchKernelEx(&zc, k_zero_tc5, dSrc, n_src, dW, n_dw, timeline_slot());
-        if (ze != cudaSuccess) {
-            set_error("attn_bwd(zero): launch: %s", cudaGetErrorString(ze));
-            return SBA_ERR_CUDA;
-        }
-    }
-    add_launches(1);
-    return check_launch("attn_bwd(zero)");
-}
-
-int attn_bwd_post(const float* dSrc, const float* ctx, const float* W, float* dW, float* dCtx, int B, int idf, int cdf,
-                  int L, cudaStream_t st) {
-    if (dW == nullptr && dCtx == nullptr) return SBA_OK;
-    const int n_dw = dW != nullptr ? 64 * ((cdf + 31) / 32) : 0;
-    const int grid = n_dw + (dCtx != nullptr ? B : 0);
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(256);
-    cfg.dynamicSmemBytes = (size_t)(128 * kPostCS + 64 * kPostDS) * sizeof(float);       // 52 KB: above the default limit
-    static bool attr_set_of[64] = {false};
-    int pdev = 0;
-    cudaGetDevice(&pdev);
-    bool& attr_set = attr_set_of[pdev & 63];
-    if (!attr_set) {
-        cudaFuncSetAttribute(k_bwd_post_tc5<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.dynamicSmemBytes);
-        cudaFuncSetAttribute(k_bwd_post_tc5<48>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.dynamicSmemBytes);
-        cudaFuncSetAttribute(k_bwd_post_tc5<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.dynamicSmemBytes);
-        attr_set = true;
-    }
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    const int tl = timeline_slot();
-    cudaError_t e;
-    if (idf == 32) e = cudaLaunchKernelEx(&cfg, k_bwd_post_tc5<32>, dSrc, ctx, W, dW, dCtx, B, cdf, L, n_dw, tl);
-    else if (idf == 48) e = cudaLaunchKernelEx(&cfg, k_bwd_post_tc5<48>, dSrc, ctx, W, dW, dCtx, B, cdf, L, n_dw, tl);
-    else if (idf == 64) e = cudaLaunchKernelEx(&cfg, k_bwd_post_tc5<64>, dSrc, ctx, W, dW, dCtx, B, cdf, L, n_dw, tl);
-    else {
-        set_error("attn_bwd(post): idf=%d not covered", idf);
-        return SBA_ERR_UNSUPPORTED;
-    }
-    if (e != cudaSuccess) {
-        set_error("attn_bwd(post): launch: %s", cudaGetErrorString(e));
-        return SBA_ERR_CUDA;
-    }
-    add_launches(1);
-    return check_launch("attn_bwd(post)");
-}
-
 bool tc5_bwd_supports(const AttnShape& s) { return tc5_supports(s) && s.dtype == SBA_BF16; }
+
+size_t attn_bwd_workspace_floats(int B, int idf, int cdf, int L) {
+    int dev = 0, sms = 0;
+    if (current_device(&dev, &sms, "attn_bwd_workspace") != SBA_OK) sms = 160;     // no device (build check): an upper bound
+    return tc5_bwd_ws(B, idf, cdf, L, sms).total;
+}
 
 int tc5_attn_bwd(const void* x, const float* ctx, const float* W, const float* srcT, const uint8_t* mask,
                  const uint32_t* mask_bits, const void* g_c,
-                 const void* g_attn, void* dX, float* dSrc, float* dW, float* dCtx, const AttnShape& s, cudaStream_t st) {
+                 const void* g_attn, void* dX, float* ws, size_t ws_floats, float* dW, float* dCtx, const AttnShape& s,
+                 cudaStream_t st) {
+    int dev = 0, sms = 0;
+    int rc = current_device(&dev, &sms, "attn_bwd(tcgen05)");
+    if (rc) return rc;
+    const Tc5BwdWs w = tc5_bwd_ws(s.B, s.idf, s.cdf, s.L, sms);
+    if (ws_floats < w.total) {
+        set_error("attn_bwd(tcgen05): workspace of %zu floats given, %zu needed (sba_attn_bwd_workspace_floats)", ws_floats,
+                  w.total);
+        return SBA_ERR_ARG;
+    }
     Tc5BwdParams p{};
-    p.srcT = srcT; p.mask = mask; p.mask_bits = mask_bits; p.ga = g_attn; p.dSrc = dSrc; p.ctx = ctx; p.W = W; p.dW = dW; p.dCtx = dCtx;
-    p.B = s.B; p.L = s.L; p.Q = s.Q; p.cdf = s.cdf; p.mask_mode = s.mask_mode;
+    p.srcT = srcT; p.mask = mask; p.mask_bits = mask_bits; p.ga = g_attn;
+    p.part = ws + w.part;
+    p.counters = reinterpret_cast<uint32_t*>(ws + w.counters);
+    p.n_counters = w.n_counters;
+    p.B = s.B; p.L = s.L; p.Q = s.Q; p.mask_mode = s.mask_mode;
+    p.g_rows = s.c_rows > 0 ? s.c_rows : s.idf;
+    p.g_row0 = s.c_rows > 0 ? s.c_row0 : 0;
     p.tiles_per_sample = s.Q / tc5::TQ;
     p.n_tiles = s.B * p.tiles_per_sample;
-    int rc = -1;
-    if (s.idf == 32) rc = dispatch_ga<32>(x, g_c, dX, p, st);
-    else if (s.idf == 48) rc = dispatch_ga<48>(x, g_c, dX, p, st);
-    else if (s.idf == 64) rc = dispatch_ga<64>(x, g_c, dX, p, st);
+    Tc5FinishParams f{};
+    f.part = p.part; f.ctx = ctx; f.W = W; f.dSrc = ws; f.dW = dW; f.dCtx = dCtx; f.dwp = ws + w.dwp; f.counters = p.counters;
+    f.B = s.B; f.cdf = s.cdf; f.L = s.L; f.LP = w.lp;
+    f.tiles_per_sample = p.tiles_per_sample; f.n_tiles = p.n_tiles; f.groups = w.groups; f.nb = w.nb;
+    rc = -1;
+    if (s.idf == 32) rc = dispatch_ga<32>(x, g_c, dX, p, f, st);
+    else if (s.idf == 48) rc = dispatch_ga<48>(x, g_c, dX, p, f, st);
+    else if (s.idf == 64) rc = dispatch_ga<64>(x, g_c, dX, p, f, st);
     if (rc == -1) {
         set_error("attn_bwd(tcgen05): unsupported shape idf=%d L=%d", s.idf, s.L);
         return SBA_ERR_UNSUPPORTED;

@@ -22,29 +22,60 @@
 // x - trunc(x) is written by the consumers into a second shared-memory tile.
 //
 // Reference semantics: AttnGAN2/code/GlobalAttention.py:82-121 (oracle/attention.py).
-#include <cstdlib>
-
+#include "host_util.h"
 #include "kernels.h"
 #include "tc5_common.cuh"
 
 namespace sba {
 namespace tc5 {
 
+namespace {
+typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                             const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                             CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda); resolved once (thread-safe static)
+EncodeFn encode_fn() {
+    static const EncodeFn fn = [] {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qres);
+        return (e == cudaSuccess && qres == cudaDriverEntryPointSuccess) ? reinterpret_cast<EncodeFn>(f) : (EncodeFn) nullptr;
+    }();
+    return fn;
+}
+// A tensor map is a pure function of (base, dtype, shape, box, swizzle): the training loop calls with the same
+// few tensors' shapes over and over (and the caching allocator hands the same blocks back), so the last maps
+// are kept per host thread instead of being re-encoded on every launch.
+struct MapKey {
+    const void* base;
+    int dtype, rows, cols, box_rows, box_cols, swizzle;
+    bool operator==(const MapKey& o) const {
+        return base == o.base && dtype == o.dtype && rows == o.rows && cols == o.cols && box_rows == o.box_rows &&
+               box_cols == o.box_cols && swizzle == o.swizzle;
+    }
+};
+constexpr int kMapCache = 32;
+struct MapCache {
+    MapKey key[kMapCache];
+    CUtensorMap map[kMapCache];
+    int used = 0, next = 0;
+};
+thread_local MapCache g_maps;
+}  // namespace
+
 int make_tile_map(CUtensorMap* out, const void* base, int dtype, int rows, int cols, int box_rows, int box_cols,
                   bool swizzle) {
-    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-    static EncodeFn encode = nullptr;
-    if (encode == nullptr) {
-        void* fn = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
-        if (e != cudaSuccess || fn == nullptr || qres != cudaDriverEntryPointSuccess) {
-            set_error("cuTensorMapEncodeTiled is not available from this driver: %s", cudaGetErrorString(e));
-            return SBA_ERR_CUDA;
+    const MapKey key{base, dtype, rows, cols, box_rows, box_cols, swizzle ? 1 : 0};
+    MapCache& mc = g_maps;
+    for (int i = 0; i < mc.used; ++i)
+        if (mc.key[i] == key) {
+            *out = mc.map[i];
+            return SBA_OK;
         }
-        encode = reinterpret_cast<EncodeFn>(fn);
+    const EncodeFn encode = encode_fn();
+    if (encode == nullptr) {
+        set_error("cuTensorMapEncodeTiled is not available from this driver");
+        return SBA_ERR_CUDA;
     }
     const int es = dtype == SBA_F32 ? 4 : 2;
     const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
@@ -62,6 +93,9 @@ int make_tile_map(CUtensorMap* out, const void* base, int dtype, int rows, int c
                   box_rows, box_cols);
         return SBA_ERR_CUDA;
     }
+    const int slot = mc.used < kMapCache ? mc.used++ : (mc.next = (mc.next + 1) % kMapCache);
+    mc.key[slot] = key;
+    mc.map[slot] = *out;
     return SBA_OK;
 }
 
@@ -76,7 +110,9 @@ struct Tc5FwdParams {
     const float* W;       // [idf, cdf]
     int cdf;
     const uint8_t* mask;
-    void* c_code;
+    void* c_code;         // [B, c_rows, Q]: weightedContext goes to rows [c_row0, c_row0 + idf) of every sample
+    int c_rows, c_row0;   // (c_rows = idf, c_row0 = 0: a plain [B, idf, Q] tensor; 2*idf / idf: second half of the
+                          //  concatenated h_c_code buffer of NEXT_STAGE_G, model_bert.py:460-461)
     void* attn;
     uint32_t* mask_bits;
     int B, L, Q, mask_mode;
@@ -86,6 +122,7 @@ struct Tc5FwdParams {
     int static_tiles;     // tiles of the contiguous static share every CTA starts with (0: all tiles are dynamic)
     int chunk;            // tiles per dynamic chunk
     int dyn_first;        // first tile of the dynamic region = gridDim.x * static_tiles
+    unsigned long long* tl;   // development timeline stamps (tc5_common.cuh), NULL in the product library
 };
 
 constexpr int pow2_cols(int n) { return n <= 32 ? 32 : n <= 64 ? 64 : n <= 128 ? 128 : n <= 256 ? 256 : 512; }
@@ -144,19 +181,19 @@ struct Tc5FwdCfg {
 __global__ void __launch_bounds__(256) k_project_tc5(const float* __restrict__ ctx, const float* __restrict__ W,
                                                      float* __restrict__ srcT, const uint8_t* __restrict__ mask,
                                                      uint32_t* __restrict__ mask_bits, uint32_t* __restrict__ sched, int idf,
-                                                     int cdf, int L) {
+                                                     int cdf, int L, int early_trigger, unsigned long long* tl) {
     // Launched as a programmatic dependent of whatever precedes it in the stream, which only hides its launch
     // latency: it waits for that work to complete BEFORE it lets its own dependent (the streaming kernel,
     // whose producer starts reading x at once) go, so nothing downstream can run ahead of upstream results.
     asm volatile("griddepcontrol.wait;" ::: "memory");
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (early_trigger) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (threadIdx.x == 0) SBA_TL(tl, 0);
     if (blockIdx.x == 0 && threadIdx.x == 0) *sched = 0u;        // chunk counter of the streaming kernel's tile scheduler
-    // caption padding mask -> one 32-bit word per caption (bit l = word l is padding), by the first block of each sample
-    if (mask != nullptr && blockIdx.x % (idf / 8) == 0 && threadIdx.x < 32) {
-        const int cap = blockIdx.x / (idf / 8);
-        const uint32_t bits = __ballot_sync(0xffffffffu, (int)threadIdx.x < L && mask[(size_t)cap * L + threadIdx.x] != 0);
-        if (threadIdx.x == 0) mask_bits[cap] = bits;
-    }
+    // caption padding mask -> one 32-bit word per caption (bit l = word l is padding), by the first block of each sample;
+    // the byte is requested here, with everything else, and consumed after the FMAs (one memory round trip in all)
+    const bool mask_warp = mask != nullptr && blockIdx.x % (idf / 8) == 0 && threadIdx.x < 32;
+    uint8_t mask_byte = 0;
+    if (mask_warp && (int)threadIdx.x < L) mask_byte = mask[(size_t)(blockIdx.x / (idf / 8)) * L + threadIdx.x];
     __shared__ __align__(16) float w_s[8][8][32];
     __shared__ float red_s[8][8][32];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -207,6 +244,11 @@ __global__ void __launch_bounds__(256) k_project_tc5(const float* __restrict__ c
             }
         }
     }
+    if (!early_trigger) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (mask_warp) {
+        const uint32_t bits = __ballot_sync(0xffffffffu, mask_byte != 0);
+        if (threadIdx.x == 0) mask_bits[blockIdx.x / (idf / 8)] = bits;
+    }
 #pragma unroll
     for (int k = 0; k < 8; ++k) red_s[warp][k][lane] = acc[k];
     __syncthreads();
@@ -219,6 +261,7 @@ __global__ void __launch_bounds__(256) k_project_tc5(const float* __restrict__ c
             srcT[((size_t)b * idf + i0 + k) * L + l] = a;
         }
     }
+    if (threadIdx.x == 0) SBA_TL(tl, 1);
 }
 
 
@@ -260,6 +303,7 @@ __global__ void __launch_bounds__(kThreads, Tc5FwdCfg<T, IDF, NQ>::CTAS_PER_SM)
     // a programmatic dependent behind this grid (the head kernel of the next call) may become resident now; it
     // parks in griddepcontrol.wait until this grid has completed, which takes its launch latency off the stream
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (tid == 0) SBA_TL(p.tl, 2);
     const int CH = p.chunk, ST = p.static_tiles;
     // first chunk: this CTA's static share, or (no static share) dynamic chunk blockIdx.x
     const int w_begin = (int)blockIdx.x * (ST > 0 ? ST : CH);
@@ -510,6 +554,7 @@ __global__ void __launch_bounds__(kThreads, Tc5FwdCfg<T, IDF, NQ>::CTAS_PER_SM)
         };
 
         asm volatile("griddepcontrol.wait;" ::: "memory");      // srcT of k_project_tc5 is complete and visible
+        if (ct == 0) SBA_TL(p.tl, 6);
         if (!rd.done()) make_lo(0);
 
         for (int j = 0; !rd.done(); ++j) {
@@ -534,7 +579,7 @@ __global__ void __launch_bounds__(kThreads, Tc5FwdCfg<T, IDF, NQ>::CTAS_PER_SM)
 
             // ---- mask (GlobalAttention.py:104-108) + softmax over words (:109) -----------------------
             uint32_t mb = pad_bits;
-            if (p.mask != nullptr) mb |= __ldg(p.mask_bits + (p.mask_mode == SBA_MASK_PER_SAMPLE ? (uint32_t)b : cap));
+            if (p.mask != nullptr) mb |= __ldcg(p.mask_bits + (p.mask_mode == SBA_MASK_PER_SAMPLE ? (uint32_t)b : cap));   // written by the PDL predecessor: no ld.global.nc
             float s[LP];
             float m = -INFINITY;
 #pragma unroll
@@ -625,7 +670,7 @@ __global__ void __launch_bounds__(kThreads, Tc5FwdCfg<T, IDF, NQ>::CTAS_PER_SM)
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) {
-                tma_store_2d(&tma_c, q0, b * IDF, so_c);
+                tma_store_2d(&tma_c, q0, b * p.c_rows + p.c_row0, so_c);
                 bulk_commit();
             }
 
@@ -633,6 +678,7 @@ __global__ void __launch_bounds__(kThreads, Tc5FwdCfg<T, IDF, NQ>::CTAS_PER_SM)
             cap += step_mod;
             if (cap >= Bu) cap -= Bu;
         }
+        if (ct == 0) SBA_TL(p.tl, 7);
         if (lane == 0) bulk_wait<0>();                 // all output stores have landed before the CTA retires
         tc_fence_before();
     }
@@ -642,101 +688,67 @@ __global__ void __launch_bounds__(kThreads, Tc5FwdCfg<T, IDF, NQ>::CTAS_PER_SM)
         tc_fence_after();
         tmem_dealloc(tmem_base, C::TMEM_COLS);
     }
+    if (tid == 0) SBA_TL(p.tl, 3);
 }
 
 template <typename T, int IDF, int NQ>
 int launch_fwd_tc5(const void* x, const Tc5FwdParams& p_in, int dtype, cudaStream_t st) {
     Tc5FwdParams p = p_in;
-    const float* ctx = p.ctx;
-    const float* W = p.W;
-    float* srcT = p.srcT;
-    const int cdf = p.cdf;
     using C = Tc5FwdCfg<T, IDF, NQ>;
     auto kern = k_attn_fwd_tc5<T, IDF, NQ>;
-    const size_t smem = (size_t)C::SMEM_BYTES + 1024 + 16;
-    // per device (a process may drive several): SM count, and whether this kernel's dynamic shared memory
-    // limit has been raised there (smem is a compile-time constant of the instantiation)
-    static int sms_of[64] = {0};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev < 0 || dev >= 64) {
-        set_error("%s(tcgen05): device index %d not supported", "attn_fwd", dev);
-        return SBA_ERR_UNSUPPORTED;
-    }
-    if (smem > 220 * 1024) {
-        set_error("%s(tcgen05): %zu bytes of shared memory needed", "attn_fwd", smem);
-        return SBA_ERR_UNSUPPORTED;
-    }
-    if (sms_of[dev] == 0) {
-        int n = 0;
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess || n < 1) {
-            set_error("%s(tcgen05): cudaFuncSetAttribute(%zu B): %s", "attn_fwd", smem, cudaGetErrorString(e));
-            return SBA_ERR_CUDA;
-        }
-        sms_of[dev] = n;
-    }
-    const int sms = sms_of[dev];
-    const size_t smem_set = smem;
+    constexpr size_t smem = (size_t)C::SMEM_BYTES + 1024 + 16;
+    static_assert(smem <= 220 * 1024, "shared memory budget of the tcgen05 forward exceeded");
+    int dev = 0, sms = 0;
+    int rc = current_device(&dev, &sms, "attn_fwd(tcgen05)");
+    if (rc) return rc;
+    static std::atomic<unsigned long long> smem_done{0};
+    rc = ensure_dynamic_smem(kern, smem, dev, smem_done, "attn_fwd(tcgen05)");
+    if (rc) return rc;
     // Resident CTAs per SM: the occupancy API answers 1 for kernels that allocate tensor memory, the
     // hardware co-schedules as many as registers, shared memory and the 512 TMEM columns allow.
-    int per_sm = (int)((227 * 1024) / (smem_set + 1024));
+    int per_sm = (int)((227 * 1024) / (smem + 1024));
     if (per_sm > C::CTAS_PER_SM) per_sm = C::CTAS_PER_SM;
     if (per_sm < 1) per_sm = 1;
-    if (getenv("SBA_TC5_CTAS_PER_SM")) per_sm = atoi(getenv("SBA_TC5_CTAS_PER_SM"));
-    const int max_ctas = sms * per_sm;
     // Tile schedule: every CTA starts with a contiguous static share (few sample switches), the rest is handed
     // out dynamically in small chunks so that SMs that stream faster take more (per-SM rates differ by +-40 %).
-    int grid = p.n_tiles < max_ctas ? p.n_tiles : max_ctas;
+    // Short streams (a few tiles per CTA): whole static shares, single leftover tiles go to whoever is first.
+    int pct = -1, ch = -1;
+    int early_trigger = 1;          // the streaming kernel may become resident (prologue, x prefetch) under the projection
+#ifdef SBA_DEV_AIDS
     {
-        // short streams (a few tiles per CTA): whole static shares, single leftover tiles go to whoever is first
-        int pct = p.n_tiles < 8 * grid ? 100 : 80, ch = p.n_tiles < 8 * grid ? 1 : 2;
-        if (getenv("SBA_TC5_STATIC")) pct = atoi(getenv("SBA_TC5_STATIC"));
-        if (getenv("SBA_TC5_CHUNK")) ch = atoi(getenv("SBA_TC5_CHUNK"));
-        if (pct < 0 || pct > 100) pct = 80;
-        if (ch < 1) ch = 1;
-        p.static_tiles = (int)((long long)p.n_tiles * pct / 100 / grid);
-        p.chunk = ch;
-        if (p.static_tiles == 0 && grid > (p.n_tiles + ch - 1) / ch) grid = (p.n_tiles + ch - 1) / ch;   // one first chunk each
-        p.dyn_first = grid * p.static_tiles;
+        const DevTuning& tu = dev_tuning();
+        if (tu.late_trigger > 0) early_trigger = 0;
+        if (tu.ctas_per_sm > 0) per_sm = tu.ctas_per_sm;
+        pct = tu.static_pct;
+        ch = tu.chunk;
     }
+#endif
+    const int max_ctas = sms * per_sm;
+    int grid = p.n_tiles < max_ctas ? p.n_tiles : max_ctas;
+    if (pct < 0 || pct > 100) pct = p.n_tiles < 8 * grid ? 100 : 80;
+    if (ch < 1) ch = p.n_tiles < 8 * grid ? 1 : 2;
+    p.static_tiles = (int)((long long)p.n_tiles * pct / 100 / grid);
+    p.chunk = ch;
+    if (p.static_tiles == 0 && grid > (p.n_tiles + ch - 1) / ch) grid = (p.n_tiles + ch - 1) / ch;   // one first chunk each
+    p.dyn_first = grid * p.static_tiles;
+    p.tl = SBA_TL_SLOT();
     CUtensorMap tmx, tma_attn, tma_c;
     const int es = dtype == SBA_F32 ? 4 : 2;
-    int rc = make_tile_map(&tmx, x, dtype, p.B * IDF, p.Q, IDF, 128 / es, true);
+    rc = make_tile_map(&tmx, x, dtype, p.B * IDF, p.Q, IDF, 128 / es, true);
     if (!rc) rc = make_tile_map(&tma_attn, p.attn, dtype, p.B * p.L, p.Q, p.L, 32, false);
-    if (!rc) rc = make_tile_map(&tma_c, p.c_code, dtype, p.B * IDF, p.Q, IDF, 32, false);
+    if (!rc) rc = make_tile_map(&tma_c, p.c_code, dtype, p.B * p.c_rows, p.Q, IDF, 32, false);
     if (rc) return rc;
-    const int pgrid = p.B * (IDF / 8);
     {
-        cudaLaunchConfig_t pc = {};
-        pc.gridDim = dim3(pgrid);
-        pc.blockDim = dim3(256);
-        pc.stream = st;
-        cudaLaunchAttribute pa[1];
-        pa[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        pa[0].val.programmaticStreamSerializationAllowed = 1;
-        pc.attrs = pa;
-        pc.numAttrs = 1;
-        cudaError_t pe = cudaLaunchKernelEx(&pc, k_project_tc5, ctx, W, srcT, p.mask, p.mask_bits, p.sched, (int)IDF, cdf, p.L);
+        PdlLaunch pl(dim3(p.B * (IDF / 8)), dim3(256), 0, st);
+        cudaError_t pe = cudaLaunchKernelEx(&pl.cfg, k_project_tc5, p.ctx, p.W, p.srcT, p.mask, p.mask_bits, p.sched,
+                                            (int)IDF, p.cdf, p.L, early_trigger, p.tl);
         if (pe != cudaSuccess) {
             set_error("project(tcgen05): launch: %s", cudaGetErrorString(pe));
             return SBA_ERR_CUDA;
         }
     }
-    rc = check_launch("project(tcgen05)");
-    if (rc) return rc;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(kThreads);
-    cfg.dynamicSmemBytes = smem_set;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmx, tma_attn, tma_c, p);
+    PdlLaunch ml(dim3(grid), dim3(kThreads), smem, st);
+    cudaError_t e = cudaLaunchKernelEx(&ml.cfg, kern, tmx, tma_attn, tma_c, p);
     if (e != cudaSuccess) {
         set_error("attn_fwd(tcgen05): launch: %s", cudaGetErrorString(e));
         return SBA_ERR_CUDA;
@@ -776,6 +788,8 @@ int tc5_attn_fwd(const void* x, const float* ctx, const float* W, const uint8_t*
     Tc5FwdParams p{};
     p.srcT = srcT; p.ctx = ctx; p.W = W; p.cdf = s.cdf; p.mask = mask; p.c_code = c_code; p.attn = attn; p.mask_bits = mask_bits;
     p.B = s.B; p.L = s.L; p.Q = s.Q; p.mask_mode = s.mask_mode;
+    p.c_rows = s.c_rows > 0 ? s.c_rows : s.idf;
+    p.c_row0 = s.c_rows > 0 ? s.c_row0 : 0;
     p.tiles_per_sample = s.Q / tc5::TQ;
     p.n_tiles = s.B * p.tiles_per_sample;
     p.sched = mask_bits + s.B;            // scratch holds 3B words: [0, B) mask words, [B] chunk counter

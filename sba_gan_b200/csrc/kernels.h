@@ -7,6 +7,9 @@ namespace sba {
 struct AttnShape {
     int B, idf, cdf, L, Q;
     int dtype, mask_mode;
+    // forward output placement (tcgen05 family): c_code is written into rows [c_row0, c_row0 + idf) of a
+    // [B, c_rows, Q] buffer; c_rows = 0 means a plain [B, idf, Q] tensor.  Backward: the same for g_c.
+    int c_rows = 0, c_row0 = 0;
 };
 
 // attn_simt.cu - CUDA-core (FFMA + warp-shuffle) kernels, any shape with L <= 32
@@ -33,17 +36,20 @@ bool tc5_supports(const AttnShape& s);
 int tc5_attn_fwd(const void* x, const float* ctx, const float* W, const uint8_t* mask, void* c_code, void* attn,
                  float* srcT, uint32_t* mask_bits, const AttnShape& s, cudaStream_t st);
 
-// dW (+)= sum_b dSrc[b] . ctx[b]^T (dW zeroed by the caller's launch sequence) and dCtx[b] = W^T . dSrc[b];
-// launched as a programmatic dependent of the kernel that produced dSrc
-// zero-fill grid in front of a backward kernel (which waits for it with griddepcontrol.wait before its first atomic)
+// attn_bwd_post.cu - helpers of the mma.sync backward: a zero-fill grid in front of it (it accumulates dSrc with
+// atomics) and dW (+)= sum_b dSrc[b] . ctx[b]^T, dCtx[b] = W^T . dSrc[b] behind it, both programmatic dependents
 int attn_bwd_zero(float* dSrc, size_t n_src, float* dW, size_t n_dw, cudaStream_t st);
 int attn_bwd_post(const float* dSrc, const float* ctx, const float* W, float* dW, float* dCtx, int B, int idf, int cdf,
                   int L, cudaStream_t st);
-bool tc5_bwd_supports(const AttnShape& s);     // bf16 tensors for now; fp32 backward stays on the mma.sync family
-// dSrc holds B*idf*L floats followed by B+1 scratch words, like mma_attn_bwd
+
+// attn_tc5_bwd.cu - tcgen05 backward (bf16 tensors; fp32 backward stays on the mma.sync family): streaming kernel
+// + finish kernel, no zero fill, no atomics.  `ws` is the caller's workspace of attn_bwd_workspace_floats() floats:
+// [0, B*idf*L) receives dSrc, the rest holds per-(CTA, sample) partial sums and the finish kernel's scratch.
+bool tc5_bwd_supports(const AttnShape& s);
+size_t attn_bwd_workspace_floats(int B, int idf, int cdf, int L);
 int tc5_attn_bwd(const void* x, const float* ctx, const float* W, const float* srcT, const uint8_t* mask,
-                 const uint32_t* mask_bits, const void* g_c,
-                 const void* g_attn, void* dX, float* dSrc, float* dW, float* dCtx, const AttnShape& s, cudaStream_t st);
+                 const uint32_t* mask_bits, const void* g_c, const void* g_attn, void* dX, float* ws, size_t ws_floats,
+                 float* dW, float* dCtx, const AttnShape& s, cudaStream_t st);
 
 // words_loss.cu - fused DAMSM region-word similarity (kernel c) and its backward
 size_t words_bwd_workspace_bytes(int B_img, int B_cap, int nef, int R, int Lw);
@@ -53,5 +59,17 @@ int words_sim_fwd(const float* img, const float* words, const int* cap_lens, flo
 int words_sim_bwd(const float* img, const float* words, const int* cap_lens, const float* d_sim, float* d_img,
                   float* d_words, void* workspace, int B_img, int B_cap, int row_offset, int nef, int R, int Lw, float g1,
                   float g2, float g3, float eps, cudaStream_t st);
+
+// match_loss.cu - the B x B matching tail of words_loss / sent_loss: class masking + two-way cross-entropy, and
+// sent_loss's cosine score matrix
+// lse: [4*B] floats (row / column log-sum-exp, then the picked label entries), kept for the backward
+int match_ce_fwd(const float* scores, const int* cls, const long long* labels, float* losses, float* lse, int B,
+                 cudaStream_t st);
+int match_ce_bwd(const float* scores, const int* cls, const long long* labels, const float* lse, const float* g,
+                 float* d_scores, int B, cudaStream_t st);
+int sent_scores_fwd(const float* cnn, const float* rnn, float* scores, float* norms, int B, int nef, float g3, float eps,
+                    cudaStream_t st);
+int sent_scores_bwd(const float* cnn, const float* rnn, const float* norms, const float* scores, const float* d_scores,
+                    float* d_cnn, float* d_rnn, int B, int nef, float g3, float eps, cudaStream_t st);
 
 }  // namespace sba

@@ -305,6 +305,30 @@ constexpr int kThreads = 64 + kConsumers;
 int make_tile_map(CUtensorMap* out, const void* base, int dtype, int rows, int cols, int box_rows, int box_cols,
                   bool swizzle);
 
+// ---- development aids (python -m sba_gan_b200.build --dev; csrc/dev_aids.cu) ------------------------
+// Kernel parameter blocks always carry a `tl` pointer (NULL in the product library, where the stamps
+// below compile to nothing): 8 globaltimer stamps per ABI call, even = earliest, odd = latest over CTAs:
+//   0/1 head kernel (projection) first instruction / last exit     2/3 streaming kernel entry / exit
+//   4/5 tail kernel (backward finish) past its grid dependency / exit
+//   6   streaming kernel past its grid dependency                  7   streaming kernel: last tile done
+#ifdef SBA_DEV_AIDS
+struct DevTuning { int ctas_per_sm, static_pct, chunk, late_trigger; };   // SBA_TC5_CTAS_PER_SM / _STATIC / _CHUNK / _LATE_TRIGGER, read once
+const DevTuning& dev_tuning();
+unsigned long long* timeline_slot();                           // device pointer to this call's 8 stamps, or NULL
+__device__ __forceinline__ void tl_stamp(unsigned long long* tl, int stamp) {
+    if (tl == nullptr) return;
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    if (stamp & 1) atomicMax(tl + stamp, t);
+    else atomicMin(tl + stamp, t);
+}
+#define SBA_TL(tl, stamp) ::sba::tc5::tl_stamp(tl, stamp)
+#define SBA_TL_SLOT() ::sba::tc5::timeline_slot()
+#else
+#define SBA_TL(tl, stamp) ((void)0)
+#define SBA_TL_SLOT() nullptr
+#endif
+
 // ----------------------------------------------------------------------------------------------
 // Dynamic tile schedule.  SMs do not stream at the same rate once the memory system is saturated
 // (per-SM duration of an equal static share spreads by +-40 % on B200, grouped by TPC position),

@@ -2,8 +2,6 @@
 arithmetic is libsba_attn.so's.  Mirrors AttnGAN2/code/GlobalAttention.py:82-121."""
 from __future__ import annotations
 
-import weakref
-
 import torch
 
 from . import _abi
@@ -32,21 +30,27 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
-# fp32 copy of the most recent word-feature tensor: both generator stages receive the SAME word_embs
-# (model_bert.py:580-588), so the second stage reuses the first stage's copy.  Keyed on the tensor
-# object (weak reference) and its version counter, never on a raw pointer.
-_ctx32_cache = {"ref": None, "version": -1, "value": None}
-
-
 def _context_fp32(context):
+    """fp32, contiguous view / copy of the word features.  Converted per call: the tensor is only
+    B x cdf x L elements, and a cache keyed on the tensor object would go stale under CUDA-graph
+    replay and ``.data`` writes (neither bumps ``_version``)."""
     if context.dtype == torch.float32 and context.is_contiguous():
         return context.detach()
-    c = _ctx32_cache
-    if c["ref"] is not None and c["ref"]() is context and c["version"] == context._version:
-        return c["value"]
-    value = context.detach().to(torch.float32).contiguous()
-    c["ref"], c["version"], c["value"] = weakref.ref(context), context._version, value
-    return value
+    return context.detach().to(torch.float32).contiguous()
+
+
+ALGO_NAMES = {v: k for k, v in _ALGOS.items()}
+
+
+def last_algo() -> str:
+    """Kernel family ("simt" | "mma" | "tc5") that served the last attention call of this thread."""
+    return ALGO_NAMES.get(_abi.load().sba_last_algo(), "?")
+
+
+def bwd_workspace(B, idf, cdf, L, device):
+    """Workspace of sba_attn_bwd (include/sba_attn.h): uninitialised, nothing needs zeroing."""
+    n = _abi.load().sba_attn_bwd_workspace_floats(B, idf, cdf, L)
+    return torch.empty((n,), dtype=torch.float32, device=device)
 
 
 def attn_forward_raw(x, context, weight, mask_u8, mask_mode, algo):
@@ -71,7 +75,7 @@ def attn_forward_raw(x, context, weight, mask_u8, mask_mode, algo):
 
 class _WordRegionAttention(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, context, weight, mask_u8, mask_mode, algo):
+    def forward(ctx, x, context, weight, mask_u8, mask_mode, algo, algo_bwd):
         _require_cuda(x, context, weight, mask_u8)
         if x.dtype not in _DTYPES:
             raise RuntimeError(f"sba_gan_b200: unsupported dtype {x.dtype} (float32 or bfloat16)")
@@ -81,7 +85,7 @@ class _WordRegionAttention(torch.autograd.Function):
         ctx.set_materialize_grads(False)
         c_code, attn, srcT, mask_bits, ctx32, w32 = attn_forward_raw(x, context, weight, mask_u8, mask_mode, algo)
         ctx.save_for_backward(x, ctx32, w32, mask_u8, srcT, mask_bits)
-        ctx.meta = (mask_mode, algo, context.dtype, weight.dtype, tuple(weight.shape))
+        ctx.meta = (mask_mode, algo_bwd, context.dtype, weight.dtype, tuple(weight.shape))
         return c_code, attn
 
     @staticmethod
@@ -99,27 +103,29 @@ class _WordRegionAttention(torch.autograd.Function):
         if g_attn is not None:
             g_attn = g_attn.to(x.dtype).contiguous()
         dX = torch.empty_like(x)
-        dSrc = torch.empty((B * idf * L + B + 1,), dtype=torch.float32, device=x.device)   # + scratch words, see sba_attn.h
+        ws = bwd_workspace(B, idf, cdf, L, x.device)
         dW = torch.empty((idf, cdf), dtype=torch.float32, device=x.device) if need_w else None
         dCtx = torch.empty((B, cdf, L), dtype=torch.float32, device=x.device) if need_ctx else None
         rc = lib.sba_attn_bwd(_ptr(x), _ptr(ctx32), _ptr(w32), _ptr(mask_u8), _ptr(srcT), _ptr(mask_bits), _ptr(g_c),
-                              _ptr(g_attn), _ptr(dX), _ptr(dSrc), _ptr(dW), _ptr(dCtx), B, idf, cdf, L, Q,
+                              _ptr(g_attn), _ptr(dX), _ptr(ws), ws.numel(), _ptr(dW), _ptr(dCtx), B, idf, cdf, L, Q,
                               _DTYPES[x.dtype], mask_mode, algo, _stream())
         _abi.check(rc, "sba_attn_bwd")
         launch_counter["n"] += _abi.last_launch_count()
         return (dX if need_x else None,
                 dCtx.to(ctx_dtype) if need_ctx else None,
                 dW.reshape(w_shape).to(w_dtype) if need_w else None,
-                None, None, None)
+                None, None, None, None)
 
 
-def word_region_attention(x, context, weight, mask=None, mask_mode="reference", algo="auto"):
+def word_region_attention(x, context, weight, mask=None, mask_mode="reference", algo="auto", algo_bwd=None):
     """Fused GlobalAttentionGeneral.forward (GlobalAttention.py:82-121).
 
     x B x idf x ih x iw; context B x cdf x L; weight [idf, cdf, 1, 1] (conv_context.weight);
     mask B x L bool/uint8 (True = padding word) or None.
     Returns (weightedContext B x idf x ih x iw, attn B x L x ih x iw), differentiable in
-    x, context and weight.
+    x, context and weight.  ``algo`` picks the kernel family ("auto" | "simt" | "mma" | "tc5");
+    an explicit family is honoured strictly (a shape it does not cover raises).  ``algo_bwd``
+    picks the backward's family separately (default: the same as ``algo``).
     """
     if x.dim() != 4 or context.dim() != 3:
         raise RuntimeError("word_region_attention: x must be B x idf x ih x iw and context B x cdf x L")
@@ -138,4 +144,5 @@ def word_region_attention(x, context, weight, mask=None, mask_mode="reference", 
             mask_u8 = mask.view(torch.uint8)                      # same bytes, no copy kernel
         else:
             mask_u8 = mask.to(device=x.device, dtype=torch.uint8).contiguous()
-    return _WordRegionAttention.apply(x, context, weight, mask_u8, _MASK_MODES[mask_mode], _ALGOS[algo])
+    return _WordRegionAttention.apply(x, context, weight, mask_u8, _MASK_MODES[mask_mode], _ALGOS[algo],
+                                      _ALGOS[algo if algo_bwd is None else algo_bwd])

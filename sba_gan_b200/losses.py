@@ -1,11 +1,17 @@
-"""Drop-in ``func_attention`` and ``words_loss`` (AttnGAN2/code/GlobalAttention.py:31-69,
-AttnGAN2/code/miscc/losses.py:62-132) over the fused sm_100a kernel (c).
+"""Drop-in ``func_attention``, ``words_loss`` and ``sent_loss`` (AttnGAN2/code/GlobalAttention.py:31-69,
+AttnGAN2/code/miscc/losses.py:20-59, 62-132) over the fused sm_100a kernel (c) and the matching-tail
+kernels (csrc/match_loss.cu).
 
 ``words_loss`` keeps the reference's signature and return value
 ``(loss0, loss1, att_maps)`` including the ``labels=None`` and ``class_ids=None`` modes
 (trainer_bert.py:205-208).  The gammas come from the reference's global ``cfg`` when its
 ``miscc.config`` module is imported (losses.py:91, 106, 123), else from keyword arguments
 (defaults of miscc/config.py:43-45).
+
+Nothing here synchronises with the host in the training path: the reference's
+``cap_lens.data.tolist()`` (losses.py:71) is deferred until somebody actually indexes ``att_maps``
+(``LazyAttMaps``), the class mask is derived on the device from the class ids instead of numpy + H2D
+(losses.py:73-76, 116-121), and the two cross-entropies run in one fused kernel pair.
 """
 from __future__ import annotations
 
@@ -100,6 +106,126 @@ def words_similarity(img_features, words_emb, cap_lens, gamma1, gamma2, gamma3, 
     return (sim, att) if want_att_maps else sim
 
 
+class LazyAttMaps:
+    """The ``att_maps`` list of words_loss (losses.py:92: B tensors 1 x T_i x ih x iw) without the
+    device->host synchronisation the slicing by caption length needs: the lengths are fetched
+    (``.tolist()``) the first time an element is looked at.  The training loops discard
+    ``att_maps`` (trainer_bert.py:294-296 via generator_loss, pretrain_DAMSM_bert.py:80-81), so there
+    the step never waits for the GPU; ``save_img_results`` (trainer_bert.py:205-216) indexes it and
+    gets ordinary tensors."""
+
+    def __init__(self, att, cap_lens, ih, iw):
+        self._att, self._lens, self._hw, self._items = att, cap_lens, (ih, iw), None
+
+    def _materialise(self):
+        if self._items is None:
+            lens = self._lens.tolist() if torch.is_tensor(self._lens) else list(self._lens)       # losses.py:71
+            B, (ih, iw) = self._att.shape[0], self._hw
+            self._items = [self._att[i, :int(lens[i])].reshape(1, int(lens[i]), ih, iw) for i in range(B)]
+        return self._items
+
+    def __len__(self):
+        return self._att.shape[0]
+
+    def __getitem__(self, i):
+        return self._materialise()[i]
+
+    def __iter__(self):
+        return iter(self._materialise())
+
+
+class _MatchCrossEntropy(torch.autograd.Function):
+    """(loss0, loss1) = (CE(scores, labels), CE(scores^T, labels)) with same-class masking
+    (losses.py:53-59 / 124-129), one fused kernel pair; backward one kernel."""
+
+    @staticmethod
+    def forward(ctx, scores, class_ids_i32, labels_i64):
+        _require_cuda(scores, class_ids_i32, labels_i64)
+        lib = _abi.load()
+        B = scores.shape[0]
+        s32 = scores.detach().to(torch.float32).contiguous()
+        losses = torch.empty((2,), dtype=torch.float32, device=scores.device)
+        lse = torch.empty((4 * B,), dtype=torch.float32, device=scores.device)
+        rc = lib.sba_match_ce_fwd(_ptr(s32), _ptr(class_ids_i32), _ptr(labels_i64), _ptr(losses), _ptr(lse), B, _stream())
+        _abi.check(rc, "sba_match_ce_fwd")
+        launch_counter["n"] += _abi.last_launch_count()
+        ctx.save_for_backward(s32, class_ids_i32, labels_i64, lse)
+        ctx.dtype = scores.dtype
+        return losses[0], losses[1]
+
+    @staticmethod
+    def backward(ctx, g0, g1):
+        s32, cls, labels, lse = ctx.saved_tensors
+        lib = _abi.load()
+        B = s32.shape[0]
+        zero = torch.zeros((), dtype=torch.float32, device=s32.device)
+        g = torch.stack([zero if g0 is None else g0.to(torch.float32), zero if g1 is None else g1.to(torch.float32)])
+        d = torch.empty_like(s32)
+        rc = lib.sba_match_ce_bwd(_ptr(s32), _ptr(cls), _ptr(labels), _ptr(lse), _ptr(g), _ptr(d), B, _stream())
+        _abi.check(rc, "sba_match_ce_bwd")
+        launch_counter["n"] += _abi.last_launch_count()
+        return d.to(ctx.dtype), None, None
+
+
+def match_cross_entropy(scores, labels, class_ids=None):
+    """The tail shared by words_loss and sent_loss: entry (i, j), i != j, of the B x B ``scores`` counts as
+    -inf when class_ids[i] == class_ids[j]; returns (CE(scores, labels), CE(scores^T, labels))."""
+    if scores.dim() != 2 or scores.shape[0] != scores.shape[1]:
+        raise RuntimeError("match_cross_entropy: scores must be B x B")
+    cls = None
+    if class_ids is not None:
+        cls = torch.as_tensor(class_ids).to(device=scores.device, dtype=torch.int32).contiguous()
+    lab = labels.detach().to(device=scores.device, dtype=torch.int64).contiguous()
+    return _MatchCrossEntropy.apply(scores, cls, lab)
+
+
+class _SentScores(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, cnn, rnn, gamma3, eps):
+        _require_cuda(cnn, rnn)
+        lib = _abi.load()
+        B, nef = cnn.shape
+        a = cnn.detach().to(torch.float32).contiguous()
+        b = rnn.detach().to(torch.float32).contiguous()
+        scores = torch.empty((B, B), dtype=torch.float32, device=cnn.device)
+        norms = torch.empty((2 * B,), dtype=torch.float32, device=cnn.device)
+        rc = lib.sba_sent_scores_fwd(_ptr(a), _ptr(b), _ptr(scores), _ptr(norms), B, nef, gamma3, eps, _stream())
+        _abi.check(rc, "sba_sent_scores_fwd")
+        launch_counter["n"] += _abi.last_launch_count()
+        ctx.save_for_backward(a, b, norms, scores)
+        ctx.meta = (gamma3, eps, cnn.dtype, rnn.dtype)
+        return scores
+
+    @staticmethod
+    def backward(ctx, d_scores):
+        a, b, norms, scores = ctx.saved_tensors
+        gamma3, eps, dt_a, dt_b = ctx.meta
+        lib = _abi.load()
+        B, nef = a.shape
+        d = d_scores.to(torch.float32).contiguous()
+        d_a, d_b = torch.empty_like(a), torch.empty_like(b)
+        rc = lib.sba_sent_scores_bwd(_ptr(a), _ptr(b), _ptr(norms), _ptr(scores), _ptr(d), _ptr(d_a), _ptr(d_b), B, nef,
+                                     gamma3, eps, _stream())
+        _abi.check(rc, "sba_sent_scores_bwd")
+        launch_counter["n"] += _abi.last_launch_count()
+        return d_a.to(dt_a), d_b.to(dt_b), None, None
+
+
+def sent_loss(cnn_code, rnn_code, labels, class_ids, batch_size, eps=1e-8, gamma3=None):
+    """sent_loss(cnn_code, rnn_code, labels, class_ids, batch_size, eps=1e-8) -> (loss0, loss1), same as
+    miscc/losses.py:20-59: cosine scores x gamma3, same-class masking, two cross-entropies.
+    cnn_code, rnn_code: batch x nef."""
+    g3 = _cfg_gammas()[2] if gamma3 is None else gamma3
+    if cnn_code.dim() == 3:                 # the reference also accepts 1 x batch x nef (losses.py:37-39)
+        cnn_code, rnn_code = cnn_code.squeeze(0), rnn_code.squeeze(0)
+    if cnn_code.dim() != 2 or cnn_code.shape != rnn_code.shape:
+        raise RuntimeError("sent_loss: cnn_code and rnn_code must both be batch x nef")
+    if labels is None:
+        return None, None
+    scores = _SentScores.apply(cnn_code, rnn_code, float(g3), float(eps))
+    return match_cross_entropy(scores, labels, class_ids)
+
+
 def class_mask(class_ids, device):
     """masks[i, j] = class_ids[i] == class_ids[j] and i != j (losses.py:73-76, 116-121),
     built on the device (the reference builds it in numpy and copies it over)."""
@@ -110,12 +236,14 @@ def class_mask(class_ids, device):
 
 
 def words_loss(img_features, words_emb, labels, cap_lens, class_ids, batch_size, gamma1=None, gamma2=None,
-               gamma3=None, eps=1e-8):
+               gamma3=None, eps=1e-8, att_maps=True):
     """words_loss(img_features, words_emb, labels, cap_lens, class_ids, batch_size)
     -> (loss0, loss1, att_maps), same as miscc/losses.py:62-132.
 
     words_emb: batch x nef x seq_len; img_features: batch x nef x 17 x 17.
-    att_maps: list of batch tensors 1 x cap_len_i x 17 x 17 (losses.py:92).
+    att_maps: sequence of batch tensors 1 x cap_len_i x 17 x 17 (losses.py:92), sliced lazily
+    (``LazyAttMaps``: no host synchronisation unless it is indexed); ``att_maps=False`` (an extension:
+    the training loops discard them) skips writing the maps altogether and returns None in their place.
     """
     g = _cfg_gammas()
     g1 = g[0] if gamma1 is None else gamma1
@@ -124,18 +252,16 @@ def words_loss(img_features, words_emb, labels, cap_lens, class_ids, batch_size,
     B = int(batch_size)
     img = img_features[:B]
     words = words_emb[:B]
-    lens_host = cap_lens.detach().tolist() if torch.is_tensor(cap_lens) else list(cap_lens)   # losses.py:71
-    lens_host = [int(v) for v in lens_host[:B]]
+    lens = cap_lens[:B] if torch.is_tensor(cap_lens) else list(cap_lens)[:B]
     ih, iw = img.shape[2], img.shape[3]
-    sim, att = words_similarity(img, words, lens_host, g1, g2, g3, eps, 0, want_att_maps=True)
-    att_maps = [att[i, :lens_host[i]].reshape(1, lens_host[i], ih, iw) for i in range(B)]
+    want = bool(att_maps) or labels is None
+    res = words_similarity(img, words, lens, g1, g2, g3, eps, 0, want_att_maps=want)
+    sim, att = res if want else (res, None)
+    maps = LazyAttMaps(att, lens, ih, iw) if want else None
     if labels is None:
-        return None, None, att_maps
-    if class_ids is not None:
-        sim = sim.masked_fill(class_mask(class_ids, sim.device), float("-inf"))     # losses.py:124-125
-    loss0 = F.cross_entropy(sim, labels)                    # losses.py:128
-    loss1 = F.cross_entropy(sim.transpose(0, 1), labels)    # losses.py:129
-    return loss0, loss1, att_maps
+        return None, None, maps
+    loss0, loss1 = match_cross_entropy(sim, labels, class_ids)     # losses.py:116-129
+    return loss0, loss1, maps
 
 
 def func_attention(query, context, gamma1):

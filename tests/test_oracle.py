@@ -134,3 +134,23 @@ def test_cpu_timing_path_agrees_with_oracle():
     dX, dW, _, _ = attn_backward(d["x"], d["context"], d["weight"], d["mask"], d["g_c"])
     for got, ref in ((c, cr), (a, ar), (dx, dX), (dw, dW)):
         assert normalised_max_err(got.reshape(ref.shape), ref) <= 2e-6
+
+
+@pytest.mark.parametrize("tag", ["f32", "f64"])
+@pytest.mark.parametrize("name", ["sl_b6", "sl_b12_dupclass", "sl_b5_noclass"])
+def test_sent_loss_oracle_matches_reference(golden_dir, name, tag):
+    """sent_loss (losses.py:20-59): restatement against the reference's own run, losses and both gradients."""
+    from oracle import sent_loss
+    from tests.cases import SL_CASES, synth_sent_inputs
+    B, nef, seed, g3, use_cls = SL_CASES[name]
+    g = _load(golden_dir, name, tag)
+    cnn, rnn, cls = synth_sent_inputs(B, nef, seed, DT[tag])
+    np.testing.assert_allclose(np.concatenate([_checksum(cnn), _checksum(rnn)]), g["in_sum"], rtol=1e-12)
+    a, b = cnn.clone().requires_grad_(True), rnn.clone().requires_grad_(True)
+    l0, l1 = sent_loss(a, b, torch.arange(B), cls if use_cls else None, B, gamma3=g3)
+    (l0 + 2.0 * l1).backward()
+    tol = TOL[tag]
+    assert abs(l0.item() - g["loss0"].item()) <= tol * max(1.0, abs(g["loss0"].item()))
+    assert abs(l1.item() - g["loss1"].item()) <= tol * max(1.0, abs(g["loss1"].item()))
+    assert normalised_max_err(a.grad, torch.from_numpy(g["d_cnn"])) <= 10 * tol
+    assert normalised_max_err(b.grad, torch.from_numpy(g["d_rnn"])) <= 10 * tol

@@ -149,3 +149,91 @@ def test_gammas_default_to_reference_cfg():
                                   d["class_ids"], 4, 4.0, 5.0, 10.0)
     assert abs(l0.item() - r0.item()) <= TOL_LOSS * max(1.0, abs(r0.item()))
     assert abs(l1.item() - r1.item()) <= TOL_LOSS * max(1.0, abs(r1.item()))
+
+
+# ---- the B x B matching tail: sent_loss and the shared two-way cross-entropy ----
+@pytest.mark.parametrize("name", ["sl_b6", "sl_b12_dupclass", "sl_b5_noclass"])
+def test_sent_loss_matches_reference_golden(golden_dir, name):
+    """sent_loss (losses.py:20-59) through the fused score + cross-entropy kernels against the reference's
+    own run: both losses and the gradients w.r.t. cnn_code and rnn_code."""
+    from sba_gan_b200 import sent_loss
+    from tests.cases import SL_CASES, synth_sent_inputs
+    B, nef, seed, g3, use_cls = SL_CASES[name]
+    g = np.load(os.path.join(golden_dir, f"{name}_f32.npz"))
+    cnn, rnn, cls = synth_sent_inputs(B, nef, seed, torch.float32)
+    a, b = cnn.cuda().requires_grad_(True), rnn.cuda().requires_grad_(True)
+    l0, l1 = sent_loss(a, b, torch.arange(B).cuda(), cls if use_cls else None, B, gamma3=g3)
+    (l0 + 2.0 * l1).backward()
+    assert abs(l0.item() - g["loss0"].item()) <= TOL_LOSS * max(1.0, abs(g["loss0"].item()))
+    assert abs(l1.item() - g["loss1"].item()) <= TOL_LOSS * max(1.0, abs(g["loss1"].item()))
+    assert normalised_max_err(a.grad.cpu(), torch.from_numpy(g["d_cnn"])) <= TOL_GRAD
+    assert normalised_max_err(b.grad.cpu(), torch.from_numpy(g["d_rnn"])) <= TOL_GRAD
+
+
+@pytest.mark.parametrize("B,nef", [(48, 256), (256, 256), (20, 100), (300, 40)])
+def test_sent_loss_vs_oracle_fp64(B, nef):
+    from sba_gan_b200 import sent_loss
+    rs = np.random.RandomState(B)
+    cnn, rnn = torch.from_numpy(rs.standard_normal((B, nef))), torch.from_numpy(np.tanh(rs.standard_normal((B, nef))))
+    cls = rs.randint(1, max(2, B // 3) + 1, size=B)
+    labels = torch.arange(B)
+    a, b = cnn.float().cuda().requires_grad_(True), rnn.float().cuda().requires_grad_(True)
+    l0, l1 = sent_loss(a, b, labels.cuda(), cls, B, gamma3=10.0)
+    (l0 + 0.5 * l1).backward()
+    ra, rb = cnn.float().double().requires_grad_(True), rnn.float().double().requires_grad_(True)
+    r0, r1 = oracle.sent_loss(ra, rb, labels, cls, B, gamma3=10.0)
+    (r0 + 0.5 * r1).backward()
+    assert abs(l0.item() - r0.item()) <= TOL_LOSS * max(1.0, abs(r0.item()))
+    assert abs(l1.item() - r1.item()) <= TOL_LOSS * max(1.0, abs(r1.item()))
+    assert normalised_max_err(a.grad.cpu(), ra.grad) <= TOL_GRAD
+    assert normalised_max_err(b.grad.cpu(), rb.grad) <= TOL_GRAD
+
+
+def test_match_cross_entropy_general_labels_and_masked_rows():
+    """The shared tail with arbitrary labels (not arange), duplicate classes, no class ids, and d_scores exactly
+    zero at masked entries (the reference masks on .data, losses.py:124-125)."""
+    from sba_gan_b200 import match_cross_entropy
+    B = 37
+    g = torch.Generator().manual_seed(3)
+    s = torch.randn(B, B, generator=g) * 4
+    labels = torch.randint(0, B, (B,), generator=g)
+    cls = torch.randint(1, 6, (B,), generator=g)
+    for c in (cls, None):
+        sg = s.cuda().requires_grad_(True)
+        l0, l1 = match_cross_entropy(sg, labels.cuda(), c)
+        (l0 * 1.5 + l1).backward()
+        rs_ = s.double().requires_grad_(True)
+        r0, r1, masked = oracle.ce_tail(rs_, labels, None if c is None else c.numpy())
+        # a label that points at a masked entry gives +inf in the reference too; skip the comparison of such rows
+        if torch.isfinite(r0) and torch.isfinite(r1):
+            (r0 * 1.5 + r1).backward()
+            assert abs(l0.item() - r0.item()) <= TOL_LOSS * max(1.0, abs(r0.item()))
+            assert abs(l1.item() - r1.item()) <= TOL_LOSS * max(1.0, abs(r1.item()))
+            assert normalised_max_err(sg.grad.cpu(), rs_.grad) <= TOL_GRAD
+        if c is not None:
+            same = (c[:, None] == c[None, :]) & ~torch.eye(B, dtype=torch.bool)
+            assert sg.grad.cpu()[same].abs().max().item() == 0.0
+
+
+def test_words_loss_training_path_does_not_wait_for_the_gpu():
+    """the reference's cap_lens.tolist() (losses.py:71) is deferred.  Under
+    torch.cuda.set_sync_debug_mode("error") every blocking device->host transfer raises: forward and backward of
+    words_loss must pass, and indexing att_maps (the visualisation path) is what triggers the transfer."""
+    from sba_gan_b200 import words_loss
+    d = synth_words_loss_inputs(6, 256, 18, 17, 17, seed=9)
+    img = d["img_features"].cuda().requires_grad_(True)
+    words, labels, lens = d["words_emb"].cuda(), d["labels"].cuda(), d["cap_lens"].cuda()
+    cls = torch.as_tensor(d["class_ids"]).cuda()
+    torch.cuda.synchronize()
+    torch.cuda.set_sync_debug_mode("error")
+    try:
+        l0, l1, maps = words_loss(img, words, labels, lens, cls, 6, 4.0, 5.0, 10.0)
+        (l0 + l1).backward()
+        l0b, l1b, none_maps = words_loss(img, words, labels, lens, cls, 6, 4.0, 5.0, 10.0, att_maps=False)
+        assert none_maps is None and len(maps) == 6
+        with pytest.raises(RuntimeError):
+            maps[0]
+    finally:
+        torch.cuda.set_sync_debug_mode("default")
+    assert maps[0].shape == (1, int(d["cap_lens"][0]), 17, 17)
+    assert torch.equal(l0, l0b) and torch.equal(l1, l1b)

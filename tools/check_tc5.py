@@ -75,11 +75,11 @@ def run(B, idf, cdf, L, hw, dt, mode, use_mask, with_ga=False):
     msg = f"B={B} idf={idf} L={L} {hw}x{hw} {str(dt)[6:]} mode={mode} mask={use_mask}: fwd c {nerr(c, cr):.2e} attn {nerr(a, ar):.2e}"
     if which in ("bwd", "all"):
         dX = torch.empty_like(x)
-        dSrc = torch.zeros(B * idf * L + B + 1, device=dev)
+        dSrc = torch.full((lib.sba_attn_bwd_workspace_floats(B, idf, cdf, L),), float("nan"), device=dev)
         dW = torch.empty(idf, cdf, device=dev)
         dCtx = torch.empty(B, cdf, L, device=dev)
         rc = lib.sba_attn_bwd(x.data_ptr(), ctx.data_ptr(), W.data_ptr(), mp, srcT.data_ptr(), mb.data_ptr(), g.data_ptr(),
-                              ga.data_ptr() if ga is not None else None, dX.data_ptr(), dSrc.data_ptr(), dW.data_ptr(),
+                              ga.data_ptr() if ga is not None else None, dX.data_ptr(), dSrc.data_ptr(), dSrc.numel(), dW.data_ptr(),
                               dCtx.data_ptr(), B, idf, cdf, L, Q, _DTYPES[dt], mode, algo, st)
         _abi.check(rc, "bwd")
         torch.cuda.synchronize()

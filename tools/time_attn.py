@@ -29,7 +29,7 @@ for B, hw in [(b, h) for b in BS for h in (64, 128)]:
     mask = (torch.arange(L)[None] >= lens[:, None]).to(torch.uint8).to(dev)
     srcT = torch.empty(B, idf, L, device=dev)
     mb = torch.empty(3 * B, dtype=torch.int32, device=dev)
-    dSrc = torch.empty(B * idf * L + B + 1, device=dev)
+    dSrc = torch.empty(lib.sba_attn_bwd_workspace_floats(B, idf, cdf, L), device=dev)
     dW = torch.empty(idf, cdf, device=dev)
     st_holder = [torch.cuda.current_stream().cuda_stream]
     dcode = _DTYPES[dt]
@@ -43,7 +43,7 @@ for B, hw in [(b, h) for b in BS for h in (64, 128)]:
     def bwd(k):
         x, g, c, a, dx = sets[k % nset]
         rc = lib.sba_attn_bwd(x.data_ptr(), ctx.data_ptr(), W.data_ptr(), mask.data_ptr(), srcT.data_ptr(), mb.data_ptr(),
-                              g.data_ptr(), None, dx.data_ptr(), dSrc.data_ptr(), dW.data_ptr(), None, B, idf, cdf, L, Q,
+                              g.data_ptr(), None, dx.data_ptr(), dSrc.data_ptr(), dSrc.numel(), dW.data_ptr(), None, B, idf, cdf, L, Q,
                               dcode, 0, algo, st_holder[0])
         _abi.check(rc, "bwd")
 
