@@ -92,7 +92,7 @@ SBA_API int sba_attn_supported(int which, int algo, int B, int idf, int cdf, int
 
 /* ---- autograd backward of the above ------------------------------
  * srcT     [B, idf, L] fp32         from the forward
- * scratch  [3*B] uint32             from the forward (mask words; ignored when mask == NULL)
+ * scratch  [3*B] uint32             from the forward (mask words)
  * g_c      [B, idf, Q] dtype        grad of c_code
  * g_attn   [B, L, Q]   dtype nullable grad of attn (NULL in GAN training: attn is discarded,
  *                                   trainer_bert.py:267)
@@ -107,7 +107,7 @@ SBA_API int sba_attn_supported(int which, int algo, int B, int idf, int cdf, int
  */
 SBA_API size_t sba_attn_bwd_workspace_floats(int B, int idf, int cdf, int L);
 SBA_API int sba_attn_bwd(const void* x, const float* ctx, const float* W, const uint8_t* mask,
-                 const float* srcT, const uint32_t* scratch,
+                 const float* srcT, uint32_t* scratch,
                  const void* g_c, const void* g_attn,
                  void* dX, float* ws, size_t ws_floats, float* dW, float* dCtx,
                  int B, int idf, int cdf, int L, int Q,
@@ -125,7 +125,7 @@ SBA_API int sba_attn_fwd_into(const void* x, const float* ctx, const float* W, c
                  void* c_buf, int c_rows, int c_row0, void* attn, float* srcT, uint32_t* scratch,
                  int B, int idf, int cdf, int L, int Q, int dtype, int mask_mode, void* stream);
 SBA_API int sba_attn_bwd_from(const void* x, const float* ctx, const float* W, const uint8_t* mask,
-                 const float* srcT, const uint32_t* scratch,
+                 const float* srcT, uint32_t* scratch,
                  const void* g_buf, int g_rows, int g_row0, const void* g_attn,
                  void* dX, float* ws, size_t ws_floats, float* dW, float* dCtx,
                  int B, int idf, int cdf, int L, int Q, int dtype, int mask_mode, void* stream);

@@ -145,11 +145,11 @@ static int attn_fwd_impl(const void* x, const float* ctx, const float* W, const 
 }
 
 static int attn_bwd_impl(const void* x, const float* ctx, const float* W, const uint8_t* mask, const float* srcT,
-                         const uint32_t* mask_bits, const void* g_c, const void* g_attn, void* dX, float* ws,
+                         uint32_t* mask_bits, const void* g_c, const void* g_attn, void* dX, float* ws,
                          size_t ws_floats, float* dW, float* dCtx, AttnShape s, int algo, void* stream, const char* fn) {
     g_launches = 0;
     g_err[0] = 0;
-    if (!x || !ctx || !W || !srcT || !g_c || !dX || !ws || (mask && !mask_bits)) {
+    if (!x || !ctx || !W || !srcT || !g_c || !dX || !ws || !mask_bits) {
         set_error("%s: null pointer argument", fn);
         return SBA_ERR_ARG;
     }
@@ -200,7 +200,7 @@ int sba_attn_fwd(const void* x, const float* ctx, const float* W, const uint8_t*
 }
 
 int sba_attn_bwd(const void* x, const float* ctx, const float* W, const uint8_t* mask, const float* srcT,
-                 const uint32_t* mask_bits, const void* g_c, const void* g_attn, void* dX, float* ws, size_t ws_floats,
+                 uint32_t* mask_bits, const void* g_c, const void* g_attn, void* dX, float* ws, size_t ws_floats,
                  float* dW, float* dCtx, int B, int idf, int cdf, int L, int Q, int dtype, int mask_mode, int algo,
                  void* stream) {
     return attn_bwd_impl(x, ctx, W, mask, srcT, mask_bits, g_c, g_attn, dX, ws, ws_floats, dW, dCtx,
@@ -224,7 +224,7 @@ int sba_attn_fwd_into(const void* x, const float* ctx, const float* W, const uin
 }
 
 int sba_attn_bwd_from(const void* x, const float* ctx, const float* W, const uint8_t* mask, const float* srcT,
-                      const uint32_t* mask_bits, const void* g_buf, int g_rows, int g_row0, const void* g_attn, void* dX,
+                      uint32_t* mask_bits, const void* g_buf, int g_rows, int g_row0, const void* g_attn, void* dX,
                       float* ws, size_t ws_floats, float* dW, float* dCtx, int B, int idf, int cdf, int L, int Q, int dtype,
                       int mask_mode, void* stream) {
     if (g_rows < idf || g_row0 < 0 || g_row0 + idf > g_rows) {

@@ -24,11 +24,12 @@
 // MMA2(j), so the first stage of tile j+1 overlaps the tensor core and the second stage of tile j.
 // At a sample boundary the pipeline drains (the operands are rebuilt only after the last MMA of the
 // old sample has retired, the accumulator is handed back after it has been read).
-// A small kernel behind it (k_bwd_finish_tc5, a programmatic dependent that is resident early) adds the
-// slots of every sample in a FIXED order -> dSrc[b], forms dW = sum_b dSrc[b] . ctx[b]^T over 16 sample
-// groups whose partial products the last-arriving block of each column slice adds in group order, and
-// dCtx[b] = W^T . dSrc[b].  Nothing is zero-filled and nothing is accumulated with atomics: the whole
-// backward is two kernels and bit-reproducible run to run (data-parallel replicas stay identical).
+// A small kernel behind it (k_bwd_finish_tc5, a programmatic dependent) adds the slots of every sample in CTA
+// order -> dSrc[b], forms dW = sum_b dSrc[b] . ctx[b]^T
+// over 16 sample groups whose partial products the last-arriving block of each column slice adds in group
+// order, and dCtx[b] = W^T . dSrc[b].  Nothing is zero-filled and no value is accumulated with atomics
+// (counters only decide WHO adds, every sum has a fixed order): the whole backward is two kernels and
+// bit-reproducible run to run (data-parallel replicas stay identical).
 #include "host_util.h"
 #include "kernels.h"
 #include "tc5_common.cuh"
@@ -95,18 +96,21 @@ struct Tc5BwdCfg {
 };
 
 // ------------------------------------------------------------------------------------------------
-// Finish kernel: dSrc[b] = sum of the sample's partial slots (fixed order), dW, dCtx.
-//   blocks [0, n_dw)        : (sample group grp, slice of 4 output channels i).  Per round of up to `nb` samples
-//                             (K = nb * L <= 96 rows of the flattened (sample, word) axis) the block stages
-//                             cs [K][256 c] = ctx^T of those samples - BEFORE griddepcontrol.wait, i.e. while the
-//                             streaming kernel is still running - and, after it, ds [K][4] = the slot sums of its
-//                             4 channels: one batch of up to 8 independent 16-byte loads per thread (one L2 round
-//                             trip).  Thread = input channel c: dW[i0..i0+3][c] += sum_k ds[k][.] cs[k][c], one
-//                             conflict-free LDS + one broadcast LDS.128 per 4 FMAs.  The group's partial goes to
-//                             dwp[grp]; the block that arrives last at its channel slice's counter adds the
-//                             `groups` partials in group order (again one batch of loads) and writes dW.
+// Finish kernel: dSrc[b] = sum of the sample's partial slots (CTA order), dW, dCtx.
+//   blocks [0, n_dw)        : (slice cg of 32 input channels c, sample group grp), 1024 threads, rounds of up to 4 samples.
+//                             thread = (sample kq of the round, output channel i, 4 input channels c):
+//                               before griddepcontrol.wait (ctx does not depend on the streaming kernel):
+//                                 cs [(sample, word)][32 c] = ctx^T of the first round, one 16-byte load per thread;
+//                               after it: ds [sample][i][LP] = slot sums, one batch of up to 8 independent 16-byte loads
+//                                 per (sample, i, 4 words) item; L FMAs x 4 per thread (one broadcast LDS + one LDS.128
+//                                 per 4 FMAs); the 4 samples of a round meet in shared memory in sample order.
+//                             The group's partial [idf x 32] goes to dwp[cg][grp]; the block that arrives last at the
+//                             slice's counter adds the `groups` partials in group order (4 loads per thread).
 //   blocks [n_dw, n_dw + B) : dCtx of one sample (only when words need a gradient)
-// After the grid dependency the critical path is: slot loads -> FMAs -> partial store + counter -> partial loads.
+// This kernel runs once per call on an otherwise idle GPU, so nothing hides latency: every dependent step (global
+// round trip, barrier, cold instruction fetch) is exposed and instructions cost ~2.5 cycles each per thread at 8
+// warps per SM.  Hence many threads with a few dozen instructions each and exactly one batch of loads per phase.
+// (Measured on the way here at B=64: 256-thread blocks with the same phases 9.7 us; rolled loops 15 us.)
 // ------------------------------------------------------------------------------------------------
 struct Tc5FinishParams {
     const float* part;    // [n_ctas + B][idf][LP]
@@ -115,130 +119,190 @@ struct Tc5FinishParams {
     float* dSrc;          // [B, idf, L] out
     float* dW;            // [idf, cdf] out, nullable
     float* dCtx;          // [B, cdf, L] out, nullable
-    float* dwp;           // [groups][idf][cdf] group partials of dW
-    uint32_t* counters;   // [1 + idf/4], zeroed by the streaming kernel
+    float* dwp;           // [cslices][groups][idf][32] group partials of dW
+    uint32_t* counters;   // [1 + cslices], zeroed by the streaming kernel
     int B, cdf, L, LP;
     int tiles_per_sample, n_tiles, n_ctas;    // tile -> CTA map of the streaming kernel
-    int groups, nb, n_dw;                     // sample groups, samples per round, number of dW blocks
+    int groups, n_dw;
+    int ctx_aligned;      // ctx is 16-byte aligned (vector loads)
     unsigned long long* tl;
 };
 
 // CTA k of the streaming kernel owns tiles [floor(k n / G), floor((k + 1) n / G)): the CTA that owns tile t
 __device__ __forceinline__ int tile_owner(int t, int n_tiles, int n_ctas) {
+    // 32-bit when (t + 1) * n_ctas cannot overflow (n_tiles * n_ctas < 2^32: always, short of 14 M tiles)
+    if ((unsigned long long)n_tiles * (unsigned)n_ctas < (1ull << 32))
+        return (int)((((unsigned)t + 1u) * (unsigned)n_ctas - 1u) / (unsigned)n_tiles);
     return (int)((((long long)t + 1) * n_ctas - 1) / n_tiles);
 }
 
-constexpr int kFinK = 96;          // rows of the flattened (sample, word) axis per round
-constexpr int kFinC = 256;         // input channels per pass = threads per block
-constexpr int kFinSlots = 8;       // slots loaded in one batch (more: a second batch)
-constexpr int kFinGroups = 16;     // at most this many sample groups (partials added by the last block)
+constexpr int kFinThreads = 1024;
+constexpr int kFinRound = 4;       // samples per round = thread groups of 256
+constexpr int kFinCS = 36;         // row stride (floats) of cs: 16-byte aligned rows, 4-bank skew
+constexpr int kFinSlots = 8;       // slots loaded in one batch (more: further batches)
+constexpr int kFinGroups = 16;     // at most this many sample groups (their partials are added by the last block)
+
 template <int IDF>
-__global__ void __launch_bounds__(kFinC) k_bwd_finish_tc5(const Tc5FinishParams p) {
+__global__ void __launch_bounds__(kFinThreads) k_bwd_finish_tc5(const Tc5FinishParams p) {
     extern __shared__ __align__(16) float sm[];
     __shared__ int s_last;
+    constexpr int NH = IDF / 32 + (IDF % 32 != 0);     // output channels per thread: i0, i0 + 32
     const int tid = threadIdx.x;
     const int B = p.B, cdf = p.cdf, L = p.L, LP = p.LP, TPS = p.tiles_per_sample;
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");      // (the head kernel of the next call)
+    if (tid == 0) { SBA_TL(p.tl, 8); SBA_TL(p.tl, 9); }
     if ((int)blockIdx.x < p.n_dw) {
-        float* cs = sm;                          // [kFinK][kFinC]
-        float* ds = sm + kFinK * kFinC;          // [kFinK][4]
-        constexpr int NSL = IDF / 4;             // channel slices
-        const int grp = blockIdx.x / NSL, sl = blockIdx.x - grp * NSL;
-        const int i0 = sl * 4;
-        const int b_lo = (int)(((long long)B * grp) / p.groups), b_hi = (int)(((long long)B * (grp + 1)) / p.groups);
+        float* cs = sm;                                   // [kFinRound * 32][kFinCS]  ctx^T of the round: row = (sample, word)
+        float* ds = sm + kFinRound * 32 * kFinCS;         // [kFinRound][IDF][LP]      slot sums; later the 4 samples' products
+        const int cg = blockIdx.x / p.groups, grp = blockIdx.x - cg * p.groups;
+        const int c0 = cg * 32, nc = cdf - c0 < 32 ? cdf - c0 : 32;
+        const int b_lo = B * grp / p.groups, b_hi = B * (grp + 1) / p.groups;
+        const int kq = tid >> 8, i0 = (tid >> 3) & 31, cq = (tid & 7) * 4;
         const int LP4 = LP >> 2;
-        bool waited = false;
-        for (int cc = 0; cc < cdf; cc += kFinC) {            // (cdf <= 256: one pass)
-            const int c = cc + tid;
-            float acc[4] = {0.f, 0.f, 0.f, 0.f};
-            for (int bb = b_lo; bb < b_hi; bb += p.nb) {
-                const int nb = b_hi - bb < p.nb ? b_hi - bb : p.nb;
-                const int K = nb * L;
-                __syncthreads();
-                // cs[k = (s, l)][c] = ctx[bb + s][c][l]: independent of the streaming kernel.  Thread = channel c
-                // reads its nb rows of L contiguous words; consecutive threads write consecutive shared words.
-                if (c < cdf) {
-                    for (int sidx = 0; sidx < nb; ++sidx) {
-                        const float* row = p.ctx + ((size_t)(bb + sidx) * cdf + c) * L;
-                        for (int l = 0; l < L; ++l) cs[(sidx * L + l) * kFinC + tid] = __ldg(row + l);
-                    }
-                }
-                // slot sums of (sample s, channel i0 + r, words 4q..4q+3): nb * 4 * LP4 items, <= 160
-                const int items = nb * 4 * LP4;
-                const bool mine = tid < items;
-                int sidx = 0, r = 0, q = 0, k_lo = 0, k_hi = -1;
-                if (mine) {
-                    sidx = tid / (4 * LP4);
-                    const int rem = tid - sidx * 4 * LP4;
-                    r = rem / LP4;
-                    q = rem - r * LP4;
-                    k_lo = tile_owner((bb + sidx) * TPS, p.n_tiles, p.n_ctas);
-                    k_hi = tile_owner((bb + sidx + 1) * TPS - 1, p.n_tiles, p.n_ctas);
-                }
-                if (!waited) {
-                    asm volatile("griddepcontrol.wait;" ::: "memory");      // every slot is complete and visible
-                    if (tid == 0) SBA_TL(p.tl, 4);
-                    waited = true;
-                }
-                if (mine) {
-                    const int b = bb + sidx;
-                    const float* base = p.part + ((size_t)b * IDF + i0 + r) * LP + 4 * q;      // slot (k + b): + k * IDF * LP
-                    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-                    for (int k0 = k_lo; k0 <= k_hi; k0 += kFinSlots) {
-                        float4 v[kFinSlots];
+        const float inv_L = 1.0f / (float)L;
+        const int cvec = (nc * L) >> 2;                   // float4s of one sample's [nc][L] ctx block
+        const bool cvec_ok = ((nc * L) & 3) == 0 && p.ctx_aligned;
+        float acc[NH][4];
 #pragma unroll
-                        for (int u = 0; u < kFinSlots; ++u)
-                            v[u] = (k0 + u <= k_hi) ? __ldcg(reinterpret_cast<const float4*>(base + (size_t)(k0 + u + b) * IDF * LP))
-                                                    : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-                        for (int u = 0; u < kFinSlots; ++u) { a.x += v[u].x; a.y += v[u].y; a.z += v[u].z; a.w += v[u].w; }
-                    }
-                    const float av[4] = {a.x, a.y, a.z, a.w};
+        for (int h = 0; h < NH; ++h) acc[h][0] = acc[h][1] = acc[h][2] = acc[h][3] = 0.f;
+
+        auto stage_ctx = [&](int bb, int nb) {            // cs[(s, l)][c] = ctx[bb + s][c0 + c][l]
+            if (cvec_ok) {
+                for (int f = tid; f < nb * cvec; f += kFinThreads) {
+                    const int sidx = f / cvec, r = f - sidx * cvec;
+                    const float4 v4 = __ldg(reinterpret_cast<const float4*>(p.ctx + ((size_t)(bb + sidx) * cdf + c0) * L) + r);
+                    const float v[4] = {v4.x, v4.y, v4.z, v4.w};
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
-                        const int l = 4 * q + e;
-                        if (l < L) {
-                            ds[(sidx * L + l) * 4 + r] = av[e];
-                            if (cc == 0) p.dSrc[((size_t)b * IDF + i0 + r) * L + l] = av[e];
+                        const int el = 4 * r + e;                     // element of the [nc][L] block
+                        const int c = (int)(((float)el + 0.5f) * inv_L), l = el - c * L;
+                        cs[(sidx * L + l) * kFinCS + c] = v[e];
+                    }
+                }
+            } else {
+                for (int el = tid; el < nb * nc * L; el += kFinThreads) {
+                    const int sidx = el / (nc * L), r = el - sidx * nc * L;
+                    const int c = r / L, l = r - c * L;
+                    cs[(sidx * L + l) * kFinCS + c] = __ldg(p.ctx + ((size_t)(bb + sidx) * cdf + c0) * L + r);
+                }
+            }
+        };
+        stage_ctx(b_lo, b_hi - b_lo < kFinRound ? b_hi - b_lo : kFinRound);      // ahead of the grid dependency
+        asm volatile("griddepcontrol.wait;" ::: "memory");          // every slot is complete and visible
+        if (tid == 0) { SBA_TL(p.tl, 4); SBA_TL(p.tl, 10); SBA_TL(p.tl, 11); }
+        for (int bb = b_lo; bb < b_hi; bb += kFinRound) {
+            const int nb = b_hi - bb < kFinRound ? b_hi - bb : kFinRound;
+            if (bb > b_lo) {
+                __syncthreads();                         // the previous round is done with cs / ds
+                stage_ctx(bb, nb);
+            }
+            // slot sums: item = (sample s, channel i, float4 q), one batch of up to 8 loads each
+            for (int item = tid; item < nb * IDF * LP4; item += kFinThreads) {
+                const int row = item / LP4, q = item - row * LP4;
+                const int sidx = row / IDF, i = row - sidx * IDF;
+                const int b = bb + sidx;
+                const int k_lo = tile_owner(b * TPS, p.n_tiles, p.n_ctas), k_hi = tile_owner((b + 1) * TPS - 1, p.n_tiles, p.n_ctas);
+                const float4* sp = reinterpret_cast<const float4*>(p.part + ((size_t)(k_lo + b) * IDF + i) * LP) + q;
+                float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int k0 = k_lo; k0 <= k_hi; k0 += kFinSlots, sp += (size_t)kFinSlots * IDF * LP4) {
+                    float4 v[kFinSlots];
+#pragma unroll
+                    for (int u = 0; u < kFinSlots; ++u)
+                        v[u] = (k0 + u <= k_hi) ? __ldcg(sp + (size_t)u * IDF * LP4) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                    for (int u = 0; u < kFinSlots; ++u) { a.x += v[u].x; a.y += v[u].y; a.z += v[u].z; a.w += v[u].w; }
+                }
+                reinterpret_cast<float4*>(ds)[item] = a;              // ds[(s * IDF + i) * LP + 4 q]
+                if (cg == 0) {
+                    float* o = p.dSrc + ((size_t)b * IDF + i) * L + 4 * q;
+                    if (4 * q < L) o[0] = a.x;
+                    if (4 * q + 1 < L) o[1] = a.y;
+                    if (4 * q + 2 < L) o[2] = a.z;
+                    if (4 * q + 3 < L) o[3] = a.w;
+                }
+            }
+            __syncthreads();
+            if (tid == 0 && bb == b_lo) { SBA_TL(p.tl, 12); SBA_TL(p.tl, 13); }
+            if (kq < nb) {
+                const float* cc = cs + kq * L * kFinCS + cq;
+#pragma unroll
+                for (int h = 0; h < NH; ++h) {
+                    const int i = i0 + 32 * h;
+                    if (i < IDF) {
+                        const float* d0p = ds + (kq * IDF + i) * LP;
+#pragma unroll 6
+                        for (int l = 0; l < L; ++l) {
+                            const float4 c4 = *reinterpret_cast<const float4*>(cc + l * kFinCS);
+                            const float d0 = d0p[l];
+                            acc[h][0] = fmaf(d0, c4.x, acc[h][0]); acc[h][1] = fmaf(d0, c4.y, acc[h][1]);
+                            acc[h][2] = fmaf(d0, c4.z, acc[h][2]); acc[h][3] = fmaf(d0, c4.w, acc[h][3]);
                         }
                     }
                 }
-                __syncthreads();
-#pragma unroll 8
-                for (int k = 0; k < K; ++k) {
-                    const float cv = cs[k * kFinC + tid];
-                    const float4 d4 = *reinterpret_cast<const float4*>(ds + 4 * k);
-                    acc[0] = fmaf(d4.x, cv, acc[0]); acc[1] = fmaf(d4.y, cv, acc[1]);
-                    acc[2] = fmaf(d4.z, cv, acc[2]); acc[3] = fmaf(d4.w, cv, acc[3]);
-                }
-            }
-            if (!waited) {
-                asm volatile("griddepcontrol.wait;" ::: "memory");     // (empty sample group) counters zeroed upstream
-                waited = true;
-            }
-            // group partial -> dwp[grp][i][c]
-            if (c < cdf) {
-#pragma unroll
-                for (int r = 0; r < 4; ++r) p.dwp[((size_t)grp * IDF + i0 + r) * cdf + c] = acc[r];
             }
         }
-        __threadfence();
+        if (tid == 0) { SBA_TL(p.tl, 14); SBA_TL(p.tl, 15); }
+        // the 4 thread groups (samples of a round) meet in shared memory: red[kq][i][32 c], added in kq order
+        __syncthreads();                                 // everybody is done reading ds
+        float* red = ds;                                 // (kFinRound * IDF * 32 floats <= kFinRound * IDF * LP? no: sized below)
+#pragma unroll
+        for (int h = 0; h < NH; ++h) {
+            const int i = i0 + 32 * h;
+            if (i < IDF) *reinterpret_cast<float4*>(red + ((size_t)kq * IDF + i) * 32 + cq) = make_float4(acc[h][0], acc[h][1], acc[h][2], acc[h][3]);
+        }
         __syncthreads();
-        if (tid == 0) s_last = (atomicAdd(p.counters + 1 + sl, 1u) == (uint32_t)(p.groups - 1));
+        float* mine = p.dwp + ((size_t)cg * p.groups + grp) * IDF * 32;
+        for (int o = tid; o < IDF * 8; o += kFinThreads) {            // group partial -> dwp[cg][grp][i][32]
+            float4 a = reinterpret_cast<const float4*>(red)[o];
+#pragma unroll
+            for (int k = 1; k < kFinRound; ++k) {
+                const float4 v = reinterpret_cast<const float4*>(red)[k * IDF * 8 + o];
+                a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+            }
+            reinterpret_cast<float4*>(mine)[o] = a;
+        }
         __syncthreads();
-        if (s_last) {                       // every group's partial of this channel slice is complete: add in group order
-            __threadfence();
-            for (int o = tid; o < cdf; o += kFinC) {             // 4 rows x cdf outputs, a float4 column-quad per (row, 4 c)
+        if (tid == 0) {
+            // release (cumulative over the block's stores, ordered by the barrier) / acquire on the slice counter
+            uint32_t old;
+            asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], 1;" : "=r"(old) : "l"(p.counters + 1 + cg) : "memory");
+            s_last = old == (uint32_t)(p.groups - 1);
+        }
+        __syncthreads();
+        if (tid == 0) { SBA_TL(p.tl, 0); SBA_TL(p.tl, 1); }
+        if (s_last) {
+            // every group's partial of this channel slice is complete: thread = (4 consecutive groups gq, output float4 o)
+            const float4* base = reinterpret_cast<const float4*>(p.dwp + (size_t)cg * p.groups * IDF * 32);
+            float4* red4 = reinterpret_cast<float4*>(red);
+            for (int o0 = 0; o0 < IDF * 8; o0 += 256) {
+                const int o = o0 + (tid & 255), gq = tid >> 8;
+                float4 v[4];
 #pragma unroll
-                for (int r = 0; r < 4; ++r) {
-                    float v[kFinGroups];
+                for (int u = 0; u < 4; ++u)
+                    v[u] = (o < IDF * 8 && 4 * gq + u < p.groups) ? __ldcg(base + (size_t)(4 * gq + u) * IDF * 8 + o)
+                                                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+                float4 a = v[0];
 #pragma unroll
-                    for (int g = 0; g < kFinGroups; ++g)
-                        v[g] = g < p.groups ? __ldcg(p.dwp + ((size_t)g * IDF + i0 + r) * cdf + o) : 0.f;
-                    float a = 0.f;
+                for (int u = 1; u < 4; ++u) { a.x += v[u].x; a.y += v[u].y; a.z += v[u].z; a.w += v[u].w; }
+                __syncthreads();
+                red4[tid] = a;
+                __syncthreads();
+                if (tid < 256 && o < IDF * 8) {
+                    float4 r = red4[tid];
 #pragma unroll
-                    for (int g = 0; g < kFinGroups; ++g) a += v[g];
-                    p.dW[(size_t)(i0 + r) * cdf + o] = a;
+                    for (int k = 1; k < 4; ++k) {
+                        const float4 w = red4[k * 256 + tid];
+                        r.x += w.x; r.y += w.y; r.z += w.z; r.w += w.w;
+                    }
+                    const int i = o >> 3, c4 = (o & 7) * 4;
+                    float* o4 = p.dW + (size_t)i * cdf + c0 + c4;
+                    if (c4 + 3 < nc && (cdf & 3) == 0) *reinterpret_cast<float4*>(o4) = r;
+                    else {
+                        if (c4 < nc) o4[0] = r.x;
+                        if (c4 + 1 < nc) o4[1] = r.y;
+                        if (c4 + 2 < nc) o4[2] = r.z;
+                        if (c4 + 3 < nc) o4[3] = r.w;
+                    }
                 }
             }
         }
@@ -247,9 +311,11 @@ __global__ void __launch_bounds__(kFinC) k_bwd_finish_tc5(const Tc5FinishParams 
         const int b = blockIdx.x - p.n_dw;
         const int k_lo = tile_owner(b * TPS, p.n_tiles, p.n_ctas), k_hi = tile_owner((b + 1) * TPS - 1, p.n_tiles, p.n_ctas);
         asm volatile("griddepcontrol.wait;" ::: "memory");
+#pragma unroll 1
         for (int o = tid; o < IDF * LP; o += blockDim.x) {
             const int i = o / LP, l = o - i * LP;
             float a = 0.f;
+#pragma unroll 4
             for (int k = k_lo; k <= k_hi; ++k) a += __ldcg(p.part + ((size_t)(k + b) * IDF + i) * LP + l);
             if (l < L) {
                 ds[i * L + l] = a;
@@ -257,9 +323,11 @@ __global__ void __launch_bounds__(kFinC) k_bwd_finish_tc5(const Tc5FinishParams 
             }
         }
         __syncthreads();
+#pragma unroll 1
         for (int o = tid; o < cdf * L; o += blockDim.x) {
             const int c = o / L, l = o - c * L;
             float a = 0.f;
+#pragma unroll 4
             for (int i = 0; i < IDF; ++i) a = fmaf(__ldg(p.W + (size_t)i * cdf + c), ds[i * L + l], a);
             p.dCtx[(size_t)b * cdf * L + o] = a;
         }
@@ -679,19 +747,18 @@ __global__ void __launch_bounds__(kBwdThreads, Tc5BwdCfg<IDF, NQ, NST_>::CTAS_PE
 // workspace layout behind the B*idf*L + B + 1 words the other kernel families use (sizes in floats)
 struct Tc5BwdWs {
     size_t part, dwp, counters, total;
-    int slots, groups, nb, lp, n_counters;
+    int slots, groups, lp, n_counters;
 };
 Tc5BwdWs tc5_bwd_ws(int B, int idf, int cdf, int L, int sms) {
     Tc5BwdWs w{};
     w.lp = (L + 3) / 4 * 4;
     w.slots = 2 * sms + B;                                   // at most two CTAs per SM (TMEM), slot = CTA + sample
-    w.nb = kFinK / L < 4 ? kFinK / L : 4;                    // samples per round of the finish kernel (L <= 32: >= 3)
-    w.groups = (B + w.nb - 1) / w.nb < kFinGroups ? (B + w.nb - 1) / w.nb : kFinGroups;
-    w.n_counters = 1 + idf / 4;
+    w.groups = (B + kFinRound - 1) / kFinRound < kFinGroups ? (B + kFinRound - 1) / kFinRound : kFinGroups;     // B = 64: 16 x 4
+    w.n_counters = 1 + (cdf + 31) / 32;
     const size_t head = ((size_t)B * idf * L + B + 1 + 3) / 4 * 4;
     w.part = head;
     w.dwp = w.part + (size_t)w.slots * idf * w.lp;
-    w.counters = w.dwp + ((size_t)w.groups * idf * cdf + 3) / 4 * 4;
+    w.counters = w.dwp + (size_t)((cdf + 31) / 32) * w.groups * idf * 32;
     w.total = w.counters + (size_t)(w.n_counters + 3) / 4 * 4;
     return w;
 }
@@ -726,6 +793,7 @@ int launch_bwd_tc5(const void* x, const void* g, void* dX, const Tc5BwdParams& p
     if (rc) return rc;
     const int grid = p.n_tiles < max_ctas ? p.n_tiles : max_ctas;
     p.tl = f.tl = SBA_TL_SLOT();
+
     {
         PdlLaunch ml(dim3(grid), dim3(kBwdThreads), smem, st);
         cudaError_t e = cudaLaunchKernelEx(&ml.cfg, kern, tm_x, tm_g, tm_dx, p);
@@ -739,14 +807,15 @@ int launch_bwd_tc5(const void* x, const void* g, void* dX, const Tc5BwdParams& p
     if (rc) return rc;
     // finish kernel: slots -> dSrc, dW, dCtx
     f.n_ctas = grid;
-    f.n_dw = f.dW != nullptr ? f.groups * (IDF / 4) : 0;
+    f.n_dw = f.dW != nullptr ? f.groups * ((f.cdf + 31) / 32) : 0;
     const int fgrid = f.n_dw + (f.dCtx != nullptr ? f.B : 0);
     if (fgrid == 0) return SBA_OK;
-    constexpr size_t fsmem = (size_t)(kFinK * kFinC + kFinK * 4) * sizeof(float);           // 97.5 KB
+    // cs [128][36] + ds / red [4][IDF][32]: 34 KB at idf 32
+    constexpr size_t fsmem = (size_t)(kFinRound * 32 * kFinCS + kFinRound * IDF * 32) * sizeof(float);
     static std::atomic<unsigned long long> fsmem_done{0};
     rc = ensure_dynamic_smem(k_bwd_finish_tc5<IDF>, fsmem, dev, fsmem_done, "attn_bwd(finish)");
     if (rc) return rc;
-    PdlLaunch fl(dim3(fgrid), dim3(kFinC), fsmem, st);
+    PdlLaunch fl(dim3(fgrid), dim3(kFinThreads), fsmem, st);
     cudaError_t e = cudaLaunchKernelEx(&fl.cfg, k_bwd_finish_tc5<IDF>, f);
     if (e != cudaSuccess) {
         set_error("attn_bwd(finish): launch: %s", cudaGetErrorString(e));
@@ -792,7 +861,7 @@ size_t attn_bwd_workspace_floats(int B, int idf, int cdf, int L) {
 }
 
 int tc5_attn_bwd(const void* x, const float* ctx, const float* W, const float* srcT, const uint8_t* mask,
-                 const uint32_t* mask_bits, const void* g_c,
+                 uint32_t* mask_bits, const void* g_c,
                  const void* g_attn, void* dX, float* ws, size_t ws_floats, float* dW, float* dCtx, const AttnShape& s,
                  cudaStream_t st) {
     int dev = 0, sms = 0;
@@ -816,8 +885,9 @@ int tc5_attn_bwd(const void* x, const float* ctx, const float* W, const float* s
     p.n_tiles = s.B * p.tiles_per_sample;
     Tc5FinishParams f{};
     f.part = p.part; f.ctx = ctx; f.W = W; f.dSrc = ws; f.dW = dW; f.dCtx = dCtx; f.dwp = ws + w.dwp; f.counters = p.counters;
-    f.B = s.B; f.cdf = s.cdf; f.L = s.L; f.LP = w.lp;
-    f.tiles_per_sample = p.tiles_per_sample; f.n_tiles = p.n_tiles; f.groups = w.groups; f.nb = w.nb;
+    f.B = s.B; f.cdf = s.cdf; f.L = s.L; f.LP = w.lp; f.groups = w.groups;
+    f.tiles_per_sample = p.tiles_per_sample; f.n_tiles = p.n_tiles;
+    f.ctx_aligned = (reinterpret_cast<uintptr_t>(ctx) & 15u) == 0;
     rc = -1;
     if (s.idf == 32) rc = dispatch_ga<32>(x, g_c, dX, p, f, st);
     else if (s.idf == 48) rc = dispatch_ga<48>(x, g_c, dX, p, f, st);

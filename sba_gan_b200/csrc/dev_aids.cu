@@ -14,13 +14,13 @@ namespace tc5 {
 const DevTuning& dev_tuning() {
     static const DevTuning t = [] {
         auto get = [](const char* name) { const char* v = getenv(name); return v ? atoi(v) : -1; };
-        return DevTuning{get("SBA_TC5_CTAS_PER_SM"), get("SBA_TC5_STATIC"), get("SBA_TC5_CHUNK"), get("SBA_TC5_LATE_TRIGGER")};
+        return DevTuning{get("SBA_TC5_CTAS_PER_SM"), get("SBA_TC5_STATIC"), get("SBA_TC5_CHUNK"), get("SBA_TC5_LATE_TRIGGER"), get("SBA_TC5_VARIANT")};
     }();
     return t;
 }
 
 namespace {
-constexpr int kCalls = 256, kStamps = 8;
+constexpr int kCalls = 256, kStamps = 16;
 std::mutex g_mu;
 unsigned long long* g_buf = nullptr;
 int g_next = 0;
@@ -69,7 +69,7 @@ __attribute__((visibility("default"))) int sba_dev_timeline_clear(void) {
     tl_init_values();
     return 0;
 }
-// copy the stamps of the first n slots to `out` (8 values per call)
+// copy the stamps of the first n slots to `out` (16 values per call)
 __attribute__((visibility("default"))) int sba_dev_timeline_read(unsigned long long* out, int n) {
     using namespace sba::tc5;
     std::lock_guard<std::mutex> lock(g_mu);

@@ -48,7 +48,7 @@ int attn_bwd_post(const float* dSrc, const float* ctx, const float* W, float* dW
 bool tc5_bwd_supports(const AttnShape& s);
 size_t attn_bwd_workspace_floats(int B, int idf, int cdf, int L);
 int tc5_attn_bwd(const void* x, const float* ctx, const float* W, const float* srcT, const uint8_t* mask,
-                 const uint32_t* mask_bits, const void* g_c, const void* g_attn, void* dX, float* ws, size_t ws_floats,
+                 uint32_t* mask_bits, const void* g_c, const void* g_attn, void* dX, float* ws, size_t ws_floats,
                  float* dW, float* dCtx, const AttnShape& s, cudaStream_t st);
 
 // words_loss.cu - fused DAMSM region-word similarity (kernel c) and its backward

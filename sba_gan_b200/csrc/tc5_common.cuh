@@ -307,12 +307,13 @@ int make_tile_map(CUtensorMap* out, const void* base, int dtype, int rows, int c
 
 // ---- development aids (python -m sba_gan_b200.build --dev; csrc/dev_aids.cu) ------------------------
 // Kernel parameter blocks always carry a `tl` pointer (NULL in the product library, where the stamps
-// below compile to nothing): 8 globaltimer stamps per ABI call, even = earliest, odd = latest over CTAs:
+// below compile to nothing): 16 globaltimer stamps per ABI call, even = earliest, odd = latest over CTAs:
 //   0/1 head kernel (projection) first instruction / last exit     2/3 streaming kernel entry / exit
 //   4/5 tail kernel (backward finish) past its grid dependency / exit
 //   6   streaming kernel past its grid dependency                  7   streaming kernel: last tile done
+//   8/9 tail kernel block entry   10/11 past its dependency   12/13 first round staged   14/15 partial stored + counted
 #ifdef SBA_DEV_AIDS
-struct DevTuning { int ctas_per_sm, static_pct, chunk, late_trigger; };   // SBA_TC5_CTAS_PER_SM / _STATIC / _CHUNK / _LATE_TRIGGER, read once
+struct DevTuning { int ctas_per_sm, static_pct, chunk, late_trigger, variant; };   // SBA_TC5_CTAS_PER_SM / _STATIC / _CHUNK / _LATE_TRIGGER / _VARIANT, read once
 const DevTuning& dev_tuning();
 unsigned long long* timeline_slot();                           // device pointer to this call's 8 stamps, or NULL
 __device__ __forceinline__ void tl_stamp(unsigned long long* tl, int stamp) {

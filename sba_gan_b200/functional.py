@@ -42,9 +42,14 @@ def _context_fp32(context):
 ALGO_NAMES = {v: k for k, v in _ALGOS.items()}
 
 
-def last_algo() -> str:
-    """Kernel family ("simt" | "mma" | "tc5") that served the last attention call of this thread."""
-    return ALGO_NAMES.get(_abi.load().sba_last_algo(), "?")
+# kernel family that served the most recent forward / backward call of this process.  (The C ABI keeps it per host
+# thread - sba_last_algo() - and autograd runs backward on its own thread, so it is read right behind each call.)
+_last_algo = {"fwd": "?", "bwd": "?"}
+
+
+def last_algo(which: str = "fwd") -> str:
+    """Kernel family ("simt" | "mma" | "tc5") that served the last attention forward ("fwd") / backward ("bwd")."""
+    return _last_algo[which]
 
 
 def bwd_workspace(B, idf, cdf, L, device):
@@ -70,6 +75,7 @@ def attn_forward_raw(x, context, weight, mask_u8, mask_mode, algo):
                           _ptr(mask_bits), B, idf, cdf, L, Q, _DTYPES[x.dtype], mask_mode, algo, _stream())
     _abi.check(rc, "sba_attn_fwd")
     launch_counter["n"] += _abi.last_launch_count()
+    _last_algo["fwd"] = ALGO_NAMES.get(lib.sba_last_algo(), "?")
     return c_code, attn, srcT, mask_bits, ctx32, w32
 
 
@@ -111,6 +117,7 @@ class _WordRegionAttention(torch.autograd.Function):
                               _DTYPES[x.dtype], mask_mode, algo, _stream())
         _abi.check(rc, "sba_attn_bwd")
         launch_counter["n"] += _abi.last_launch_count()
+        _last_algo["bwd"] = ALGO_NAMES.get(lib.sba_last_algo(), "?")
         return (dX if need_x else None,
                 dCtx.to(ctx_dtype) if need_ctx else None,
                 dW.reshape(w_shape).to(w_dtype) if need_w else None,

@@ -64,12 +64,12 @@ def _run(d, masked, algo="auto", dtype=torch.float32, mask_mode="reference", ctx
     ctx = d["context"].cuda().to(dtype).requires_grad_(ctx_grad)
     m.applyMask(d["mask"].cuda() if masked else None)
     c, attn = m(x, ctx)
-    ran_fwd = last_algo()
+    ran_fwd = last_algo("fwd")
     loss = (c.float() * d["g_c"].cuda().float()).sum()
     if "g_attn" in d:
         loss = loss + (attn.float() * d["g_attn"].cuda().float()).sum()
     loss.backward()
-    ran_bwd = last_algo()
+    ran_bwd = last_algo("bwd")
     torch.cuda.synchronize()
     if algo != "auto":          # the family that was asked for is the family that ran (never a silent substitute)
         assert ran_fwd == algo and ran_bwd == m.algo_bwd, (algo, ran_fwd, ran_bwd)

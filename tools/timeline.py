@@ -71,7 +71,8 @@ torch.cuda.synchronize()
 raw.sba_dev_timeline_clear()
 gr.replay()
 torch.cuda.synchronize()
-buf = (ctypes.c_ulonglong * (8 * n))()
+NS = 16
+buf = (ctypes.c_ulonglong * (NS * n))()
 raw.sba_dev_timeline_read(buf, n)
 v = list(buf)
 NONE_MIN, t0 = 2 ** 64 - 1, min(x for x in v if 0 < x < 2 ** 64 - 1)
@@ -80,8 +81,11 @@ print(f"{which} B={B} {hw}x{hw} {dt}: {n} calls, us since the first stamp")
 print("call | head first..last      | stream entry  past-dep  last-tile      exit | finish past-dep..exit   | period")
 prev = None
 for c in range(n):
-    r = v[8 * c:8 * c + 8]
+    r = v[NS * c:NS * c + NS]
     end = max(x for x in (r[1], r[3], r[5]) if x not in (0, NONE_MIN))
     period = "" if prev is None else f"{(end - prev) * 1e-3:7.2f}"
     prev = end
     print(f"{c:4d} | {us(r[0])}..{us(r[1])} | {us(r[2])} {us(r[6])} {us(r[7])} {us(r[3])} | {us(r[4])}..{us(r[5])} | {period}")
+    if r[8] not in (0, NONE_MIN) and c >= n - 3:
+        print(f"       finish blocks: entry {us(r[8])}..{us(r[9])} past-dep {us(r[10])}..{us(r[11])} staged {us(r[12])}..{us(r[13])} "
+              f"FMAs done {us(r[14])}..{us(r[15])} counted {us(r[0])}..{us(r[1])}")
