@@ -108,7 +108,8 @@ def make_inputs(hw, seed, dtype, device, pin=False, batch=B_PER_GPU):
     g = torch.Generator().manual_seed(seed)
     x = torch.randn(batch, IDF, hw, hw, generator=g).to(dtype)
     gc = torch.randn(batch, IDF, hw, hw, generator=g).to(dtype)
-    ctx = torch.tanh(torch.randn(batch, CDF, L, generator=g)).to(dtype)
+    ctx = torch.tanh(torch.randn(batch, CDF, L, generator=g))    # word features stay fp32: the frozen text encoder's output
+                                                                 # (trainer_bert.py:256-257), a small per-caption tensor
     lens = torch.sort(torch.randint(5, L + 1, (batch,), generator=g), descending=True).values
     mask = torch.arange(L)[None, :] >= lens[:, None]
     if pin:
@@ -238,6 +239,8 @@ class AttentionStep:
             self.mods.append(m)
         self.sets = [[make_inputs(hw, 1234 + cx.rank + 17 * s + hw, dtype, device) for hw in STAGES] for s in range(nsets)]
         for st_ in self.sets:                         # both generator stages attend over the SAME word features and mask
+            if att_cls is not None:
+                st_[0][2] = st_[0][2].to(dtype)       # (eager reference ops: everything in one dtype)
             st_[1][2], st_[1][3] = st_[0][2], st_[0][3]    # (model_bert.py:580-588)
         for s in self.sets:
             for st in s:
@@ -525,25 +528,35 @@ def sub_words_loss(cx):
 def sub_gan_step(cx, steps=6, batch=20):
     """BASELINE configs[3]: the full G+D adversarial step (harness/gan_step.py: trainer_bert.py:251-304 step body,
     bird_style networks restated from scratch, synthetic data, random init), batch-sharded, manual flattened gradient
-    all-reduce per network; fused hot path vs the reference's eager ops for the same two operators."""
+    all-reduce per network.  Variants: fused = drop-in attention module + words_loss / sent_loss kernels; fused_stage = the
+    same with attention + AdaIN + cat of NEXT_STAGE_G.forward as one operator (sba_gan_b200.stage, bf16 tensors);
+    eager = the reference's eager ops for the same operators.  fp32 as the reference trains, and bf16 autocast."""
     from harness.gan_step import Trainer
-    out = {"batch_per_gpu": batch, "global_batch": batch * cx.world, "steps": steps, "dtype": "fp32"}
-    for attention in ("fused", "eager"):
+    out = {"batch_per_gpu": batch, "global_batch": batch * cx.world, "steps": steps}
+    for name, attention, amp in (("fused", "fused", False), ("eager", "eager", False), ("fused_bf16", "fused", True),
+                                 ("fused_stage_bf16", "fused_stage", True), ("eager_bf16", "eager", True)):
         tr = Trainer(batch, cx.device, attention, cx.world, seed=1234 + cx.rank)
+
+        def one():
+            if amp:
+                with torch.autocast("cuda", dtype=torch.bfloat16):
+                    return tr.step()
+            return tr.step()
         for _ in range(3):
-            tr.step()
+            one()
         cx.barrier()
         e0, e1 = ev(), ev()
         e0.record()
         for _ in range(steps):
-            tr.step()
+            one()
         e1.record()
         cx.barrier()
         ms = cx.max_over_ranks(e0.elapsed_time(e1) / steps)
-        out[attention] = {"imgs_per_s": round(batch * cx.world / (ms * 1e-3), 1), "ms_per_step": round(ms, 2)}
+        out[name] = {"imgs_per_s": round(batch * cx.world / (ms * 1e-3), 1), "ms_per_step": round(ms, 2)}
         del tr
         torch.cuda.empty_cache()
     out["speedup_fused_vs_eager"] = round(out["fused"]["imgs_per_s"] / out["eager"]["imgs_per_s"], 3)
+    out["speedup_fused_stage_vs_eager_bf16"] = round(out["fused_stage_bf16"]["imgs_per_s"] / out["eager_bf16"]["imgs_per_s"], 3)
     return out
 
 
@@ -615,7 +628,7 @@ def run_ours(args, cx):
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms, 4), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
         "config": {"workload": WORKLOAD, "B_per_gpu": B_PER_GPU, "regions": [hw * hw for hw in STAGES],
-                   "io_dtype": args.dtype, "param_dtype": "fp32", "accumulate": "fp32", "algo": args.algo,
+                   "io_dtype": args.dtype, "param_dtype": "fp32", "word_features_dtype": "fp32", "accumulate": "fp32", "algo": args.algo,
                    "launch": "eager" if args.no_graph else "cuda-graph replay", "mask": "ragged, reference mod-B order",
                    "g_attn": None, "exchange": "one flattened 64 KB all-reduce of both conv_context weight gradients per step",
                    "l2": "inputs larger than L2: one step streams %d MB per GPU over 3 rotating buffer sets" %

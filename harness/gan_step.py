@@ -109,8 +109,9 @@ class AdaIN(nn.Module):
 
 
 class NextStage(nn.Module):
-    def __init__(self, att_cls):
+    def __init__(self, att_cls, fuse_stage=False):
         super().__init__()
+        self.fuse_stage = fuse_stage            # attention + AdaIN + cat as one operator (sba_gan_b200.stage)
         self.att = att_cls(NGF, NEF)
         self.adain2 = AdaIN(NGF)
         self.residual = nn.Sequential(*[ResBlock(2 * NGF) for _ in range(RNUM)])
@@ -118,20 +119,24 @@ class NextStage(nn.Module):
 
     def forward(self, h, w_code, words, mask):
         self.att.applyMask(mask)
+        if self.fuse_stage:
+            from sba_gan_b200.stage import next_stage_attention
+            h_c, att = next_stage_attention(self.att, self.adain2, h, w_code, words)
+            return self.upsample(self.residual(h_c)), att
         c_code, att = self.att(h, words)
         h = self.adain2(h, w_code)
         return self.upsample(self.residual(torch.cat((h, c_code), 1))), att
 
 
 class Generator(nn.Module):
-    def __init__(self, att_cls):
+    def __init__(self, att_cls, fuse_stage=False):
         super().__init__()
         self.ca_fc = nn.Linear(NEF, 4 * NCF)
         self.mapping = nn.Sequential(nn.Linear(ZDIM, WDIM, bias=False), *[nn.Linear(WDIM, WDIM, bias=False) for _ in range(7)])
         g = 16 * NGF
         self.fc = nn.Sequential(nn.Linear(NCF, g * 4 * 4 * 2, bias=False), nn.BatchNorm1d(g * 4 * 4 * 2), GLU())
         self.ups = nn.Sequential(up_block(g, g // 2), up_block(g // 2, g // 4), up_block(g // 4, g // 8), up_block(g // 8, g // 16))
-        self.h_net2, self.h_net3 = NextStage(att_cls), NextStage(att_cls)
+        self.h_net2, self.h_net3 = NextStage(att_cls, fuse_stage), NextStage(att_cls, fuse_stage)
         self.img = nn.ModuleList([nn.Sequential(conv3(NGF, 3), nn.Tanh()) for _ in range(3)])
 
     def forward(self, z, sent, words, mask):
@@ -259,13 +264,15 @@ class Trainer:
 
     def __init__(self, batch, device, attention="fused", world=1, seed=0):
         torch.manual_seed(seed)
-        if attention == "fused":
-            from sba_gan_b200 import GlobalAttentionGeneral as att_cls, words_loss as wl
-            self.words_loss = lambda img, w, lab, lens, cls, B: wl(img, w, lab, lens, cls, B, GAMMA1, GAMMA2, GAMMA3)
+        if attention in ("fused", "fused_stage"):
+            from sba_gan_b200 import GlobalAttentionGeneral as att_cls, words_loss as wl, sent_loss as sl
+            self.words_loss = lambda img, w, lab, lens, cls, B: wl(img, w, lab, lens, cls, B, GAMMA1, GAMMA2, GAMMA3,
+                                                                   att_maps=False)
+            self.sent_loss = lambda code, sent, lab, cls: sl(code, sent, lab, cls, self.B, gamma3=GAMMA3)
         else:
-            att_cls, self.words_loss = EagerAttention, eager_words_loss
+            att_cls, self.words_loss, self.sent_loss = EagerAttention, eager_words_loss, sent_loss
         self.B, self.dev, self.world = batch, device, world
-        self.G = Generator(att_cls).to(device)
+        self.G = Generator(att_cls, fuse_stage=(attention == "fused_stage")).to(device)
         self.Ds = [Discriminator(s).to(device) for s in (64, 128, 256)]
         self.img_enc = ImageEncoder().to(device).eval()
         self.txt_enc = TextEncoder().to(device).eval()
@@ -311,7 +318,7 @@ class Trainer:
             errG = errG + bce(D.UNCOND_DNET(h), self.ones) + bce(D.COND_DNET(h, sent), self.ones)
         feat, code = self.img_enc(fake[-1])
         w0, w1, _ = self.words_loss(feat, words, self.labels, self.lens, self.cls, B)
-        s0, s1 = sent_loss(code, sent, self.labels, self.cls)
+        s0, s1 = self.sent_loss(code, sent, self.labels, self.cls)
         kl = -0.5 * torch.mean(1 + logvar - mu.pow(2) - logvar.exp())
         errG = errG + (w0 + w1 + s0 + s1) * LAMBDA + kl
         errG.backward()

@@ -164,6 +164,25 @@ SBA_API int sba_words_sim_bwd(const float* img, const float* words, const int32_
 SBA_API int sba_func_attention(const float* query, const float* context, float* wc, float* attn,
                        int B, int nef, int T, int R, float gamma1, void* stream);
 
+/* ---- the caller's AdaIN, written next to c_code ----------------------
+ * ADAIN_NORM.forward (model_bert.py:367-374) of NEXT_STAGE_G.forward (:458-461):
+ *   out[b, out_row0 + c, :] = (gamma[b,c] + 1) * instance_norm(x[b, c, :]) + beta[b,c]
+ * with InstanceNorm2d semantics (biased variance over the Q pixels of the row, eps, no affine,
+ * no running statistics).  out is a [B, out_rows, Q] buffer - with out_rows = 2*C, out_row0 = 0
+ * and sba_attn_fwd_into writing c_code into rows [C, 2C) the reference's
+ * torch.cat((h_code, c_code), 1) is complete without a copy.  One read + one write of x.
+ * x       [B, C, Q] dtype            style [B, 2C] fp32 = (gamma | beta) (the output of ADAIN_NORM.style)
+ * stats   [2*B*C] fp32 out: (mean, rstd) per row, kept for the backward
+ * Backward: g_buf [B, g_rows, Q] is the gradient of the buffer, rows [g_row0, g_row0 + C) are read in
+ * place; dX [B, C, Q] receives (accumulate = 0) or is incremented by (accumulate = 1: on top of the
+ * attention's dX) the gradient w.r.t. x; d_style [B, 2C] = (d gamma | d beta).
+ */
+SBA_API int sba_adain_fwd(const void* x, const float* style, void* out, int out_rows, int out_row0,
+                     float* stats, int B, int C, int Q, int dtype, float eps, void* stream);
+SBA_API int sba_adain_bwd(const void* x, const float* style, const float* stats,
+                     const void* g_buf, int g_rows, int g_row0, void* dX, int accumulate, float* d_style,
+                     int B, int C, int Q, int dtype, void* stream);
+
 /* ---- the B x B matching tail of words_loss and sent_loss -----------
  * sba_match_ce_*: same-class masking + the two cross-entropies (miscc/losses.py:24-34, 53-59 and
  * :73-76, 116-129).  Entry (i, j), i != j, counts as -inf when class_ids[i] == class_ids[j]

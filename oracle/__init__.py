@@ -13,7 +13,7 @@ them on seeded inputs and commits inputs+outputs under ``tests/golden/``;
 """
 from .attention import (  # noqa: F401
     project_words, attn_forward, attn_backward, func_attention,
-    words_similarity, words_loss, words_loss_backward, ce_tail, sent_scores, sent_loss,
+    words_similarity, words_loss, words_loss_backward, ce_tail, sent_scores, sent_loss, adain_cat,
 )
 from .synth import (  # noqa: F401
     synth_attention_inputs, synth_words_loss_inputs, normalised_max_err,

@@ -169,6 +169,16 @@ def ce_tail(sim, labels, class_ids):
     return loss0, loss1, sim
 
 
+def adain_cat(h_code, style, c_code, eps=1e-5):
+    """ADAIN_NORM.forward (model_bert.py:367-374) followed by the concatenation of NEXT_STAGE_G.forward (:460-461):
+    cat(((gamma + 1) * InstanceNorm2d(h_code) + beta, c_code), 1) with style = (gamma | beta) B x 2C."""
+    gamma, beta = style[:, :, None, None].chunk(2, 1)                       # :368-369
+    mean = h_code.mean(dim=(2, 3), keepdim=True)
+    var = h_code.var(dim=(2, 3), unbiased=False, keepdim=True)              # nn.InstanceNorm2d: biased variance
+    out = (gamma + 1.0) * ((h_code - mean) / torch.sqrt(var + eps)) + beta  # :371-372
+    return torch.cat((out, c_code), 1)                                      # :461
+
+
 def sent_scores(cnn_code, rnn_code, gamma3=10.0, eps=1e-8):
     """The B x B score matrix of sent_loss (losses.py:42-49) before class masking:
     scores[i, j] = gamma3 * <cnn_i, rnn_j> / max(|cnn_i| |rnn_j|, eps)."""

@@ -44,6 +44,60 @@ def import_reference():
     return ref_ga, ref_losses, cfg
 
 
+def import_reference_models():
+    """model_bert.py of the reference (G_NET, NEXT_STAGE_G, ADAIN_NORM ...) with stand-ins for the two
+    uninstalled packages it names at import time; bird_style.yml dimensions."""
+    import_reference()
+    ppb = types.ModuleType("pytorch_pretrained_bert")
+    ppb.BertModel = type("BertModel", (), {})
+    sys.modules.setdefault("pytorch_pretrained_bert", ppb)
+    from miscc.config import cfg
+    cfg.GAN.GF_DIM, cfg.GAN.DF_DIM, cfg.GAN.Z_DIM, cfg.GAN.R_NUM = 32, 64, 100, 2      # cfg/bird_style.yml
+    cfg.TREE.BRANCH_NUM, cfg.TEXT.EMBEDDING_DIM, cfg.GAN.CONDITION_DIM = 3, 256, 100
+    import model_bert
+    return model_bert, cfg
+
+
+STAGE_CASES = {
+    # name: (B, idf, cdf, L, ih, iw, seed)      attention + AdaIN + cat of NEXT_STAGE_G.forward (model_bert.py:458-461)
+    "stage_b3_16x8": (3, 32, 256, 18, 16, 8, 51),
+    "stage_b2_16x16": (2, 32, 256, 12, 16, 16, 52),
+}
+
+
+def synth_stage_inputs(B, idf, cdf, L, ih, iw, seed, dtype, w_dim):
+    d = synth_attention_inputs(B, idf, cdf, L, ih, iw, seed=seed, dtype=dtype, with_g_attn=True)
+    rs = np.random.RandomState(seed + 1000)
+    d["w_code"] = torch.from_numpy(rs.standard_normal((B, w_dim))).to(dtype)
+    d["style_weight"] = torch.from_numpy(rs.standard_normal((2 * idf, w_dim)) / np.sqrt(w_dim)).to(dtype)
+    d["style_bias"] = torch.from_numpy(0.1 * rs.standard_normal(2 * idf)).to(dtype)
+    d["g_buf"] = torch.from_numpy(rs.standard_normal((B, 2 * idf, ih, iw))).to(dtype)
+    return d
+
+
+def run_stage(model_bert, cfg, ref_ga, spec, dtype):
+    B, idf, cdf, L, ih, iw, seed = spec
+    d = synth_stage_inputs(B, idf, cdf, L, ih, iw, seed, dtype, cfg.GAN.W_DIM)
+    att = ref_ga.GlobalAttentionGeneral(idf, cdf).to(dtype)
+    adain = model_bert.ADAIN_NORM(idf).to(dtype)
+    with torch.no_grad():
+        att.conv_context.weight.copy_(d["weight"])
+        adain.style.weight.copy_(d["style_weight"])
+        adain.style.bias.copy_(d["style_bias"])
+    h = d["x"].clone().requires_grad_(True)
+    w = d["w_code"].clone().requires_grad_(True)
+    ctx = d["context"].clone().requires_grad_(True)
+    att.applyMask(d["mask"])
+    c_code, attn = att(h, ctx)                       # model_bert.py:458-459
+    hn = adain(h, w)                                 # :460
+    h_c = torch.cat((hn, c_code), 1)                 # :461
+    ((h_c * d["g_buf"]).sum() + (attn * d["g_attn"]).sum()).backward()
+    return dict(h_c_code=h_c.detach().numpy(), attn=attn.detach().numpy(), dX=h.grad.numpy(), dCtx=ctx.grad.numpy(),
+                dW=att.conv_context.weight.grad.numpy(), d_w_code=w.grad.numpy(),
+                d_style_weight=adain.style.weight.grad.numpy(), d_style_bias=adain.style.bias.grad.numpy(),
+                in_sum=np.concatenate([checksum(d["x"]), checksum(d["w_code"]), checksum(d["g_buf"])]))
+
+
 ATTN_CASES = {
     # name: (B, idf, cdf, L, ih, iw, seed, masked, with_g_attn)
     "attn_b3_q64_rag": (3, 32, 256, 18, 8, 8, 11, True, True),       # Q % B != 0
@@ -185,6 +239,9 @@ def main():
         np.savez_compressed(os.path.join(outdir, f"func_attention_{tag}.npz"), **run_func_attention(ref_ga, dtype))
         for name, spec in SL_CASES.items():
             np.savez_compressed(os.path.join(outdir, f"{name}_{tag}.npz"), **run_sent_loss(ref_losses, cfg, spec, dtype))
+        model_bert, _ = import_reference_models()
+        for name, spec in STAGE_CASES.items():
+            np.savez_compressed(os.path.join(outdir, f"{name}_{tag}.npz"), **run_stage(model_bert, cfg, ref_ga, spec, dtype))
     total = sum(os.path.getsize(os.path.join(outdir, f)) for f in os.listdir(outdir))
     print(f"wrote {len(os.listdir(outdir))} fixtures, {total / 1e6:.2f} MB, torch {torch.__version__}")
 

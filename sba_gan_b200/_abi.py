@@ -32,6 +32,8 @@ SYMBOLS = {
     "sba_words_sim_bwd_workspace_bytes": (c_size_t, [c_int] * 5),
     "sba_words_sim_bwd": (c_int, [c_void_p] * 7 + [c_int] * 6 + [c_float] * 4 + [c_void_p]),
     "sba_func_attention": (c_int, [c_void_p] * 4 + [c_int] * 4 + [c_float] + [c_void_p]),
+    "sba_adain_fwd": (c_int, [c_void_p] * 3 + [c_int] * 2 + [c_void_p] + [c_int] * 4 + [c_float] + [c_void_p]),
+    "sba_adain_bwd": (c_int, [c_void_p] * 4 + [c_int] * 2 + [c_void_p] + [c_int] + [c_void_p] + [c_int] * 4 + [c_void_p]),
     "sba_match_ce_fwd": (c_int, [c_void_p] * 5 + [c_int] + [c_void_p]),
     "sba_match_ce_bwd": (c_int, [c_void_p] * 6 + [c_int] + [c_void_p]),
     "sba_sent_scores_fwd": (c_int, [c_void_p] * 4 + [c_int] * 2 + [c_float] * 2 + [c_void_p]),

@@ -350,4 +350,36 @@ int sba_sent_scores_bwd(const float* cnn, const float* rnn, const float* norms, 
                            static_cast<cudaStream_t>(stream));
 }
 
+int sba_adain_fwd(const void* x, const float* style, void* out, int out_rows, int out_row0, float* stats, int B, int C,
+                  int Q, int dtype, float eps, void* stream) {
+    g_launches = 0;
+    g_err[0] = 0;
+    if (!x || !style || !out || !stats || B <= 0 || C <= 0 || Q <= 0 || (dtype != SBA_F32 && dtype != SBA_BF16)) {
+        set_error("sba_adain_fwd: null pointer, non-positive size or unknown dtype");
+        return SBA_ERR_ARG;
+    }
+    if (out_rows < C || out_row0 < 0 || out_row0 + C > out_rows) {
+        set_error("sba_adain_fwd: rows [%d, %d) do not fit a %d-row buffer", out_row0, out_row0 + C, out_rows);
+        return SBA_ERR_ARG;
+    }
+    return adain_fwd(x, style, out, out_rows, out_row0, stats, B, C, Q, dtype, eps, static_cast<cudaStream_t>(stream));
+}
+
+int sba_adain_bwd(const void* x, const float* style, const float* stats, const void* g_buf, int g_rows, int g_row0, void* dX,
+                  int accumulate, float* d_style, int B, int C, int Q, int dtype, void* stream) {
+    g_launches = 0;
+    g_err[0] = 0;
+    if (!x || !style || !stats || !g_buf || !dX || !d_style || B <= 0 || C <= 0 || Q <= 0 ||
+        (dtype != SBA_F32 && dtype != SBA_BF16)) {
+        set_error("sba_adain_bwd: null pointer, non-positive size or unknown dtype");
+        return SBA_ERR_ARG;
+    }
+    if (g_rows < C || g_row0 < 0 || g_row0 + C > g_rows) {
+        set_error("sba_adain_bwd: rows [%d, %d) do not fit a %d-row buffer", g_row0, g_row0 + C, g_rows);
+        return SBA_ERR_ARG;
+    }
+    return adain_bwd(x, style, stats, g_buf, g_rows, g_row0, dX, accumulate, d_style, B, C, Q, dtype,
+                     static_cast<cudaStream_t>(stream));
+}
+
 }  // extern "C"

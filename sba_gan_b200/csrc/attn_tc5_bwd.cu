@@ -140,7 +140,7 @@ constexpr int kFinThreads = 1024;
 constexpr int kFinRound = 4;       // samples per round = thread groups of 256
 constexpr int kFinCS = 36;         // row stride (floats) of cs: 16-byte aligned rows, 4-bank skew
 constexpr int kFinSlots = 8;       // slots loaded in one batch (more: further batches)
-constexpr int kFinGroups = 16;     // at most this many sample groups (their partials are added by the last block)
+constexpr int kFinGroups = 64;     // at most this many sample groups (their partials are added by the last block)
 
 template <int IDF>
 __global__ void __launch_bounds__(kFinThreads) k_bwd_finish_tc5(const Tc5FinishParams p) {
@@ -271,19 +271,24 @@ __global__ void __launch_bounds__(kFinThreads) k_bwd_finish_tc5(const Tc5FinishP
         __syncthreads();
         if (tid == 0) { SBA_TL(p.tl, 0); SBA_TL(p.tl, 1); }
         if (s_last) {
-            // every group's partial of this channel slice is complete: thread = (4 consecutive groups gq, output float4 o)
+            // every group's partial of this channel slice is complete: thread = (quarter gq of the groups, output float4 o);
+            // each thread adds its groups in order (batches of 8 independent loads), the quarters meet in shared memory
             const float4* base = reinterpret_cast<const float4*>(p.dwp + (size_t)cg * p.groups * IDF * 32);
             float4* red4 = reinterpret_cast<float4*>(red);
+            const int gper = (p.groups + 3) >> 2;
             for (int o0 = 0; o0 < IDF * 8; o0 += 256) {
                 const int o = o0 + (tid & 255), gq = tid >> 8;
-                float4 v[4];
+                const int g_lo = gq * gper, g_hi = (g_lo + gper < p.groups ? g_lo + gper : p.groups);
+                float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int g0 = g_lo; g0 < g_hi; g0 += 8) {
+                    float4 v[8];
 #pragma unroll
-                for (int u = 0; u < 4; ++u)
-                    v[u] = (o < IDF * 8 && 4 * gq + u < p.groups) ? __ldcg(base + (size_t)(4 * gq + u) * IDF * 8 + o)
-                                                                   : make_float4(0.f, 0.f, 0.f, 0.f);
-                float4 a = v[0];
+                    for (int u = 0; u < 8; ++u)
+                        v[u] = (o < IDF * 8 && g0 + u < g_hi) ? __ldcg(base + (size_t)(g0 + u) * IDF * 8 + o)
+                                                              : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-                for (int u = 1; u < 4; ++u) { a.x += v[u].x; a.y += v[u].y; a.z += v[u].z; a.w += v[u].w; }
+                    for (int u = 0; u < 8; ++u) { a.x += v[u].x; a.y += v[u].y; a.z += v[u].z; a.w += v[u].w; }
+                }
                 __syncthreads();
                 red4[tid] = a;
                 __syncthreads();
@@ -753,7 +758,14 @@ Tc5BwdWs tc5_bwd_ws(int B, int idf, int cdf, int L, int sms) {
     Tc5BwdWs w{};
     w.lp = (L + 3) / 4 * 4;
     w.slots = 2 * sms + B;                                   // at most two CTAs per SM (TMEM), slot = CTA + sample
-    w.groups = (B + kFinRound - 1) / kFinRound < kFinGroups ? (B + kFinRound - 1) / kFinRound : kFinGroups;     // B = 64: 16 x 4
+    // All blocks (cslices x groups) must be resident at once, and a 1024-thread block with 64 registers per thread fills
+    // an SM: B = 64 -> 16 groups of 4 samples = 128 blocks, one round each; larger batches take several rounds per group.
+    // (Measured: two 32-register blocks per SM instead cost 3 us at B = 64 and gain nothing at B = 128 / 256.)
+    const int cslices = (cdf + 31) / 32;
+    int gmax = sms / cslices;
+    if (gmax > kFinGroups) gmax = kFinGroups;
+    if (gmax < 1) gmax = 1;
+    w.groups = (B + kFinRound - 1) / kFinRound < gmax ? (B + kFinRound - 1) / kFinRound : gmax;
     w.n_counters = 1 + (cdf + 31) / 32;
     const size_t head = ((size_t)B * idf * L + B + 1 + 3) / 4 * 4;
     w.part = head;

@@ -72,4 +72,11 @@ int sent_scores_fwd(const float* cnn, const float* rnn, float* scores, float* no
 int sent_scores_bwd(const float* cnn, const float* rnn, const float* norms, const float* scores, const float* d_scores,
                     float* d_cnn, float* d_rnn, int B, int nef, float g3, float eps, cudaStream_t st);
 
+// adain.cu - the caller's AdaIN written into the concatenated buffer next to c_code
+// style [B, 2C] fp32 = (gamma | beta); stats [2 * B * C] fp32 = (mean, rstd) per row, kept for the backward
+int adain_fwd(const void* x, const float* style, void* out, int out_rows, int out_row0, float* stats, int B, int C, int Q,
+              int dtype, float eps, cudaStream_t st);
+int adain_bwd(const void* x, const float* style, const float* stats, const void* g_buf, int g_rows, int g_row0, void* dX,
+              int accumulate, float* d_style, int B, int C, int Q, int dtype, cudaStream_t st);
+
 }  // namespace sba

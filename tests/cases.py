@@ -7,4 +7,5 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-from oracle.make_golden import ATTN_CASES, WL_CASES, SL_CASES, SUBSAMPLE, F64_SKIP, synth_sent_inputs  # noqa: E402,F401
+from oracle.make_golden import (ATTN_CASES, WL_CASES, SL_CASES, STAGE_CASES, SUBSAMPLE, F64_SKIP,  # noqa: E402,F401
+                                synth_sent_inputs, synth_stage_inputs)

@@ -154,3 +154,34 @@ def test_sent_loss_oracle_matches_reference(golden_dir, name, tag):
     assert abs(l1.item() - g["loss1"].item()) <= tol * max(1.0, abs(g["loss1"].item()))
     assert normalised_max_err(a.grad, torch.from_numpy(g["d_cnn"])) <= 10 * tol
     assert normalised_max_err(b.grad, torch.from_numpy(g["d_rnn"])) <= 10 * tol
+
+
+@pytest.mark.parametrize("tag", ["f32", "f64"])
+@pytest.mark.parametrize("name", ["stage_b3_16x8", "stage_b2_16x16"])
+def test_stage_oracle_matches_reference(golden_dir, name, tag):
+    """Attention + ADAIN_NORM + cat of NEXT_STAGE_G.forward (model_bert.py:458-461): the restatement
+    (attn_forward + adain_cat, autograd for the gradients) against the reference modules' own run."""
+    from oracle import adain_cat
+    from oracle.attention import project_words  # noqa: F401
+    from tests.cases import STAGE_CASES, synth_stage_inputs
+    B, idf, cdf, L, ih, iw, seed = STAGE_CASES[name]
+    g = _load(golden_dir, name, tag)
+    d = synth_stage_inputs(B, idf, cdf, L, ih, iw, seed, DT[tag], 256)
+    h = d["x"].clone().requires_grad_(True)
+    w = d["w_code"].clone().requires_grad_(True)
+    sw, sb = d["style_weight"].clone().requires_grad_(True), d["style_bias"].clone().requires_grad_(True)
+    c_code, attn, _ = attn_forward(h.detach(), d["context"], d["weight"], d["mask"])
+    style = torch.nn.functional.linear(w, sw, sb)
+    h_c = adain_cat(h, style, c_code)
+    tol = TOL[tag]
+    assert normalised_max_err(h_c.detach(), torch.from_numpy(g["h_c_code"])) <= tol
+    assert normalised_max_err(attn, torch.from_numpy(g["attn"])) <= tol
+    # gradients: AdaIN part by autograd of the restatement, attention part by the closed form
+    (h_c[:, :idf] * d["g_buf"][:, :idf]).sum().backward()
+    dX_att, dW, dCtx, _ = attn_backward(d["x"], d["context"], d["weight"], d["mask"], d["g_buf"][:, idf:].contiguous(), d["g_attn"])
+    assert normalised_max_err(h.grad + dX_att, torch.from_numpy(g["dX"])) <= 10 * tol
+    assert normalised_max_err(dW, torch.from_numpy(g["dW"])) <= 10 * tol
+    assert normalised_max_err(dCtx, torch.from_numpy(g["dCtx"])) <= 10 * tol
+    assert normalised_max_err(w.grad, torch.from_numpy(g["d_w_code"])) <= 10 * tol
+    assert normalised_max_err(sw.grad, torch.from_numpy(g["d_style_weight"])) <= 10 * tol
+    assert normalised_max_err(sb.grad, torch.from_numpy(g["d_style_bias"])) <= 10 * tol
