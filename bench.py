@@ -581,16 +581,29 @@ def run_ours(args, cx):
 
     sub = {}
     if not args.no_sub:
+        only = set(args.sub.split(",")) if args.sub else None
+
+        state = {"dead": False}
+
         def leg(name, fn):
+            if only is not None and name not in only:
+                return
+            if state["dead"]:
+                sub[name] = {"skipped": "CUDA context lost in an earlier sub-record"}
+                return
             t_leg = time.time()
             try:
                 sub[name] = fn()
             except Exception as e:      # a failed side measurement must not take the headline line down
                 sub[name] = {"error": f"{type(e).__name__}: {e}"[:300]}
-                torch.cuda.synchronize()
+                try:
+                    torch.cuda.synchronize()
+                except Exception:       # sticky CUDA error: nothing more can run on this context, keep what we have
+                    state["dead"] = True
             if isinstance(sub[name], dict):
                 sub[name]["leg_seconds"] = round(time.time() - t_leg, 1)
-            cx.barrier()
+            if not state["dead"]:
+                cx.barrier()
 
         leg("sustained", lambda: sub_sustained(cx, stepper, ms))
         del stepper
@@ -635,6 +648,8 @@ def run_ours(args, cx):
                    (sum(c["bytes"] for c in calls.values()) // 2 ** 20)},
         "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "clocks": clocks, "sub": sub,
     }
+    if sub and any(isinstance(v, dict) and "skipped" in v for v in sub.values()):
+        out["context_lost"] = True
     return out
 
 
@@ -735,6 +750,7 @@ def main():
     ap.add_argument("--algo", default="auto", choices=["auto", "simt", "mma", "tc5"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sub", action="store_true", help="headline only: skip the sub-records (fp32, sustained, words_loss, gan_step ...)")
+    ap.add_argument("--sub", default="", help="comma-separated sub-records to run (default: all)")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of CUDA-graph replays")
     args = ap.parse_args()
 
@@ -759,6 +775,8 @@ def main():
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline_leg()
         print(json.dumps(out), flush=True)
+    if out.get("context_lost"):
+        os._exit(0)          # the headline has been printed; CUDA teardown on a lost context would only hang or abort
     if world > 1:
         import torch.distributed as dist
         dist.barrier()

@@ -148,6 +148,17 @@ SBA_API int sba_words_sim_fwd(const float* img, const float* words, const int32_
                       int B_img, int B_cap, int row_offset, int nef, int R, int Lw,
                       float gamma1, float gamma2, float gamma3, float eps, void* stream);
 
+/* The same on the tensor cores (tcgen05, 3xTF32: every product as hi.hi + hi.lo + lo.hi, fp32 parity kept): both
+ * contractions of func_attention as chained UMMA GEMMs per (image, 128 packed word columns), softmaxes on chip.
+ * sba_words_sim_fwd_workspace_bytes() is 0 when the shape is not covered (nef % 32, nef <= 256, R <= 384); the
+ * workspace (256-byte aligned, contents undefined on entry) holds the tf32-split, TMA-addressable operand copies.
+ * Same results as sba_words_sim_fwd (att_diag comes from the CUDA-core kernel, diagonal pairs only). */
+SBA_API size_t sba_words_sim_fwd_workspace_bytes(int B_img, int B_cap, int nef, int R, int Lw);
+SBA_API int sba_words_sim_fwd_ws(const float* img, const float* words, const int32_t* cap_lens,
+                      float* sim, float* att_diag, void* workspace, size_t workspace_bytes,
+                      int B_img, int B_cap, int row_offset, int nef, int R, int Lw,
+                      float gamma1, float gamma2, float gamma3, float eps, void* stream);
+
 /* Gradient of sim w.r.t. img (always) and words (d_words nullable: only DAMSM pre-training
  * needs it, pretrain_DAMSM_bert.py:86-92).  d_img [B_img, nef, R] and d_words
  * [B_cap, nef, Lw] are overwritten.  `workspace` holds per-pair intermediates

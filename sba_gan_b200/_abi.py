@@ -29,6 +29,8 @@ SYMBOLS = {
     "sba_attn_bwd_from": (c_int, [c_void_p] * 7 + [c_int] * 2 + [c_void_p] * 3 + [c_size_t] + [c_void_p] * 2 + [c_int] * 7
                           + [c_void_p]),
     "sba_words_sim_fwd": (c_int, [c_void_p] * 5 + [c_int] * 6 + [c_float] * 4 + [c_void_p]),
+    "sba_words_sim_fwd_workspace_bytes": (c_size_t, [c_int] * 5),
+    "sba_words_sim_fwd_ws": (c_int, [c_void_p] * 6 + [c_size_t] + [c_int] * 6 + [c_float] * 4 + [c_void_p]),
     "sba_words_sim_bwd_workspace_bytes": (c_size_t, [c_int] * 5),
     "sba_words_sim_bwd": (c_int, [c_void_p] * 7 + [c_int] * 6 + [c_float] * 4 + [c_void_p]),
     "sba_func_attention": (c_int, [c_void_p] * 4 + [c_int] * 4 + [c_float] + [c_void_p]),

@@ -12,7 +12,7 @@ CSRC = os.path.join(PKG, "csrc")
 LIB_DIR = os.path.join(PKG, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libsba_attn.so")
 SOURCES = ["abi.cu", "attn_simt.cu", "attn_mma_fwd.cu", "attn_mma_bwd.cu", "attn_bwd_post.cu", "attn_tc5_fwd.cu", "attn_tc5_bwd.cu",
-           "words_loss.cu", "match_loss.cu", "adain.cu", "dev_aids.cu"]
+           "words_loss.cu", "words_tc5.cu", "match_loss.cu", "adain.cu", "dev_aids.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr",

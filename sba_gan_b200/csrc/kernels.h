@@ -60,6 +60,16 @@ int words_sim_bwd(const float* img, const float* words, const int* cap_lens, con
                   float* d_words, void* workspace, int B_img, int B_cap, int row_offset, int nef, int R, int Lw, float g1,
                   float g2, float g3, float eps, cudaStream_t st);
 
+int words_att_diag(const float* img, const float* words, const int* cap_lens, float* att_diag, int B_img, int B_cap,
+                   int row_offset, int nef, int R, int Lw, float g1, cudaStream_t st);
+
+// words_tc5.cu - the forward of kernel (c) on tcgen05 (3xTF32 UMMA): sim only; the diagonal attention maps stay with
+// words_att_diag.  `workspace`: words_tc5_workspace_bytes() bytes (0 = shape not covered), 256-byte aligned.
+bool words_tc5_supports(int B_img, int B_cap, int nef, int R, int Lw);
+size_t words_tc5_workspace_bytes(int B_img, int B_cap, int nef, int R, int Lw);
+int words_sim_fwd_tc5(const float* img, const float* words, const int* cap_lens, float* sim, void* workspace, size_t ws_bytes,
+                      int B_img, int B_cap, int nef, int R, int Lw, float g1, float g2, float g3, float eps, cudaStream_t st);
+
 // match_loss.cu - the B x B matching tail of words_loss / sent_loss: class masking + two-way cross-entropy, and
 // sent_loss's cosine score matrix
 // lse: [4*B] floats (row / column log-sum-exp, then the picked label entries), kept for the backward

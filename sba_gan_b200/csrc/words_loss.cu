@@ -110,8 +110,9 @@ struct WordsArgs {
     float* kappa;           // BWD [B_cap][Lw] (zeroed by the caller), nullable
     int B_img, B_cap, row_offset, nef, R, Lw;
     float g1, g2, g3, eps;
-    int paired;             // func_attention mode: image j against caption j only, length fixed_T
-    int fixed_T;
+    int paired;             // func_attention mode: image j against caption j + pair_shift only; length fixed_T, or
+    int fixed_T;            // cap_lens[caption] when cap_lens is given (the diagonal attention maps of words_loss)
+    int pair_shift;
 };
 
 // [KC x RP] channel-major tile of image j -> shared memory, asynchronously (cp.async, zero fill)
@@ -143,7 +144,7 @@ __device__ __forceinline__ void load_w_regs(const WordsArgs& a, int j, int cap0,
             const int rem = idx - kk * (C::NC * C::TP);
             const int cp = rem / C::TP, t = rem - cp * C::TP;
             const int c = c0 + kk;
-            const int ii = a.paired ? j : cap0 + cp;
+            const int ii = a.paired ? j + a.pair_shift : cap0 + cp;
             if (c < a.nef && t < T_s[cp]) {
                 val = __ldg(a.words + ((size_t)ii * a.nef + c) * a.Lw + t);
                 if (DWC) {
@@ -254,12 +255,12 @@ __global__ void __launch_bounds__(C::kThreads, 1) k_words(const WordsArgs a) {
     const int cap = tid / TPC, tc = tid - cap * TPC, wic = tc >> 5;
     const int j = blockIdx.y;
     const int cap0 = blockIdx.x * NC;
-    const int i = a.paired ? j : cap0 + cap;
-    const bool valid = a.paired ? (cap == 0) : (i < a.B_cap);
+    const int i = a.paired ? j + a.pair_shift : cap0 + cap;
+    const bool valid = a.paired ? (cap == 0 && i < a.B_cap) : (i < a.B_cap);
     if (tid < NC) {
-        const int ii = a.paired ? j : cap0 + tid;
-        const bool v = a.paired ? (tid == 0) : (ii < a.B_cap);
-        int T = v ? (a.paired ? a.fixed_T : a.cap_lens[ii]) : 0;
+        const int ii = a.paired ? j + a.pair_shift : cap0 + tid;
+        const bool v = a.paired ? (tid == 0 && ii < a.B_cap) : (ii < a.B_cap);
+        int T = v ? ((a.paired && a.cap_lens == nullptr) ? a.fixed_T : a.cap_lens[ii]) : 0;
         T = max(0, min(T, min(a.Lw, TP)));
         T_s[tid] = T;
     }
@@ -355,6 +356,8 @@ __global__ void __launch_bounds__(C::kThreads, 1) k_words(const WordsArgs a) {
             }
         }
     }
+
+    if (a.paired && a.sim == nullptr && a.wc_out == nullptr) return;       // only the attention maps were asked for (block-uniform)
 
     // ---- P2: wc[c,t] = sum_r X[c,r] a2[t,r] (GlobalAttention.py:67) ------------------------
     float wc[CPT][TP];
@@ -729,6 +732,17 @@ size_t words_bwd_workspace_bytes(int B_img, int B_cap, int nef, int R, int Lw) {
     const size_t v = align256((size_t)B_img * nef * B_cap * Lw * sizeof(float));
     const size_t kap = align256((size_t)B_cap * Lw * sizeof(float));
     return 2 * pair + v + kap;
+}
+
+// att_diag rows [row_offset, row_offset + B_img): the region attention of pair (local image j, caption row_offset + j) at the
+// caption's true length - all that the tensor-core forward (words_tc5.cu) leaves to this kernel
+int words_att_diag(const float* img, const float* words, const int* cap_lens, float* att_diag, int B_img, int B_cap,
+                   int row_offset, int nef, int R, int Lw, float g1, cudaStream_t st) {
+    WordsArgs a{};
+    a.img = img; a.words = words; a.cap_lens = cap_lens; a.att_diag = att_diag;
+    a.B_img = B_img; a.B_cap = B_cap; a.row_offset = row_offset; a.nef = nef; a.R = R; a.Lw = Lw;
+    a.g1 = g1; a.g2 = 1.f; a.g3 = 1.f; a.eps = 1e-8f; a.paired = 1; a.fixed_T = Lw; a.pair_shift = row_offset;
+    return dispatch_words<false>(a, st);
 }
 
 int words_sim_fwd(const float* img, const float* words, const int* cap_lens, float* sim, float* att_diag, float* wc_out,

@@ -24,6 +24,7 @@ from . import _abi
 from .functional import _ptr, _require_cuda, _stream, launch_counter
 
 DEFAULT_GAMMAS = (5.0, 5.0, 10.0)   # miscc/config.py:43-45
+FORWARD_ALGO = "auto"               # "auto": tensor-core forward where the shape is covered; "simt": always the CUDA-core kernel
 
 
 def _cfg_gammas():
@@ -49,9 +50,16 @@ class _WordsSimilarity(torch.autograd.Function):
         words32 = words.detach().to(torch.float32).contiguous()
         sim = torch.empty((B_img, B_cap), dtype=torch.float32, device=img.device)
         att = torch.zeros((B_cap, Lw, R), dtype=torch.float32, device=img.device) if want_att else None
-        rc = lib.sba_words_sim_fwd(_ptr(img32), _ptr(words32), _ptr(cap_lens_i32), _ptr(sim), _ptr(att), B_img, B_cap,
-                                   row_offset, nef, R, Lw, gammas[0], gammas[1], gammas[2], eps, _stream())
-        _abi.check(rc, "sba_words_sim_fwd")
+        ws_bytes = lib.sba_words_sim_fwd_workspace_bytes(B_img, B_cap, nef, R, Lw) if FORWARD_ALGO != "simt" else 0
+        if ws_bytes:        # tensor-core forward (tcgen05, 3xTF32)
+            ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=img.device)
+            rc = lib.sba_words_sim_fwd_ws(_ptr(img32), _ptr(words32), _ptr(cap_lens_i32), _ptr(sim), _ptr(att), _ptr(ws), ws_bytes,
+                                          B_img, B_cap, row_offset, nef, R, Lw, gammas[0], gammas[1], gammas[2], eps, _stream())
+            _abi.check(rc, "sba_words_sim_fwd_ws")
+        else:               # CUDA-core forward (shapes the tensor-core kernel does not cover)
+            rc = lib.sba_words_sim_fwd(_ptr(img32), _ptr(words32), _ptr(cap_lens_i32), _ptr(sim), _ptr(att), B_img, B_cap,
+                                       row_offset, nef, R, Lw, gammas[0], gammas[1], gammas[2], eps, _stream())
+            _abi.check(rc, "sba_words_sim_fwd")
         launch_counter["n"] += _abi.last_launch_count()
         ctx.save_for_backward(img32, words32, cap_lens_i32)
         ctx.meta = (gammas, eps, row_offset, img.dtype, words.dtype, tuple(img.shape))
