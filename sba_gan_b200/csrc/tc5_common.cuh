@@ -28,6 +28,9 @@ using mma::fence_barrier_init;
 // Bounded mbarrier wait: a protocol bug traps (-> a CUDA error the ABI reports) instead of
 // hanging the GPU box.  Every try_wait suspends for up to the hinted 20 us, so the bound is
 // between tens of milliseconds and ~1 s - far beyond any legitimate wait on this path.
+#ifndef SBA_MBAR_SPIN_LIMIT
+#define SBA_MBAR_SPIN_LIMIT (1u << 16)
+#endif
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t done;
     uint32_t spins = 0;
@@ -39,7 +42,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
             : "=r"(done)
             : "r"(bar), "r"(parity), "r"(20000u)      // suspend-time hint (ns): sleep in hardware, not in a spin loop
             : "memory");
-        if (!done && ++spins > (1u << 16)) __trap();
+        if (!done && ++spins > SBA_MBAR_SPIN_LIMIT) __trap();
     } while (!done);
 }
 

@@ -28,6 +28,28 @@ namespace sba {
 namespace {
 using namespace tc5;
 
+#ifdef SBA_DEV_AIDS
+// development build: a barrier wait that times out records WHICH wait it was and carries on (garbage results, but the
+// kernel ends and the flags can be read: sba_dev_words_timeouts) instead of trapping
+} }  // (symbol at namespace sba scope for cudaMemcpyFromSymbol)
+namespace sba { __device__ unsigned g_wt_dbg[16]; __device__ unsigned* g_wt_host = nullptr; }
+#define WT_MARK(i) do { if (sba::g_wt_host && (threadIdx.x & 31) == 0) atomicAdd(sba::g_wt_host + (i), 1u); } while (0)
+namespace sba { namespace {
+using namespace tc5;
+__device__ __forceinline__ void wt_wait(uint32_t bar, uint32_t parity, int id) {
+    uint32_t done, spins = 0;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(bar), "r"(parity), "r"(20000u) : "memory");
+        if (!done && ++spins > (1u << 14)) { atomicAdd(&g_wt_dbg[id], 1u); if (g_wt_host) atomicAdd(g_wt_host + id, 1u); return; }
+    } while (!done);
+}
+#define WT_WAIT(bar, parity, id) wt_wait(bar, parity, id)
+#else
+#define WT_WAIT(bar, parity, id) mbar_wait(bar, parity)
+#define WT_MARK(i) ((void)0)
+#endif
+
 constexpr int kWtThreads = 64 + 256;      // producer warp, MMA warp, 8 epilogue warps
 constexpr int kNB = 128;                  // word columns per CTA
 constexpr int kHalf = 64;                 // columns per half block (one epilogue warp per lane quarter each)
@@ -36,6 +58,7 @@ constexpr int kTileBytes = 128 * kKC * 4; // one [128 rows][32 floats] operand t
 constexpr int kStageBytes = 4 * kTileBytes;       // G1: A hi, A lo, B hi, B lo;  G2: X hi, X lo ([256][32] each)
 constexpr int kStages = 2;
 constexpr int kEBufs = 2;
+static_assert(kEBufs == 2, "the e_free barriers are indexed by k & 3 and waited on for chunk k - 2");
 constexpr int kEBufBytes = 2 * kTileBytes;        // e hi, e lo
 constexpr int kMaxChunks = 12;                    // regions / 32, R <= 384
 
@@ -50,9 +73,18 @@ struct WtParams {
     const int* col_cap;        // [ncols] caption of the column, -1 = padding
     const int* col_T;          // [ncols] length of the caption if this is its first column, else 0
     const WtPlan* plan;
-    float* sim;                // [B_img][B_cap]
+    float* sim;                // [B_img][B_cap]   (forward)
     int B_cap, nef, R, MT, RKC;
     float g1l2e, g2, g3, eps;  // gamma1 * log2(e), gamma2, gamma3
+    // backward, phase A (the forward again, with the upstream gradient): per (image, column) scalars and wc
+    const float* d_sim;        // [B_img][B_cap]
+    const int* cap_col;        // [B_cap] first column of each caption
+    float4* scal;              // [B_img][ncols] (alpha = d num, beta = d|wc| / |wc|, D = sum_r a2 da2, 1 / Z)
+    float* v;                  // [B_img][nef][ncols]  beta * wc   (A operand of the second d_img GEMM)
+    float* wct_hi;             // [B_img][ncols][nef]  wc split in tf32 hi / lo: B operand of V = X^T wc in phase B
+    float* wct_lo;
+    int ncols;
+    float g1;
 };
 
 // ---- pre-pass 1: pack the captions into half blocks (sequential greedy, one thread; B_cap is a few hundred) ---------
@@ -83,7 +115,8 @@ __device__ __forceinline__ void split_tf32(float v, float& hi, float& lo) {
 // ---- pre-pass 2: WT hi / lo [ncols][nef] and |w_n|; one block per 8 columns, thread = channel --------------------------
 __global__ void __launch_bounds__(256) k_wt_words(const float* __restrict__ words, const int* __restrict__ col_cap,
                                                   const int* __restrict__ cap_col, float* __restrict__ wt_hi,
-                                                  float* __restrict__ wt_lo, float* __restrict__ ww, int nef, int Lw) {
+                                                  float* __restrict__ wt_lo, float* __restrict__ ww,
+                                                  float* __restrict__ wc_packed, int ncols, int nef, int Lw) {
     __shared__ float red[8];
     for (int k = 0; k < 8; ++k) {
         const int n = blockIdx.x * 8 + k;
@@ -96,6 +129,7 @@ __global__ void __launch_bounds__(256) k_wt_words(const float* __restrict__ word
             split_tf32(v, hi, lo);
             wt_hi[(size_t)n * nef + c] = hi;
             wt_lo[(size_t)n * nef + c] = lo;
+            if (wc_packed != nullptr) wc_packed[(size_t)c * ncols + n] = v;       // [nef][ncols]: A operand of the d_img GEMM
             sq = fmaf(v, v, sq);
         }
 #pragma unroll
@@ -166,6 +200,7 @@ __device__ __forceinline__ void warp_arrive1(uint32_t bar, int lane) {
     if (lane == 0) mbar_arrive(bar);
 }
 
+template <bool BWD>
 __global__ void __launch_bounds__(kWtThreads, 1)
     k_words_tc5(const __grid_constant__ CUtensorMap tm_xt_hi, const __grid_constant__ CUtensorMap tm_xt_lo,
                 const __grid_constant__ CUtensorMap tm_wt_hi, const __grid_constant__ CUtensorMap tm_wt_lo,
@@ -186,8 +221,12 @@ __global__ void __launch_bounds__(kWtThreads, 1)
     unsigned long long* bar_s_full = bars + 2 * kStages;  // [2]
     unsigned long long* bar_s_free = bar_s_full + 2;      // [2]
     unsigned long long* bar_e_ready = bar_s_free + 2;     // [kEBufs]
-    unsigned long long* bar_e_free = bar_e_ready + kEBufs;  // [kEBufs]
-    unsigned long long* bar_d_full = bar_e_free + kEBufs;   // [1]
+    // e_free is per chunk residue k & 3, not per buffer: the two warp pairs that share a buffer (q and q ^ 2) run
+    // independently, so a waiter on a per-buffer barrier can be TWO completions behind and a parity wait would alias
+    // (it passes on the stale phase and overwrites a chunk that has not been consumed).  Chunk k waits for chunk k - 2,
+    // i.e. completion (k - 2) / 4 + 1 of bar_e_free[(k - 2) & 3], and saw completion (k - 2) / 4 one tile earlier.
+    unsigned long long* bar_e_free = bar_e_ready + kEBufs;  // [4]
+    unsigned long long* bar_d_full = bar_e_free + 4;        // [1]
     uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(bar_d_full + 1);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -197,7 +236,8 @@ __global__ void __launch_bounds__(kWtThreads, 1)
         if (sbase & 1023u) __trap();
         for (int s = 0; s < kStages; ++s) { mbar_init(smem_u32(&bar_full[s]), 1); mbar_init(smem_u32(&bar_empty[s]), 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(&bar_s_full[s]), 1); mbar_init(smem_u32(&bar_s_free[s]), 8); }
-        for (int s = 0; s < kEBufs; ++s) { mbar_init(smem_u32(&bar_e_ready[s]), 2); mbar_init(smem_u32(&bar_e_free[s]), 1); }
+        for (int s = 0; s < kEBufs; ++s) mbar_init(smem_u32(&bar_e_ready[s]), 2);
+        for (int s = 0; s < 4; ++s) mbar_init(smem_u32(&bar_e_free[s]), 1);
         mbar_init(smem_u32(bar_d_full), 1);
         fence_barrier_init();
     }
@@ -213,7 +253,7 @@ __global__ void __launch_bounds__(kWtThreads, 1)
         int s = 0;
         auto stage_g1 = [&](int m, int kc) {
             const int st = s % kStages;
-            if (s >= kStages) mbar_wait(smem_u32(&bar_empty[st]), (uint32_t)((s / kStages) - 1) & 1u);
+            if (s >= kStages) WT_WAIT(smem_u32(&bar_empty[st]), (uint32_t)((s / kStages) - 1) & 1u, 9);
             if (elect_one()) {
                 const uint32_t full = smem_u32(&bar_full[st]), dst = s_ring + st * kStageBytes;
                 mbar_expect_tx(full, (uint32_t)kStageBytes);
@@ -227,7 +267,7 @@ __global__ void __launch_bounds__(kWtThreads, 1)
         };
         auto stage_g2 = [&](int k) {
             const int st = s % kStages;
-            if (s >= kStages) mbar_wait(smem_u32(&bar_empty[st]), (uint32_t)((s / kStages) - 1) & 1u);
+            if (s >= kStages) WT_WAIT(smem_u32(&bar_empty[st]), (uint32_t)((s / kStages) - 1) & 1u, 9);
             if (elect_one()) {
                 const uint32_t full = smem_u32(&bar_full[st]), dst = s_ring + st * kStageBytes;
                 mbar_expect_tx(full, (uint32_t)(2 * nef * kKC * 4));
@@ -254,11 +294,11 @@ __global__ void __launch_bounds__(kWtThreads, 1)
         bool d_started = false;
         auto g1 = [&](int m) {
             const int buf = m & 1;
-            if (m >= 2) mbar_wait(smem_u32(&bar_s_free[buf]), (uint32_t)((m >> 1) - 1) & 1u);
+            if (m >= 2) WT_WAIT(smem_u32(&bar_s_free[buf]), (uint32_t)((m >> 1) - 1) & 1u, 10);
             const uint32_t d = tmem_base + COL_S + 128 * buf;
             for (int kc = 0; kc < KCH; ++kc, ++s) {
                 const int st = s % kStages;
-                mbar_wait(smem_u32(&bar_full[st]), (uint32_t)(s / kStages) & 1u);
+                WT_WAIT(smem_u32(&bar_full[st]), (uint32_t)(s / kStages) & 1u, 11);
                 tc_fence_after();
                 const uint32_t base = s_ring + st * kStageBytes;
                 const uint32_t a_hi = desc_lo(base, 16), a_lo = desc_lo(base + kTileBytes, 16);
@@ -283,8 +323,8 @@ __global__ void __launch_bounds__(kWtThreads, 1)
                 const int k = 4 * m + q;
                 if (k >= RKC) break;
                 const int eb = k % kEBufs, st = s % kStages;
-                mbar_wait(smem_u32(&bar_e_ready[eb]), (uint32_t)(k / kEBufs) & 1u);
-                mbar_wait(smem_u32(&bar_full[st]), (uint32_t)(s / kStages) & 1u);
+                WT_WAIT(smem_u32(&bar_e_ready[eb]), (uint32_t)(k / kEBufs) & 1u, 12);
+                WT_WAIT(smem_u32(&bar_full[st]), (uint32_t)(s / kStages) & 1u, 11);
                 tc_fence_after();
                 const uint32_t eh = desc_lo(s_e + eb * kEBufBytes, 16), el = desc_lo(s_e + eb * kEBufBytes + kTileBytes, 16);
                 const uint32_t xb = s_ring + st * kStageBytes;
@@ -298,7 +338,7 @@ __global__ void __launch_bounds__(kWtThreads, 1)
                         umma_ss<true>(tmem_base + COL_D, el + o, kHi, xh + o, kHi, idesc2, 1u);
                     }
                     umma_commit(smem_u32(&bar_empty[st]));
-                    umma_commit(smem_u32(&bar_e_free[eb]));
+                    umma_commit(smem_u32(&bar_e_free[k & 3]));
                 }
                 __syncwarp();
                 d_started = true;
@@ -337,7 +377,7 @@ __global__ void __launch_bounds__(kWtThreads, 1)
             const int k = 4 * m + q;                       // region chunk this warp produces
             const bool exists = k < RKC;
             const int buf = m & 1;
-            mbar_wait(smem_u32(&bar_s_full[buf]), (uint32_t)(m >> 1) & 1u);
+            WT_WAIT(smem_u32(&bar_s_full[buf]), (uint32_t)(m >> 1) & 1u, 13);
             tc_fence_after();
             uint32_t sr[kHalf];
             if (exists) {
@@ -392,7 +432,7 @@ __global__ void __launch_bounds__(kWtThreads, 1)
             }
             // e hi / lo -> chunk buffer rows n = hf * 64 + c, 32 regions per 128-byte row, 16-byte chunks XOR-swizzled with n & 7
             const int eb = k % kEBufs;
-            if (k >= kEBufs) mbar_wait(smem_u32(&bar_e_free[eb]), (uint32_t)((k / kEBufs) - 1) & 1u);
+            if (k >= kEBufs) WT_WAIT(smem_u32(&bar_e_free[(k - kEBufs) & 3]), (uint32_t)((k - kEBufs) >> 2) & 1u, 14);
             unsigned char* eh = g_e + eb * kEBufBytes;
 #pragma unroll
             for (int c = 0; c < kHalf; ++c) {
@@ -409,7 +449,7 @@ __global__ void __launch_bounds__(kWtThreads, 1)
         // ---- final epilogue: thread = word column n (the four warps whose lanes cover 0..127) ---------------------------
         if (ew < 4) {
             const int n = 32 * q + lane, ng = nb * kNB + n;
-            mbar_wait(smem_u32(bar_d_full), 0u);
+            WT_WAIT(smem_u32(bar_d_full), 0u, 15);
             tc_fence_after();
             float num = 0.f, wn2 = 0.f;
             const float4* wh = reinterpret_cast<const float4*>(p.wt_hi + (size_t)ng * nef);
@@ -434,41 +474,330 @@ __global__ void __launch_bounds__(kWtThreads, 1)
             float Z = 0.f;
             mma::named_bar_sync(2, 128);                   // every zp entry of this CTA has been written (all chunks are done:
             for (int k = 0; k < RKC; ++k) Z += zp[k * kNB + n];     // d_full follows the last G2, which follows e_ready)
-            const bool cv = p.col_cap[ng] >= 0;
-            float ex = 0.f;
+            const int cap = p.col_cap[ng];
+            const bool cv = cap >= 0;
+            float ex = 0.f, invZ = 0.f, den = 1.f, wn = 0.f;
             if (cv) {
-                const float invZ = 1.0f / Z;
-                const float den = fmaxf(p.ww[ng] * sqrtf(wn2) * invZ, p.eps);        // losses.py:17
-                ex = expf(p.g2 * (num * invZ) / den);                                 // losses.py:106
+                invZ = 1.0f / Z;
+                wn = sqrtf(wn2) * invZ;                                              // |wc_n|
+                den = fmaxf(p.ww[ng] * wn, p.eps);                                   // losses.py:17
+                ex = expf(p.g2 * (num * invZ) / den);                                // losses.py:106
             }
             exs[n] = ex;
             mma::named_bar_sync(2, 128);
             const int T = p.col_T[ng];
-            if (T > 0) {
-                float E = 0.f;
-                for (int t = 0; t < T; ++t) E += exs[n + t];
-                p.sim[(size_t)j * p.B_cap + p.col_cap[ng]] = p.g3 * logf(E);        // losses.py:107-108, 123
+            if constexpr (!BWD) {
+                if (T > 0) {
+                    float E = 0.f;
+                    for (int t = 0; t < T; ++t) E += exs[n + t];
+                    p.sim[(size_t)j * p.B_cap + cap] = p.g3 * logf(E);              // losses.py:107-108, 123
+                }
+            } else {
+                // E of this column's caption: summed by the caption's first column, looked up by the others
+                float* Es = zp;                                  // (zp has been consumed: reuse its first 128 words)
+                mma::named_bar_sync(2, 128);
+                if (T > 0) {
+                    float E = 0.f;
+                    for (int t = 0; t < T; ++t) E += exs[n + t];
+                    Es[n] = E;
+                }
+                mma::named_bar_sync(2, 128);
+                float alpha = 0.f, beta = 0.f, D = 0.f;
+                if (cv) {
+                    const float E = Es[p.cap_col[cap] - nb * kNB];
+                    const float g = p.d_sim[(size_t)j * p.B_cap + cap];
+                    const float numt = num * invZ;                                   // <w_n, wc_n>
+                    const float gcos = g * p.g3 / E * p.g2 * ex;
+                    const float prod = p.ww[ng] * wn;
+                    alpha = gcos / den;                                              // d num
+                    const float d_den = prod > p.eps ? -gcos * numt / (den * den) : 0.f;
+                    beta = wn > 0.f ? d_den * p.ww[ng] / wn : 0.f;                   // d|wc| / |wc|
+                    D = alpha * numt + beta * wn * wn;                               // sum_r a2[r, n] da2[r, n]
+                }
+                p.scal[(size_t)j * p.ncols + ng] = make_float4(alpha, beta, D, invZ);
+                // second pass over wc: v = beta wc (rows = channels: consecutive threads write consecutive columns) and
+                // wc^T split into tf32 hi / lo (this thread's row, 128 contiguous bytes per chunk)
+                float* vcol = p.v + (size_t)j * nef * p.ncols + ng;
+                float4* th = reinterpret_cast<float4*>(p.wct_hi + ((size_t)j * p.ncols + ng) * nef);
+                float4* tlo = reinterpret_cast<float4*>(p.wct_lo + ((size_t)j * p.ncols + ng) * nef);
+                __syncwarp();                    // (lane-dependent code above; tcgen05.ld is warp-collective)
+                tc_fence_after();
+                for (int c0 = 0; c0 < nef; c0 += 32) {
+                    uint32_t d[32];
+                    tmem_ld<32>(tl + COL_D + c0, d);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int c4 = 0; c4 < 8; ++c4) {
+                        float hi[4], lo[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float wc = __uint_as_float(d[4 * c4 + e]) * invZ;
+                            vcol[(size_t)(c0 + 4 * c4 + e) * p.ncols] = beta * wc;
+                            hi[e] = tf32_rna(wc);
+                            lo[e] = tf32_rna(wc - hi[e]);
+                        }
+                        th[(c0 >> 2) + c4] = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                        tlo[(c0 >> 2) + c4] = make_float4(lo[0], lo[1], lo[2], lo[3]);
+                    }
+                }
             }
         }
+        WT_MARK(22);
         tc_fence_before();
     }
+    WT_MARK(23);
     __syncthreads();
+    WT_MARK(24);
     if (warp == kMmaWarp) {
         tc_fence_after();
         tmem_dealloc(tmem_base, 512);
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Backward, phase B: per (image j, 128-column block) recompute S = X^T W (G1) and form V = X^T wc (G3, same A tiles, B =
+// wc^T from phase A), then, thread = region row,
+//   a1 = softmax over each caption's words of S,  a2 = exp(gamma1 (a1 - 1)) / Z
+//   da2 = alpha S + beta V,   dz = a2 (da2 - D),   t = a1 gamma1 dz,   ds = t - a1 sum_{caption} t,   u = ds + alpha a2
+// (D_n = sum_r a2 da2 = alpha <w_n, wc_n> + beta |wc_n|^2 is known from phase A: no reduction over regions here) and
+// store a2[j][n][r], u[j][n][r] for the two d_img GEMMs (oracle/attention.py::words_loss_backward; the CUDA-core
+// kernel of words_loss.cu materialises the same u / a2).
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int kBStageBytes = 6 * kTileBytes;      // A hi, A lo, W hi, W lo, wc hi, wc lo: 96 KB
+struct WtBwdParams {
+    const int* col_cap;
+    const WtPlan* plan;
+    const float4* scal;        // [B_img][ncols]
+    float* u;                  // [B_img][ncols][R]
+    float* a2;                 // [B_img][ncols][R]
+    int nef, R, MT, RKC, ncols;
+    float g1, g1l2e;
+};
+
+__global__ void __launch_bounds__(kWtThreads, 1)
+    k_words_bwd_tc5(const __grid_constant__ CUtensorMap tm_xt_hi, const __grid_constant__ CUtensorMap tm_xt_lo,
+                    const __grid_constant__ CUtensorMap tm_wt_hi, const __grid_constant__ CUtensorMap tm_wt_lo,
+                    const __grid_constant__ CUtensorMap tm_wc_hi, const __grid_constant__ CUtensorMap tm_wc_lo, const WtBwdParams p) {
+    const int nb = blockIdx.x, j = blockIdx.y;
+    if (2 * nb >= p.plan->n_half) return;
+
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    const uint32_t sbase = smem_u32(smem_raw);
+    const uint32_t s_ring = sbase;
+    float4* scs = reinterpret_cast<float4*>(smem_raw + kStages * kBStageBytes);        // [128] per-column scalars
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(scs + kNB);
+    unsigned long long* bar_full = bars;                  // [kStages]
+    unsigned long long* bar_empty = bars + kStages;       // [kStages]
+    unsigned long long* bar_t_full = bars + 2 * kStages;  // [2]  S and V of a region tile are complete
+    unsigned long long* bar_t_free = bar_t_full + 2;      // [2]
+    uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(bar_t_free + 2);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int nef = p.nef, MT = p.MT, RKC = p.RKC, KCH = nef / kKC;
+
+    if (tid == 0) {
+#ifdef SBA_DEV_AIDS
+        if (sbase & 1023u) atomicAdd(&g_wt_dbg[8], 1u);
+#else
+        if (sbase & 1023u) __trap();
+#endif
+        for (int s = 0; s < kStages; ++s) { mbar_init(smem_u32(&bar_full[s]), 1); mbar_init(smem_u32(&bar_empty[s]), 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(&bar_t_full[s]), 1); mbar_init(smem_u32(&bar_t_free[s]), 8); }
+        fence_barrier_init();
+    }
+    if (tid >= 64 && tid < 64 + kNB) scs[tid - 64] = p.scal[(size_t)j * p.ncols + nb * kNB + tid - 64];
+    if (warp == kMmaWarp) tmem_alloc(smem_u32(tmem_base_s), 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_base_s, 0);
+    WT_MARK(16);
+
+    if (warp == kProducerWarp) {
+        int s = 0;
+        for (int m = 0; m < MT; ++m)
+            for (int kc = 0; kc < KCH; ++kc, ++s) {
+                const int st = s % kStages;
+                if (s >= kStages) WT_WAIT(smem_u32(&bar_empty[st]), (uint32_t)((s / kStages) - 1) & 1u, 0);
+                if (elect_one()) {
+                    const uint32_t full = smem_u32(&bar_full[st]), dst = s_ring + st * kBStageBytes;
+                    mbar_expect_tx(full, (uint32_t)kBStageBytes);
+                    tma_load_2d(dst, &tm_xt_hi, kc * kKC, (j * MT + m) * 128, full);
+                    tma_load_2d(dst + kTileBytes, &tm_xt_lo, kc * kKC, (j * MT + m) * 128, full);
+                    tma_load_2d(dst + 2 * kTileBytes, &tm_wt_hi, kc * kKC, nb * kNB, full);
+                    tma_load_2d(dst + 3 * kTileBytes, &tm_wt_lo, kc * kKC, nb * kNB, full);
+                    tma_load_2d(dst + 4 * kTileBytes, &tm_wc_hi, kc * kKC, j * p.ncols + nb * kNB, full);
+                    tma_load_2d(dst + 5 * kTileBytes, &tm_wc_lo, kc * kKC, j * p.ncols + nb * kNB, full);
+                }
+                __syncwarp();
+            }
+        WT_MARK(17);
+    } else if (warp == kMmaWarp) {
+        constexpr uint32_t kHi = desc_hi(1024, kSwizzle128B);
+        const uint32_t idesc = make_idesc(2, 0, 0, 128, kNB);
+        int s = 0;
+        for (int m = 0; m < MT; ++m) {
+            const int buf = m & 1;
+            if (m >= 2) WT_WAIT(smem_u32(&bar_t_free[buf]), (uint32_t)((m >> 1) - 1) & 1u, 1);
+            const uint32_t dS = tmem_base + 256 * buf, dV = dS + 128;
+            for (int kc = 0; kc < KCH; ++kc, ++s) {
+                const int st = s % kStages;
+                WT_WAIT(smem_u32(&bar_full[st]), (uint32_t)(s / kStages) & 1u, 2);
+                tc_fence_after();
+                const uint32_t base = s_ring + st * kBStageBytes;
+                const uint32_t a_hi = desc_lo(base, 16), a_lo = desc_lo(base + kTileBytes, 16);
+                const uint32_t w_hi = desc_lo(base + 2 * kTileBytes, 16), w_lo = desc_lo(base + 3 * kTileBytes, 16);
+                const uint32_t c_hi = desc_lo(base + 4 * kTileBytes, 16), c_lo = desc_lo(base + 5 * kTileBytes, 16);
+                if (elect_one()) {
+#pragma unroll
+                    for (int ks = 0; ks < kKC / 8; ++ks) {
+                        const uint32_t o = (uint32_t)(ks * 2);
+                        const uint32_t acc = (kc > 0 || ks > 0) ? 1u : 0u;
+                        umma_ss<true>(dS, a_hi + o, kHi, w_hi + o, kHi, idesc, acc);
+                        umma_ss<true>(dS, a_hi + o, kHi, w_lo + o, kHi, idesc, 1u);
+                        umma_ss<true>(dS, a_lo + o, kHi, w_hi + o, kHi, idesc, 1u);
+                        umma_ss<true>(dV, a_hi + o, kHi, c_hi + o, kHi, idesc, acc);
+                        umma_ss<true>(dV, a_hi + o, kHi, c_lo + o, kHi, idesc, 1u);
+                        umma_ss<true>(dV, a_lo + o, kHi, c_hi + o, kHi, idesc, 1u);
+                    }
+                    umma_commit(smem_u32(&bar_empty[st]));
+                }
+                __syncwarp();
+            }
+            if (elect_one()) umma_commit(smem_u32(&bar_t_full[buf]));
+            __syncwarp();
+            WT_MARK(18);
+        }
+    } else {
+        const int ew = warp - kFirstConsumerWarp, q = warp & 3, hf = ew >> 2;
+        const uint32_t tl = tmem_base + ((uint32_t)(q * 32) << 16);
+        const int ncol0 = nb * kNB + hf * kHalf;
+        unsigned long long valid = 0ull, first = 0ull;
+        {
+            const int c0v = p.col_cap[ncol0 + lane], c1v = p.col_cap[ncol0 + 32 + lane];
+            // (every lane takes part in every shuffle: none of them inside a short-circuit expression)
+            const int prev0 = __shfl_up_sync(0xffffffffu, c0v, 1), prev1 = __shfl_up_sync(0xffffffffu, c1v, 1);
+            const int last0 = __shfl_sync(0xffffffffu, c0v, 31);
+            const bool f0 = c0v >= 0 && (lane == 0 || prev0 != c0v);
+            const bool f1 = c1v >= 0 && ((lane == 0 ? last0 : prev1) != c1v);
+            valid = (unsigned long long)__ballot_sync(0xffffffffu, c0v >= 0) |
+                    ((unsigned long long)__ballot_sync(0xffffffffu, c1v >= 0) << 32);
+            first = (unsigned long long)__ballot_sync(0xffffffffu, f0) | ((unsigned long long)__ballot_sync(0xffffffffu, f1) << 32);
+        }
+        const unsigned long long last = valid & ((first >> 1) | ~(valid >> 1));
+        constexpr float kLog2e = 1.4426950408889634f;
+        const float4* sc = scs + hf * kHalf;
+
+        for (int m = 0; m < MT; ++m) {
+            const bool exists = 4 * m + q < RKC;
+            const int buf = m & 1;
+            WT_WAIT(smem_u32(&bar_t_full[buf]), (uint32_t)(m >> 1) & 1u, 3);
+            tc_fence_after();
+            if (!exists) {
+                tc_fence_before();
+                warp_arrive1(smem_u32(&bar_t_free[buf]), lane);
+                continue;
+            }
+            const int r = 128 * m + 32 * q + lane;
+            const bool rv = r < p.R;
+            const uint32_t tS = tl + 256 * buf + hf * kHalf, tV = tS + 128;
+            // (1) a1 = softmax over the words of each caption (as the forward)
+            uint32_t rb[kHalf];
+            float a1[kHalf];
+            tmem_ld<kHalf>(tS, rb);
+            tmem_wait_ld();
+            float run = -INFINITY;
+#pragma unroll
+            for (int c = 0; c < kHalf; ++c) {
+                const float x = __uint_as_float(rb[c]);
+                run = ((first >> c) & 1ull) ? x : fmaxf(run, x);
+                a1[c] = x;
+                rb[c] = __float_as_uint(run);
+            }
+            float seg = 0.f;
+#pragma unroll
+            for (int c = kHalf - 1; c >= 0; --c) {
+                seg = ((last >> c) & 1ull) ? __uint_as_float(rb[c]) : seg;
+                a1[c] = mma::ex2_approx((a1[c] - seg) * kLog2e);
+            }
+            run = 0.f;
+#pragma unroll
+            for (int c = 0; c < kHalf; ++c) {
+                run = ((first >> c) & 1ull) ? a1[c] : run + a1[c];
+                rb[c] = __float_as_uint(run);
+            }
+            seg = 1.f;
+#pragma unroll
+            for (int c = kHalf - 1; c >= 0; --c) {
+                seg = ((last >> c) & 1ull) ? mma::rcp_approx(__uint_as_float(rb[c])) : seg;
+                a1[c] *= seg;
+            }
+            // (2) t = a1 gamma1 a2 (alpha S + beta V - D), running sum per caption into rb; a2 goes out
+            float* a2o = p.a2 + ((size_t)j * p.ncols + ncol0) * p.R + r;
+            run = 0.f;
+#pragma unroll
+            for (int g0 = 0; g0 < kHalf; g0 += 16) {
+                uint32_t s16[16], v16[16];
+                __syncwarp();                                    // (the stores below are lane-dependent)
+                tmem_ld<16>(tS + g0, s16);
+                tmem_ld<16>(tV + g0, v16);
+                tmem_wait_ld();
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                    const int c = g0 + k;
+                    const float4 cs4 = sc[c];                    // alpha, beta, D, 1 / Z
+                    const bool ok = rv && ((valid >> c) & 1ull);
+                    const float a2 = ok ? mma::ex2_approx((a1[c] - 1.f) * p.g1l2e) * cs4.w : 0.f;
+                    const float da2 = fmaf(cs4.x, __uint_as_float(s16[k]), cs4.y * __uint_as_float(v16[k]));
+                    const float t = a1[c] * p.g1 * a2 * (da2 - cs4.z);
+                    run = ((first >> c) & 1ull) ? t : run + t;
+                    rb[c] = __float_as_uint(run);
+                    if (rv) a2o[(size_t)c * p.R] = a2;
+                }
+            }
+            tc_fence_before();
+            warp_arrive1(smem_u32(&bar_t_free[buf]), lane);
+            // (3) ds = t - a1 (sum of t over the caption), u = ds + alpha a2; t is recovered from the running sums
+            float* uo = p.u + ((size_t)j * p.ncols + ncol0) * p.R + r;
+            seg = 0.f;
+#pragma unroll
+            for (int c = kHalf - 1; c >= 0; --c) {
+                const float rc = __uint_as_float(rb[c]);
+                seg = ((last >> c) & 1ull) ? rc : seg;
+                const float t = ((first >> c) & 1ull) ? rc : rc - __uint_as_float(rb[c > 0 ? c - 1 : 0]);
+                const float4 cs4 = sc[c];
+                const bool ok = rv && ((valid >> c) & 1ull);
+                const float a2 = ok ? mma::ex2_approx((a1[c] - 1.f) * p.g1l2e) * cs4.w : 0.f;
+                const float uu = ok ? t - a1[c] * seg + cs4.x * a2 : 0.f;
+                if (rv) uo[(size_t)c * p.R] = uu;
+            }
+            __syncwarp();
+            WT_MARK(19);
+        }
+        tc_fence_before();
+        WT_MARK(20);
+    }
+    __syncthreads();
+    WT_MARK(21);
+    if (warp == kMmaWarp) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+constexpr size_t kWtBwdSmem = (size_t)kStages * kBStageBytes + kNB * 16 + (2 * kStages + 4 + 1) * 8;
+
 constexpr size_t kWtSmem = (size_t)kStages * kStageBytes + (size_t)kEBufs * kEBufBytes + (size_t)(kMaxChunks * kNB + kNB) * 4 +
-                           (2 * kStages + 4 + 2 * kEBufs + 2) * 8;
+                           (2 * kStages + 4 + kEBufs + 4 + 2) * 8;
 
 inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 struct WtLayout {
     int ncols, n_half_max, MT, RKC, RKP, RMP;
     size_t plan, cap_col, col_cap, col_T, ww, wt_hi, wt_lo, x_hi, x_lo, xt_hi, xt_lo, total;
+    size_t wc_packed, scal, v, wct_hi, wct_lo, u, a2;       // backward only
 };
-WtLayout wt_layout(int B_img, int B_cap, int nef, int R, int Lw) {
+WtLayout wt_layout(int B_img, int B_cap, int nef, int R, int Lw, bool bwd = false) {
     WtLayout w{};
     const int per_half = kHalf / Lw < 1 ? 1 : kHalf / Lw;            // captions per half block, worst case
     w.n_half_max = (B_cap + per_half - 1) / per_half;
@@ -491,6 +820,15 @@ WtLayout wt_layout(int B_img, int B_cap, int nef, int R, int Lw) {
     w.x_lo = take((size_t)B_img * nef * w.RKP * 4);
     w.xt_hi = take((size_t)B_img * w.RMP * nef * 4);
     w.xt_lo = take((size_t)B_img * w.RMP * nef * 4);
+    if (bwd) {
+        w.wc_packed = take((size_t)nef * w.ncols * 4);
+        w.scal = take((size_t)B_img * w.ncols * 16);
+        w.v = take((size_t)B_img * nef * w.ncols * 4);
+        w.wct_hi = take((size_t)B_img * w.ncols * nef * 4);
+        w.wct_lo = take((size_t)B_img * w.ncols * nef * 4);
+        w.u = take((size_t)B_img * w.ncols * R * 4);
+        w.a2 = take((size_t)B_img * w.ncols * R * 4);
+    }
     w.total = o;
     return w;
 }
@@ -553,7 +891,7 @@ int words_sim_fwd_tc5(const float* img, const float* words, const int* cap_lens,
     int rc = current_device(&dev, &sms, "words_sim_fwd(tcgen05)");
     if (rc) return rc;
     static std::atomic<unsigned long long> smem_done{0};
-    rc = ensure_dynamic_smem(k_words_tc5, kWtSmem, dev, smem_done, "words_sim_fwd(tcgen05)");
+    rc = ensure_dynamic_smem(k_words_tc5<false>, kWtSmem, dev, smem_done, "words_sim_fwd(tcgen05)");
     if (rc) return rc;
     char* ws = static_cast<char*>(workspace);
     WtPlan* plan = reinterpret_cast<WtPlan*>(ws + w.plan);
@@ -569,7 +907,7 @@ int words_sim_fwd_tc5(const float* img, const float* words, const int* cap_lens,
     float* xt_lo = reinterpret_cast<float*>(ws + w.xt_lo);
 
     k_wt_plan<<<1, 256, 0, st>>>(cap_lens, B_cap, Lw, cap_col, plan, col_cap, col_T, w.ncols);
-    k_wt_words<<<w.ncols / 8, 256, 0, st>>>(words, col_cap, cap_col, wt_hi, wt_lo, ww, nef, Lw);
+    k_wt_words<<<w.ncols / 8, 256, 0, st>>>(words, col_cap, cap_col, wt_hi, wt_lo, ww, nullptr, w.ncols, nef, Lw);
     k_wt_images<<<dim3(w.RMP / 32, nef / 32, B_img), 256, 0, st>>>(img, x_hi, x_lo, xt_hi, xt_lo, nef, R, w.RKP, w.RMP);
     add_launches(3);
     rc = check_launch("words_sim_fwd(tcgen05 pre-pass)");
@@ -587,9 +925,107 @@ int words_sim_fwd_tc5(const float* img, const float* words, const int* cap_lens,
     p.wt_hi = wt_hi; p.wt_lo = wt_lo; p.ww = ww; p.col_cap = col_cap; p.col_T = col_T; p.plan = plan; p.sim = sim;
     p.B_cap = B_cap; p.nef = nef; p.R = R; p.MT = w.MT; p.RKC = w.RKC;
     p.g1l2e = g1 * 1.4426950408889634f; p.g2 = g2; p.g3 = g3; p.eps = eps;
-    k_words_tc5<<<dim3(w.n_half_max / 2, B_img), kWtThreads, kWtSmem, st>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], p);
+    k_words_tc5<false><<<dim3(w.n_half_max / 2, B_img), kWtThreads, kWtSmem, st>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], p);
     add_launches(1);
     return check_launch("words_sim_fwd(tcgen05)");
 }
 
+size_t words_tc5_bwd_workspace_bytes(int B_img, int B_cap, int nef, int R, int Lw) {
+    if (!words_tc5_supports(B_img, B_cap, nef, R, Lw)) return 0;
+    const WtLayout w = wt_layout(B_img, B_cap, nef, R, Lw, true);
+    if ((long long)B_img * w.ncols >= (1ll << 31) / 2) return 0;       // TMA row coordinates of wc^T
+    return w.total;
+}
+
+// d_img only (GAN training: the words are detached, trainer_bert.py:257); d_words stays with the CUDA-core backward
+int words_sim_bwd_tc5(const float* img, const float* words, const int* cap_lens, const float* d_sim, float* d_img,
+                      void* workspace, size_t ws_bytes, int B_img, int B_cap, int nef, int R, int Lw, float g1, float g2,
+                      float g3, float eps, cudaStream_t st) {
+    if (!words_tc5_supports(B_img, B_cap, nef, R, Lw)) {
+        set_error("words_sim_bwd(tcgen05): shape nef=%d R=%d Lw=%d not covered", nef, R, Lw);
+        return SBA_ERR_UNSUPPORTED;
+    }
+    const WtLayout w = wt_layout(B_img, B_cap, nef, R, Lw, true);
+    if (ws_bytes < w.total || (reinterpret_cast<uintptr_t>(workspace) & 255u)) {
+        set_error("words_sim_bwd(tcgen05): workspace of %zu bytes given, %zu (256-byte aligned) needed", ws_bytes, w.total);
+        return SBA_ERR_ARG;
+    }
+    int dev = 0, sms = 0;
+    int rc = current_device(&dev, &sms, "words_sim_bwd(tcgen05)");
+    if (rc) return rc;
+    static std::atomic<unsigned long long> smem_a{0}, smem_b{0};
+    rc = ensure_dynamic_smem(k_words_tc5<true>, kWtSmem, dev, smem_a, "words_sim_bwd(tcgen05)");
+    if (!rc) rc = ensure_dynamic_smem(k_words_bwd_tc5, kWtBwdSmem, dev, smem_b, "words_sim_bwd(tcgen05)");
+    if (rc) return rc;
+    char* ws = static_cast<char*>(workspace);
+    WtPlan* plan = reinterpret_cast<WtPlan*>(ws + w.plan);
+    int* cap_col = reinterpret_cast<int*>(ws + w.cap_col);
+    int* col_cap = reinterpret_cast<int*>(ws + w.col_cap);
+    int* col_T = reinterpret_cast<int*>(ws + w.col_T);
+    float* ww = reinterpret_cast<float*>(ws + w.ww);
+    float* wt_hi = reinterpret_cast<float*>(ws + w.wt_hi);
+    float* wt_lo = reinterpret_cast<float*>(ws + w.wt_lo);
+    float* x_hi = reinterpret_cast<float*>(ws + w.x_hi);
+    float* x_lo = reinterpret_cast<float*>(ws + w.x_lo);
+    float* xt_hi = reinterpret_cast<float*>(ws + w.xt_hi);
+    float* xt_lo = reinterpret_cast<float*>(ws + w.xt_lo);
+    float* wc_packed = reinterpret_cast<float*>(ws + w.wc_packed);
+    float4* scal = reinterpret_cast<float4*>(ws + w.scal);
+    float* v = reinterpret_cast<float*>(ws + w.v);
+    float* wct_hi = reinterpret_cast<float*>(ws + w.wct_hi);
+    float* wct_lo = reinterpret_cast<float*>(ws + w.wct_lo);
+    float* u = reinterpret_cast<float*>(ws + w.u);
+    float* a2 = reinterpret_cast<float*>(ws + w.a2);
+
+    k_wt_plan<<<1, 256, 0, st>>>(cap_lens, B_cap, Lw, cap_col, plan, col_cap, col_T, w.ncols);
+    k_wt_words<<<w.ncols / 8, 256, 0, st>>>(words, col_cap, cap_col, wt_hi, wt_lo, ww, wc_packed, w.ncols, nef, Lw);
+    k_wt_images<<<dim3(w.RMP / 32, nef / 32, B_img), 256, 0, st>>>(img, x_hi, x_lo, xt_hi, xt_lo, nef, R, w.RKP, w.RMP);
+    add_launches(3);
+    rc = check_launch("words_sim_bwd(tcgen05 pre-pass)");
+    if (rc) return rc;
+
+    CUtensorMap tm[8];
+    rc = make_k128_map(&tm[0], xt_hi, (long long)B_img * w.RMP, nef, 128);
+    if (!rc) rc = make_k128_map(&tm[1], xt_lo, (long long)B_img * w.RMP, nef, 128);
+    if (!rc) rc = make_k128_map(&tm[2], wt_hi, w.ncols, nef, 128);
+    if (!rc) rc = make_k128_map(&tm[3], wt_lo, w.ncols, nef, 128);
+    if (!rc) rc = make_k128_map(&tm[4], x_hi, (long long)B_img * nef, w.RKP, nef);
+    if (!rc) rc = make_k128_map(&tm[5], x_lo, (long long)B_img * nef, w.RKP, nef);
+    if (!rc) rc = make_k128_map(&tm[6], wct_hi, (long long)B_img * w.ncols, nef, 128);
+    if (!rc) rc = make_k128_map(&tm[7], wct_lo, (long long)B_img * w.ncols, nef, 128);
+    if (rc) return rc;
+    WtParams p{};
+    p.wt_hi = wt_hi; p.wt_lo = wt_lo; p.ww = ww; p.col_cap = col_cap; p.col_T = col_T; p.plan = plan; p.sim = nullptr;
+    p.B_cap = B_cap; p.nef = nef; p.R = R; p.MT = w.MT; p.RKC = w.RKC;
+    p.g1l2e = g1 * 1.4426950408889634f; p.g2 = g2; p.g3 = g3; p.eps = eps;
+    p.d_sim = d_sim; p.cap_col = cap_col; p.scal = scal; p.v = v; p.wct_hi = wct_hi; p.wct_lo = wct_lo; p.ncols = w.ncols; p.g1 = g1;
+    const dim3 grid(w.n_half_max / 2, B_img);
+    k_words_tc5<true><<<grid, kWtThreads, kWtSmem, st>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], p);
+    rc = check_launch("words_sim_bwd(tcgen05 phase A)");
+    if (rc) return rc;
+    WtBwdParams b{};
+    b.col_cap = col_cap; b.plan = plan; b.scal = scal; b.u = u; b.a2 = a2;
+    b.nef = nef; b.R = R; b.MT = w.MT; b.RKC = w.RKC; b.ncols = w.ncols; b.g1 = g1; b.g1l2e = p.g1l2e;
+    k_words_bwd_tc5<<<grid, kWtThreads, kWtBwdSmem, st>>>(tm[0], tm[1], tm[2], tm[3], tm[6], tm[7], b);
+    add_launches(2);
+    rc = check_launch("words_sim_bwd(tcgen05 phase B)");
+    if (rc) return rc;
+    return words_dimg_gemms(wc_packed, u, v, a2, d_img, B_img, nef, R, w.ncols, &plan->n_half, st);
+}
+
 }  // namespace sba
+
+#ifdef SBA_DEV_AIDS
+// progress / timeout counters in mapped host memory: readable while a kernel hangs
+extern "C" __attribute__((visibility("default"))) unsigned* sba_dev_words_progress(void) {
+    static unsigned* host = nullptr;
+    if (host == nullptr) {
+        cudaHostAlloc(&host, 32 * sizeof(unsigned), cudaHostAllocMapped);
+        for (int i = 0; i < 32; ++i) host[i] = 0;
+        unsigned* dev = nullptr;
+        cudaHostGetDevicePointer(&dev, host, 0);
+        cudaMemcpyToSymbol(sba::g_wt_host, &dev, sizeof(dev));
+    }
+    return host;
+}
+#endif

@@ -101,18 +101,70 @@ def test_full_size_b256_rows_and_sharding():
     assert normalised_max_err(full[rows].cpu(), ref) <= TOL_LOSS
 
 
-def test_gan_training_mode_words_detached():
-    """trainer_bert.py:257 detaches the words: only d_img is produced."""
-    d = synth_words_loss_inputs(6, 256, 18, 17, 17, seed=8)
-    l0, l1, _, d_img, d_words = _run(d, 6, (4.0, 5.0, 10.0), True, True, need_words_grad=False)
+@pytest.mark.parametrize("spec", [
+    # B, nef, L, ih, iw, gammas
+    (6, 256, 18, 17, 17, (4.0, 5.0, 10.0)),
+    (48, 256, 18, 17, 17, (4.0, 5.0, 10.0)),     # BASELINE configs[2], B=48
+    (4, 256, 25, 17, 17, (4.0, 5.0, 10.0)),      # two captions per 64-column half block
+    (3, 128, 32, 9, 9, (4.0, 5.0, 10.0)),        # maximum words, one 128-region tile
+    (7, 64, 5, 3, 4, (1.0, 2.0, 3.0)),           # tiny: 12 regions, twelve captions' worth of words per half block
+    (9, 256, 18, 17, 17, (10.0, 5.0, 10.0)),     # sharp gamma1
+])
+def test_gan_training_mode_words_detached(spec):
+    """trainer_bert.py:257 detaches the words: only d_img is produced - on the tensor-core backward
+    (sba_words_sim_bwd_tc) wherever the shape is covered."""
+    B, nef, L, ih, iw, gammas = spec
+    d = synth_words_loss_inputs(B, nef, L, ih, iw, seed=8 + B, min_len=1, n_classes=max(2, B // 3))
+    l0, l1, _, d_img, d_words = _run(d, B, gammas, True, True, need_words_grad=False)
     assert d_words is None and d_img is not None
-    sim = oracle.words_similarity(d["img_features"].double(), d["words_emb"].double(), d["cap_lens"].tolist(),
-                                  4.0, 5.0, 10.0).requires_grad_(True)
+    lens = d["cap_lens"].tolist()
+    sim = oracle.words_similarity(d["img_features"].double(), d["words_emb"].double(), lens, *gammas).requires_grad_(True)
     r0, r1, _ = oracle.ce_tail(sim, d["labels"], d["class_ids"])
     (r0 + r1).backward()
-    rd_img, _ = oracle.words_loss_backward(d["img_features"].double(), d["words_emb"].double(),
-                                           d["cap_lens"].tolist(), sim.grad, 4.0, 5.0, 10.0)
+    rd_img, _ = oracle.words_loss_backward(d["img_features"].double(), d["words_emb"].double(), lens, sim.grad, *gammas)
+    assert abs(l0.item() - r0.item()) <= TOL_LOSS * max(1.0, abs(r0.item()))
     assert normalised_max_err(d_img.cpu(), rd_img) <= TOL_GRAD
+
+
+@pytest.mark.parametrize("name", [n for n in WL_CASES if WL_CASES[n][8]])
+def test_words_detached_matches_reference_golden(golden_dir, name):
+    """d_img of the words-detached path against the reference's own autograd (the golden d_img does not depend on
+    whether the words require a gradient)."""
+    B, nef, L, ih, iw, seed, gammas, use_cls, use_lab = WL_CASES[name]
+    g = np.load(os.path.join(golden_dir, f"{name}_f32.npz"))
+    d = synth_words_loss_inputs(B, nef, L, ih, iw, seed=seed, n_classes=max(2, B // 2))
+    _, _, _, d_img, d_words = _run(d, B, gammas, use_cls, use_lab, need_words_grad=False)
+    assert d_words is None
+    assert normalised_max_err(d_img.cpu(), torch.from_numpy(g["d_img"])) <= TOL_GRAD
+
+
+@pytest.mark.parametrize("B", [128, 256])
+def test_tensor_core_backward_full_size_vs_cuda_core(B):
+    """BASELINE configs[2] sizes: the tensor-core d_img against the CUDA-core backward (itself checked against the
+    oracle above), and run-to-run bit-stable (fixed-order reductions; also a soak for the barrier protocol: a stale
+    chunk buffer shows up as a changed bit long before it shows up as a wrong loss)."""
+    from sba_gan_b200 import losses
+    d = synth_words_loss_inputs(B, 256, 18, 17, 17, seed=77 + B)
+    img, words, lens = d["img_features"].cuda(), d["words_emb"].cuda(), d["cap_lens"].cuda()
+    labels, cls = d["labels"].cuda(), d["class_ids"]
+
+    def grad(algo):
+        losses.FORWARD_ALGO = algo
+        try:
+            x = img.clone().requires_grad_(True)
+            l0, l1, _ = losses.words_loss(x, words, labels, lens, cls, B, 4.0, 5.0, 10.0, att_maps=False)
+            (gi,) = torch.autograd.grad(l0 + l1, [x])
+            return l0.detach(), gi
+        finally:
+            losses.FORWARD_ALGO = "auto"
+
+    l_tc, g_tc = grad("auto")
+    l_cc, g_cc = grad("simt")
+    assert abs(l_tc.item() - l_cc.item()) <= TOL_LOSS * max(1.0, abs(l_cc.item()))
+    assert normalised_max_err(g_tc.cpu(), g_cc.cpu().double()) <= TOL_GRAD
+    for _ in range(4 if B == 256 else 8):
+        l_again, g_again = grad("auto")
+        assert torch.equal(l_again, l_tc) and torch.equal(g_again, g_tc)
 
 
 @pytest.mark.parametrize("tag", ["f32"])

@@ -55,3 +55,40 @@ for (B, nef, L, hw) in [(6, 256, 18, 17), (48, 256, 18, 17), (5, 64, 12, 6), (7,
             torch.cuda.synchronize()
             print(f"   {algo}: {e0.elapsed_time(e1) / 5:.3f} ms per forward", flush=True)
 print("done")
+
+# ---- backward (d_img only): tensor-core path vs CUDA-core path vs fp64 autograd of the restatement
+from sba_gan_b200.losses import words_loss  # noqa: E402
+for (B, nef, L, hw) in [(6, 256, 18, 17), (48, 256, 18, 17), (5, 64, 12, 6), (9, 256, 7, 17), (128, 256, 18, 17), (256, 256, 18, 17)]:
+    g = torch.Generator().manual_seed(B + 1)
+    img = torch.randn(B, nef, hw, hw, generator=g).cuda()
+    words = torch.tanh(torch.randn(B, nef, L, generator=g)).cuda()
+    lens = torch.sort(torch.randint(1, L + 1, (B,), generator=g), descending=True).values.cuda()
+    cls = torch.randint(1, 50, (B,), generator=g).cuda()
+    labels = torch.arange(B).cuda()
+    grads, times = {}, {}
+    for algo in ("simt", "auto"):
+        losses.FORWARD_ALGO = algo
+        x = img.clone().requires_grad_(True)
+        l0, l1, _ = words_loss(x, words, labels, lens, cls, B, 4.0, 5.0, 10.0, att_maps=False)
+        (gi,) = torch.autograd.grad(l0 + l1, [x])
+        grads[algo] = gi
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+        e0.record()
+        for _ in range(3):
+            l0, l1, _ = words_loss(x, words, labels, lens, cls, B, 4.0, 5.0, 10.0, att_maps=False)
+            torch.autograd.grad(l0 + l1, [x])
+        e1.record()
+        torch.cuda.synchronize()
+        times[algo] = e0.elapsed_time(e1) / 3
+    msg = f"bwd B={B} nef={nef} L={L} R={hw*hw}: tc5 vs simt {((grads['auto'] - grads['simt']).abs().max() / grads['simt'].abs().max()).item():.2e}"
+    if B <= 9:
+        x64 = img.double().clone().requires_grad_(True)
+        sim = ref_sim(x64, words, lens.cpu(), 4.0, 5.0, 10.0)
+        same = (cls[:, None] == cls[None, :]) & ~torch.eye(B, dtype=torch.bool, device="cuda")
+        sim = sim.masked_fill(same, float("-inf"))
+        loss = torch.nn.functional.cross_entropy(sim, labels) + torch.nn.functional.cross_entropy(sim.t(), labels)
+        (gr,) = torch.autograd.grad(loss, [x64])
+        msg += f" | vs fp64: simt {((grads['simt'].double() - gr).abs().max() / gr.abs().max()).item():.2e} tc5 {((grads['auto'].double() - gr).abs().max() / gr.abs().max()).item():.2e}"
+    print(msg + f" | fwd+bwd simt {times['simt']:.3f} ms  tc5 {times['auto']:.3f} ms", flush=True)
+print("bwd done")
