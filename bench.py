@@ -492,13 +492,16 @@ def sub_words_loss(cx):
                 with torch.no_grad():
                     words_similarity(img, words, lens, 4.0, 5.0, 10.0)
 
-            def fb(wg=False):
+            def fb(wg=False, maps=False):
                 w = words.detach().requires_grad_(wg)
-                l0, l1, _ = words_loss(img, w, labels, lens, cls, B, 4.0, 5.0, 10.0)
+                l0, l1, _ = words_loss(img, w, labels, lens, cls, B, 4.0, 5.0, 10.0, att_maps=maps)
                 torch.autograd.grad(l0 + l1, [img, w] if wg else [img])
 
             n = 20 if B <= 64 else 5
+            # fwd_bwd_img: the GAN training call (words detached, trainer_bert.py:257; the maps it returns are dropped);
+            # *_attmaps: the same with the reference's third return value written out; *_img_words: DAMSM pre-training
             tf, tb, tw = timeit(fwd, n), timeit(fb, n), timeit(lambda: fb(True), n)
+            rec["fwd_bwd_img_attmaps_ms"] = round(timeit(lambda: fb(False, True), n), 3)
             rec.update(fwd_ms=round(tf, 3), fwd_tflops=round(flops_f / (tf * 1e-3) / 1e12, 2),
                        fwd_frac_of_ffma_ceiling=round(flops_f / (tf * 1e-3) / 1e12 / FFMA_TFLOPS, 3),
                        fwd_bwd_img_ms=round(tb, 3), fwd_bwd_img_words_ms=round(tw, 3),

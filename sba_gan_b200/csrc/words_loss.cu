@@ -566,7 +566,6 @@ struct GemmArgs {
     const float* B; long long sB_batch, sB_kb; int kbB, ldb, transB;
     float* C; long long sC_batch, sC_nb; int nbC, ldc, accumulate;
     int M, N, K, splits;
-    const int* K_dev; int K_unit;      // optional device-side bound: K = min(K, *K_dev * K_unit)
 };
 
 template <int BN>
@@ -580,7 +579,7 @@ __global__ void __launch_bounds__(256, 2) k_gemm(const GemmArgs g) {
     const int tx = tid & 15, ty = tid >> 4;
     const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
     const int b = blockIdx.z / g.splits, z = blockIdx.z - b * g.splits;
-    const int K = g.K_dev != nullptr ? min(g.K, *g.K_dev * g.K_unit) : g.K;
+    const int K = g.K;
     const int kper = ceil_div(ceil_div(K, g.splits), BK) * BK;
     const int kbeg = z * kper, kend = min(K, kbeg + kper);
     const float* A = g.A + (size_t)b * g.sA_batch;
@@ -755,25 +754,6 @@ int words_sim_fwd(const float* img, const float* words, const int* cap_lens, flo
     a.B_img = B_img; a.B_cap = B_cap; a.row_offset = row_offset; a.nef = nef; a.R = R; a.Lw = Lw;
     a.g1 = g1; a.g2 = g2; a.g3 = g3; a.eps = eps; a.paired = paired; a.fixed_T = Lw;
     return dispatch_words<false>(a, st);
-}
-
-// d_img[j] = Wc [nef x K] . u_j [K x R] + v_j [nef x K] . a2_j [K x R] over the PACKED word columns of the tensor-core
-// backward (words_tc5.cu): K = min(ncols, 64 * *n_half_dev) columns are in use
-int words_dimg_gemms(const float* wc_packed, const float* u, const float* v, const float* a2, float* d_img, int B_img, int nef,
-                     int R, int ncols, const int* n_half_dev, cudaStream_t st) {
-    const int big = 0x7fffffff;
-    GemmArgs g{};
-    g.A = wc_packed; g.sA_batch = 0; g.sA_kb = 0; g.kbA = big; g.lda = ncols;
-    g.B = u; g.sB_batch = (long long)ncols * R; g.sB_kb = 0; g.kbB = big; g.ldb = R; g.transB = 0;
-    g.C = d_img; g.sC_batch = (long long)nef * R; g.sC_nb = 0; g.nbC = big; g.ldc = R; g.accumulate = 0;
-    g.M = nef; g.N = R; g.K = ncols; g.splits = 1; g.K_dev = n_half_dev; g.K_unit = 64;
-    dim3 grid(ceil_div(R, 64), ceil_div(nef, 128), B_img);
-    k_gemm<64><<<grid, 256, 0, st>>>(g);
-    g.A = v; g.sA_batch = (long long)nef * ncols;
-    g.B = a2; g.accumulate = 1;
-    k_gemm<64><<<grid, 256, 0, st>>>(g);
-    add_launches(2);
-    return check_launch("words_sim_bwd(d_img gemm)");
 }
 
 int words_sim_bwd(const float* img, const float* words, const int* cap_lens, const float* d_sim, float* d_img,

@@ -80,7 +80,8 @@ struct WtParams {
     const float* d_sim;        // [B_img][B_cap]
     const int* cap_col;        // [B_cap] first column of each caption
     float4* scal;              // [B_img][ncols] (alpha = d num, beta = d|wc| / |wc|, D = sum_r a2 da2, 1 / Z)
-    float* v;                  // [B_img][nef][ncols]  beta * wc   (A operand of the second d_img GEMM)
+    float* v_hi;               // [B_img][nef][ncols]  beta * wc split in tf32 hi / lo: B operand of the d_img GEMM's second term
+    float* v_lo;
     float* wct_hi;             // [B_img][ncols][nef]  wc split in tf32 hi / lo: B operand of V = X^T wc in phase B
     float* wct_lo;
     int ncols;
@@ -116,7 +117,8 @@ __device__ __forceinline__ void split_tf32(float v, float& hi, float& lo) {
 __global__ void __launch_bounds__(256) k_wt_words(const float* __restrict__ words, const int* __restrict__ col_cap,
                                                   const int* __restrict__ cap_col, float* __restrict__ wt_hi,
                                                   float* __restrict__ wt_lo, float* __restrict__ ww,
-                                                  float* __restrict__ wc_packed, int ncols, int nef, int Lw) {
+                                                  float* __restrict__ wcp_hi, float* __restrict__ wcp_lo, int ncols, int nef,
+                                                  int Lw) {
     __shared__ float red[8];
     for (int k = 0; k < 8; ++k) {
         const int n = blockIdx.x * 8 + k;
@@ -129,7 +131,10 @@ __global__ void __launch_bounds__(256) k_wt_words(const float* __restrict__ word
             split_tf32(v, hi, lo);
             wt_hi[(size_t)n * nef + c] = hi;
             wt_lo[(size_t)n * nef + c] = lo;
-            if (wc_packed != nullptr) wc_packed[(size_t)c * ncols + n] = v;       // [nef][ncols]: A operand of the d_img GEMM
+            if (wcp_hi != nullptr) {                  // [nef][ncols]: B operand of the d_img GEMM's first term (backward only)
+                wcp_hi[(size_t)c * ncols + n] = hi;
+                wcp_lo[(size_t)c * ncols + n] = lo;
+            }
             sq = fmaf(v, v, sq);
         }
 #pragma unroll
@@ -515,9 +520,10 @@ __global__ void __launch_bounds__(kWtThreads, 1)
                     D = alpha * numt + beta * wn * wn;                               // sum_r a2[r, n] da2[r, n]
                 }
                 p.scal[(size_t)j * p.ncols + ng] = make_float4(alpha, beta, D, invZ);
-                // second pass over wc: v = beta wc (rows = channels: consecutive threads write consecutive columns) and
+                // second pass over wc: v = beta wc in tf32 hi / lo (rows = channels: consecutive threads write consecutive columns) and
                 // wc^T split into tf32 hi / lo (this thread's row, 128 contiguous bytes per chunk)
-                float* vcol = p.v + (size_t)j * nef * p.ncols + ng;
+                float* vh = p.v_hi + (size_t)j * nef * p.ncols + ng;
+                float* vl = p.v_lo + (size_t)j * nef * p.ncols + ng;
                 float4* th = reinterpret_cast<float4*>(p.wct_hi + ((size_t)j * p.ncols + ng) * nef);
                 float4* tlo = reinterpret_cast<float4*>(p.wct_lo + ((size_t)j * p.ncols + ng) * nef);
                 __syncwarp();                    // (lane-dependent code above; tcgen05.ld is warp-collective)
@@ -532,7 +538,10 @@ __global__ void __launch_bounds__(kWtThreads, 1)
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
                             const float wc = __uint_as_float(d[4 * c4 + e]) * invZ;
-                            vcol[(size_t)(c0 + 4 * c4 + e) * p.ncols] = beta * wc;
+                            float bh, bl;
+                            split_tf32(beta * wc, bh, bl);
+                            vh[(size_t)(c0 + 4 * c4 + e) * p.ncols] = bh;
+                            vl[(size_t)(c0 + 4 * c4 + e) * p.ncols] = bl;
                             hi[e] = tf32_rna(wc);
                             lo[e] = tf32_rna(wc - hi[e]);
                         }
@@ -560,16 +569,19 @@ __global__ void __launch_bounds__(kWtThreads, 1)
 //   a1 = softmax over each caption's words of S,  a2 = exp(gamma1 (a1 - 1)) / Z
 //   da2 = alpha S + beta V,   dz = a2 (da2 - D),   t = a1 gamma1 dz,   ds = t - a1 sum_{caption} t,   u = ds + alpha a2
 // (D_n = sum_r a2 da2 = alpha <w_n, wc_n> + beta |wc_n|^2 is known from phase A: no reduction over regions here) and
-// store a2[j][n][r], u[j][n][r] for the two d_img GEMMs (oracle/attention.py::words_loss_backward; the CUDA-core
-// kernel of words_loss.cu materialises the same u / a2).
+// store a2^T[j][r][n], u^T[j][r][n] (tf32 hi / lo) for the d_img GEMM below (oracle/attention.py::words_loss_backward;
+// the CUDA-core kernel of words_loss.cu materialises the same u / a2).
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int kBStageBytes = 6 * kTileBytes;      // A hi, A lo, W hi, W lo, wc hi, wc lo: 96 KB
+constexpr int kBStageF4 = 2 * 32 * 4;             // float4 per epilogue warp: 16 columns of 32 regions, hi and lo (4 KB)
 struct WtBwdParams {
     const int* col_cap;
     const WtPlan* plan;
     const float4* scal;        // [B_img][ncols]
-    float* u;                  // [B_img][ncols][R]
-    float* a2;                 // [B_img][ncols][R]
+    float* u_hi;               // [B_img * R][ncols]  u^T and a2^T (regions = rows, columns contiguous), tf32 hi / lo:
+    float* u_lo;               //                     the K-major A operands of the d_img GEMM
+    float* a2_hi;
+    float* a2_lo;
     int nef, R, MT, RKC, ncols;
     float g1, g1l2e;
 };
@@ -585,7 +597,8 @@ __global__ void __launch_bounds__(kWtThreads, 1)
     const uint32_t sbase = smem_u32(smem_raw);
     const uint32_t s_ring = sbase;
     float4* scs = reinterpret_cast<float4*>(smem_raw + kStages * kBStageBytes);        // [128] per-column scalars
-    unsigned long long* bars = reinterpret_cast<unsigned long long*>(scs + kNB);
+    float4* stg_all = scs + kNB;                          // [8 warps][hi, lo][32 regions][4 x float4]: output staging
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(stg_all + 8 * kBStageF4);
     unsigned long long* bar_full = bars;                  // [kStages]
     unsigned long long* bar_empty = bars + kStages;       // [kStages]
     unsigned long long* bar_t_full = bars + 2 * kStages;  // [2]  S and V of a region tile are complete
@@ -733,11 +746,38 @@ __global__ void __launch_bounds__(kWtThreads, 1)
                 a1[c] *= seg;
             }
             // (2) t = a1 gamma1 a2 (alpha S + beta V - D), running sum per caption into rb; a2 goes out
-            float* a2o = p.a2 + ((size_t)j * p.ncols + ncol0) * p.R + r;
+            // u^T / a2^T rows [region][column]: a thread owns a region and 16 columns at a time, the warp stores them
+            // through its staging tile so that every store instruction writes 8 whole 64-byte row pieces
+            // (float4 slots XOR-swizzled with (region >> 1) & 3: conflict-free both ways)
+            float4* stg = stg_all + ew * kBStageF4;
+            const int r_base = 128 * m + 32 * q;
+            const size_t obase = ((size_t)j * p.R + r_base) * p.ncols + ncol0;       // first region row of this warp
+            auto flush16 = [&](float* __restrict__ dst_hi, float* __restrict__ dst_lo, const float (&h)[16], const float (&l)[16],
+                               int col0) {
+                __syncwarp();                                     // the previous flush has been read out
+#pragma unroll
+                for (int k4 = 0; k4 < 4; ++k4) {
+                    const int slot = lane * 4 + (k4 ^ ((lane >> 1) & 3));
+                    stg[slot] = make_float4(h[4 * k4], h[4 * k4 + 1], h[4 * k4 + 2], h[4 * k4 + 3]);
+                    stg[128 + slot] = make_float4(l[4 * k4], l[4 * k4 + 1], l[4 * k4 + 2], l[4 * k4 + 3]);
+                }
+                __syncwarp();
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int row = 8 * i + (lane >> 2), k4 = lane & 3;
+                    if (r_base + row < p.R) {
+                        const int slot = row * 4 + (k4 ^ ((row >> 1) & 3));
+                        const size_t o = obase + (size_t)row * p.ncols + col0 + 4 * k4;
+                        *reinterpret_cast<float4*>(dst_hi + o) = stg[slot];
+                        *reinterpret_cast<float4*>(dst_lo + o) = stg[128 + slot];
+                    }
+                }
+            };
             run = 0.f;
 #pragma unroll
             for (int g0 = 0; g0 < kHalf; g0 += 16) {
                 uint32_t s16[16], v16[16];
+                float ah[16], al[16];
                 __syncwarp();                                    // (the stores below are lane-dependent)
                 tmem_ld<16>(tS + g0, s16);
                 tmem_ld<16>(tV + g0, v16);
@@ -752,13 +792,14 @@ __global__ void __launch_bounds__(kWtThreads, 1)
                     const float t = a1[c] * p.g1 * a2 * (da2 - cs4.z);
                     run = ((first >> c) & 1ull) ? t : run + t;
                     rb[c] = __float_as_uint(run);
-                    if (rv) a2o[(size_t)c * p.R] = a2;
+                    split_tf32(a2, ah[k], al[k]);
                 }
+                flush16(p.a2_hi, p.a2_lo, ah, al, g0);
             }
             tc_fence_before();
             warp_arrive1(smem_u32(&bar_t_free[buf]), lane);
             // (3) ds = t - a1 (sum of t over the caption), u = ds + alpha a2; t is recovered from the running sums
-            float* uo = p.u + ((size_t)j * p.ncols + ncol0) * p.R + r;
+            float uh[16], ul[16];
             seg = 0.f;
 #pragma unroll
             for (int c = kHalf - 1; c >= 0; --c) {
@@ -769,7 +810,8 @@ __global__ void __launch_bounds__(kWtThreads, 1)
                 const bool ok = rv && ((valid >> c) & 1ull);
                 const float a2 = ok ? mma::ex2_approx((a1[c] - 1.f) * p.g1l2e) * cs4.w : 0.f;
                 const float uu = ok ? t - a1[c] * seg + cs4.x * a2 : 0.f;
-                if (rv) uo[(size_t)c * p.R] = uu;
+                split_tf32(uu, uh[c & 15], ul[c & 15]);
+                if ((c & 15) == 0) flush16(p.u_hi, p.u_lo, uh, ul, c);
             }
             __syncwarp();
             WT_MARK(19);
@@ -785,7 +827,125 @@ __global__ void __launch_bounds__(kWtThreads, 1)
     }
 }
 
-constexpr size_t kWtBwdSmem = (size_t)kStages * kBStageBytes + kNB * 16 + (2 * kStages + 4 + 1) * 8;
+// ------------------------------------------------------------------------------------------------------------------
+// Backward, d_img: per (image j, 128-region tile m)
+//   d_img[j][c][r] = sum_n u[j][n][r] w[c][n] + sum_n a2[j][n][r] v[j][c][n]
+// as ONE accumulation D[r][c] over the concatenated K = (columns of term 1 | columns of term 2): A = u^T / a2^T tiles
+// [128 regions][32 columns], B = wcp / v[j] tiles [nef channels][32 columns], all K-major 128-byte swizzled fp32, 3xTF32.
+// D (128 lanes x nef columns) stays in TMEM for the whole K loop (2 * 64 * n_half / 32 stages); the epilogue's thread =
+// region, so every store instruction of a warp writes 32 consecutive regions of one channel.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int kGThreads = 64 + 128;                       // producer warp, MMA warp, 4 epilogue warps
+constexpr int kGBTileBytes = 256 * kKC * 4;               // B operand tile: up to 256 channels
+constexpr int kGStageBytes = 2 * kTileBytes + 2 * kGBTileBytes;      // A hi, A lo, B hi, B lo: 96 KB
+struct WtGemmParams {
+    const WtPlan* plan;
+    float* d_img;              // [B_img][nef][R]
+    int nef, R;
+};
+
+__global__ void __launch_bounds__(kGThreads, 1)
+    k_words_dimg_tc5(const __grid_constant__ CUtensorMap tm_u_hi, const __grid_constant__ CUtensorMap tm_u_lo,
+                     const __grid_constant__ CUtensorMap tm_a2_hi, const __grid_constant__ CUtensorMap tm_a2_lo,
+                     const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
+                     const __grid_constant__ CUtensorMap tm_v_hi, const __grid_constant__ CUtensorMap tm_v_lo,
+                     const WtGemmParams p) {
+    const int m = blockIdx.x, j = blockIdx.y;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    const uint32_t sbase = smem_u32(smem_raw);
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem_raw + kStages * kGStageBytes);
+    unsigned long long* bar_full = bars;                  // [kStages]
+    unsigned long long* bar_empty = bars + kStages;       // [kStages]
+    unsigned long long* bar_d_full = bars + 2 * kStages;  // [1]
+    uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(bar_d_full + 1);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int nef = p.nef;
+    const int KCH = p.plan->n_half * (kHalf / kKC);       // stages per term
+    const int NS = 2 * KCH;
+
+    if (tid == 0) {
+        if (sbase & 1023u) __trap();
+        for (int s = 0; s < kStages; ++s) { mbar_init(smem_u32(&bar_full[s]), 1); mbar_init(smem_u32(&bar_empty[s]), 1); }
+        mbar_init(smem_u32(bar_d_full), 1);
+        fence_barrier_init();
+    }
+    if (warp == kMmaWarp) tmem_alloc(smem_u32(tmem_base_s), 256);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_base_s, 0);
+
+    if (warp == kProducerWarp) {
+        for (int s = 0; s < NS; ++s) {
+            const int st = s % kStages;
+            if (s >= kStages) mbar_wait(smem_u32(&bar_empty[st]), (uint32_t)((s / kStages) - 1) & 1u);
+            if (elect_one()) {
+                const uint32_t full = smem_u32(&bar_full[st]), dst = sbase + st * kGStageBytes;
+                const bool second = s >= KCH;
+                const int kc = (second ? s - KCH : s) * kKC;
+                mbar_expect_tx(full, (uint32_t)(2 * kTileBytes + 2 * nef * kKC * 4));
+                tma_load_2d(dst, second ? &tm_a2_hi : &tm_u_hi, kc, j * p.R + m * 128, full);
+                tma_load_2d(dst + kTileBytes, second ? &tm_a2_lo : &tm_u_lo, kc, j * p.R + m * 128, full);
+                tma_load_2d(dst + 2 * kTileBytes, second ? &tm_v_hi : &tm_w_hi, kc, second ? j * nef : 0, full);
+                tma_load_2d(dst + 2 * kTileBytes + kGBTileBytes, second ? &tm_v_lo : &tm_w_lo, kc, second ? j * nef : 0, full);
+            }
+            __syncwarp();
+        }
+    } else if (warp == kMmaWarp) {
+        constexpr uint32_t kHi = desc_hi(1024, kSwizzle128B);
+        const uint32_t idesc = make_idesc(2, 0, 0, 128, nef);
+        for (int s = 0; s < NS; ++s) {
+            const int st = s % kStages;
+            mbar_wait(smem_u32(&bar_full[st]), (uint32_t)(s / kStages) & 1u);
+            tc_fence_after();
+            const uint32_t base = sbase + st * kGStageBytes;
+            const uint32_t a_hi = desc_lo(base, 16), a_lo = desc_lo(base + kTileBytes, 16);
+            const uint32_t b_hi = desc_lo(base + 2 * kTileBytes, 16), b_lo = desc_lo(base + 2 * kTileBytes + kGBTileBytes, 16);
+            if (elect_one()) {
+#pragma unroll
+                for (int ks = 0; ks < kKC / 8; ++ks) {
+                    const uint32_t o = (uint32_t)(ks * 2);
+                    umma_ss<true>(tmem_base, a_hi + o, kHi, b_hi + o, kHi, idesc, (s > 0 || ks > 0) ? 1u : 0u);
+                    umma_ss<true>(tmem_base, a_hi + o, kHi, b_lo + o, kHi, idesc, 1u);
+                    umma_ss<true>(tmem_base, a_lo + o, kHi, b_hi + o, kHi, idesc, 1u);
+                }
+                umma_commit(smem_u32(&bar_empty[st]));
+            }
+            __syncwarp();
+        }
+        if (elect_one()) umma_commit(smem_u32(bar_d_full));
+        __syncwarp();
+    } else {
+        const int q = warp & 3;
+        const uint32_t tl = tmem_base + ((uint32_t)(q * 32) << 16);
+        const int r = m * 128 + q * 32 + lane;
+        float* out = p.d_img + (size_t)j * nef * p.R + r;
+        mbar_wait(smem_u32(bar_d_full), 0u);
+        tc_fence_after();
+        for (int c0 = 0; c0 < nef; c0 += 32) {
+            uint32_t d[32];
+            tmem_ld<32>(tl + c0, d);
+            tmem_wait_ld();
+            if (r < p.R) {
+#pragma unroll
+                for (int c = 0; c < 32; ++c) out[(size_t)(c0 + c) * p.R] = __uint_as_float(d[c]);
+            }
+            __syncwarp();                            // (tcgen05.ld is warp-collective; the stores are lane-dependent)
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == kMmaWarp) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 256);
+    }
+}
+
+constexpr size_t kWtGemmSmem = (size_t)kStages * kGStageBytes + (2 * kStages + 1 + 1) * 8;
+
+constexpr size_t kWtBwdSmem = (size_t)kStages * kBStageBytes + kNB * 16 + 8 * kBStageF4 * 16 + (2 * kStages + 4 + 1) * 8;
+static_assert(kWtBwdSmem <= 232448, "phase B: operand ring + output staging must fit the 227 KB of one CTA");
 
 constexpr size_t kWtSmem = (size_t)kStages * kStageBytes + (size_t)kEBufs * kEBufBytes + (size_t)(kMaxChunks * kNB + kNB) * 4 +
                            (2 * kStages + 4 + kEBufs + 4 + 2) * 8;
@@ -795,7 +955,7 @@ inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
 struct WtLayout {
     int ncols, n_half_max, MT, RKC, RKP, RMP;
     size_t plan, cap_col, col_cap, col_T, ww, wt_hi, wt_lo, x_hi, x_lo, xt_hi, xt_lo, total;
-    size_t wc_packed, scal, v, wct_hi, wct_lo, u, a2;       // backward only
+    size_t wcp_hi, wcp_lo, scal, v_hi, v_lo, wct_hi, wct_lo, u_hi, u_lo, a2_hi, a2_lo;       // backward only
 };
 WtLayout wt_layout(int B_img, int B_cap, int nef, int R, int Lw, bool bwd = false) {
     WtLayout w{};
@@ -821,13 +981,17 @@ WtLayout wt_layout(int B_img, int B_cap, int nef, int R, int Lw, bool bwd = fals
     w.xt_hi = take((size_t)B_img * w.RMP * nef * 4);
     w.xt_lo = take((size_t)B_img * w.RMP * nef * 4);
     if (bwd) {
-        w.wc_packed = take((size_t)nef * w.ncols * 4);
+        w.wcp_hi = take((size_t)nef * w.ncols * 4);
+        w.wcp_lo = take((size_t)nef * w.ncols * 4);
         w.scal = take((size_t)B_img * w.ncols * 16);
-        w.v = take((size_t)B_img * nef * w.ncols * 4);
+        w.v_hi = take((size_t)B_img * nef * w.ncols * 4);
+        w.v_lo = take((size_t)B_img * nef * w.ncols * 4);
         w.wct_hi = take((size_t)B_img * w.ncols * nef * 4);
         w.wct_lo = take((size_t)B_img * w.ncols * nef * 4);
-        w.u = take((size_t)B_img * w.ncols * R * 4);
-        w.a2 = take((size_t)B_img * w.ncols * R * 4);
+        w.u_hi = take((size_t)B_img * R * w.ncols * 4);
+        w.u_lo = take((size_t)B_img * R * w.ncols * 4);
+        w.a2_hi = take((size_t)B_img * R * w.ncols * 4);
+        w.a2_lo = take((size_t)B_img * R * w.ncols * 4);
     }
     w.total = o;
     return w;
@@ -907,7 +1071,7 @@ int words_sim_fwd_tc5(const float* img, const float* words, const int* cap_lens,
     float* xt_lo = reinterpret_cast<float*>(ws + w.xt_lo);
 
     k_wt_plan<<<1, 256, 0, st>>>(cap_lens, B_cap, Lw, cap_col, plan, col_cap, col_T, w.ncols);
-    k_wt_words<<<w.ncols / 8, 256, 0, st>>>(words, col_cap, cap_col, wt_hi, wt_lo, ww, nullptr, w.ncols, nef, Lw);
+    k_wt_words<<<w.ncols / 8, 256, 0, st>>>(words, col_cap, cap_col, wt_hi, wt_lo, ww, nullptr, nullptr, w.ncols, nef, Lw);
     k_wt_images<<<dim3(w.RMP / 32, nef / 32, B_img), 256, 0, st>>>(img, x_hi, x_lo, xt_hi, xt_lo, nef, R, w.RKP, w.RMP);
     add_launches(3);
     rc = check_launch("words_sim_fwd(tcgen05 pre-pass)");
@@ -953,9 +1117,10 @@ int words_sim_bwd_tc5(const float* img, const float* words, const int* cap_lens,
     int dev = 0, sms = 0;
     int rc = current_device(&dev, &sms, "words_sim_bwd(tcgen05)");
     if (rc) return rc;
-    static std::atomic<unsigned long long> smem_a{0}, smem_b{0};
+    static std::atomic<unsigned long long> smem_a{0}, smem_b{0}, smem_c{0};
     rc = ensure_dynamic_smem(k_words_tc5<true>, kWtSmem, dev, smem_a, "words_sim_bwd(tcgen05)");
     if (!rc) rc = ensure_dynamic_smem(k_words_bwd_tc5, kWtBwdSmem, dev, smem_b, "words_sim_bwd(tcgen05)");
+    if (!rc) rc = ensure_dynamic_smem(k_words_dimg_tc5, kWtGemmSmem, dev, smem_c, "words_sim_bwd(tcgen05)");
     if (rc) return rc;
     char* ws = static_cast<char*>(workspace);
     WtPlan* plan = reinterpret_cast<WtPlan*>(ws + w.plan);
@@ -969,22 +1134,26 @@ int words_sim_bwd_tc5(const float* img, const float* words, const int* cap_lens,
     float* x_lo = reinterpret_cast<float*>(ws + w.x_lo);
     float* xt_hi = reinterpret_cast<float*>(ws + w.xt_hi);
     float* xt_lo = reinterpret_cast<float*>(ws + w.xt_lo);
-    float* wc_packed = reinterpret_cast<float*>(ws + w.wc_packed);
+    float* wcp_hi = reinterpret_cast<float*>(ws + w.wcp_hi);
+    float* wcp_lo = reinterpret_cast<float*>(ws + w.wcp_lo);
     float4* scal = reinterpret_cast<float4*>(ws + w.scal);
-    float* v = reinterpret_cast<float*>(ws + w.v);
+    float* v_hi = reinterpret_cast<float*>(ws + w.v_hi);
+    float* v_lo = reinterpret_cast<float*>(ws + w.v_lo);
     float* wct_hi = reinterpret_cast<float*>(ws + w.wct_hi);
     float* wct_lo = reinterpret_cast<float*>(ws + w.wct_lo);
-    float* u = reinterpret_cast<float*>(ws + w.u);
-    float* a2 = reinterpret_cast<float*>(ws + w.a2);
+    float* u_hi = reinterpret_cast<float*>(ws + w.u_hi);
+    float* u_lo = reinterpret_cast<float*>(ws + w.u_lo);
+    float* a2_hi = reinterpret_cast<float*>(ws + w.a2_hi);
+    float* a2_lo = reinterpret_cast<float*>(ws + w.a2_lo);
 
     k_wt_plan<<<1, 256, 0, st>>>(cap_lens, B_cap, Lw, cap_col, plan, col_cap, col_T, w.ncols);
-    k_wt_words<<<w.ncols / 8, 256, 0, st>>>(words, col_cap, cap_col, wt_hi, wt_lo, ww, wc_packed, w.ncols, nef, Lw);
+    k_wt_words<<<w.ncols / 8, 256, 0, st>>>(words, col_cap, cap_col, wt_hi, wt_lo, ww, wcp_hi, wcp_lo, w.ncols, nef, Lw);
     k_wt_images<<<dim3(w.RMP / 32, nef / 32, B_img), 256, 0, st>>>(img, x_hi, x_lo, xt_hi, xt_lo, nef, R, w.RKP, w.RMP);
     add_launches(3);
     rc = check_launch("words_sim_bwd(tcgen05 pre-pass)");
     if (rc) return rc;
 
-    CUtensorMap tm[8];
+    CUtensorMap tm[16];
     rc = make_k128_map(&tm[0], xt_hi, (long long)B_img * w.RMP, nef, 128);
     if (!rc) rc = make_k128_map(&tm[1], xt_lo, (long long)B_img * w.RMP, nef, 128);
     if (!rc) rc = make_k128_map(&tm[2], wt_hi, w.ncols, nef, 128);
@@ -993,24 +1162,39 @@ int words_sim_bwd_tc5(const float* img, const float* words, const int* cap_lens,
     if (!rc) rc = make_k128_map(&tm[5], x_lo, (long long)B_img * nef, w.RKP, nef);
     if (!rc) rc = make_k128_map(&tm[6], wct_hi, (long long)B_img * w.ncols, nef, 128);
     if (!rc) rc = make_k128_map(&tm[7], wct_lo, (long long)B_img * w.ncols, nef, 128);
+    // the d_img GEMM: A = u^T / a2^T [B_img * R][ncols] (tiles of 128 regions; rows past the last image read as zero),
+    // B = wcp [nef][ncols] and v [B_img * nef][ncols]
+    if (!rc) rc = make_k128_map(&tm[8], u_hi, (long long)B_img * R, w.ncols, 128);
+    if (!rc) rc = make_k128_map(&tm[9], u_lo, (long long)B_img * R, w.ncols, 128);
+    if (!rc) rc = make_k128_map(&tm[10], a2_hi, (long long)B_img * R, w.ncols, 128);
+    if (!rc) rc = make_k128_map(&tm[11], a2_lo, (long long)B_img * R, w.ncols, 128);
+    if (!rc) rc = make_k128_map(&tm[12], wcp_hi, nef, w.ncols, nef);
+    if (!rc) rc = make_k128_map(&tm[13], wcp_lo, nef, w.ncols, nef);
+    if (!rc) rc = make_k128_map(&tm[14], v_hi, (long long)B_img * nef, w.ncols, nef);
+    if (!rc) rc = make_k128_map(&tm[15], v_lo, (long long)B_img * nef, w.ncols, nef);
     if (rc) return rc;
     WtParams p{};
     p.wt_hi = wt_hi; p.wt_lo = wt_lo; p.ww = ww; p.col_cap = col_cap; p.col_T = col_T; p.plan = plan; p.sim = nullptr;
     p.B_cap = B_cap; p.nef = nef; p.R = R; p.MT = w.MT; p.RKC = w.RKC;
     p.g1l2e = g1 * 1.4426950408889634f; p.g2 = g2; p.g3 = g3; p.eps = eps;
-    p.d_sim = d_sim; p.cap_col = cap_col; p.scal = scal; p.v = v; p.wct_hi = wct_hi; p.wct_lo = wct_lo; p.ncols = w.ncols; p.g1 = g1;
+    p.d_sim = d_sim; p.cap_col = cap_col; p.scal = scal; p.v_hi = v_hi; p.v_lo = v_lo; p.wct_hi = wct_hi; p.wct_lo = wct_lo;
+    p.ncols = w.ncols; p.g1 = g1;
     const dim3 grid(w.n_half_max / 2, B_img);
     k_words_tc5<true><<<grid, kWtThreads, kWtSmem, st>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], p);
     rc = check_launch("words_sim_bwd(tcgen05 phase A)");
     if (rc) return rc;
     WtBwdParams b{};
-    b.col_cap = col_cap; b.plan = plan; b.scal = scal; b.u = u; b.a2 = a2;
+    b.col_cap = col_cap; b.plan = plan; b.scal = scal; b.u_hi = u_hi; b.u_lo = u_lo; b.a2_hi = a2_hi; b.a2_lo = a2_lo;
     b.nef = nef; b.R = R; b.MT = w.MT; b.RKC = w.RKC; b.ncols = w.ncols; b.g1 = g1; b.g1l2e = p.g1l2e;
     k_words_bwd_tc5<<<grid, kWtThreads, kWtBwdSmem, st>>>(tm[0], tm[1], tm[2], tm[3], tm[6], tm[7], b);
-    add_launches(2);
     rc = check_launch("words_sim_bwd(tcgen05 phase B)");
     if (rc) return rc;
-    return words_dimg_gemms(wc_packed, u, v, a2, d_img, B_img, nef, R, w.ncols, &plan->n_half, st);
+    WtGemmParams g{};
+    g.plan = plan; g.d_img = d_img; g.nef = nef; g.R = R;
+    k_words_dimg_tc5<<<dim3(w.MT, B_img), kGThreads, kWtGemmSmem, st>>>(tm[8], tm[9], tm[10], tm[11], tm[12], tm[13], tm[14],
+                                                                         tm[15], g);
+    add_launches(3);
+    return check_launch("words_sim_bwd(tcgen05 d_img)");
 }
 
 }  // namespace sba
