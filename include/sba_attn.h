@@ -219,14 +219,15 @@ SBA_API int sba_sent_scores_bwd(const float* cnn, const float* rnn, const float*
                      const float* d_scores, float* d_cnn, float* d_rnn,
                      int B, int nef, float gamma3, float eps, void* stream);
 
-/* Gradient of sim w.r.t. img on the tensor cores (tcgen05, 3xTF32), for the case that needs no gradient w.r.t. the
- * words (GAN training: trainer_bert.py:257 detaches them): the forward again with the upstream gradient (per-column
- * scalars, wc), then S = X^T W and V = X^T wc as chained UMMA GEMMs with both softmax backwards on chip, then the two
- * d_img GEMMs.  sba_words_sim_bwd_tc_workspace_bytes() is 0 when the shape is not covered.  Same result as
- * sba_words_sim_bwd with d_words == NULL. */
-SBA_API size_t sba_words_sim_bwd_tc_workspace_bytes(int B_img, int B_cap, int nef, int R, int Lw);
+/* Backward of sba_words_sim_fwd_ws on the tensor cores (tcgen05, 3xTF32): the forward again with the upstream gradient
+ * (per-column scalars, wc), then S = X^T W and V = X^T wc as chained UMMA GEMMs with both softmax backwards on chip, then
+ * d_img as one GEMM over the word columns and - when d_words is not NULL - d_words as one split-K GEMM over (image,
+ * region) whose partials are added in a fixed order.  d_words == NULL is the GAN-training call (trainer_bert.py:257
+ * detaches the words); non-NULL is DAMSM pre-training (pretrain_DAMSM.py:88-96).  The workspace query takes the same
+ * choice (need_words) and returns 0 when the shape is not covered.  Same results as sba_words_sim_bwd. */
+SBA_API size_t sba_words_sim_bwd_tc_workspace_bytes(int B_img, int B_cap, int nef, int R, int Lw, int need_words);
 SBA_API int sba_words_sim_bwd_tc(const float* img, const float* words, const int32_t* cap_lens,
-                      const float* d_sim, float* d_img, void* workspace, size_t workspace_bytes,
+                      const float* d_sim, float* d_img, float* d_words, void* workspace, size_t workspace_bytes,
                       int B_img, int B_cap, int row_offset, int nef, int R, int Lw,
                       float gamma1, float gamma2, float gamma3, float eps, void* stream);
 

@@ -31,8 +31,8 @@ SYMBOLS = {
     "sba_words_sim_fwd": (c_int, [c_void_p] * 5 + [c_int] * 6 + [c_float] * 4 + [c_void_p]),
     "sba_words_sim_fwd_workspace_bytes": (c_size_t, [c_int] * 5),
     "sba_words_sim_fwd_ws": (c_int, [c_void_p] * 6 + [c_size_t] + [c_int] * 6 + [c_float] * 4 + [c_void_p]),
-    "sba_words_sim_bwd_tc_workspace_bytes": (c_size_t, [c_int] * 5),
-    "sba_words_sim_bwd_tc": (c_int, [c_void_p] * 6 + [c_size_t] + [c_int] * 6 + [c_float] * 4 + [c_void_p]),
+    "sba_words_sim_bwd_tc_workspace_bytes": (c_size_t, [c_int] * 6),
+    "sba_words_sim_bwd_tc": (c_int, [c_void_p] * 7 + [c_size_t] + [c_int] * 6 + [c_float] * 4 + [c_void_p]),
     "sba_words_sim_bwd_workspace_bytes": (c_size_t, [c_int] * 5),
     "sba_words_sim_bwd": (c_int, [c_void_p] * 7 + [c_int] * 6 + [c_float] * 4 + [c_void_p]),
     "sba_func_attention": (c_int, [c_void_p] * 4 + [c_int] * 4 + [c_float] + [c_void_p]),

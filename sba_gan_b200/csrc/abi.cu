@@ -288,14 +288,14 @@ int sba_words_sim_fwd_ws(const float* img, const float* words, const int32_t* ca
     return words_att_diag(img, words, cap_lens, att_diag, B_img, B_cap, row_offset, nef, R, Lw, gamma1, st);
 }
 
-size_t sba_words_sim_bwd_tc_workspace_bytes(int B_img, int B_cap, int nef, int R, int Lw) {
+size_t sba_words_sim_bwd_tc_workspace_bytes(int B_img, int B_cap, int nef, int R, int Lw, int need_words) {
     if (B_img <= 0 || B_cap <= 0 || nef <= 0 || R <= 0 || Lw <= 0) return 0;
-    return words_tc5_bwd_workspace_bytes(B_img, B_cap, nef, R, Lw);
+    return words_tc5_bwd_workspace_bytes(B_img, B_cap, nef, R, Lw, need_words != 0);
 }
 
 int sba_words_sim_bwd_tc(const float* img, const float* words, const int32_t* cap_lens, const float* d_sim, float* d_img,
-                         void* workspace, size_t workspace_bytes, int B_img, int B_cap, int row_offset, int nef, int R, int Lw,
-                         float gamma1, float gamma2, float gamma3, float eps, void* stream) {
+                         float* d_words, void* workspace, size_t workspace_bytes, int B_img, int B_cap, int row_offset, int nef,
+                         int R, int Lw, float gamma1, float gamma2, float gamma3, float eps, void* stream) {
     g_launches = 0;
     g_err[0] = 0;
     (void)row_offset;        // the similarity of a pair does not depend on where the image rows sit in the global batch
@@ -305,8 +305,8 @@ int sba_words_sim_bwd_tc(const float* img, const float* words, const int32_t* ca
     }
     int rc = check_words_shape("sba_words_sim_bwd_tc", B_img, B_cap, nef, R, Lw);
     if (rc) return rc;
-    return words_sim_bwd_tc5(img, words, cap_lens, d_sim, d_img, workspace, workspace_bytes, B_img, B_cap, nef, R, Lw, gamma1,
-                             gamma2, gamma3, eps, static_cast<cudaStream_t>(stream));
+    return words_sim_bwd_tc5(img, words, cap_lens, d_sim, d_img, d_words, workspace, workspace_bytes, B_img, B_cap, nef, R, Lw,
+                             gamma1, gamma2, gamma3, eps, static_cast<cudaStream_t>(stream));
 }
 
 size_t sba_words_sim_bwd_workspace_bytes(int B_img, int B_cap, int nef, int R, int Lw) {

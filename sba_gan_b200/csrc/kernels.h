@@ -70,13 +70,13 @@ size_t words_tc5_workspace_bytes(int B_img, int B_cap, int nef, int R, int Lw);
 int words_sim_fwd_tc5(const float* img, const float* words, const int* cap_lens, float* sim, void* workspace, size_t ws_bytes,
                       int B_img, int B_cap, int nef, int R, int Lw, float g1, float g2, float g3, float eps, cudaStream_t st);
 
-// backward of the same on the tensor cores, d_img only (words detached: GAN training); needs
+// backward of the same on the tensor cores: d_img, and d_words when asked for (NULL: words detached, GAN training); needs
 // words_tc5_bwd_workspace_bytes() bytes (0 = not covered): phase A (forward again + per-column scalars, wc), phase B
 // (u^T, a2^T) and the d_img GEMM, all tcgen05 3xTF32.
-size_t words_tc5_bwd_workspace_bytes(int B_img, int B_cap, int nef, int R, int Lw);
+size_t words_tc5_bwd_workspace_bytes(int B_img, int B_cap, int nef, int R, int Lw, bool need_words);
 int words_sim_bwd_tc5(const float* img, const float* words, const int* cap_lens, const float* d_sim, float* d_img,
-                      void* workspace, size_t ws_bytes, int B_img, int B_cap, int nef, int R, int Lw, float g1, float g2,
-                      float g3, float eps, cudaStream_t st);
+                      float* d_words, void* workspace, size_t ws_bytes, int B_img, int B_cap, int nef, int R, int Lw, float g1,
+                      float g2, float g3, float eps, cudaStream_t st);
 
 // match_loss.cu - the B x B matching tail of words_loss / sent_loss: class masking + two-way cross-entropy, and
 // sent_loss's cosine score matrix

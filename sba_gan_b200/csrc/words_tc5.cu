@@ -84,6 +84,7 @@ struct WtParams {
     float* v_lo;
     float* wct_hi;             // [B_img][ncols][nef]  wc split in tf32 hi / lo: B operand of V = X^T wc in phase B
     float* wct_lo;
+    float* kap;                // [B_img][ncols] d|w_n| * |w_n| share of this image (beta |wc|^2), or NULL (no word gradients)
     int ncols;
     float g1;
 };
@@ -520,6 +521,7 @@ __global__ void __launch_bounds__(kWtThreads, 1)
                     D = alpha * numt + beta * wn * wn;                               // sum_r a2[r, n] da2[r, n]
                 }
                 p.scal[(size_t)j * p.ncols + ng] = make_float4(alpha, beta, D, invZ);
+                if (p.kap != nullptr) p.kap[(size_t)j * p.ncols + ng] = beta * wn * wn;      // = d_den |w| |wc| (losses.py:17)
                 // second pass over wc: v = beta wc in tf32 hi / lo (rows = channels: consecutive threads write consecutive columns) and
                 // wc^T split into tf32 hi / lo (this thread's row, 128 contiguous bytes per chunk)
                 float* vh = p.v_hi + (size_t)j * nef * p.ncols + ng;
@@ -573,7 +575,6 @@ __global__ void __launch_bounds__(kWtThreads, 1)
 // the CUDA-core kernel of words_loss.cu materialises the same u / a2).
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int kBStageBytes = 6 * kTileBytes;      // A hi, A lo, W hi, W lo, wc hi, wc lo: 96 KB
-constexpr int kBStageF4 = 2 * 32 * 4;             // float4 per epilogue warp: 16 columns of 32 regions, hi and lo (4 KB)
 struct WtBwdParams {
     const int* col_cap;
     const WtPlan* plan;
@@ -582,10 +583,14 @@ struct WtBwdParams {
     float* u_lo;               //                     the K-major A operands of the d_img GEMM
     float* a2_hi;
     float* a2_lo;
+    float* u2_hi;              // [B_img * ncols][RKP]  u again, columns = rows, regions contiguous (zero for r >= R):
+    float* u2_lo;              //                       K-major A operand of the d_words GEMM; NULL = no word gradients
+    int RKP;
     int nef, R, MT, RKC, ncols;
     float g1, g1l2e;
 };
 
+template <bool WORDS>
 __global__ void __launch_bounds__(kWtThreads, 1)
     k_words_bwd_tc5(const __grid_constant__ CUtensorMap tm_xt_hi, const __grid_constant__ CUtensorMap tm_xt_lo,
                     const __grid_constant__ CUtensorMap tm_wt_hi, const __grid_constant__ CUtensorMap tm_wt_lo,
@@ -597,8 +602,7 @@ __global__ void __launch_bounds__(kWtThreads, 1)
     const uint32_t sbase = smem_u32(smem_raw);
     const uint32_t s_ring = sbase;
     float4* scs = reinterpret_cast<float4*>(smem_raw + kStages * kBStageBytes);        // [128] per-column scalars
-    float4* stg_all = scs + kNB;                          // [8 warps][hi, lo][32 regions][4 x float4]: output staging
-    unsigned long long* bars = reinterpret_cast<unsigned long long*>(stg_all + 8 * kBStageF4);
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(scs + kNB);
     unsigned long long* bar_full = bars;                  // [kStages]
     unsigned long long* bar_empty = bars + kStages;       // [kStages]
     unsigned long long* bar_t_full = bars + 2 * kStages;  // [2]  S and V of a region tile are complete
@@ -746,38 +750,15 @@ __global__ void __launch_bounds__(kWtThreads, 1)
                 a1[c] *= seg;
             }
             // (2) t = a1 gamma1 a2 (alpha S + beta V - D), running sum per caption into rb; a2 goes out
-            // u^T / a2^T rows [region][column]: a thread owns a region and 16 columns at a time, the warp stores them
-            // through its staging tile so that every store instruction writes 8 whole 64-byte row pieces
-            // (float4 slots XOR-swizzled with (region >> 1) & 3: conflict-free both ways)
-            float4* stg = stg_all + ew * kBStageF4;
-            const int r_base = 128 * m + 32 * q;
-            const size_t obase = ((size_t)j * p.R + r_base) * p.ncols + ncol0;       // first region row of this warp
-            auto flush16 = [&](float* __restrict__ dst_hi, float* __restrict__ dst_lo, const float (&h)[16], const float (&l)[16],
-                               int col0) {
-                __syncwarp();                                     // the previous flush has been read out
-#pragma unroll
-                for (int k4 = 0; k4 < 4; ++k4) {
-                    const int slot = lane * 4 + (k4 ^ ((lane >> 1) & 3));
-                    stg[slot] = make_float4(h[4 * k4], h[4 * k4 + 1], h[4 * k4 + 2], h[4 * k4 + 3]);
-                    stg[128 + slot] = make_float4(l[4 * k4], l[4 * k4 + 1], l[4 * k4 + 2], l[4 * k4 + 3]);
-                }
-                __syncwarp();
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int row = 8 * i + (lane >> 2), k4 = lane & 3;
-                    if (r_base + row < p.R) {
-                        const int slot = row * 4 + (k4 ^ ((row >> 1) & 3));
-                        const size_t o = obase + (size_t)row * p.ncols + col0 + 4 * k4;
-                        *reinterpret_cast<float4*>(dst_hi + o) = stg[slot];
-                        *reinterpret_cast<float4*>(dst_lo + o) = stg[128 + slot];
-                    }
-                }
-            };
+            // u^T / a2^T rows [region][column]: this thread's region row, 16-byte pieces (staging them through shared
+            // memory into whole 64-byte row pieces per store instruction was measured: no faster - the kernel is bound by
+            // its dependent scans, not by store requests)
+            const size_t orow = ((size_t)j * p.R + r) * p.ncols + ncol0;
             run = 0.f;
 #pragma unroll
             for (int g0 = 0; g0 < kHalf; g0 += 16) {
                 uint32_t s16[16], v16[16];
-                float ah[16], al[16];
+                float ah[4], al[4];
                 __syncwarp();                                    // (the stores below are lane-dependent)
                 tmem_ld<16>(tS + g0, s16);
                 tmem_ld<16>(tV + g0, v16);
@@ -792,14 +773,17 @@ __global__ void __launch_bounds__(kWtThreads, 1)
                     const float t = a1[c] * p.g1 * a2 * (da2 - cs4.z);
                     run = ((first >> c) & 1ull) ? t : run + t;
                     rb[c] = __float_as_uint(run);
-                    split_tf32(a2, ah[k], al[k]);
+                    split_tf32(a2, ah[k & 3], al[k & 3]);
+                    if ((k & 3) == 3 && rv) {
+                        *reinterpret_cast<float4*>(p.a2_hi + orow + c - 3) = make_float4(ah[0], ah[1], ah[2], ah[3]);
+                        *reinterpret_cast<float4*>(p.a2_lo + orow + c - 3) = make_float4(al[0], al[1], al[2], al[3]);
+                    }
                 }
-                flush16(p.a2_hi, p.a2_lo, ah, al, g0);
             }
             tc_fence_before();
             warp_arrive1(smem_u32(&bar_t_free[buf]), lane);
             // (3) ds = t - a1 (sum of t over the caption), u = ds + alpha a2; t is recovered from the running sums
-            float uh[16], ul[16];
+            float uh[4], ul[4];
             seg = 0.f;
 #pragma unroll
             for (int c = kHalf - 1; c >= 0; --c) {
@@ -810,8 +794,16 @@ __global__ void __launch_bounds__(kWtThreads, 1)
                 const bool ok = rv && ((valid >> c) & 1ull);
                 const float a2 = ok ? mma::ex2_approx((a1[c] - 1.f) * p.g1l2e) * cs4.w : 0.f;
                 const float uu = ok ? t - a1[c] * seg + cs4.x * a2 : 0.f;
-                split_tf32(uu, uh[c & 15], ul[c & 15]);
-                if ((c & 15) == 0) flush16(p.u_hi, p.u_lo, uh, ul, c);
+                split_tf32(uu, uh[c & 3], ul[c & 3]);
+                if constexpr (WORDS) {               // every existing warp's regions are < RKP; zero beyond R
+                    const size_t o2 = ((size_t)j * p.ncols + ncol0 + c) * p.RKP + r;
+                    p.u2_hi[o2] = uh[c & 3];
+                    p.u2_lo[o2] = ul[c & 3];
+                }
+                if ((c & 3) == 0 && rv) {
+                    *reinterpret_cast<float4*>(p.u_hi + orow + c) = make_float4(uh[0], uh[1], uh[2], uh[3]);
+                    *reinterpret_cast<float4*>(p.u_lo + orow + c) = make_float4(ul[0], ul[1], ul[2], ul[3]);
+                }
             }
             __syncwarp();
             WT_MARK(19);
@@ -842,15 +834,24 @@ struct WtGemmParams {
     const WtPlan* plan;
     float* d_img;              // [B_img][nef][R]
     int nef, R;
+    // d_words mode: part[split][n][c] = sum over the split's images j and all regions r of u[j][n][r] X_j[c][r]
+    float* part;               // [splits][ncols][nef]
+    int ncols, B_img, RKC;
 };
 
+// WORDS = false: the d_img GEMM above, CTA = (region tile, image).
+// WORDS = true : the word-gradient GEMM  part[n][c] = sum_{j in split} sum_r u[j][n][r] X_j[c][r]  (M = 128 word columns,
+//                N = nef, K = (image, region chunk)), CTA = (128-column block, split of the images); A = u2 hi / lo (maps 0, 1),
+//                B = X hi / lo (maps 4, 5: the forward's G2 operand).  The splits are added in order by k_wt_dwords.
+template <bool WORDS>
 __global__ void __launch_bounds__(kGThreads, 1)
     k_words_dimg_tc5(const __grid_constant__ CUtensorMap tm_u_hi, const __grid_constant__ CUtensorMap tm_u_lo,
                      const __grid_constant__ CUtensorMap tm_a2_hi, const __grid_constant__ CUtensorMap tm_a2_lo,
                      const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
                      const __grid_constant__ CUtensorMap tm_v_hi, const __grid_constant__ CUtensorMap tm_v_lo,
                      const WtGemmParams p) {
-    const int m = blockIdx.x, j = blockIdx.y;
+    const int m = blockIdx.x, j = blockIdx.y;           // WORDS: m = column block, j = split
+    if (WORDS && 2 * m >= p.plan->n_half) return;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const uint32_t sbase = smem_u32(smem_raw);
     unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem_raw + kStages * kGStageBytes);
@@ -861,8 +862,11 @@ __global__ void __launch_bounds__(kGThreads, 1)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int nef = p.nef;
-    const int KCH = p.plan->n_half * (kHalf / kKC);       // stages per term
-    const int NS = 2 * KCH;
+    const int KCH = p.plan->n_half * (kHalf / kKC);       // d_img: stages per term
+    // d_words: images [j0, j1) of this split, RKC region chunks each
+    const int j0 = WORDS ? (int)(((long long)j * p.B_img) / gridDim.y) : 0;
+    const int j1 = WORDS ? (int)(((long long)(j + 1) * p.B_img) / gridDim.y) : 0;
+    const int NS = WORDS ? (j1 - j0) * p.RKC : 2 * KCH;
 
     if (tid == 0) {
         if (sbase & 1023u) __trap();
@@ -882,13 +886,21 @@ __global__ void __launch_bounds__(kGThreads, 1)
             if (s >= kStages) mbar_wait(smem_u32(&bar_empty[st]), (uint32_t)((s / kStages) - 1) & 1u);
             if (elect_one()) {
                 const uint32_t full = smem_u32(&bar_full[st]), dst = sbase + st * kGStageBytes;
-                const bool second = s >= KCH;
-                const int kc = (second ? s - KCH : s) * kKC;
                 mbar_expect_tx(full, (uint32_t)(2 * kTileBytes + 2 * nef * kKC * 4));
-                tma_load_2d(dst, second ? &tm_a2_hi : &tm_u_hi, kc, j * p.R + m * 128, full);
-                tma_load_2d(dst + kTileBytes, second ? &tm_a2_lo : &tm_u_lo, kc, j * p.R + m * 128, full);
-                tma_load_2d(dst + 2 * kTileBytes, second ? &tm_v_hi : &tm_w_hi, kc, second ? j * nef : 0, full);
-                tma_load_2d(dst + 2 * kTileBytes + kGBTileBytes, second ? &tm_v_lo : &tm_w_lo, kc, second ? j * nef : 0, full);
+                if constexpr (WORDS) {
+                    const int jj = j0 + s / p.RKC, kc = (s - (jj - j0) * p.RKC) * kKC;
+                    tma_load_2d(dst, &tm_u_hi, kc, jj * p.ncols + m * 128, full);
+                    tma_load_2d(dst + kTileBytes, &tm_u_lo, kc, jj * p.ncols + m * 128, full);
+                    tma_load_2d(dst + 2 * kTileBytes, &tm_w_hi, kc, jj * nef, full);
+                    tma_load_2d(dst + 2 * kTileBytes + kGBTileBytes, &tm_w_lo, kc, jj * nef, full);
+                } else {
+                    const bool second = s >= KCH;
+                    const int kc = (second ? s - KCH : s) * kKC;
+                    tma_load_2d(dst, second ? &tm_a2_hi : &tm_u_hi, kc, j * p.R + m * 128, full);
+                    tma_load_2d(dst + kTileBytes, second ? &tm_a2_lo : &tm_u_lo, kc, j * p.R + m * 128, full);
+                    tma_load_2d(dst + 2 * kTileBytes, second ? &tm_v_hi : &tm_w_hi, kc, second ? j * nef : 0, full);
+                    tma_load_2d(dst + 2 * kTileBytes + kGBTileBytes, second ? &tm_v_lo : &tm_w_lo, kc, second ? j * nef : 0, full);
+                }
             }
             __syncwarp();
         }
@@ -919,17 +931,25 @@ __global__ void __launch_bounds__(kGThreads, 1)
     } else {
         const int q = warp & 3;
         const uint32_t tl = tmem_base + ((uint32_t)(q * 32) << 16);
-        const int r = m * 128 + q * 32 + lane;
-        float* out = p.d_img + (size_t)j * nef * p.R + r;
+        const int r = m * 128 + q * 32 + lane;           // d_img: region; d_words: word column
         mbar_wait(smem_u32(bar_d_full), 0u);
         tc_fence_after();
         for (int c0 = 0; c0 < nef; c0 += 32) {
             uint32_t d[32];
             tmem_ld<32>(tl + c0, d);
             tmem_wait_ld();
-            if (r < p.R) {
+            if constexpr (WORDS) {
+                float4* out = reinterpret_cast<float4*>(p.part + ((size_t)j * p.ncols + r) * nef + c0);
 #pragma unroll
-                for (int c = 0; c < 32; ++c) out[(size_t)(c0 + c) * p.R] = __uint_as_float(d[c]);
+                for (int c4 = 0; c4 < 8; ++c4)
+                    out[c4] = make_float4(__uint_as_float(d[4 * c4]), __uint_as_float(d[4 * c4 + 1]), __uint_as_float(d[4 * c4 + 2]),
+                                          __uint_as_float(d[4 * c4 + 3]));
+            } else {
+                float* out = p.d_img + (size_t)j * nef * p.R + r;
+                if (r < p.R) {
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) out[(size_t)(c0 + c) * p.R] = __uint_as_float(d[c]);
+                }
             }
             __syncwarp();                            // (tcgen05.ld is warp-collective; the stores are lane-dependent)
         }
@@ -944,8 +964,44 @@ __global__ void __launch_bounds__(kGThreads, 1)
 
 constexpr size_t kWtGemmSmem = (size_t)kStages * kGStageBytes + (2 * kStages + 1 + 1) * 8;
 
-constexpr size_t kWtBwdSmem = (size_t)kStages * kBStageBytes + kNB * 16 + 8 * kBStageF4 * 16 + (2 * kStages + 4 + 1) * 8;
-static_assert(kWtBwdSmem <= 232448, "phase B: operand ring + output staging must fit the 227 KB of one CTA");
+// d_words[i][c][t] = sum of the split partials (in split order) + (sum_j kap[j][n]) / |w_n|^2 * w_n[c]  for the caption's
+// T_i words, 0 beyond (losses.py:72-76 slices the caption; autograd leaves the padding's gradient at zero).
+// block = (caption i), thread = channel c (strided)
+__global__ void __launch_bounds__(256) k_wt_dwords(const float* __restrict__ part, const float* __restrict__ kap,
+                                                   const float* __restrict__ wt_hi, const float* __restrict__ wt_lo,
+                                                   const float* __restrict__ ww, const int* __restrict__ cap_col,
+                                                   const int* __restrict__ cap_lens, float* __restrict__ d_words, int splits,
+                                                   int ncols, int nef, int B_img, int Lw) {
+    __shared__ float kn[32];
+    const int i = blockIdx.x;
+    int T = cap_lens[i];
+    T = T < 0 ? 0 : (T > Lw ? Lw : T);
+    const int n0 = cap_col[i];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int t = warp; t < T; t += 8) {          // kappa_t: images added in order by one lane-strided tree per word
+        float a = 0.f;
+        for (int j = lane; j < B_img; j += 32) a += kap[(size_t)j * ncols + n0 + t];
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+        const float w = ww[n0 + t];
+        if (lane == 0) kn[t] = w > 0.f ? a / (w * w) : 0.f;
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < nef; c += 256) {
+        float* out = d_words + ((size_t)i * nef + c) * Lw;
+        for (int t = 0; t < Lw; ++t) {
+            float a = 0.f;
+            if (t < T) {
+                const size_t o = (size_t)(n0 + t) * nef + c;
+                for (int s = 0; s < splits; ++s) a += part[(size_t)s * ncols * nef + o];
+                a = fmaf(kn[t], wt_hi[o] + wt_lo[o], a);
+            }
+            out[t] = a;
+        }
+    }
+}
+
+constexpr size_t kWtBwdSmem = (size_t)kStages * kBStageBytes + kNB * 16 + (2 * kStages + 4 + 1) * 8;
 
 constexpr size_t kWtSmem = (size_t)kStages * kStageBytes + (size_t)kEBufs * kEBufBytes + (size_t)(kMaxChunks * kNB + kNB) * 4 +
                            (2 * kStages + 4 + kEBufs + 4 + 2) * 8;
@@ -956,8 +1012,10 @@ struct WtLayout {
     int ncols, n_half_max, MT, RKC, RKP, RMP;
     size_t plan, cap_col, col_cap, col_T, ww, wt_hi, wt_lo, x_hi, x_lo, xt_hi, xt_lo, total;
     size_t wcp_hi, wcp_lo, scal, v_hi, v_lo, wct_hi, wct_lo, u_hi, u_lo, a2_hi, a2_lo;       // backward only
+    size_t kap, u2_hi, u2_lo, part;                                                          // word gradients only
+    int splits;
 };
-WtLayout wt_layout(int B_img, int B_cap, int nef, int R, int Lw, bool bwd = false) {
+WtLayout wt_layout(int B_img, int B_cap, int nef, int R, int Lw, bool bwd = false, bool dwords = false) {
     WtLayout w{};
     const int per_half = kHalf / Lw < 1 ? 1 : kHalf / Lw;            // captions per half block, worst case
     w.n_half_max = (B_cap + per_half - 1) / per_half;
@@ -992,6 +1050,13 @@ WtLayout wt_layout(int B_img, int B_cap, int nef, int R, int Lw, bool bwd = fals
         w.u_lo = take((size_t)B_img * R * w.ncols * 4);
         w.a2_hi = take((size_t)B_img * R * w.ncols * 4);
         w.a2_lo = take((size_t)B_img * R * w.ncols * 4);
+    }
+    w.splits = B_img < 16 ? B_img : 16;           // image splits of the d_words GEMM (partials added in order)
+    if (bwd && dwords) {
+        w.kap = take((size_t)B_img * w.ncols * 4);
+        w.u2_hi = take((size_t)B_img * w.ncols * w.RKP * 4);
+        w.u2_lo = take((size_t)B_img * w.ncols * w.RKP * 4);
+        w.part = take((size_t)w.splits * w.ncols * nef * 4);
     }
     w.total = o;
     return w;
@@ -1094,22 +1159,23 @@ int words_sim_fwd_tc5(const float* img, const float* words, const int* cap_lens,
     return check_launch("words_sim_fwd(tcgen05)");
 }
 
-size_t words_tc5_bwd_workspace_bytes(int B_img, int B_cap, int nef, int R, int Lw) {
+size_t words_tc5_bwd_workspace_bytes(int B_img, int B_cap, int nef, int R, int Lw, bool need_words) {
     if (!words_tc5_supports(B_img, B_cap, nef, R, Lw)) return 0;
-    const WtLayout w = wt_layout(B_img, B_cap, nef, R, Lw, true);
+    const WtLayout w = wt_layout(B_img, B_cap, nef, R, Lw, true, need_words);
     if ((long long)B_img * w.ncols >= (1ll << 31) / 2) return 0;       // TMA row coordinates of wc^T
     return w.total;
 }
 
-// d_img only (GAN training: the words are detached, trainer_bert.py:257); d_words stays with the CUDA-core backward
+// d_img always; d_words (nullable: GAN training detaches the words, trainer_bert.py:257) for DAMSM pre-training
 int words_sim_bwd_tc5(const float* img, const float* words, const int* cap_lens, const float* d_sim, float* d_img,
-                      void* workspace, size_t ws_bytes, int B_img, int B_cap, int nef, int R, int Lw, float g1, float g2,
-                      float g3, float eps, cudaStream_t st) {
+                      float* d_words, void* workspace, size_t ws_bytes, int B_img, int B_cap, int nef, int R, int Lw, float g1,
+                      float g2, float g3, float eps, cudaStream_t st) {
     if (!words_tc5_supports(B_img, B_cap, nef, R, Lw)) {
         set_error("words_sim_bwd(tcgen05): shape nef=%d R=%d Lw=%d not covered", nef, R, Lw);
         return SBA_ERR_UNSUPPORTED;
     }
-    const WtLayout w = wt_layout(B_img, B_cap, nef, R, Lw, true);
+    const bool dwords = d_words != nullptr;
+    const WtLayout w = wt_layout(B_img, B_cap, nef, R, Lw, true, dwords);
     if (ws_bytes < w.total || (reinterpret_cast<uintptr_t>(workspace) & 255u)) {
         set_error("words_sim_bwd(tcgen05): workspace of %zu bytes given, %zu (256-byte aligned) needed", ws_bytes, w.total);
         return SBA_ERR_ARG;
@@ -1117,10 +1183,12 @@ int words_sim_bwd_tc5(const float* img, const float* words, const int* cap_lens,
     int dev = 0, sms = 0;
     int rc = current_device(&dev, &sms, "words_sim_bwd(tcgen05)");
     if (rc) return rc;
-    static std::atomic<unsigned long long> smem_a{0}, smem_b{0}, smem_c{0};
+    static std::atomic<unsigned long long> smem_a{0}, smem_b{0}, smem_c{0}, smem_d{0}, smem_e{0};
     rc = ensure_dynamic_smem(k_words_tc5<true>, kWtSmem, dev, smem_a, "words_sim_bwd(tcgen05)");
-    if (!rc) rc = ensure_dynamic_smem(k_words_bwd_tc5, kWtBwdSmem, dev, smem_b, "words_sim_bwd(tcgen05)");
-    if (!rc) rc = ensure_dynamic_smem(k_words_dimg_tc5, kWtGemmSmem, dev, smem_c, "words_sim_bwd(tcgen05)");
+    if (!rc) rc = ensure_dynamic_smem(k_words_bwd_tc5<false>, kWtBwdSmem, dev, smem_b, "words_sim_bwd(tcgen05)");
+    if (!rc) rc = ensure_dynamic_smem(k_words_bwd_tc5<true>, kWtBwdSmem, dev, smem_e, "words_sim_bwd(tcgen05)");
+    if (!rc) rc = ensure_dynamic_smem(k_words_dimg_tc5<false>, kWtGemmSmem, dev, smem_c, "words_sim_bwd(tcgen05)");
+    if (!rc) rc = ensure_dynamic_smem(k_words_dimg_tc5<true>, kWtGemmSmem, dev, smem_d, "words_sim_bwd(tcgen05)");
     if (rc) return rc;
     char* ws = static_cast<char*>(workspace);
     WtPlan* plan = reinterpret_cast<WtPlan*>(ws + w.plan);
@@ -1145,6 +1213,10 @@ int words_sim_bwd_tc5(const float* img, const float* words, const int* cap_lens,
     float* u_lo = reinterpret_cast<float*>(ws + w.u_lo);
     float* a2_hi = reinterpret_cast<float*>(ws + w.a2_hi);
     float* a2_lo = reinterpret_cast<float*>(ws + w.a2_lo);
+    float* kap = dwords ? reinterpret_cast<float*>(ws + w.kap) : nullptr;
+    float* u2_hi = dwords ? reinterpret_cast<float*>(ws + w.u2_hi) : nullptr;
+    float* u2_lo = dwords ? reinterpret_cast<float*>(ws + w.u2_lo) : nullptr;
+    float* part = dwords ? reinterpret_cast<float*>(ws + w.part) : nullptr;
 
     k_wt_plan<<<1, 256, 0, st>>>(cap_lens, B_cap, Lw, cap_col, plan, col_cap, col_T, w.ncols);
     k_wt_words<<<w.ncols / 8, 256, 0, st>>>(words, col_cap, cap_col, wt_hi, wt_lo, ww, wcp_hi, wcp_lo, w.ncols, nef, Lw);
@@ -1153,7 +1225,7 @@ int words_sim_bwd_tc5(const float* img, const float* words, const int* cap_lens,
     rc = check_launch("words_sim_bwd(tcgen05 pre-pass)");
     if (rc) return rc;
 
-    CUtensorMap tm[16];
+    CUtensorMap tm[18];
     rc = make_k128_map(&tm[0], xt_hi, (long long)B_img * w.RMP, nef, 128);
     if (!rc) rc = make_k128_map(&tm[1], xt_lo, (long long)B_img * w.RMP, nef, 128);
     if (!rc) rc = make_k128_map(&tm[2], wt_hi, w.ncols, nef, 128);
@@ -1172,29 +1244,45 @@ int words_sim_bwd_tc5(const float* img, const float* words, const int* cap_lens,
     if (!rc) rc = make_k128_map(&tm[13], wcp_lo, nef, w.ncols, nef);
     if (!rc) rc = make_k128_map(&tm[14], v_hi, (long long)B_img * nef, w.ncols, nef);
     if (!rc) rc = make_k128_map(&tm[15], v_lo, (long long)B_img * nef, w.ncols, nef);
+    if (dwords) {
+        if (!rc) rc = make_k128_map(&tm[16], u2_hi, (long long)B_img * w.ncols, w.RKP, 128);
+        if (!rc) rc = make_k128_map(&tm[17], u2_lo, (long long)B_img * w.ncols, w.RKP, 128);
+    }
     if (rc) return rc;
     WtParams p{};
     p.wt_hi = wt_hi; p.wt_lo = wt_lo; p.ww = ww; p.col_cap = col_cap; p.col_T = col_T; p.plan = plan; p.sim = nullptr;
     p.B_cap = B_cap; p.nef = nef; p.R = R; p.MT = w.MT; p.RKC = w.RKC;
     p.g1l2e = g1 * 1.4426950408889634f; p.g2 = g2; p.g3 = g3; p.eps = eps;
     p.d_sim = d_sim; p.cap_col = cap_col; p.scal = scal; p.v_hi = v_hi; p.v_lo = v_lo; p.wct_hi = wct_hi; p.wct_lo = wct_lo;
-    p.ncols = w.ncols; p.g1 = g1;
+    p.ncols = w.ncols; p.g1 = g1; p.kap = kap;
     const dim3 grid(w.n_half_max / 2, B_img);
     k_words_tc5<true><<<grid, kWtThreads, kWtSmem, st>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], p);
     rc = check_launch("words_sim_bwd(tcgen05 phase A)");
     if (rc) return rc;
     WtBwdParams b{};
     b.col_cap = col_cap; b.plan = plan; b.scal = scal; b.u_hi = u_hi; b.u_lo = u_lo; b.a2_hi = a2_hi; b.a2_lo = a2_lo;
+    b.u2_hi = u2_hi; b.u2_lo = u2_lo; b.RKP = w.RKP;
     b.nef = nef; b.R = R; b.MT = w.MT; b.RKC = w.RKC; b.ncols = w.ncols; b.g1 = g1; b.g1l2e = p.g1l2e;
-    k_words_bwd_tc5<<<grid, kWtThreads, kWtBwdSmem, st>>>(tm[0], tm[1], tm[2], tm[3], tm[6], tm[7], b);
+    if (dwords)
+        k_words_bwd_tc5<true><<<grid, kWtThreads, kWtBwdSmem, st>>>(tm[0], tm[1], tm[2], tm[3], tm[6], tm[7], b);
+    else
+        k_words_bwd_tc5<false><<<grid, kWtThreads, kWtBwdSmem, st>>>(tm[0], tm[1], tm[2], tm[3], tm[6], tm[7], b);
     rc = check_launch("words_sim_bwd(tcgen05 phase B)");
     if (rc) return rc;
     WtGemmParams g{};
     g.plan = plan; g.d_img = d_img; g.nef = nef; g.R = R;
-    k_words_dimg_tc5<<<dim3(w.MT, B_img), kGThreads, kWtGemmSmem, st>>>(tm[8], tm[9], tm[10], tm[11], tm[12], tm[13], tm[14],
-                                                                         tm[15], g);
+    k_words_dimg_tc5<false><<<dim3(w.MT, B_img), kGThreads, kWtGemmSmem, st>>>(tm[8], tm[9], tm[10], tm[11], tm[12], tm[13],
+                                                                                tm[14], tm[15], g);
     add_launches(3);
-    return check_launch("words_sim_bwd(tcgen05 d_img)");
+    rc = check_launch("words_sim_bwd(tcgen05 d_img)");
+    if (rc || !dwords) return rc;
+    g.part = part; g.ncols = w.ncols; g.B_img = B_img; g.RKC = w.RKC;
+    // (maps 2, 3, 6, 7 are unused in this mode; 4, 5 = X hi / lo as in the forward's second GEMM)
+    k_words_dimg_tc5<true><<<dim3(w.n_half_max / 2, w.splits), kGThreads, kWtGemmSmem, st>>>(tm[16], tm[17], tm[16], tm[17], tm[4],
+                                                                                              tm[5], tm[4], tm[5], g);
+    k_wt_dwords<<<B_cap, 256, 0, st>>>(part, kap, wt_hi, wt_lo, ww, cap_col, cap_lens, d_words, w.splits, w.ncols, nef, B_img, Lw);
+    add_launches(2);
+    return check_launch("words_sim_bwd(tcgen05 d_words)");
 }
 
 }  // namespace sba

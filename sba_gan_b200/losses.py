@@ -79,17 +79,19 @@ class _WordsSimilarity(torch.autograd.Function):
         if not (need_img or need_words):
             return None, None, None, None, None, None, None
         d_sim = d_sim.to(torch.float32).contiguous()
-        tc_bytes = (lib.sba_words_sim_bwd_tc_workspace_bytes(B_img, B_cap, nef, R, Lw)
-                    if (FORWARD_ALGO != "simt" and not need_words) else 0)
-        if tc_bytes:        # tensor-core backward: d_img only (words detached, as in GAN training)
+        tc_bytes = (lib.sba_words_sim_bwd_tc_workspace_bytes(B_img, B_cap, nef, R, Lw, int(need_words))
+                    if FORWARD_ALGO != "simt" else 0)
+        if tc_bytes:        # tensor-core backward: d_img, and d_words unless the words are detached (GAN training)
             ws = torch.empty((tc_bytes,), dtype=torch.uint8, device=img32.device)
             d_img = torch.empty_like(img32)
-            rc = lib.sba_words_sim_bwd_tc(_ptr(img32), _ptr(words32), _ptr(cap_lens_i32), _ptr(d_sim), _ptr(d_img), _ptr(ws),
-                                          tc_bytes, B_img, B_cap, row_offset, nef, R, Lw, gammas[0], gammas[1], gammas[2], eps,
-                                          _stream())
+            d_words = torch.empty_like(words32) if need_words else None
+            rc = lib.sba_words_sim_bwd_tc(_ptr(img32), _ptr(words32), _ptr(cap_lens_i32), _ptr(d_sim), _ptr(d_img), _ptr(d_words),
+                                          _ptr(ws), tc_bytes, B_img, B_cap, row_offset, nef, R, Lw, gammas[0], gammas[1],
+                                          gammas[2], eps, _stream())
             _abi.check(rc, "sba_words_sim_bwd_tc")
             launch_counter["n"] += _abi.last_launch_count()
-            return (d_img.to(img_dtype) if need_img else None, None, None, None, None, None, None)
+            return (d_img.to(img_dtype) if need_img else None, d_words.to(words_dtype) if need_words else None,
+                    None, None, None, None, None)
         nbytes = lib.sba_words_sim_bwd_workspace_bytes(B_img, B_cap, nef, R, Lw)
         ws = torch.empty((nbytes,), dtype=torch.uint8, device=img32.device)
         d_img = torch.empty_like(img32)

@@ -140,7 +140,7 @@ def test_words_detached_matches_reference_golden(golden_dir, name):
 
 @pytest.mark.parametrize("B", [128, 256])
 def test_tensor_core_backward_full_size_vs_cuda_core(B):
-    """BASELINE configs[2] sizes: the tensor-core d_img against the CUDA-core backward (itself checked against the
+    """BASELINE configs[2] sizes: the tensor-core d_img / d_words against the CUDA-core backward (itself checked against the
     oracle above), and run-to-run bit-stable (fixed-order reductions; also a soak for the barrier protocol: a stale
     chunk buffer shows up as a changed bit long before it shows up as a wrong loss)."""
     from sba_gan_b200 import losses
@@ -148,13 +148,14 @@ def test_tensor_core_backward_full_size_vs_cuda_core(B):
     img, words, lens = d["img_features"].cuda(), d["words_emb"].cuda(), d["cap_lens"].cuda()
     labels, cls = d["labels"].cuda(), d["class_ids"]
 
-    def grad(algo):
+    def grad(algo, with_words=False):
         losses.FORWARD_ALGO = algo
         try:
             x = img.clone().requires_grad_(True)
-            l0, l1, _ = losses.words_loss(x, words, labels, lens, cls, B, 4.0, 5.0, 10.0, att_maps=False)
-            (gi,) = torch.autograd.grad(l0 + l1, [x])
-            return l0.detach(), gi
+            w = words.clone().requires_grad_(with_words)
+            l0, l1, _ = losses.words_loss(x, w, labels, lens, cls, B, 4.0, 5.0, 10.0, att_maps=False)
+            g = torch.autograd.grad(l0 + l1, [x, w] if with_words else [x])
+            return (l0.detach(),) + tuple(g)
         finally:
             losses.FORWARD_ALGO = "auto"
 
@@ -165,6 +166,15 @@ def test_tensor_core_backward_full_size_vs_cuda_core(B):
     for _ in range(4 if B == 256 else 8):
         l_again, g_again = grad("auto")
         assert torch.equal(l_again, l_tc) and torch.equal(g_again, g_tc)
+    # DAMSM pre-training: word gradients too (split-K GEMM over (image, region), partials added in a fixed order)
+    _, gi_tc, gw_tc = grad("auto", True)
+    _, gi_cc, gw_cc = grad("simt", True)
+    assert torch.equal(gi_tc, g_tc)
+    assert normalised_max_err(gw_tc.cpu(), gw_cc.cpu().double()) <= TOL_GRAD
+    _, _, gw_again = grad("auto", True)
+    assert torch.equal(gw_again, gw_tc)
+    pad = torch.arange(words.shape[2], device="cuda")[None, :] >= lens[:, None]
+    assert (gw_tc.permute(0, 2, 1)[pad] == 0).all()          # no gradient beyond a caption's length
 
 
 @pytest.mark.parametrize("tag", ["f32"])

@@ -65,30 +65,40 @@ for (B, nef, L, hw) in [(6, 256, 18, 17), (48, 256, 18, 17), (5, 64, 12, 6), (9,
     lens = torch.sort(torch.randint(1, L + 1, (B,), generator=g), descending=True).values.cuda()
     cls = torch.randint(1, 50, (B,), generator=g).cuda()
     labels = torch.arange(B).cuda()
-    grads, times = {}, {}
+    grads, gw, times, times_w = {}, {}, {}, {}
     for algo in ("simt", "auto"):
         losses.FORWARD_ALGO = algo
         x = img.clone().requires_grad_(True)
         l0, l1, _ = words_loss(x, words, labels, lens, cls, B, 4.0, 5.0, 10.0, att_maps=False)
         (gi,) = torch.autograd.grad(l0 + l1, [x])
         grads[algo] = gi
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
-        e0.record()
-        for _ in range(3):
-            l0, l1, _ = words_loss(x, words, labels, lens, cls, B, 4.0, 5.0, 10.0, att_maps=False)
-            torch.autograd.grad(l0 + l1, [x])
-        e1.record()
-        torch.cuda.synchronize()
-        times[algo] = e0.elapsed_time(e1) / 3
-    msg = f"bwd B={B} nef={nef} L={L} R={hw*hw}: tc5 vs simt {((grads['auto'] - grads['simt']).abs().max() / grads['simt'].abs().max()).item():.2e}"
+        w = words.clone().requires_grad_(True)
+        l0, l1, _ = words_loss(x, w, labels, lens, cls, B, 4.0, 5.0, 10.0, att_maps=False)
+        gi2, gw[algo] = torch.autograd.grad(l0 + l1, [x, w])
+        assert torch.equal(gi2, gi) or algo == "simt", "d_img differs between the detached and the full backward"
+        for wg, tt in ((False, times), (True, times_w)):
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+            e0.record()
+            for _ in range(3):
+                ww_ = words.clone().requires_grad_(wg)
+                l0, l1, _ = words_loss(x, ww_, labels, lens, cls, B, 4.0, 5.0, 10.0, att_maps=False)
+                torch.autograd.grad(l0 + l1, [x, ww_] if wg else [x])
+            e1.record()
+            torch.cuda.synchronize()
+            tt[algo] = e0.elapsed_time(e1) / 3
+    rel = lambda a, b: ((a.double() - b.double()).abs().max() / b.double().abs().max()).item()  # noqa: E731
+    msg = f"bwd B={B} nef={nef} L={L} R={hw*hw}: tc5 vs simt d_img {rel(grads['auto'], grads['simt']):.2e} d_words {rel(gw['auto'], gw['simt']):.2e}"
     if B <= 9:
         x64 = img.double().clone().requires_grad_(True)
-        sim = ref_sim(x64, words, lens.cpu(), 4.0, 5.0, 10.0)
+        w64 = words.double().clone().requires_grad_(True)
+        sim = ref_sim(x64, w64, lens.cpu(), 4.0, 5.0, 10.0)
         same = (cls[:, None] == cls[None, :]) & ~torch.eye(B, dtype=torch.bool, device="cuda")
         sim = sim.masked_fill(same, float("-inf"))
         loss = torch.nn.functional.cross_entropy(sim, labels) + torch.nn.functional.cross_entropy(sim.t(), labels)
-        (gr,) = torch.autograd.grad(loss, [x64])
-        msg += f" | vs fp64: simt {((grads['simt'].double() - gr).abs().max() / gr.abs().max()).item():.2e} tc5 {((grads['auto'].double() - gr).abs().max() / gr.abs().max()).item():.2e}"
-    print(msg + f" | fwd+bwd simt {times['simt']:.3f} ms  tc5 {times['auto']:.3f} ms", flush=True)
+        gr, gwr = torch.autograd.grad(loss, [x64, w64])
+        msg += (f" | vs fp64 d_img: simt {rel(grads['simt'], gr):.2e} tc5 {rel(grads['auto'], gr):.2e}"
+                f"  d_words: simt {rel(gw['simt'], gwr):.2e} tc5 {rel(gw['auto'], gwr):.2e}")
+    print(msg + f" | fwd+bwd(img) simt {times['simt']:.3f} tc5 {times['auto']:.3f} ms | fwd+bwd(img,words) simt {times_w['simt']:.3f} tc5 {times_w['auto']:.3f} ms",
+          flush=True)
 print("bwd done")
