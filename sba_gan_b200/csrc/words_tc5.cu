@@ -89,23 +89,36 @@ struct WtParams {
     float g1;
 };
 
-// ---- pre-pass 1: pack the captions into half blocks (sequential greedy, one thread; B_cap is a few hundred) ---------
-__global__ void k_wt_plan(const int* __restrict__ cap_lens, int B_cap, int Lw, int* __restrict__ cap_col, WtPlan* plan,
-                          int* __restrict__ col_cap, int* __restrict__ col_T, int ncols) {
+// ---- pre-pass 1: pack the captions into half blocks (greedy, in caption order) -----------------------------------------
+// One block.  The lengths are staged in shared memory by all threads, one thread walks them (a few cycles per caption:
+// no global round trip inside the sequential part), then all threads fill the per-column tables.
+constexpr int kPlanMaxCaps = 4096;
+__global__ void __launch_bounds__(256) k_wt_plan(const int* __restrict__ cap_lens, int B_cap, int Lw, int* __restrict__ cap_col,
+                                                 WtPlan* plan, int* __restrict__ col_cap, int* __restrict__ col_T, int ncols) {
+    __shared__ short s_T[kPlanMaxCaps];
+    __shared__ int s_col[kPlanMaxCaps];
     for (int n = threadIdx.x; n < ncols; n += blockDim.x) { col_cap[n] = -1; col_T[n] = 0; }
+    for (int i = threadIdx.x; i < B_cap; i += blockDim.x) {
+        const int T = cap_lens[i];
+        s_T[i] = (short)(T < 0 ? 0 : (T > Lw ? Lw : T));
+    }
     __syncthreads();
     if (threadIdx.x == 0) {
         int h = 0, off = 0;
         for (int i = 0; i < B_cap; ++i) {
-            int T = cap_lens[i];
-            T = T < 0 ? 0 : (T > Lw ? Lw : T);
+            const int T = s_T[i];
             if (off + T > kHalf) { ++h; off = 0; }
-            cap_col[i] = h * kHalf + off;
-            if (T > 0) col_T[h * kHalf + off] = T;
-            for (int t = 0; t < T; ++t) col_cap[h * kHalf + off + t] = i;
+            s_col[i] = h * kHalf + off;
             off += T;
         }
         plan->n_half = h + 1;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < B_cap; i += blockDim.x) {
+        const int c0 = s_col[i], T = s_T[i];
+        cap_col[i] = c0;
+        if (T > 0) col_T[c0] = T;
+        for (int t = 0; t < T; ++t) col_cap[c0 + t] = i;
     }
 }
 
@@ -1097,6 +1110,7 @@ int make_k128_map(CUtensorMap* out, const void* base, long long rows, int cols, 
 
 bool words_tc5_supports(int B_img, int B_cap, int nef, int R, int Lw) {
     return nef % 32 == 0 && nef >= 32 && nef <= 256 && R >= 1 && R <= 384 && Lw >= 1 && Lw <= 32 && B_img >= 1 && B_cap >= 1 &&
+           B_cap <= kPlanMaxCaps &&
            (long long)B_img * 384 * nef < (1ll << 31);
 }
 
