@@ -223,7 +223,7 @@ SBA_API int sba_sent_scores_bwd(const float* cnn, const float* rnn, const float*
  * (per-column scalars, wc), then S = X^T W and V = X^T wc as chained UMMA GEMMs with both softmax backwards on chip, then
  * d_img as one GEMM over the word columns and - when d_words is not NULL - d_words as one split-K GEMM over (image,
  * region) whose partials are added in a fixed order.  d_words == NULL is the GAN-training call (trainer_bert.py:257
- * detaches the words); non-NULL is DAMSM pre-training (pretrain_DAMSM.py:88-96).  The workspace query takes the same
+ * detaches the words); non-NULL is DAMSM pre-training (pretrain_DAMSM.py:80-91).  The workspace query takes the same
  * choice (need_words) and returns 0 when the shape is not covered.  Same results as sba_words_sim_bwd. */
 SBA_API size_t sba_words_sim_bwd_tc_workspace_bytes(int B_img, int B_cap, int nef, int R, int Lw, int need_words);
 SBA_API int sba_words_sim_bwd_tc(const float* img, const float* words, const int32_t* cap_lens,
