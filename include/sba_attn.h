@@ -58,6 +58,8 @@ enum { SBA_MASK_REFERENCE = 0, SBA_MASK_PER_SAMPLE = 1 };
  *  MMA     : warp-level mma.sync with TMA-staged tiles
  *  TCGEN05 : tcgen05.mma with TMEM accumulators, TMA tensor loads / stores, one pixel per thread */
 enum { SBA_ALGO_AUTO = 0, SBA_ALGO_SIMT = 1, SBA_ALGO_MMA = 2, SBA_ALGO_TCGEN05 = 3 };
+/* which of a call's two kernels to launch (sba_attn_fwd_phase / sba_attn_bwd_phase) */
+enum { SBA_PHASE_ALL = 0, SBA_PHASE_FIRST = 1, SBA_PHASE_SECOND = 2 };
 
 SBA_API int sba_abi_version(void);
 SBA_API const char* sba_last_error(void);
@@ -112,6 +114,29 @@ SBA_API int sba_attn_bwd(const void* x, const float* ctx, const float* W, const 
                  void* dX, float* ws, size_t ws_floats, float* dW, float* dCtx,
                  int B, int idf, int cdf, int L, int Q,
                  int dtype, int mask_mode, int algo, void* stream);
+
+/* ---- the two kernels of a call, separately (tcgen05 family only) ----------------------
+ * Both calls consist of a streaming kernel over the pixels and a small kernel that does not touch them:
+ *   forward : FIRST  = the projection sourceT = conv_context(context) (+ mask words): needs only ctx, W, mask and
+ *                      writes srcT / scratch - it can run as soon as the word features exist (in G_NET.forward,
+ *                      model_bert.py:580-588, that is before the first stage has produced h_code), on any stream;
+ *             SECOND = the streaming kernel: needs x, mask, srcT / scratch of a completed FIRST, writes c_code, attn.
+ *   backward: FIRST  = the streaming kernel: writes dX and the partial sums in ws;
+ *             SECOND = the finish kernel: ws -> dW, dCtx (parameter / word-feature gradients: nothing in the backward
+ *                      chain waits for them, so it can run on a side stream under the next layer's backward).
+ * Ordering between the phases is the caller's (same stream, or an event).  SBA_PHASE_ALL = the plain calls above.
+ * Pointers a phase does not use may be NULL.  Results are bit-identical to the one-call form.
+ */
+SBA_API int sba_attn_fwd_phase(const void* x, const float* ctx, const float* W, const uint8_t* mask,
+                 void* c_code, void* attn, float* srcT, uint32_t* scratch,
+                 int B, int idf, int cdf, int L, int Q,
+                 int dtype, int mask_mode, int phase, void* stream);
+SBA_API int sba_attn_bwd_phase(const void* x, const float* ctx, const float* W, const uint8_t* mask,
+                 const float* srcT, uint32_t* scratch,
+                 const void* g_c, const void* g_attn,
+                 void* dX, float* ws, size_t ws_floats, float* dW, float* dCtx,
+                 int B, int idf, int cdf, int L, int Q,
+                 int dtype, int mask_mode, int phase, void* stream);
 
 /* ---- the caller's torch.cat((h_code, c_code), 1) folded into the attention ----------
  * (NEXT_STAGE_G.forward, model_bert.py:459-461)

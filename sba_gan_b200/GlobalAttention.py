@@ -45,8 +45,33 @@ class GlobalAttentionGeneral(nn.Module):
     def applyMask(self, mask):
         self.mask = mask  # batch x sourceL, sticky until the next call (GlobalAttention.py:79-80)
 
+    def prepare(self, context, stream=None):
+        """Optional (an extension; the reference has no counterpart): run this call's projection
+        ``sourceT = conv_context(context)`` now, on ``stream`` (default: the current stream), so that the next
+        ``forward(input, context)`` with the same word features, weight and mask launches only the streaming kernel.
+        In ``G_NET.forward`` (model_bert.py:580-588) ``word_embs`` and the mask exist before ``h_net1`` has produced
+        the first ``h_code``: ``h_net2.att`` / ``h_net3.att`` can be prepared on a side stream under it.  A stale
+        preparation (anything changed in between) is ignored.  Call ``applyMask`` first."""
+        from .functional import _MASK_MODES, prepare_projection
+        mask_u8 = None
+        if self.mask is not None:
+            m = self.mask.detach()
+            mask_u8 = (m.view(torch.uint8) if m.dtype == torch.bool and m.device == context.device and m.is_contiguous()
+                       else m.to(device=context.device, dtype=torch.uint8).contiguous())
+        self._prepared = (prepare_projection(context, self.conv_context.weight, mask_u8, _MASK_MODES[self.mask_mode], stream)
+                          if context.is_cuda and self.algo in ("auto", "tc5") else None)
+        self._prepared_mask = (self.mask, mask_u8)
+        return self._prepared is not None
+
     def forward(self, input, context):
         """input: batch x idf x ih x iw (queryL = ih*iw); context: batch x cdf x sourceL
         returns (weightedContext batch x idf x ih x iw, attn batch x sourceL x ih x iw)."""
-        return word_region_attention(input, context, self.conv_context.weight, self.mask,
-                                     mask_mode=self.mask_mode, algo=self.algo, algo_bwd=self.algo_bwd)
+        prepared, mask = getattr(self, "_prepared", None), self.mask
+        if prepared is not None:
+            self._prepared = None                                   # one preparation serves one call
+            if self._prepared_mask[0] is self.mask:
+                mask = self._prepared_mask[1]                       # the very bytes the projection read
+            else:
+                prepared = None
+        return word_region_attention(input, context, self.conv_context.weight, mask,
+                                     mask_mode=self.mask_mode, algo=self.algo, algo_bwd=self.algo_bwd, prepared=prepared)

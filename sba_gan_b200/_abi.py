@@ -14,6 +14,7 @@ SBA_F32, SBA_BF16 = 0, 1
 SBA_MASK_REFERENCE, SBA_MASK_PER_SAMPLE = 0, 1
 SBA_ALGO_AUTO, SBA_ALGO_SIMT, SBA_ALGO_MMA, SBA_ALGO_TCGEN05 = 0, 1, 2, 3
 ABI_VERSION = 4
+SBA_PHASE_ALL, SBA_PHASE_FIRST, SBA_PHASE_SECOND = 0, 1, 2
 
 # every symbol include/sba_attn.h declares: (restype, argtypes)
 SYMBOLS = {
@@ -25,6 +26,8 @@ SYMBOLS = {
     "sba_attn_supported": (c_int, [c_int] * 8),
     "sba_attn_bwd_workspace_floats": (c_size_t, [c_int] * 4),
     "sba_attn_bwd": (c_int, [c_void_p] * 10 + [c_size_t] + [c_void_p] * 2 + [c_int] * 8 + [c_void_p]),
+    "sba_attn_fwd_phase": (c_int, [c_void_p] * 8 + [c_int] * 8 + [c_void_p]),
+    "sba_attn_bwd_phase": (c_int, [c_void_p] * 10 + [c_size_t] + [c_void_p] * 2 + [c_int] * 8 + [c_void_p]),
     "sba_attn_fwd_into": (c_int, [c_void_p] * 5 + [c_int] * 2 + [c_void_p] * 3 + [c_int] * 7 + [c_void_p]),
     "sba_attn_bwd_from": (c_int, [c_void_p] * 7 + [c_int] * 2 + [c_void_p] * 3 + [c_size_t] + [c_void_p] * 2 + [c_int] * 7
                           + [c_void_p]),

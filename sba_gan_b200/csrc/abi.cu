@@ -110,7 +110,12 @@ static int attn_fwd_impl(const void* x, const float* ctx, const float* W, const 
                          float* srcT, uint32_t* mask_bits, AttnShape s, int algo, void* stream, const char* fn) {
     g_launches = 0;
     g_err[0] = 0;
-    if (!x || !ctx || !W || !c_code || !attn || !srcT || !mask_bits) {
+    const bool first = s.phase != SBA_PHASE_SECOND, second = s.phase != SBA_PHASE_FIRST;
+    if (s.phase < SBA_PHASE_ALL || s.phase > SBA_PHASE_SECOND) {
+        set_error("%s: phase %d is not one of SBA_PHASE_*", fn, s.phase);
+        return SBA_ERR_ARG;
+    }
+    if (!srcT || !mask_bits || (first && (!ctx || !W)) || (second && (!x || !c_code || !attn))) {
         set_error("%s: null pointer argument", fn);
         return SBA_ERR_ARG;
     }
@@ -119,7 +124,8 @@ static int attn_fwd_impl(const void* x, const float* ctx, const float* W, const 
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const bool strided = s.c_rows > 0;          // c_code goes into a wider buffer: tensor-map stores only
     const bool can_mma = !strided && mma_supports(s) && aligned16(x);
-    const bool can_tc5 = tc5_supports(s) && aligned16(x) && aligned16(W) && aligned16(c_code) && aligned16(attn);
+    const bool can_tc5 = tc5_supports(s) && (!first || aligned16(W)) &&
+                         (!second || (aligned16(x) && aligned16(c_code) && aligned16(attn)));
     if (algo == SBA_ALGO_TCGEN05 || (algo == SBA_ALGO_AUTO && can_tc5) || strided) {
         if (!can_tc5) {
             set_error("%s: SBA_ALGO_TCGEN05 does not cover idf=%d L=%d Q=%d B=%d (or x is not 16-byte aligned)", fn, s.idf,
@@ -149,7 +155,12 @@ static int attn_bwd_impl(const void* x, const float* ctx, const float* W, const 
                          size_t ws_floats, float* dW, float* dCtx, AttnShape s, int algo, void* stream, const char* fn) {
     g_launches = 0;
     g_err[0] = 0;
-    if (!x || !ctx || !W || !srcT || !g_c || !dX || !ws || !mask_bits) {
+    const bool first = s.phase != SBA_PHASE_SECOND, second = s.phase != SBA_PHASE_FIRST;
+    if (s.phase < SBA_PHASE_ALL || s.phase > SBA_PHASE_SECOND) {
+        set_error("%s: phase %d is not one of SBA_PHASE_*", fn, s.phase);
+        return SBA_ERR_ARG;
+    }
+    if (!ws || (first && (!x || !srcT || !g_c || !dX || !mask_bits)) || (second && (!ctx || !W))) {
         set_error("%s: null pointer argument", fn);
         return SBA_ERR_ARG;
     }
@@ -162,7 +173,7 @@ static int attn_bwd_impl(const void* x, const float* ctx, const float* W, const 
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const bool strided = s.c_rows > 0;          // g_c is a slice of a wider buffer: tensor-map loads only
     const bool can_mma = !strided && mma_supports(s) && aligned16(x) && aligned16(g_c);
-    const bool can_tc5 = tc5_bwd_supports(s) && aligned16(x) && aligned16(g_c) && aligned16(dX) && aligned16(ws);
+    const bool can_tc5 = tc5_bwd_supports(s) && aligned16(ws) && (!first || (aligned16(x) && aligned16(g_c) && aligned16(dX)));
     if (algo == SBA_ALGO_TCGEN05 || (algo == SBA_ALGO_AUTO && can_tc5) || strided) {
         if (!can_tc5) {
             set_error("%s: SBA_ALGO_TCGEN05 does not cover idf=%d L=%d Q=%d B=%d dtype=%d (bf16 tensors, 16-byte aligned)", fn,
@@ -205,6 +216,26 @@ int sba_attn_bwd(const void* x, const float* ctx, const float* W, const uint8_t*
                  void* stream) {
     return attn_bwd_impl(x, ctx, W, mask, srcT, mask_bits, g_c, g_attn, dX, ws, ws_floats, dW, dCtx,
                          AttnShape{B, idf, cdf, L, Q, dtype, mask_mode}, algo, stream, "sba_attn_bwd");
+}
+
+// One kernel of a call at a time (tcgen05 family): the projection / finish kernels do not touch the pixel tensors and can
+// be scheduled off the critical path by the caller (include/sba_attn.h).
+int sba_attn_fwd_phase(const void* x, const float* ctx, const float* W, const uint8_t* mask, void* c_code, void* attn,
+                       float* srcT, uint32_t* mask_bits, int B, int idf, int cdf, int L, int Q, int dtype, int mask_mode,
+                       int phase, void* stream) {
+    AttnShape s{B, idf, cdf, L, Q, dtype, mask_mode};
+    s.phase = phase;
+    return attn_fwd_impl(x, ctx, W, mask, c_code, attn, srcT, mask_bits, s, SBA_ALGO_TCGEN05, stream, "sba_attn_fwd_phase");
+}
+
+int sba_attn_bwd_phase(const void* x, const float* ctx, const float* W, const uint8_t* mask, const float* srcT,
+                       uint32_t* mask_bits, const void* g_c, const void* g_attn, void* dX, float* ws, size_t ws_floats,
+                       float* dW, float* dCtx, int B, int idf, int cdf, int L, int Q, int dtype, int mask_mode, int phase,
+                       void* stream) {
+    AttnShape s{B, idf, cdf, L, Q, dtype, mask_mode};
+    s.phase = phase;
+    return attn_bwd_impl(x, ctx, W, mask, srcT, mask_bits, g_c, g_attn, dX, ws, ws_floats, dW, dCtx, s, SBA_ALGO_TCGEN05, stream,
+                         "sba_attn_bwd_phase");
 }
 
 // NEXT_STAGE_G's torch.cat((h_code, c_code), 1) folded into the attention (model_bert.py:460-461): the forward

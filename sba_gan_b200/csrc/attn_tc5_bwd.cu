@@ -776,7 +776,7 @@ Tc5BwdWs tc5_bwd_ws(int B, int idf, int cdf, int L, int sms) {
 }
 
 template <int IDF, int NQ, bool HAS_GA, int NST_>
-int launch_bwd_tc5(const void* x, const void* g, void* dX, const Tc5BwdParams& p_in, const Tc5FinishParams& f_in,
+int launch_bwd_tc5(const void* x, const void* g, void* dX, const Tc5BwdParams& p_in, const Tc5FinishParams& f_in, int phase,
                    cudaStream_t st) {
     using C = Tc5BwdCfg<IDF, NQ, NST_>;
     auto kern = k_attn_bwd_tc5<IDF, NQ, HAS_GA, NST_>;
@@ -798,25 +798,25 @@ int launch_bwd_tc5(const void* x, const void* g, void* dX, const Tc5BwdParams& p
     const int max_ctas = sms * per_sm;
     Tc5BwdParams p = p_in;
     Tc5FinishParams f = f_in;
-    CUtensorMap tm_x, tm_g, tm_dx;
-    rc = make_tile_map(&tm_x, x, SBA_BF16, p.B * IDF, p.Q, IDF, 64, true);
-    if (!rc) rc = make_tile_map(&tm_g, g, SBA_BF16, p.B * p.g_rows, p.Q, IDF, 64, true);
-    if (!rc) rc = make_tile_map(&tm_dx, dX, SBA_BF16, p.B * IDF, p.Q, IDF, 32, false);
-    if (rc) return rc;
-    const int grid = p.n_tiles < max_ctas ? p.n_tiles : max_ctas;
-    p.tl = f.tl = SBA_TL_SLOT();
+    const int grid = p.n_tiles < max_ctas ? p.n_tiles : max_ctas;      // (a function of the shape and the device only:
+    p.tl = f.tl = SBA_TL_SLOT();                                       //  the finish phase recomputes the same value)
 
-    {
+    if (phase != SBA_PHASE_SECOND) {
+        CUtensorMap tm_x, tm_g, tm_dx;
+        rc = make_tile_map(&tm_x, x, SBA_BF16, p.B * IDF, p.Q, IDF, 64, true);
+        if (!rc) rc = make_tile_map(&tm_g, g, SBA_BF16, p.B * p.g_rows, p.Q, IDF, 64, true);
+        if (!rc) rc = make_tile_map(&tm_dx, dX, SBA_BF16, p.B * IDF, p.Q, IDF, 32, false);
+        if (rc) return rc;
         PdlLaunch ml(dim3(grid), dim3(kBwdThreads), smem, st);
         cudaError_t e = cudaLaunchKernelEx(&ml.cfg, kern, tm_x, tm_g, tm_dx, p);
         if (e != cudaSuccess) {
             set_error("attn_bwd(tcgen05): launch: %s", cudaGetErrorString(e));
             return SBA_ERR_CUDA;
         }
+        add_launches(1);
+        rc = check_launch("attn_bwd(tcgen05)");
+        if (rc || phase == SBA_PHASE_FIRST) return rc;
     }
-    add_launches(1);
-    rc = check_launch("attn_bwd(tcgen05)");
-    if (rc) return rc;
     // finish kernel: slots -> dSrc, dW, dCtx
     f.n_ctas = grid;
     f.n_dw = f.dW != nullptr ? f.groups * ((f.cdf + 31) / 32) : 0;
@@ -838,7 +838,8 @@ int launch_bwd_tc5(const void* x, const void* g, void* dX, const Tc5BwdParams& p
 }
 
 template <int IDF, bool HAS_GA>
-int dispatch_nq(const void* x, const void* g, void* dX, const Tc5BwdParams& p, const Tc5FinishParams& f, cudaStream_t st) {
+int dispatch_nq(const void* x, const void* g, void* dX, const Tc5BwdParams& p, const Tc5FinishParams& f, int phase,
+                cudaStream_t st) {
     // long streams at idf 32 (>= 16 tiles per CTA of a 2-per-SM grid, e.g. 128x128 at B >= 40) take the 4-deep ring:
     // it still fits two CTAs per SM there and measured 2-4 % faster; short streams lose to its longer prologue
     constexpr bool kDeep = IDF == 32;
@@ -846,9 +847,9 @@ int dispatch_nq(const void* x, const void* g, void* dX, const Tc5BwdParams& p, c
 #define SBA_BWD_CASE(n)                                                                     \
     case n:                                                                                 \
         if constexpr (kDeep) {                                                              \
-            if (deep) return launch_bwd_tc5<IDF, n, HAS_GA, 4>(x, g, dX, p, f, st);         \
+            if (deep) return launch_bwd_tc5<IDF, n, HAS_GA, 4>(x, g, dX, p, f, phase, st);         \
         }                                                                                   \
-        return launch_bwd_tc5<IDF, n, HAS_GA, 3>(x, g, dX, p, f, st);
+        return launch_bwd_tc5<IDF, n, HAS_GA, 3>(x, g, dX, p, f, phase, st);
     switch ((p.L + 3) / 4) {
         SBA_BWD_CASE(1) SBA_BWD_CASE(2) SBA_BWD_CASE(3) SBA_BWD_CASE(4)
         SBA_BWD_CASE(5) SBA_BWD_CASE(6) SBA_BWD_CASE(7) SBA_BWD_CASE(8)
@@ -858,8 +859,9 @@ int dispatch_nq(const void* x, const void* g, void* dX, const Tc5BwdParams& p, c
 }
 
 template <int IDF>
-int dispatch_ga(const void* x, const void* g, void* dX, const Tc5BwdParams& p, const Tc5FinishParams& f, cudaStream_t st) {
-    return p.ga != nullptr ? dispatch_nq<IDF, true>(x, g, dX, p, f, st) : dispatch_nq<IDF, false>(x, g, dX, p, f, st);
+int dispatch_ga(const void* x, const void* g, void* dX, const Tc5BwdParams& p, const Tc5FinishParams& f, int phase,
+                cudaStream_t st) {
+    return p.ga != nullptr ? dispatch_nq<IDF, true>(x, g, dX, p, f, phase, st) : dispatch_nq<IDF, false>(x, g, dX, p, f, phase, st);
 }
 
 }  // namespace
@@ -901,9 +903,9 @@ int tc5_attn_bwd(const void* x, const float* ctx, const float* W, const float* s
     f.tiles_per_sample = p.tiles_per_sample; f.n_tiles = p.n_tiles;
     f.ctx_aligned = (reinterpret_cast<uintptr_t>(ctx) & 15u) == 0;
     rc = -1;
-    if (s.idf == 32) rc = dispatch_ga<32>(x, g_c, dX, p, f, st);
-    else if (s.idf == 48) rc = dispatch_ga<48>(x, g_c, dX, p, f, st);
-    else if (s.idf == 64) rc = dispatch_ga<64>(x, g_c, dX, p, f, st);
+    if (s.idf == 32) rc = dispatch_ga<32>(x, g_c, dX, p, f, s.phase, st);
+    else if (s.idf == 48) rc = dispatch_ga<48>(x, g_c, dX, p, f, s.phase, st);
+    else if (s.idf == 64) rc = dispatch_ga<64>(x, g_c, dX, p, f, s.phase, st);
     if (rc == -1) {
         set_error("attn_bwd(tcgen05): unsupported shape idf=%d L=%d", s.idf, s.L);
         return SBA_ERR_UNSUPPORTED;

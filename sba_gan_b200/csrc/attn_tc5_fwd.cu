@@ -72,6 +72,7 @@ int make_tile_map(CUtensorMap* out, const void* base, int dtype, int rows, int c
             *out = mc.map[i];
             return SBA_OK;
         }
+    bind_context_to_thread();
     const EncodeFn encode = encode_fn();
     if (encode == nullptr) {
         set_error("cuTensorMapEncodeTiled is not available from this driver");
@@ -123,6 +124,7 @@ struct Tc5FwdParams {
     int chunk;            // tiles per dynamic chunk
     int dyn_first;        // first tile of the dynamic region = gridDim.x * static_tiles
     unsigned long long* tl;   // development timeline stamps (tc5_common.cuh), NULL in the product library
+    int phase;            // SBA_PHASE_*: host side only
 };
 
 constexpr int pow2_cols(int n) { return n <= 32 ? 32 : n <= 64 ? 64 : n <= 128 ? 128 : n <= 256 ? 256 : 512; }
@@ -732,13 +734,7 @@ int launch_fwd_tc5(const void* x, const Tc5FwdParams& p_in, int dtype, cudaStrea
     if (p.static_tiles == 0 && grid > (p.n_tiles + ch - 1) / ch) grid = (p.n_tiles + ch - 1) / ch;   // one first chunk each
     p.dyn_first = grid * p.static_tiles;
     p.tl = SBA_TL_SLOT();
-    CUtensorMap tmx, tma_attn, tma_c;
-    const int es = dtype == SBA_F32 ? 4 : 2;
-    rc = make_tile_map(&tmx, x, dtype, p.B * IDF, p.Q, IDF, 128 / es, true);
-    if (!rc) rc = make_tile_map(&tma_attn, p.attn, dtype, p.B * p.L, p.Q, p.L, 32, false);
-    if (!rc) rc = make_tile_map(&tma_c, p.c_code, dtype, p.B * p.c_rows, p.Q, IDF, 32, false);
-    if (rc) return rc;
-    {
+    if (p.phase != SBA_PHASE_SECOND) {
         PdlLaunch pl(dim3(p.B * (IDF / 8)), dim3(256), 0, st);
         cudaError_t pe = cudaLaunchKernelEx(&pl.cfg, k_project_tc5, p.ctx, p.W, p.srcT, p.mask, p.mask_bits, p.sched,
                                             (int)IDF, p.cdf, p.L, early_trigger, p.tl);
@@ -746,14 +742,22 @@ int launch_fwd_tc5(const void* x, const Tc5FwdParams& p_in, int dtype, cudaStrea
             set_error("project(tcgen05): launch: %s", cudaGetErrorString(pe));
             return SBA_ERR_CUDA;
         }
+        add_launches(1);
+        if (p.phase == SBA_PHASE_FIRST) return check_launch("project(tcgen05)");
     }
+    CUtensorMap tmx, tma_attn, tma_c;
+    const int es = dtype == SBA_F32 ? 4 : 2;
+    rc = make_tile_map(&tmx, x, dtype, p.B * IDF, p.Q, IDF, 128 / es, true);
+    if (!rc) rc = make_tile_map(&tma_attn, p.attn, dtype, p.B * p.L, p.Q, p.L, 32, false);
+    if (!rc) rc = make_tile_map(&tma_c, p.c_code, dtype, p.B * p.c_rows, p.Q, IDF, 32, false);
+    if (rc) return rc;
     PdlLaunch ml(dim3(grid), dim3(kThreads), smem, st);
     cudaError_t e = cudaLaunchKernelEx(&ml.cfg, kern, tmx, tma_attn, tma_c, p);
     if (e != cudaSuccess) {
         set_error("attn_fwd(tcgen05): launch: %s", cudaGetErrorString(e));
         return SBA_ERR_CUDA;
     }
-    add_launches(2);
+    add_launches(1);
     return check_launch("attn_fwd(tcgen05)");
 }
 
@@ -793,6 +797,7 @@ int tc5_attn_fwd(const void* x, const float* ctx, const float* W, const uint8_t*
     p.tiles_per_sample = s.Q / tc5::TQ;
     p.n_tiles = s.B * p.tiles_per_sample;
     p.sched = mask_bits + s.B;            // scratch holds 3B words: [0, B) mask words, [B] chunk counter
+    p.phase = s.phase;
     int rc = -1;
     if (s.dtype == SBA_F32) {
         if (s.idf == 32) rc = dispatch_nq<float, 32>(x, p, s.dtype, st);

@@ -34,6 +34,20 @@ inline int current_device(int* dev_out, int* sms_out, const char* what) {
     return SBA_OK;
 }
 
+// cuTensorMapEncodeTiled is a driver entry point: it needs the device's primary context to be current on the calling
+// host thread, which only a runtime call that touches the device guarantees.  A thread that arrives after the one-time
+// attribute calls below have been made by another thread (e.g. autograd's backward thread after a first call from the
+// main thread) has made no such call yet: bind the context once per thread (found by a test that ran in that order:
+// CUDA_ERROR_INVALID_CONTEXT from the encoder).
+inline void bind_context_to_thread() {
+    thread_local int bound_dev = -1;
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && dev != bound_dev) {
+        cudaFree(nullptr);
+        bound_dev = dev;
+    }
+}
+
 // Raise a kernel's dynamic shared-memory limit once per device.  `done` is a call-site static bit mask
 // (one bit per device); setting the attribute twice from racing threads is harmless.
 template <class Kern>

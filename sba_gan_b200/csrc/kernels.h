@@ -10,6 +10,9 @@ struct AttnShape {
     // forward output placement (tcgen05 family): c_code is written into rows [c_row0, c_row0 + idf) of a
     // [B, c_rows, Q] buffer; c_rows = 0 means a plain [B, idf, Q] tensor.  Backward: the same for g_c.
     int c_rows = 0, c_row0 = 0;
+    // tcgen05 family: which of the call's two kernels to launch (SBA_PHASE_*): the first one (forward: projection;
+    // backward: streaming kernel), the second one (forward: streaming kernel; backward: finish kernel) or both
+    int phase = 0;
 };
 
 // attn_simt.cu - CUDA-core (FFMA + warp-shuffle) kernels, any shape with L <= 32

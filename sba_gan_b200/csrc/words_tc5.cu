@@ -1088,6 +1088,7 @@ int make_k128_map(CUtensorMap* out, const void* base, long long rows, int cols, 
         cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qres);
         return (e == cudaSuccess && qres == cudaDriverEntryPointSuccess) ? reinterpret_cast<EncodeFn>(f) : (EncodeFn) nullptr;
     }();
+    bind_context_to_thread();
     if (encode == nullptr) {
         set_error("cuTensorMapEncodeTiled is not available from this driver");
         return SBA_ERR_CUDA;

@@ -79,9 +79,53 @@ def attn_forward_raw(x, context, weight, mask_u8, mask_mode, algo):
     return c_code, attn, srcT, mask_bits, ctx32, w32
 
 
+class PreparedProjection:
+    """sourceT = conv_context(context) (+ the mask words) of one attention call, computed ahead of the call
+    (``prepare_projection``): the first of the forward's two kernels needs only the word features and the weight."""
+    __slots__ = ("key", "srcT", "scratch", "ctx32", "w32", "event")
+
+
+def _projection_key(context, weight, mask_u8, mask_mode):
+    return (context.data_ptr(), context._version, tuple(context.shape), weight.data_ptr(), weight._version,
+            None if mask_u8 is None else (mask_u8.data_ptr(), mask_u8._version), mask_mode)
+
+
+def prepare_projection(context, weight, mask_u8, mask_mode, stream=None):
+    """Run the projection kernel of the tcgen05 forward now (``sba_attn_fwd_phase(.., SBA_PHASE_FIRST)``), on ``stream``
+    (a torch.cuda.Stream; default: the current one).  Returns a PreparedProjection for ``word_region_attention(..,
+    prepared=)`` or None where the tcgen05 family does not cover the shape.  In ``G_NET.forward`` (model_bert.py:580-588)
+    the word features exist before the first stage has produced ``h_code``: both stages' projections can run on a side
+    stream under ``h_net1``."""
+    _require_cuda(context, weight, mask_u8)
+    lib = _abi.load()
+    B, cdf, L = context.shape
+    idf = weight.numel() // cdf
+    if not lib.sba_attn_supported(0, _abi.SBA_ALGO_TCGEN05, B, idf, cdf, L, 128, _abi.SBA_BF16):
+        return None
+    cur = torch.cuda.current_stream(context.device)
+    st = stream if stream is not None else cur
+    if st is not cur:
+        st.wait_stream(cur)                       # the word features / weight were produced on the caller's stream
+    pp = PreparedProjection()
+    with torch.cuda.stream(st):
+        pp.ctx32 = _context_fp32(context)
+        pp.w32 = weight.detach().reshape(idf, cdf).to(torch.float32).contiguous()
+        pp.srcT = torch.empty((B, idf, L), dtype=torch.float32, device=context.device)
+        pp.scratch = torch.empty((3 * B,), dtype=torch.int32, device=context.device)
+        rc = lib.sba_attn_fwd_phase(None, _ptr(pp.ctx32), _ptr(pp.w32), _ptr(mask_u8), None, None, _ptr(pp.srcT),
+                                    _ptr(pp.scratch), B, idf, cdf, L, 128, _abi.SBA_BF16, mask_mode, _abi.SBA_PHASE_FIRST,
+                                    st.cuda_stream)
+        _abi.check(rc, "sba_attn_fwd_phase(projection)")
+        launch_counter["n"] += _abi.last_launch_count()
+        pp.event = torch.cuda.Event()
+        pp.event.record(st)
+    pp.key = _projection_key(context, weight, mask_u8, mask_mode)
+    return pp
+
+
 class _WordRegionAttention(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, context, weight, mask_u8, mask_mode, algo, algo_bwd):
+    def forward(ctx, x, context, weight, mask_u8, mask_mode, algo, algo_bwd, prepared=None):
         _require_cuda(x, context, weight, mask_u8)
         if x.dtype not in _DTYPES:
             raise RuntimeError(f"sba_gan_b200: unsupported dtype {x.dtype} (float32 or bfloat16)")
@@ -89,7 +133,10 @@ class _WordRegionAttention(torch.autograd.Function):
         # an unused output (attn is discarded in training, trainer_bert.py:267) must reach backward as
         # None, not as a materialised zero tensor the kernel would have to stream
         ctx.set_materialize_grads(False)
-        c_code, attn, srcT, mask_bits, ctx32, w32 = attn_forward_raw(x, context, weight, mask_u8, mask_mode, algo)
+        if prepared is not None:
+            c_code, attn, srcT, mask_bits, ctx32, w32 = _attn_forward_prepared(x, mask_u8, mask_mode, prepared)
+        else:
+            c_code, attn, srcT, mask_bits, ctx32, w32 = attn_forward_raw(x, context, weight, mask_u8, mask_mode, algo)
         ctx.save_for_backward(x, ctx32, w32, mask_u8, srcT, mask_bits)
         ctx.meta = (mask_mode, algo_bwd, context.dtype, weight.dtype, tuple(weight.shape))
         return c_code, attn
@@ -121,10 +168,29 @@ class _WordRegionAttention(torch.autograd.Function):
         return (dX if need_x else None,
                 dCtx.to(ctx_dtype) if need_ctx else None,
                 dW.reshape(w_shape).to(w_dtype) if need_w else None,
-                None, None, None, None)
+                None, None, None, None, None)
 
 
-def word_region_attention(x, context, weight, mask=None, mask_mode="reference", algo="auto", algo_bwd=None):
+def _attn_forward_prepared(x, mask_u8, mask_mode, pp):
+    """The streaming kernel alone, behind a projection that ``prepare_projection`` already ran."""
+    lib = _abi.load()
+    B, idf, ih, iw = x.shape
+    cdf, L = pp.ctx32.shape[1], pp.ctx32.shape[2]
+    c_code = torch.empty_like(x)
+    attn = torch.empty((B, L, ih, iw), dtype=x.dtype, device=x.device)
+    cur = torch.cuda.current_stream(x.device)
+    cur.wait_event(pp.event)
+    for t in (pp.srcT, pp.scratch, pp.ctx32, pp.w32):
+        t.record_stream(cur)
+    rc = lib.sba_attn_fwd_phase(_ptr(x), None, None, _ptr(mask_u8), _ptr(c_code), _ptr(attn), _ptr(pp.srcT), _ptr(pp.scratch),
+                                B, idf, cdf, L, ih * iw, _DTYPES[x.dtype], mask_mode, _abi.SBA_PHASE_SECOND, _stream())
+    _abi.check(rc, "sba_attn_fwd_phase(stream)")
+    launch_counter["n"] += _abi.last_launch_count()
+    _last_algo["fwd"] = ALGO_NAMES.get(lib.sba_last_algo(), "?")
+    return c_code, attn, pp.srcT, pp.scratch, pp.ctx32, pp.w32
+
+
+def word_region_attention(x, context, weight, mask=None, mask_mode="reference", algo="auto", algo_bwd=None, prepared=None):
     """Fused GlobalAttentionGeneral.forward (GlobalAttention.py:82-121).
 
     x B x idf x ih x iw; context B x cdf x L; weight [idf, cdf, 1, 1] (conv_context.weight);
@@ -151,5 +217,13 @@ def word_region_attention(x, context, weight, mask=None, mask_mode="reference", 
             mask_u8 = mask.view(torch.uint8)                      # same bytes, no copy kernel
         else:
             mask_u8 = mask.to(device=x.device, dtype=torch.uint8).contiguous()
+    if prepared is not None:
+        lib = _abi.load()
+        ok = (x.is_cuda and x.dtype in _DTYPES and algo in ("auto", "tc5") and
+              prepared.key == _projection_key(context, weight, mask_u8, _MASK_MODES[mask_mode]) and
+              lib.sba_attn_supported(0, _abi.SBA_ALGO_TCGEN05, x.shape[0], x.shape[1], context.shape[1], context.shape[2],
+                                     x.shape[2] * x.shape[3], _DTYPES[x.dtype]) and x.data_ptr() % 16 == 0)
+        if not ok:
+            prepared = None                       # stale or not applicable: the whole call, projection included
     return _WordRegionAttention.apply(x, context, weight, mask_u8, _MASK_MODES[mask_mode], _ALGOS[algo],
-                                      _ALGOS[algo if algo_bwd is None else algo_bwd])
+                                      _ALGOS[algo if algo_bwd is None else algo_bwd], prepared)

@@ -333,3 +333,119 @@ def test_sustained_back_to_back_launches_stay_correct(algo, dt, hw):
     else:
         err = normalised_max_err(dW, first[3])       # fp32 atomics (mma.sync backward): order-dependent rounding only
         assert err < 1e-4, err
+
+
+@pytest.mark.parametrize("dt,hw", [(torch.bfloat16, 64), (torch.bfloat16, 128), (torch.float32, 64)])
+def test_phase_entry_points_equal_the_whole_call(dt, hw):
+    """sba_attn_fwd_phase / sba_attn_bwd_phase: the projection (forward) and the finish kernel (backward) launched
+    separately - on another stream, ordered by an event - give bit-identical results to the one-call form."""
+    from sba_gan_b200 import _abi
+    lib = _abi.load()
+    B, idf, cdf, L, Q = 64, 32, 256, 18, hw * hw
+    g = torch.Generator().manual_seed(11)
+    dcode = 1 if dt == torch.bfloat16 else 0
+    x = torch.randn(B, idf, Q, generator=g).cuda().to(dt)
+    gc = torch.randn(B, idf, Q, generator=g).cuda().to(dt)
+    ctx = torch.tanh(torch.randn(B, cdf, L, generator=g)).cuda()
+    W = (torch.randn(idf, cdf, generator=g) / 16).cuda()
+    lens = torch.randint(5, L + 1, (B,), generator=g)
+    mask = (torch.arange(L)[None] >= lens[:, None]).to(torch.uint8).cuda()
+    nws = lib.sba_attn_bwd_workspace_floats(B, idf, cdf, L)
+
+    def buffers():
+        return dict(c=torch.empty_like(x), a=torch.empty(B, L, Q, device="cuda", dtype=dt), dx=torch.empty_like(x),
+                    srcT=torch.empty(B, idf, L, device="cuda"), scratch=torch.empty(3 * B, dtype=torch.int32, device="cuda"),
+                    ws=torch.empty(nws, device="cuda"), dW=torch.empty(idf, cdf, device="cuda"),
+                    dCtx=torch.empty(B, cdf, L, device="cuda"))
+
+    main = torch.cuda.current_stream()
+    side = torch.cuda.Stream()
+    one, two = buffers(), buffers()
+    bwd = dt == torch.bfloat16                       # the tcgen05 backward covers bf16 tensors
+    s = main.cuda_stream
+    _abi.check(lib.sba_attn_fwd(x.data_ptr(), ctx.data_ptr(), W.data_ptr(), mask.data_ptr(), one["c"].data_ptr(),
+                                one["a"].data_ptr(), one["srcT"].data_ptr(), one["scratch"].data_ptr(), B, idf, cdf, L, Q, dcode, 0,
+                                _abi.SBA_ALGO_TCGEN05, s), "fwd")
+    if bwd:
+        _abi.check(lib.sba_attn_bwd(x.data_ptr(), ctx.data_ptr(), W.data_ptr(), mask.data_ptr(), one["srcT"].data_ptr(),
+                                    one["scratch"].data_ptr(), gc.data_ptr(), None, one["dx"].data_ptr(), one["ws"].data_ptr(), nws,
+                                    one["dW"].data_ptr(), one["dCtx"].data_ptr(), B, idf, cdf, L, Q, dcode, 0,
+                                    _abi.SBA_ALGO_TCGEN05, s), "bwd")
+    torch.cuda.synchronize()
+    # projection on the side stream, streaming kernel on the main stream behind an event
+    with torch.cuda.stream(side):
+        _abi.check(lib.sba_attn_fwd_phase(None, ctx.data_ptr(), W.data_ptr(), mask.data_ptr(), None, None, two["srcT"].data_ptr(),
+                                          two["scratch"].data_ptr(), B, idf, cdf, L, Q, dcode, 0, _abi.SBA_PHASE_FIRST,
+                                          side.cuda_stream), "project")
+        assert _abi.last_launch_count() == 1
+        ev = torch.cuda.Event()
+        ev.record(side)
+    main.wait_event(ev)
+    _abi.check(lib.sba_attn_fwd_phase(x.data_ptr(), None, None, mask.data_ptr(), two["c"].data_ptr(), two["a"].data_ptr(),
+                                      two["srcT"].data_ptr(), two["scratch"].data_ptr(), B, idf, cdf, L, Q, dcode, 0,
+                                      _abi.SBA_PHASE_SECOND, s), "stream")
+    assert _abi.last_launch_count() == 1
+    if bwd:
+        _abi.check(lib.sba_attn_bwd_phase(x.data_ptr(), None, None, mask.data_ptr(), two["srcT"].data_ptr(),
+                                          two["scratch"].data_ptr(), gc.data_ptr(), None, two["dx"].data_ptr(), two["ws"].data_ptr(),
+                                          nws, None, None, B, idf, cdf, L, Q, dcode, 0, _abi.SBA_PHASE_FIRST, s), "bwd stream")
+        ev2 = torch.cuda.Event()
+        ev2.record(main)
+        with torch.cuda.stream(side):
+            side.wait_event(ev2)
+            _abi.check(lib.sba_attn_bwd_phase(None, ctx.data_ptr(), W.data_ptr(), None, None, None, None, None, None,
+                                              two["ws"].data_ptr(), nws, two["dW"].data_ptr(), two["dCtx"].data_ptr(), B, idf, cdf,
+                                              L, Q, dcode, 0, _abi.SBA_PHASE_SECOND, side.cuda_stream), "bwd finish")
+    torch.cuda.synchronize()
+    for k in ("srcT", "c", "a") + (("dx", "dW", "dCtx") if bwd else ()):
+        assert torch.equal(one[k], two[k]), k
+    # a family that has no phases refuses
+    rc = lib.sba_attn_fwd_phase(x.data_ptr(), ctx.data_ptr(), W.data_ptr(), mask.data_ptr(), two["c"].data_ptr(),
+                                two["a"].data_ptr(), two["srcT"].data_ptr(), two["scratch"].data_ptr(), B, 40, cdf, L, Q, dcode, 0,
+                                _abi.SBA_PHASE_FIRST, s)
+    assert rc != 0
+
+
+def test_module_prepare_runs_the_projection_ahead_on_a_side_stream():
+    """GlobalAttentionGeneral.prepare(context, stream): same outputs and gradients as the plain call, one kernel in the
+    forward; a preparation that went stale (new mask, new weight) is ignored."""
+    from sba_gan_b200 import functional as F
+    torch.manual_seed(3)
+    B, idf, cdf, L, hw = 8, 32, 256, 18, 64
+    W = torch.randn(idf, cdf, 1, 1) / 16
+    m = _module(idf, cdf, W, torch.float32)
+    x = torch.randn(B, idf, hw, hw, device="cuda", dtype=torch.bfloat16)
+    ctx = torch.tanh(torch.randn(B, cdf, L, device="cuda"))
+    gc = torch.randn_like(x)
+    lens = torch.randint(5, L + 1, (B,))
+    mask = (torch.arange(L)[None] >= lens[:, None]).cuda()
+
+    def run(prep, mutate=None):
+        xs = x.clone().requires_grad_(True)
+        m.zero_grad()
+        m.applyMask(mask)
+        if prep:
+            side = torch.cuda.Stream()
+            assert m.prepare(ctx, stream=side)
+        if mutate:
+            mutate()
+        n0 = F.launch_counter["n"]
+        c, a = m(xs, ctx)
+        n_fwd = F.launch_counter["n"] - n0
+        c.backward(gc)
+        torch.cuda.synchronize()
+        return c.detach(), a.detach(), xs.grad, m.conv_context.weight.grad.clone(), n_fwd
+
+    ref = run(False)
+    got = run(True)
+    assert ref[4] == 2 and got[4] == 1               # projection + streaming kernel vs streaming kernel only
+    for r, t in zip(ref[:4], got[:4]):
+        assert torch.equal(r, t)
+    # stale: the mask is replaced after prepare -> the whole call runs, with the new mask
+    mask2 = (torch.arange(L)[None] >= (lens[:, None] - 2).clamp(min=1)).cuda()
+    stale = run(True, mutate=lambda: m.applyMask(mask2))
+    assert stale[4] == 2
+    m.applyMask(mask2)
+    xs = x.clone()
+    c2, _ = m(xs, ctx)
+    assert torch.equal(stale[0], c2.detach())
