@@ -216,6 +216,151 @@ def time_abi_calls(cx, dtype, algo, batch, stages, nsets=3, reps=12):
     return calls
 
 
+def sub_split_schedule(cx, dtype, nsets=3, reps=12):
+    """The two kernels of each call, separately (sba_attn_fwd_phase / sba_attn_bwd_phase; tcgen05 family, bf16):
+    (i) per-phase device times -> which part of a call streams the pixels and which is the small kernel around it;
+    (ii) the same step (both stages, forward + backward, ABI level) scheduled the way the real generator allows: the
+    projections depend only on the word features (available before the first stage has run, model_bert.py:580-588), the
+    finish kernels produce parameter / word-feature gradients nothing in the backward chain waits for -> both go to a
+    side stream.  All work stays inside the timed region; `serial` is the same step on one stream."""
+    from sba_gan_b200 import _abi
+    lib = _abi.load()
+    device, batch = cx.device, B_PER_GPU
+    es = 2 if dtype == torch.bfloat16 else 4
+    dcode = _abi.SBA_BF16 if dtype == torch.bfloat16 else _abi.SBA_F32
+    peaks, _ = load_peaks()
+    w32 = {hw: torch.nn.init.orthogonal_(torch.empty(IDF, CDF), 1.0).to(device) for hw in STAGES}
+    bufs = {}
+    for hw in STAGES:
+        bufs[hw] = []
+        for s in range(nsets):
+            x, gc, ctx, mask = make_inputs(hw, 9876 + cx.rank + 17 * s + hw, dtype, device, batch=batch)
+            bufs[hw].append(dict(x=x, gc=gc, ctx=ctx.float().contiguous(), mask=mask.to(torch.uint8).contiguous(),
+                                 c=torch.empty_like(x), a=torch.empty(batch, L, hw, hw, dtype=dtype, device=device),
+                                 dx=torch.empty_like(x), srcT=torch.empty(batch, IDF, L, device=device),
+                                 scr=torch.empty(3 * batch, dtype=torch.int32, device=device),
+                                 ws=torch.empty(lib.sba_attn_bwd_workspace_floats(batch, IDF, CDF, L), device=device),
+                                 dw=torch.empty(IDF, CDF, device=device)))
+
+    # a projection serves exactly ONE streaming call (the scratch words carry the call's dynamic tile counter): the
+    # per-phase timing of the streaming kernel gives every repetition its own projected (srcT, scratch) pair
+    proj = {hw: [(torch.empty(batch, IDF, L, device=device), torch.empty(3 * batch, dtype=torch.int32, device=device))
+                 for _ in range(reps)] for hw in STAGES}
+
+    def fwd(hw, s, phase, st, own=False):
+        b = bufs[hw][s % nsets]
+        srcT, scr = proj[hw][s % reps] if own else (b["srcT"], b["scr"])
+        _abi.check(lib.sba_attn_fwd_phase(b["x"].data_ptr(), b["ctx"].data_ptr(), w32[hw].data_ptr(), b["mask"].data_ptr(),
+                                          b["c"].data_ptr(), b["a"].data_ptr(), srcT.data_ptr(), scr.data_ptr(),
+                                          batch, IDF, CDF, L, hw * hw, dcode, 0, phase, st), "sba_attn_fwd_phase")
+
+    def bwd(hw, s, phase, st):
+        b = bufs[hw][s % nsets]
+        _abi.check(lib.sba_attn_bwd_phase(b["x"].data_ptr(), b["ctx"].data_ptr(), w32[hw].data_ptr(), b["mask"].data_ptr(),
+                                          b["srcT"].data_ptr(), b["scr"].data_ptr(), b["gc"].data_ptr(), None,
+                                          b["dx"].data_ptr(), b["ws"].data_ptr(), b["ws"].numel(), b["dw"].data_ptr(), None,
+                                          batch, IDF, CDF, L, hw * hw, dcode, 0, phase, st), "sba_attn_bwd_phase")
+
+    cur = torch.cuda.current_stream().cuda_stream
+    for hw in STAGES:
+        for s in range(nsets):
+            fwd(hw, s, _abi.SBA_PHASE_ALL, cur)
+            bwd(hw, s, _abi.SBA_PHASE_ALL, cur)
+    torch.cuda.synchronize()
+
+    def time_graph(body, n, before=None):
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            body()
+        if before:
+            before()
+        g.replay()
+        torch.cuda.synchronize()
+        best = None
+        for _ in range(3):
+            if before:
+                before()
+                torch.cuda.synchronize()
+            e0, e1 = ev(), ev()
+            e0.record()
+            g.replay()
+            e1.record()
+            torch.cuda.synchronize()
+            t = e0.elapsed_time(e1) * 1e-3 / n
+            best = t if best is None else min(best, t)
+        return best
+
+    phases = {}
+    for hw in STAGES:
+        px = batch * hw * hw
+        for name, fn, ph, which in (("fwd_project", fwd, _abi.SBA_PHASE_FIRST, None), ("fwd_stream", fwd, _abi.SBA_PHASE_SECOND, "fwd"),
+                                    ("bwd_stream", bwd, _abi.SBA_PHASE_FIRST, "bwd"), ("bwd_finish", bwd, _abi.SBA_PHASE_SECOND, None)):
+            own = name == "fwd_stream"
+
+            def body(fn=fn, ph=ph, hw=hw, own=own):
+                st = torch.cuda.current_stream().cuda_stream
+                for s in range(reps):
+                    if own:
+                        fn(hw, s, ph, st, True)
+                    else:
+                        fn(hw, s, ph, st)
+
+            def project_all(hw=hw):
+                st = torch.cuda.current_stream().cuda_stream
+                for s in range(reps):
+                    fwd(hw, s, _abi.SBA_PHASE_FIRST, st, True)
+            t = time_graph(body, reps, project_all if own else None)
+            rec = {"us": round(t * 1e6, 2)}
+            if which:
+                nb = algorithmic_bytes(px, es, which)
+                rec.update(gbs=round(nb / t / 1e9, 1), frac=round(nb / t / 1e9 / peaks["hbm_gbs"], 4))
+            phases[f"{name}_{hw}"] = rec
+
+    side = torch.cuda.Stream()
+    lo, hi = STAGES[0], STAGES[-1]
+
+    def step_serial(s):
+        st = torch.cuda.current_stream().cuda_stream
+        for hw in STAGES:
+            fwd(hw, s, _abi.SBA_PHASE_ALL, st)
+        for hw in reversed(STAGES):
+            bwd(hw, s, _abi.SBA_PHASE_ALL, st)
+
+    def step_split(s):
+        m = torch.cuda.current_stream()
+        side.wait_stream(m)
+        with torch.cuda.stream(side):
+            for hw in STAGES:
+                fwd(hw, s, _abi.SBA_PHASE_FIRST, side.cuda_stream)
+            evp = torch.cuda.Event()
+            evp.record(side)
+        m.wait_event(evp)                     # one join: the four streaming kernels then form an unbroken chain
+        for hw in STAGES:
+            fwd(hw, s, _abi.SBA_PHASE_SECOND, m.cuda_stream)
+        evb = {}
+        for hw in reversed(STAGES):
+            bwd(hw, s, _abi.SBA_PHASE_FIRST, m.cuda_stream)
+            evb[hw] = torch.cuda.Event()
+            evb[hw].record(m)
+        with torch.cuda.stream(side):
+            for hw in reversed(STAGES):
+                side.wait_event(evb[hw])
+                bwd(hw, s, _abi.SBA_PHASE_SECOND, side.cuda_stream)
+        m.wait_stream(side)
+
+    nrep = 6
+    out = {"phases": phases}
+    for name, fn in (("serial", step_serial), ("split", step_split)):
+        t = time_graph(lambda fn=fn: [fn(s) for s in range(nrep)], nrep)
+        t = cx.max_over_ranks(t * 1e3) * 1e-3
+        out[name] = {"ms_per_step": round(t * 1e3, 4), "value": px_per_step(cx.world) / t, "unit": "region-px/s"}
+    out["speedup_split_vs_serial"] = round(out["serial"]["ms_per_step"] / out["split"]["ms_per_step"], 3)
+    out["what"] = ("ABI-level step (fwd 64x64, fwd 128x128, bwd 128x128, bwd 64x64; CUDA-graph replay over rotating buffer sets); "
+                   "split: projections and finish kernels on a side stream, ordered by events; serial: one stream")
+    del bufs, lo, hi
+    return out
+
+
 # ------------------------------------------------------------------------------------------------
 # the headline step: device-resident, through the public module, CUDA-graph replay
 # ------------------------------------------------------------------------------------------------
@@ -624,6 +769,8 @@ def run_ours(args, cx):
             return {"value": px_per_step(world) / (oms * 1e-3), "unit": "region-px/s", "ms_per_step": round(oms, 4), "dtype": oname,
                     "step_frac": r["step_frac"], "calls": r["calls"]}
         leg(oname, other_dtype)
+        if dtype == torch.bfloat16 and args.algo in ("auto", "tc5"):
+            leg("split_schedule", lambda: sub_split_schedule(cx, dtype))
         leg("gpu_eager_baseline", lambda: sub_eager_baseline(cx, dtype, args.steps))
         leg("gpu_eager_baseline_fp32", lambda: sub_eager_baseline(cx, torch.float32, args.steps))
 

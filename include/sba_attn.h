@@ -124,7 +124,8 @@ SBA_API int sba_attn_bwd(const void* x, const float* ctx, const float* W, const 
  *   backward: FIRST  = the streaming kernel: writes dX and the partial sums in ws;
  *             SECOND = the finish kernel: ws -> dW, dCtx (parameter / word-feature gradients: nothing in the backward
  *                      chain waits for them, so it can run on a side stream under the next layer's backward).
- * Ordering between the phases is the caller's (same stream, or an event).  SBA_PHASE_ALL = the plain calls above.
+ * Ordering between the phases is the caller's (same stream, or an event).  A projection serves exactly ONE streaming
+ * call: scratch also carries that call's dynamic tile counter.  SBA_PHASE_ALL = the plain calls above.
  * Pointers a phase does not use may be NULL.  Results are bit-identical to the one-call form.
  */
 SBA_API int sba_attn_fwd_phase(const void* x, const float* ctx, const float* W, const uint8_t* mask,
