@@ -449,3 +449,46 @@ def test_module_prepare_runs_the_projection_ahead_on_a_side_stream():
     xs = x.clone()
     c2, _ = m(xs, ctx)
     assert torch.equal(stale[0], c2.detach())
+
+
+def test_bf16_context_under_graph_capture_and_replay():
+    """The module converts a bf16 context to fp32 per call (no cache keyed on the tensor object): a captured
+    forward+backward replayed after the context's CONTENTS were overwritten in place (no version bump visible to a
+    cache) must see the new values, and an eager call after the capture must not read graph-private memory."""
+    torch.manual_seed(5)
+    B, idf, cdf, L, hw = 8, 32, 256, 18, 64
+    m = _module(idf, cdf, torch.randn(idf, cdf, 1, 1) / 16, torch.bfloat16)
+    x = torch.randn(B, idf, hw, hw, device="cuda", dtype=torch.bfloat16, requires_grad=True)
+    gc = torch.randn(B, idf, hw, hw, device="cuda", dtype=torch.bfloat16)
+    ctx_a = torch.tanh(torch.randn(B, cdf, L, device="cuda")).to(torch.bfloat16)
+    ctx_b = torch.tanh(torch.randn(B, cdf, L, device="cuda")).to(torch.bfloat16)
+    ctx = ctx_a.clone()
+    m.applyMask(None)
+
+    def step():
+        c, _ = m(x, ctx)
+        dx, dw = torch.autograd.grad(c, [x, m.conv_context.weight], gc)
+        return c, dx, dw
+
+    for _ in range(3):                     # eager warm-up (what bench.py does before it captures)
+        step()
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(g, stream=side):
+            out = step()
+    torch.cuda.current_stream().wait_stream(side)
+    g.replay()
+    torch.cuda.synchronize()
+    ref_a = [t.clone() for t in step()]                      # eager, same contents
+    for o, r in zip(out, ref_a):
+        assert torch.equal(o, r)
+    ctx.copy_(ctx_b)                                         # new word features in the same storage
+    g.replay()
+    torch.cuda.synchronize()
+    ref_b = [t.clone() for t in step()]
+    for o, r in zip(out, ref_b):
+        assert torch.equal(o, r)
+    assert not torch.equal(ref_a[0], ref_b[0])
