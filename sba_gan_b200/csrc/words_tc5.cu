@@ -1,4 +1,6 @@
-// Kernel (c) forward on the 5th-generation tensor cores: the B x B DAMSM region-word similarity of words_loss
+// Kernel (c) on the 5th-generation tensor cores - forward here, backward further down (phase A = this forward kernel with
+// a template flag, phase B = k_words_bwd_tc5, then the d_img / d_words GEMMs k_words_dimg_tc5; formulas at each kernel
+// and in DESIGN.md 4.4).  Forward: the B x B DAMSM region-word similarity of words_loss
 // (AttnGAN2/code/miscc/losses.py:72-123 calling func_attention, GlobalAttention.py:31-69) as two chained
 // 3xTF32 GEMMs per (image, block of captions) with the softmaxes in between, everything on chip:
 //
