@@ -84,8 +84,9 @@ struct WtParams {
     float4* scal;              // [B_img][ncols] (alpha = d num, beta = d|wc| / |wc|, D = sum_r a2 da2, 1 / Z)
     float* v_hi;               // [B_img][nef][ncols]  beta * wc split in tf32 hi / lo: B operand of the d_img GEMM's second term
     float* v_lo;
-    float* wct_hi;             // [B_img][ncols][nef]  wc split in tf32 hi / lo: B operand of V = X^T wc in phase B
+    float* wct_hi;             // [B_img][ncols][nef]  q = alpha w + beta wc split in tf32 hi / lo: B operand of T = X^T q in phase B
     float* wct_lo;
+    float* a1;                 // [B_img * R][ncols]   the caption softmax a1[r][n] of every pair (phase B reads it back)
     float* kap;                // [B_img][ncols] d|w_n| * |w_n| share of this image (beta |wc|^2), or NULL (no word gradients)
     int ncols;
     float g1;
@@ -95,6 +96,7 @@ struct WtParams {
 // One block.  The lengths are staged in shared memory by all threads, one thread walks them (a few cycles per caption:
 // no global round trip inside the sequential part), then all threads fill the per-column tables.
 constexpr int kPlanMaxCaps = 4096;
+constexpr int kMaxCapsPerHalf = 16;       // captions per half block (phase B keeps one total per caption and thread in shared memory)
 __global__ void __launch_bounds__(256) k_wt_plan(const int* __restrict__ cap_lens, int B_cap, int Lw, int* __restrict__ cap_col,
                                                  WtPlan* plan, int* __restrict__ col_cap, int* __restrict__ col_T, int ncols) {
     __shared__ short s_T[kPlanMaxCaps];
@@ -106,12 +108,13 @@ __global__ void __launch_bounds__(256) k_wt_plan(const int* __restrict__ cap_len
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        int h = 0, off = 0;
+        int h = 0, off = 0, cnt = 0;
         for (int i = 0; i < B_cap; ++i) {
             const int T = s_T[i];
-            if (off + T > kHalf) { ++h; off = 0; }
+            if (off + T > kHalf || cnt == kMaxCapsPerHalf) { ++h; off = 0; cnt = 0; }
             s_col[i] = h * kHalf + off;
             off += T;
+            ++cnt;
         }
         plan->n_half = h + 1;
     }
@@ -433,12 +436,19 @@ __global__ void __launch_bounds__(kWtThreads, 1)
                 sr[c] = __float_as_uint(run);
             }
             seg = 1.f;
+            [[maybe_unused]] float a1q[4];
 #pragma unroll
             for (int c = kHalf - 1; c >= 0; --c) {
                 seg = ((last >> c) & 1ull) ? mma::rcp_approx(__uint_as_float(sr[c])) : seg;
                 const float a1 = v[c] * seg;
                 // e = exp(gamma1 (a1 - 1)); padding columns and regions beyond R contribute nothing
                 v[c] = (rv && ((valid >> c) & 1ull)) ? mma::ex2_approx((a1 - 1.f) * p.g1l2e) : 0.f;
+                if constexpr (BWD) {             // phase A of the backward: a1 goes out, phase B does not recompute it
+                    a1q[c & 3] = a1;
+                    if ((c & 3) == 0 && rv)
+                        *reinterpret_cast<float4*>(p.a1 + ((size_t)j * p.R + 128 * m + 32 * q + lane) * p.ncols + ncol0 + c) =
+                            make_float4(a1q[0], a1q[1], a1q[2], a1q[3]);
+                }
             }
             // column sums over this warp's 32 regions -> zp[k][column] (added in chunk order by the final epilogue)
             {
@@ -538,7 +548,8 @@ __global__ void __launch_bounds__(kWtThreads, 1)
                 p.scal[(size_t)j * p.ncols + ng] = make_float4(alpha, beta, D, invZ);
                 if (p.kap != nullptr) p.kap[(size_t)j * p.ncols + ng] = beta * wn * wn;      // = d_den |w| |wc| (losses.py:17)
                 // second pass over wc: v = beta wc in tf32 hi / lo (rows = channels: consecutive threads write consecutive columns) and
-                // wc^T split into tf32 hi / lo (this thread's row, 128 contiguous bytes per chunk)
+                // q^T = alpha w + beta wc split into tf32 hi / lo (this thread's row, 128 contiguous bytes per chunk):
+                // <X_r, q_n> = alpha S[r, n] + beta V[r, n] is the whole d a2 that phase B needs - one GEMM instead of two
                 float* vh = p.v_hi + (size_t)j * nef * p.ncols + ng;
                 float* vl = p.v_lo + (size_t)j * nef * p.ncols + ng;
                 float4* th = reinterpret_cast<float4*>(p.wct_hi + ((size_t)j * p.ncols + ng) * nef);
@@ -552,6 +563,8 @@ __global__ void __launch_bounds__(kWtThreads, 1)
 #pragma unroll
                     for (int c4 = 0; c4 < 8; ++c4) {
                         float hi[4], lo[4];
+                        const float4 a = __ldg(wh + (c0 >> 2) + c4), b = __ldg(wl + (c0 >> 2) + c4);
+                        const float w[4] = {a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w};
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
                             const float wc = __uint_as_float(d[4 * c4 + e]) * invZ;
@@ -559,8 +572,9 @@ __global__ void __launch_bounds__(kWtThreads, 1)
                             split_tf32(beta * wc, bh, bl);
                             vh[(size_t)(c0 + 4 * c4 + e) * p.ncols] = bh;
                             vl[(size_t)(c0 + 4 * c4 + e) * p.ncols] = bl;
-                            hi[e] = tf32_rna(wc);
-                            lo[e] = tf32_rna(wc - hi[e]);
+                            const float qv = fmaf(alpha, w[e], beta * wc);
+                            hi[e] = tf32_rna(qv);
+                            lo[e] = tf32_rna(qv - hi[e]);
                         }
                         th[(c0 >> 2) + c4] = make_float4(hi[0], hi[1], hi[2], hi[3]);
                         tlo[(c0 >> 2) + c4] = make_float4(lo[0], lo[1], lo[2], lo[3]);
@@ -581,19 +595,21 @@ __global__ void __launch_bounds__(kWtThreads, 1)
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// Backward, phase B: per (image j, 128-column block) recompute S = X^T W (G1) and form V = X^T wc (G3, same A tiles, B =
-// wc^T from phase A), then, thread = region row,
-//   a1 = softmax over each caption's words of S,  a2 = exp(gamma1 (a1 - 1)) / Z
-//   da2 = alpha S + beta V,   dz = a2 (da2 - D),   t = a1 gamma1 dz,   ds = t - a1 sum_{caption} t,   u = ds + alpha a2
+// Backward, phase B: per (image j, 128-column block) ONE GEMM  T = X^T q,  q_n = alpha_n w_n + beta_n wc_n  (phase A wrote
+// q^T in tf32 hi / lo), so that  T[r, n] = alpha S[r, n] + beta V[r, n] = d a2[n, r]  without recomputing S or forming V;
+// then, thread = region row, with a1[r][n] read back from phase A,
+//   a2 = exp(gamma1 (a1 - 1)) / Z,   dz = a2 (T - D),   t = a1 gamma1 dz,   ds = t - a1 sum_{caption} t,   u = ds + alpha a2
 // (D_n = sum_r a2 da2 = alpha <w_n, wc_n> + beta |wc_n|^2 is known from phase A: no reduction over regions here) and
 // store a2^T[j][r][n], u^T[j][r][n] (tf32 hi / lo) for the d_img GEMM below (oracle/attention.py::words_loss_backward;
 // the CUDA-core kernel of words_loss.cu materialises the same u / a2).
 // ------------------------------------------------------------------------------------------------------------------
-constexpr int kBStageBytes = 6 * kTileBytes;      // A hi, A lo, W hi, W lo, wc hi, wc lo: 96 KB
+constexpr int kBStageBytes = 4 * kTileBytes;      // A hi, A lo, q hi, q lo: 64 KB
+constexpr int kBStages = 3;
 struct WtBwdParams {
     const int* col_cap;
     const WtPlan* plan;
-    const float4* scal;        // [B_img][ncols]
+    const float4* scal;        // [B_img][ncols]  (alpha, beta, D, 1 / Z)
+    const float* a1;           // [B_img * R][ncols]
     float* u_hi;               // [B_img * R][ncols]  u^T and a2^T (regions = rows, columns contiguous), tf32 hi / lo:
     float* u_lo;               //                     the K-major A operands of the d_img GEMM
     float* a2_hi;
@@ -608,20 +624,20 @@ struct WtBwdParams {
 template <bool WORDS>
 __global__ void __launch_bounds__(kWtThreads, 1)
     k_words_bwd_tc5(const __grid_constant__ CUtensorMap tm_xt_hi, const __grid_constant__ CUtensorMap tm_xt_lo,
-                    const __grid_constant__ CUtensorMap tm_wt_hi, const __grid_constant__ CUtensorMap tm_wt_lo,
-                    const __grid_constant__ CUtensorMap tm_wc_hi, const __grid_constant__ CUtensorMap tm_wc_lo, const WtBwdParams p) {
+                    const __grid_constant__ CUtensorMap tm_q_hi, const __grid_constant__ CUtensorMap tm_q_lo, const WtBwdParams p) {
     const int nb = blockIdx.x, j = blockIdx.y;
     if (2 * nb >= p.plan->n_half) return;
 
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const uint32_t sbase = smem_u32(smem_raw);
     const uint32_t s_ring = sbase;
-    float4* scs = reinterpret_cast<float4*>(smem_raw + kStages * kBStageBytes);        // [128] per-column scalars
-    unsigned long long* bars = reinterpret_cast<unsigned long long*>(scs + kNB);
-    unsigned long long* bar_full = bars;                  // [kStages]
-    unsigned long long* bar_empty = bars + kStages;       // [kStages]
-    unsigned long long* bar_t_full = bars + 2 * kStages;  // [2]  S and V of a region tile are complete
-    unsigned long long* bar_t_free = bar_t_full + 2;      // [2]
+    float4* scs = reinterpret_cast<float4*>(smem_raw + kBStages * kBStageBytes);        // [128] per-column scalars
+    float* tot_all = reinterpret_cast<float*>(scs + kNB);                               // [16 captions][256 epilogue threads]
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(tot_all + kMaxCapsPerHalf * 256);
+    unsigned long long* bar_full = bars;                   // [kBStages]
+    unsigned long long* bar_empty = bars + kBStages;       // [kBStages]
+    unsigned long long* bar_t_full = bars + 2 * kBStages;  // [2]  T of a region tile is complete
+    unsigned long long* bar_t_free = bar_t_full + 2;       // [2]
     uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(bar_t_free + 2);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -633,12 +649,12 @@ __global__ void __launch_bounds__(kWtThreads, 1)
 #else
         if (sbase & 1023u) __trap();
 #endif
-        for (int s = 0; s < kStages; ++s) { mbar_init(smem_u32(&bar_full[s]), 1); mbar_init(smem_u32(&bar_empty[s]), 1); }
+        for (int s = 0; s < kBStages; ++s) { mbar_init(smem_u32(&bar_full[s]), 1); mbar_init(smem_u32(&bar_empty[s]), 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(&bar_t_full[s]), 1); mbar_init(smem_u32(&bar_t_free[s]), 8); }
         fence_barrier_init();
     }
     if (tid >= 64 && tid < 64 + kNB) scs[tid - 64] = p.scal[(size_t)j * p.ncols + nb * kNB + tid - 64];
-    if (warp == kMmaWarp) tmem_alloc(smem_u32(tmem_base_s), 512);
+    if (warp == kMmaWarp) tmem_alloc(smem_u32(tmem_base_s), 256);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -649,17 +665,15 @@ __global__ void __launch_bounds__(kWtThreads, 1)
         int s = 0;
         for (int m = 0; m < MT; ++m)
             for (int kc = 0; kc < KCH; ++kc, ++s) {
-                const int st = s % kStages;
-                if (s >= kStages) WT_WAIT(smem_u32(&bar_empty[st]), (uint32_t)((s / kStages) - 1) & 1u, 0);
+                const int st = s % kBStages;
+                if (s >= kBStages) WT_WAIT(smem_u32(&bar_empty[st]), (uint32_t)((s / kBStages) - 1) & 1u, 0);
                 if (elect_one()) {
                     const uint32_t full = smem_u32(&bar_full[st]), dst = s_ring + st * kBStageBytes;
                     mbar_expect_tx(full, (uint32_t)kBStageBytes);
                     tma_load_2d(dst, &tm_xt_hi, kc * kKC, (j * MT + m) * 128, full);
                     tma_load_2d(dst + kTileBytes, &tm_xt_lo, kc * kKC, (j * MT + m) * 128, full);
-                    tma_load_2d(dst + 2 * kTileBytes, &tm_wt_hi, kc * kKC, nb * kNB, full);
-                    tma_load_2d(dst + 3 * kTileBytes, &tm_wt_lo, kc * kKC, nb * kNB, full);
-                    tma_load_2d(dst + 4 * kTileBytes, &tm_wc_hi, kc * kKC, j * p.ncols + nb * kNB, full);
-                    tma_load_2d(dst + 5 * kTileBytes, &tm_wc_lo, kc * kKC, j * p.ncols + nb * kNB, full);
+                    tma_load_2d(dst + 2 * kTileBytes, &tm_q_hi, kc * kKC, j * p.ncols + nb * kNB, full);
+                    tma_load_2d(dst + 3 * kTileBytes, &tm_q_lo, kc * kKC, j * p.ncols + nb * kNB, full);
                 }
                 __syncwarp();
             }
@@ -671,26 +685,21 @@ __global__ void __launch_bounds__(kWtThreads, 1)
         for (int m = 0; m < MT; ++m) {
             const int buf = m & 1;
             if (m >= 2) WT_WAIT(smem_u32(&bar_t_free[buf]), (uint32_t)((m >> 1) - 1) & 1u, 1);
-            const uint32_t dS = tmem_base + 256 * buf, dV = dS + 128;
+            const uint32_t dT = tmem_base + 128 * buf;
             for (int kc = 0; kc < KCH; ++kc, ++s) {
-                const int st = s % kStages;
-                WT_WAIT(smem_u32(&bar_full[st]), (uint32_t)(s / kStages) & 1u, 2);
+                const int st = s % kBStages;
+                WT_WAIT(smem_u32(&bar_full[st]), (uint32_t)(s / kBStages) & 1u, 2);
                 tc_fence_after();
                 const uint32_t base = s_ring + st * kBStageBytes;
                 const uint32_t a_hi = desc_lo(base, 16), a_lo = desc_lo(base + kTileBytes, 16);
-                const uint32_t w_hi = desc_lo(base + 2 * kTileBytes, 16), w_lo = desc_lo(base + 3 * kTileBytes, 16);
-                const uint32_t c_hi = desc_lo(base + 4 * kTileBytes, 16), c_lo = desc_lo(base + 5 * kTileBytes, 16);
+                const uint32_t q_hi = desc_lo(base + 2 * kTileBytes, 16), q_lo = desc_lo(base + 3 * kTileBytes, 16);
                 if (elect_one()) {
 #pragma unroll
                     for (int ks = 0; ks < kKC / 8; ++ks) {
                         const uint32_t o = (uint32_t)(ks * 2);
-                        const uint32_t acc = (kc > 0 || ks > 0) ? 1u : 0u;
-                        umma_ss<true>(dS, a_hi + o, kHi, w_hi + o, kHi, idesc, acc);
-                        umma_ss<true>(dS, a_hi + o, kHi, w_lo + o, kHi, idesc, 1u);
-                        umma_ss<true>(dS, a_lo + o, kHi, w_hi + o, kHi, idesc, 1u);
-                        umma_ss<true>(dV, a_hi + o, kHi, c_hi + o, kHi, idesc, acc);
-                        umma_ss<true>(dV, a_hi + o, kHi, c_lo + o, kHi, idesc, 1u);
-                        umma_ss<true>(dV, a_lo + o, kHi, c_hi + o, kHi, idesc, 1u);
+                        umma_ss<true>(dT, a_hi + o, kHi, q_hi + o, kHi, idesc, (kc > 0 || ks > 0) ? 1u : 0u);
+                        umma_ss<true>(dT, a_hi + o, kHi, q_lo + o, kHi, idesc, 1u);
+                        umma_ss<true>(dT, a_lo + o, kHi, q_hi + o, kHi, idesc, 1u);
                     }
                     umma_commit(smem_u32(&bar_empty[st]));
                 }
@@ -717,12 +726,28 @@ __global__ void __launch_bounds__(kWtThreads, 1)
             first = (unsigned long long)__ballot_sync(0xffffffffu, f0) | ((unsigned long long)__ballot_sync(0xffffffffu, f1) << 32);
         }
         const unsigned long long last = valid & ((first >> 1) | ~(valid >> 1));
-        constexpr float kLog2e = 1.4426950408889634f;
-        const float4* sc = scs + hf * kHalf;
 
         for (int m = 0; m < MT; ++m) {
             const bool exists = 4 * m + q < RKC;
             const int buf = m & 1;
+            const int r = 128 * m + 32 * q + lane;
+            const bool rv = r < p.R;
+            const size_t orow = ((size_t)j * p.R + r) * p.ncols + ncol0;        // this region's row of a1 / u^T / a2^T
+            // Both passes walk the 64 columns forward in 16-column pieces: a1 (written by phase A) is read from global
+            // memory and T from tensor memory in each of them, and the only state carried from the first pass to the
+            // second is one total per caption, in shared memory.  (Holding a1[64] and 64 running sums in registers spilled
+            // 500-900 bytes per thread, and with 194 KB of the SM's memory carved out for the operand ring that local
+            // memory lives in L2: long-scoreboard stalls were 42 % of the kernel's samples.)
+            const float4* a1p = reinterpret_cast<const float4*>(p.a1 + orow);
+            auto load_a1 = [&](int g0, float (&a)[16]) {
+#pragma unroll
+                for (int c4 = 0; c4 < 4; ++c4) {
+                    const float4 v4 = rv ? __ldg(a1p + (g0 >> 2) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    a[4 * c4] = v4.x; a[4 * c4 + 1] = v4.y; a[4 * c4 + 2] = v4.z; a[4 * c4 + 3] = v4.w;
+                }
+            };
+            float a1[16];
+            if (exists) load_a1(0, a1);                          // in flight while the tile's T is waited for
             WT_WAIT(smem_u32(&bar_t_full[buf]), (uint32_t)(m >> 1) & 1u, 3);
             tc_fence_after();
             if (!exists) {
@@ -730,96 +755,89 @@ __global__ void __launch_bounds__(kWtThreads, 1)
                 warp_arrive1(smem_u32(&bar_t_free[buf]), lane);
                 continue;
             }
-            const int r = 128 * m + 32 * q + lane;
-            const bool rv = r < p.R;
-            const uint32_t tS = tl + 256 * buf + hf * kHalf, tV = tS + 128;
-            // (1) a1 = softmax over the words of each caption (as the forward)
-            uint32_t rb[kHalf];
-            float a1[kHalf];
-            tmem_ld<kHalf>(tS, rb);
-            tmem_wait_ld();
-            float run = -INFINITY;
+            const uint32_t tT = tl + 128 * buf + hf * kHalf;
+            float* tot = tot_all + ew * 32 + lane;               // [caption ordinal * 256]
+            // (1) t = a1 gamma1 a2 (T - D) summed per caption -> tot; a2 goes out
+            {
+                float run = 0.f;
+                int ord = 0;
 #pragma unroll
-            for (int c = 0; c < kHalf; ++c) {
-                const float x = __uint_as_float(rb[c]);
-                run = ((first >> c) & 1ull) ? x : fmaxf(run, x);
-                a1[c] = x;
-                rb[c] = __float_as_uint(run);
+                for (int g0 = 0; g0 < kHalf; g0 += 16) {
+                    uint32_t t16[16];
+                    float an[16], ah[4], al[4];
+                    __syncwarp();                                // (the stores below are lane-dependent)
+                    tmem_ld<16>(tT + g0, t16);
+                    if (g0 + 16 < kHalf) load_a1(g0 + 16, an);   // next piece
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) {
+                        const int c = g0 + k;
+                        const float4 cs4 = scs[hf * kHalf + c];  // alpha, beta, D, 1 / Z
+                        const bool ok = rv && ((valid >> c) & 1ull);
+                        const float a2 = ok ? mma::ex2_approx((a1[k] - 1.f) * p.g1l2e) * cs4.w : 0.f;
+                        const float t = a1[k] * p.g1 * a2 * (__uint_as_float(t16[k]) - cs4.z);
+                        run = ((first >> c) & 1ull) ? t : run + t;
+                        if ((last >> c) & 1ull) {                // (block-uniform)
+                            tot[ord * 256] = run;
+                            ++ord;
+                        }
+                        split_tf32(a2, ah[k & 3], al[k & 3]);
+                        if ((k & 3) == 3 && rv) {
+                            *reinterpret_cast<float4*>(p.a2_hi + orow + c - 3) = make_float4(ah[0], ah[1], ah[2], ah[3]);
+                            *reinterpret_cast<float4*>(p.a2_lo + orow + c - 3) = make_float4(al[0], al[1], al[2], al[3]);
+                        }
+                    }
+                    if (g0 + 16 < kHalf) {
+#pragma unroll
+                        for (int k = 0; k < 16; ++k) a1[k] = an[k];
+                    }
+                }
             }
-            float seg = 0.f;
+            // (2) ds = t - a1 (sum of t over the caption), u = ds + alpha a2: the same walk again
+            {
+                float uh[4], ul[4];
+                float seg = 0.f;
+                int ord = 0;
+                load_a1(0, a1);
 #pragma unroll
-            for (int c = kHalf - 1; c >= 0; --c) {
-                seg = ((last >> c) & 1ull) ? __uint_as_float(rb[c]) : seg;
-                a1[c] = mma::ex2_approx((a1[c] - seg) * kLog2e);
-            }
-            run = 0.f;
+                for (int g0 = 0; g0 < kHalf; g0 += 16) {
+                    uint32_t t16[16];
+                    float an[16];
+                    __syncwarp();
+                    tmem_ld<16>(tT + g0, t16);
+                    if (g0 + 16 < kHalf) load_a1(g0 + 16, an);
+                    tmem_wait_ld();
 #pragma unroll
-            for (int c = 0; c < kHalf; ++c) {
-                run = ((first >> c) & 1ull) ? a1[c] : run + a1[c];
-                rb[c] = __float_as_uint(run);
-            }
-            seg = 1.f;
+                    for (int k = 0; k < 16; ++k) {
+                        const int c = g0 + k;
+                        const float4 cs4 = scs[hf * kHalf + c];
+                        const bool ok = rv && ((valid >> c) & 1ull);
+                        if ((first >> c) & 1ull) {               // (block-uniform)
+                            seg = tot[ord * 256];
+                            ++ord;
+                        }
+                        const float a2 = ok ? mma::ex2_approx((a1[k] - 1.f) * p.g1l2e) * cs4.w : 0.f;
+                        const float t = a1[k] * p.g1 * a2 * (__uint_as_float(t16[k]) - cs4.z);
+                        const float uu = ok ? t - a1[k] * seg + cs4.x * a2 : 0.f;
+                        split_tf32(uu, uh[k & 3], ul[k & 3]);
+                        if constexpr (WORDS) {           // every existing warp's regions are < RKP; zero beyond R
+                            const size_t o2 = ((size_t)j * p.ncols + ncol0 + c) * p.RKP + r;
+                            p.u2_hi[o2] = uh[k & 3];
+                            p.u2_lo[o2] = ul[k & 3];
+                        }
+                        if ((k & 3) == 3 && rv) {
+                            *reinterpret_cast<float4*>(p.u_hi + orow + c - 3) = make_float4(uh[0], uh[1], uh[2], uh[3]);
+                            *reinterpret_cast<float4*>(p.u_lo + orow + c - 3) = make_float4(ul[0], ul[1], ul[2], ul[3]);
+                        }
+                    }
+                    if (g0 + 16 < kHalf) {
 #pragma unroll
-            for (int c = kHalf - 1; c >= 0; --c) {
-                seg = ((last >> c) & 1ull) ? mma::rcp_approx(__uint_as_float(rb[c])) : seg;
-                a1[c] *= seg;
-            }
-            // (2) t = a1 gamma1 a2 (alpha S + beta V - D), running sum per caption into rb; a2 goes out
-            // u^T / a2^T rows [region][column]: this thread's region row, 16-byte pieces (staging them through shared
-            // memory into whole 64-byte row pieces per store instruction was measured: no faster - the kernel is bound by
-            // its dependent scans, not by store requests)
-            const size_t orow = ((size_t)j * p.R + r) * p.ncols + ncol0;
-            run = 0.f;
-#pragma unroll
-            for (int g0 = 0; g0 < kHalf; g0 += 16) {
-                uint32_t s16[16], v16[16];
-                float ah[4], al[4];
-                __syncwarp();                                    // (the stores below are lane-dependent)
-                tmem_ld<16>(tS + g0, s16);
-                tmem_ld<16>(tV + g0, v16);
-                tmem_wait_ld();
-#pragma unroll
-                for (int k = 0; k < 16; ++k) {
-                    const int c = g0 + k;
-                    const float4 cs4 = sc[c];                    // alpha, beta, D, 1 / Z
-                    const bool ok = rv && ((valid >> c) & 1ull);
-                    const float a2 = ok ? mma::ex2_approx((a1[c] - 1.f) * p.g1l2e) * cs4.w : 0.f;
-                    const float da2 = fmaf(cs4.x, __uint_as_float(s16[k]), cs4.y * __uint_as_float(v16[k]));
-                    const float t = a1[c] * p.g1 * a2 * (da2 - cs4.z);
-                    run = ((first >> c) & 1ull) ? t : run + t;
-                    rb[c] = __float_as_uint(run);
-                    split_tf32(a2, ah[k & 3], al[k & 3]);
-                    if ((k & 3) == 3 && rv) {
-                        *reinterpret_cast<float4*>(p.a2_hi + orow + c - 3) = make_float4(ah[0], ah[1], ah[2], ah[3]);
-                        *reinterpret_cast<float4*>(p.a2_lo + orow + c - 3) = make_float4(al[0], al[1], al[2], al[3]);
+                        for (int k = 0; k < 16; ++k) a1[k] = an[k];
                     }
                 }
             }
             tc_fence_before();
             warp_arrive1(smem_u32(&bar_t_free[buf]), lane);
-            // (3) ds = t - a1 (sum of t over the caption), u = ds + alpha a2; t is recovered from the running sums
-            float uh[4], ul[4];
-            seg = 0.f;
-#pragma unroll
-            for (int c = kHalf - 1; c >= 0; --c) {
-                const float rc = __uint_as_float(rb[c]);
-                seg = ((last >> c) & 1ull) ? rc : seg;
-                const float t = ((first >> c) & 1ull) ? rc : rc - __uint_as_float(rb[c > 0 ? c - 1 : 0]);
-                const float4 cs4 = sc[c];
-                const bool ok = rv && ((valid >> c) & 1ull);
-                const float a2 = ok ? mma::ex2_approx((a1[c] - 1.f) * p.g1l2e) * cs4.w : 0.f;
-                const float uu = ok ? t - a1[c] * seg + cs4.x * a2 : 0.f;
-                split_tf32(uu, uh[c & 3], ul[c & 3]);
-                if constexpr (WORDS) {               // every existing warp's regions are < RKP; zero beyond R
-                    const size_t o2 = ((size_t)j * p.ncols + ncol0 + c) * p.RKP + r;
-                    p.u2_hi[o2] = uh[c & 3];
-                    p.u2_lo[o2] = ul[c & 3];
-                }
-                if ((c & 3) == 0 && rv) {
-                    *reinterpret_cast<float4*>(p.u_hi + orow + c) = make_float4(uh[0], uh[1], uh[2], uh[3]);
-                    *reinterpret_cast<float4*>(p.u_lo + orow + c) = make_float4(ul[0], ul[1], ul[2], ul[3]);
-                }
-            }
             __syncwarp();
             WT_MARK(19);
         }
@@ -830,7 +848,7 @@ __global__ void __launch_bounds__(kWtThreads, 1)
     WT_MARK(21);
     if (warp == kMmaWarp) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, 512);
+        tmem_dealloc(tmem_base, 256);
     }
 }
 
@@ -1016,7 +1034,8 @@ __global__ void __launch_bounds__(256) k_wt_dwords(const float* __restrict__ par
     }
 }
 
-constexpr size_t kWtBwdSmem = (size_t)kStages * kBStageBytes + kNB * 16 + (2 * kStages + 4 + 1) * 8;
+constexpr size_t kWtBwdSmem = (size_t)kBStages * kBStageBytes + kNB * 16 + kMaxCapsPerHalf * 256 * 4 + (2 * kBStages + 4 + 1) * 8;
+static_assert(kWtBwdSmem <= 232448, "phase B: operand ring + caption totals must fit the 227 KB of one CTA");
 
 constexpr size_t kWtSmem = (size_t)kStages * kStageBytes + (size_t)kEBufs * kEBufBytes + (size_t)(kMaxChunks * kNB + kNB) * 4 +
                            (2 * kStages + 4 + kEBufs + 4 + 2) * 8;
@@ -1027,12 +1046,14 @@ struct WtLayout {
     int ncols, n_half_max, MT, RKC, RKP, RMP;
     size_t plan, cap_col, col_cap, col_T, ww, wt_hi, wt_lo, x_hi, x_lo, xt_hi, xt_lo, total;
     size_t wcp_hi, wcp_lo, scal, v_hi, v_lo, wct_hi, wct_lo, u_hi, u_lo, a2_hi, a2_lo;       // backward only
+    size_t a1;                                                                               // backward only
     size_t kap, u2_hi, u2_lo, part;                                                          // word gradients only
     int splits;
 };
 WtLayout wt_layout(int B_img, int B_cap, int nef, int R, int Lw, bool bwd = false, bool dwords = false) {
     WtLayout w{};
-    const int per_half = kHalf / Lw < 1 ? 1 : kHalf / Lw;            // captions per half block, worst case
+    int per_half = kHalf / Lw < 1 ? 1 : kHalf / Lw;                  // captions per half block, worst case
+    if (per_half > kMaxCapsPerHalf) per_half = kMaxCapsPerHalf;
     w.n_half_max = (B_cap + per_half - 1) / per_half;
     w.n_half_max += w.n_half_max & 1;                                // whole 128-column blocks
     w.ncols = w.n_half_max * kHalf;
@@ -1065,6 +1086,7 @@ WtLayout wt_layout(int B_img, int B_cap, int nef, int R, int Lw, bool bwd = fals
         w.u_lo = take((size_t)B_img * R * w.ncols * 4);
         w.a2_hi = take((size_t)B_img * R * w.ncols * 4);
         w.a2_lo = take((size_t)B_img * R * w.ncols * 4);
+        w.a1 = take((size_t)B_img * R * w.ncols * 4);
     }
     w.splits = B_img < 16 ? B_img : 16;           // image splits of the d_words GEMM (partials added in order)
     if (bwd && dwords) {
@@ -1230,6 +1252,7 @@ int words_sim_bwd_tc5(const float* img, const float* words, const int* cap_lens,
     float* u_lo = reinterpret_cast<float*>(ws + w.u_lo);
     float* a2_hi = reinterpret_cast<float*>(ws + w.a2_hi);
     float* a2_lo = reinterpret_cast<float*>(ws + w.a2_lo);
+    float* a1 = reinterpret_cast<float*>(ws + w.a1);
     float* kap = dwords ? reinterpret_cast<float*>(ws + w.kap) : nullptr;
     float* u2_hi = dwords ? reinterpret_cast<float*>(ws + w.u2_hi) : nullptr;
     float* u2_lo = dwords ? reinterpret_cast<float*>(ws + w.u2_lo) : nullptr;
@@ -1271,19 +1294,19 @@ int words_sim_bwd_tc5(const float* img, const float* words, const int* cap_lens,
     p.B_cap = B_cap; p.nef = nef; p.R = R; p.MT = w.MT; p.RKC = w.RKC;
     p.g1l2e = g1 * 1.4426950408889634f; p.g2 = g2; p.g3 = g3; p.eps = eps;
     p.d_sim = d_sim; p.cap_col = cap_col; p.scal = scal; p.v_hi = v_hi; p.v_lo = v_lo; p.wct_hi = wct_hi; p.wct_lo = wct_lo;
-    p.ncols = w.ncols; p.g1 = g1; p.kap = kap;
+    p.ncols = w.ncols; p.g1 = g1; p.kap = kap; p.a1 = a1;
     const dim3 grid(w.n_half_max / 2, B_img);
     k_words_tc5<true><<<grid, kWtThreads, kWtSmem, st>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], p);
     rc = check_launch("words_sim_bwd(tcgen05 phase A)");
     if (rc) return rc;
     WtBwdParams b{};
-    b.col_cap = col_cap; b.plan = plan; b.scal = scal; b.u_hi = u_hi; b.u_lo = u_lo; b.a2_hi = a2_hi; b.a2_lo = a2_lo;
+    b.col_cap = col_cap; b.plan = plan; b.scal = scal; b.a1 = a1; b.u_hi = u_hi; b.u_lo = u_lo; b.a2_hi = a2_hi; b.a2_lo = a2_lo;
     b.u2_hi = u2_hi; b.u2_lo = u2_lo; b.RKP = w.RKP;
     b.nef = nef; b.R = R; b.MT = w.MT; b.RKC = w.RKC; b.ncols = w.ncols; b.g1 = g1; b.g1l2e = p.g1l2e;
     if (dwords)
-        k_words_bwd_tc5<true><<<grid, kWtThreads, kWtBwdSmem, st>>>(tm[0], tm[1], tm[2], tm[3], tm[6], tm[7], b);
+        k_words_bwd_tc5<true><<<grid, kWtThreads, kWtBwdSmem, st>>>(tm[0], tm[1], tm[6], tm[7], b);
     else
-        k_words_bwd_tc5<false><<<grid, kWtThreads, kWtBwdSmem, st>>>(tm[0], tm[1], tm[2], tm[3], tm[6], tm[7], b);
+        k_words_bwd_tc5<false><<<grid, kWtThreads, kWtBwdSmem, st>>>(tm[0], tm[1], tm[6], tm[7], b);
     rc = check_launch("words_sim_bwd(tcgen05 phase B)");
     if (rc) return rc;
     WtGemmParams g{};
