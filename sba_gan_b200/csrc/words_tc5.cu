@@ -733,21 +733,21 @@ __global__ void __launch_bounds__(kWtThreads, 1)
             const int r = 128 * m + 32 * q + lane;
             const bool rv = r < p.R;
             const size_t orow = ((size_t)j * p.R + r) * p.ncols + ncol0;        // this region's row of a1 / u^T / a2^T
-            // Both passes walk the 64 columns forward in 16-column pieces: a1 (written by phase A) is read from global
-            // memory and T from tensor memory in each of them, and the only state carried from the first pass to the
-            // second is one total per caption, in shared memory.  (Holding a1[64] and 64 running sums in registers spilled
-            // 500-900 bytes per thread, and with 194 KB of the SM's memory carved out for the operand ring that local
-            // memory lives in L2: long-scoreboard stalls were 42 % of the kernel's samples.)
+            // Both passes walk the 64 columns forward: a1 (written by phase A) is read from global memory once per tile,
+            // all 16 loads in flight before the tile's T is waited for; T comes from tensor memory in 16-column pieces
+            // in each pass, and the only state carried from the first pass to the second is one total per caption, in
+            // shared memory.  (A version that also held 64 running sums in registers spilled 500-900 bytes per thread, and
+            // with 194 KB of the SM's memory carved out for the operand ring that local memory lives in L2:
+            // long-scoreboard stalls were 42 % of the kernel's samples.)
             const float4* a1p = reinterpret_cast<const float4*>(p.a1 + orow);
-            auto load_a1 = [&](int g0, float (&a)[16]) {
+            float a1[kHalf];
+            if (exists) {
 #pragma unroll
-                for (int c4 = 0; c4 < 4; ++c4) {
-                    const float4 v4 = rv ? __ldg(a1p + (g0 >> 2) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    a[4 * c4] = v4.x; a[4 * c4 + 1] = v4.y; a[4 * c4 + 2] = v4.z; a[4 * c4 + 3] = v4.w;
+                for (int c4 = 0; c4 < kHalf / 4; ++c4) {
+                    const float4 v4 = rv ? __ldcs(a1p + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    a1[4 * c4] = v4.x; a1[4 * c4 + 1] = v4.y; a1[4 * c4 + 2] = v4.z; a1[4 * c4 + 3] = v4.w;
                 }
-            };
-            float a1[16];
-            if (exists) load_a1(0, a1);                          // in flight while the tile's T is waited for
+            }
             WT_WAIT(smem_u32(&bar_t_full[buf]), (uint32_t)(m >> 1) & 1u, 3);
             tc_fence_after();
             if (!exists) {
@@ -764,18 +764,17 @@ __global__ void __launch_bounds__(kWtThreads, 1)
 #pragma unroll
                 for (int g0 = 0; g0 < kHalf; g0 += 16) {
                     uint32_t t16[16];
-                    float an[16], ah[4], al[4];
+                    float ah[4], al[4];
                     __syncwarp();                                // (the stores below are lane-dependent)
                     tmem_ld<16>(tT + g0, t16);
-                    if (g0 + 16 < kHalf) load_a1(g0 + 16, an);   // next piece
                     tmem_wait_ld();
 #pragma unroll
                     for (int k = 0; k < 16; ++k) {
                         const int c = g0 + k;
                         const float4 cs4 = scs[hf * kHalf + c];  // alpha, beta, D, 1 / Z
                         const bool ok = rv && ((valid >> c) & 1ull);
-                        const float a2 = ok ? mma::ex2_approx((a1[k] - 1.f) * p.g1l2e) * cs4.w : 0.f;
-                        const float t = a1[k] * p.g1 * a2 * (__uint_as_float(t16[k]) - cs4.z);
+                        const float a2 = ok ? mma::ex2_approx((a1[c] - 1.f) * p.g1l2e) * cs4.w : 0.f;
+                        const float t = a1[c] * p.g1 * a2 * (__uint_as_float(t16[k]) - cs4.z);
                         run = ((first >> c) & 1ull) ? t : run + t;
                         if ((last >> c) & 1ull) {                // (block-uniform)
                             tot[ord * 256] = run;
@@ -787,10 +786,6 @@ __global__ void __launch_bounds__(kWtThreads, 1)
                             *reinterpret_cast<float4*>(p.a2_lo + orow + c - 3) = make_float4(al[0], al[1], al[2], al[3]);
                         }
                     }
-                    if (g0 + 16 < kHalf) {
-#pragma unroll
-                        for (int k = 0; k < 16; ++k) a1[k] = an[k];
-                    }
                 }
             }
             // (2) ds = t - a1 (sum of t over the caption), u = ds + alpha a2: the same walk again
@@ -798,14 +793,11 @@ __global__ void __launch_bounds__(kWtThreads, 1)
                 float uh[4], ul[4];
                 float seg = 0.f;
                 int ord = 0;
-                load_a1(0, a1);
 #pragma unroll
                 for (int g0 = 0; g0 < kHalf; g0 += 16) {
                     uint32_t t16[16];
-                    float an[16];
                     __syncwarp();
                     tmem_ld<16>(tT + g0, t16);
-                    if (g0 + 16 < kHalf) load_a1(g0 + 16, an);
                     tmem_wait_ld();
 #pragma unroll
                     for (int k = 0; k < 16; ++k) {
@@ -816,9 +808,9 @@ __global__ void __launch_bounds__(kWtThreads, 1)
                             seg = tot[ord * 256];
                             ++ord;
                         }
-                        const float a2 = ok ? mma::ex2_approx((a1[k] - 1.f) * p.g1l2e) * cs4.w : 0.f;
-                        const float t = a1[k] * p.g1 * a2 * (__uint_as_float(t16[k]) - cs4.z);
-                        const float uu = ok ? t - a1[k] * seg + cs4.x * a2 : 0.f;
+                        const float a2 = ok ? mma::ex2_approx((a1[c] - 1.f) * p.g1l2e) * cs4.w : 0.f;
+                        const float t = a1[c] * p.g1 * a2 * (__uint_as_float(t16[k]) - cs4.z);
+                        const float uu = ok ? t - a1[c] * seg + cs4.x * a2 : 0.f;
                         split_tf32(uu, uh[k & 3], ul[k & 3]);
                         if constexpr (WORDS) {           // every existing warp's regions are < RKP; zero beyond R
                             const size_t o2 = ((size_t)j * p.ncols + ncol0 + c) * p.RKP + r;
@@ -829,10 +821,6 @@ __global__ void __launch_bounds__(kWtThreads, 1)
                             *reinterpret_cast<float4*>(p.u_hi + orow + c - 3) = make_float4(uh[0], uh[1], uh[2], uh[3]);
                             *reinterpret_cast<float4*>(p.u_lo + orow + c - 3) = make_float4(ul[0], ul[1], ul[2], ul[3]);
                         }
-                    }
-                    if (g0 + 16 < kHalf) {
-#pragma unroll
-                        for (int k = 0; k < 16; ++k) a1[k] = an[k];
                     }
                 }
             }
