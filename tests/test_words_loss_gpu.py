@@ -63,6 +63,8 @@ def test_matches_reference_golden(golden_dir, name):
     (3, 128, 32, 9, 9, (4.0, 5.0, 10.0)),        # maximum words
     (7, 48, 5, 3, 4, (1.0, 2.0, 3.0)),           # tiny / odd
     (9, 256, 18, 17, 17, (10.0, 5.0, 10.0)),     # sharp gamma1
+    (40, 64, 3, 5, 5, (4.0, 5.0, 10.0)),         # many short captions: more than 16 would fit a 64-column half block
+                                                 # (the packing caps it at 16: one total per caption in phase B)
 ])
 def test_vs_oracle_fp64(spec):
     B, nef, L, ih, iw, gammas = spec
