@@ -34,7 +34,10 @@ using namespace tc5;
 // development build: a barrier wait that times out records WHICH wait it was and carries on (garbage results, but the
 // kernel ends and the flags can be read: sba_dev_words_timeouts) instead of trapping
 } }  // (symbol at namespace sba scope for cudaMemcpyFromSymbol)
-namespace sba { __device__ unsigned g_wt_dbg[16]; __device__ unsigned* g_wt_host = nullptr; }
+namespace sba { __device__ unsigned g_wt_dbg[16]; __device__ unsigned* g_wt_host = nullptr;
+                __device__ unsigned long long g_wt_ns[8]; }
+#define WT_NOW() ([] { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }())
+#define WT_ACC(i, dt) atomicAdd(&sba::g_wt_ns[i], (unsigned long long)(dt))
 #define WT_MARK(i) do { if (sba::g_wt_host && (threadIdx.x & 31) == 0) atomicAdd(sba::g_wt_host + (i), 1u); } while (0)
 namespace sba { namespace {
 using namespace tc5;
@@ -50,6 +53,8 @@ __device__ __forceinline__ void wt_wait(uint32_t bar, uint32_t parity, int id) {
 #else
 #define WT_WAIT(bar, parity, id) mbar_wait(bar, parity)
 #define WT_MARK(i) ((void)0)
+#define WT_NOW() 0ull
+#define WT_ACC(i, dt) ((void)0)
 #endif
 
 constexpr int kWtThreads = 64 + 256;      // producer warp, MMA warp, 8 epilogue warps
@@ -231,6 +236,7 @@ __global__ void __launch_bounds__(kWtThreads, 1)
                 const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ CUtensorMap tm_x_lo, const WtParams p) {
     const int nb = blockIdx.x, j = blockIdx.y;
     if (2 * nb >= p.plan->n_half) return;                      // the grid is sized for the worst packing
+    [[maybe_unused]] const unsigned long long t_begin = WT_NOW();
 
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const uint32_t sbase = smem_u32(smem_raw);
@@ -478,9 +484,12 @@ __global__ void __launch_bounds__(kWtThreads, 1)
         }
 
         // ---- final epilogue: thread = word column n (the four warps whose lanes cover 0..127) ---------------------------
+        [[maybe_unused]] unsigned long long t_loop = 0, t_dfull = 0;
         if (ew < 4) {
             const int n = 32 * q + lane, ng = nb * kNB + n;
+            t_loop = WT_NOW();
             WT_WAIT(smem_u32(bar_d_full), 0u, 15);
+            t_dfull = WT_NOW();
             tc_fence_after();
             float num = 0.f, wn2 = 0.f;
             const float4* wh = reinterpret_cast<const float4*>(p.wt_hi + (size_t)ng * nef);
@@ -581,6 +590,13 @@ __global__ void __launch_bounds__(kWtThreads, 1)
                     }
                 }
             }
+        }
+        if (ew == 2 && lane == 0) {          // (q = 0 warp of the final epilogue: its tile loop is the longest)
+            const unsigned long long t_end = WT_NOW();
+            WT_ACC(BWD ? 4 : 0, 1);
+            WT_ACC(BWD ? 5 : 1, t_loop - t_begin);
+            WT_ACC(BWD ? 6 : 2, t_dfull - t_loop);
+            WT_ACC(BWD ? 7 : 3, t_end - t_dfull);
         }
         WT_MARK(22);
         tc_fence_before();
@@ -1316,6 +1332,15 @@ int words_sim_bwd_tc5(const float* img, const float* words, const int* cap_lens,
 }  // namespace sba
 
 #ifdef SBA_DEV_AIDS
+// per-CTA phase times of k_words_tc5 summed over CTAs: [count, tile loop, wait for the last G2, final epilogue] x {fwd, phase A}
+extern "C" __attribute__((visibility("default"))) void sba_dev_words_times(unsigned long long* out, int reset) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out, sba::g_wt_ns, sizeof(unsigned long long) * 8);
+    if (reset) {
+        unsigned long long z[8] = {0};
+        cudaMemcpyToSymbol(sba::g_wt_ns, z, sizeof(z));
+    }
+}
 // progress / timeout counters in mapped host memory: readable while a kernel hangs
 extern "C" __attribute__((visibility("default"))) unsigned* sba_dev_words_progress(void) {
     static unsigned* host = nullptr;
