@@ -91,7 +91,9 @@ struct WtParams {
     float* v_lo;
     float* wct_hi;             // [B_img][ncols][nef]  q = alpha w + beta wc split in tf32 hi / lo: B operand of T = X^T q in phase B
     float* wct_lo;
-    float* a1;                 // [B_img * R][ncols]   the caption softmax a1[r][n] of every pair (phase B reads it back)
+    float* a1;                 // [B_img * ncols][RKP] the caption softmax a1[n][r] of every pair (phase B reads it back;
+                               //                      regions contiguous: thread = region on both sides, coalesced)
+    int RKP;
     float* kap;                // [B_img][ncols] d|w_n| * |w_n| share of this image (beta |wc|^2), or NULL (no word gradients)
     int ncols;
     float g1;
@@ -137,10 +139,10 @@ __device__ __forceinline__ void split_tf32(float v, float& hi, float& lo) {
     lo = tf32_rna(v - hi);
 }
 
-// ---- pre-pass 2: WT hi / lo [ncols][nef] and |w_n|; one block per 8 columns, thread = channel --------------------------
+// ---- pre-pass 2: WT hi / lo / unsplit [ncols][nef] and |w_n|; one block per 8 columns, thread = channel --------------------------
 __global__ void __launch_bounds__(256) k_wt_words(const float* __restrict__ words, const int* __restrict__ col_cap,
                                                   const int* __restrict__ cap_col, float* __restrict__ wt_hi,
-                                                  float* __restrict__ wt_lo, float* __restrict__ ww,
+                                                  float* __restrict__ wt_lo, float* __restrict__ wt_f, float* __restrict__ ww,
                                                   float* __restrict__ wcp_hi, float* __restrict__ wcp_lo, int ncols, int nef,
                                                   int Lw) {
     __shared__ float red[8];
@@ -155,6 +157,7 @@ __global__ void __launch_bounds__(256) k_wt_words(const float* __restrict__ word
             split_tf32(v, hi, lo);
             wt_hi[(size_t)n * nef + c] = hi;
             wt_lo[(size_t)n * nef + c] = lo;
+            wt_f[(size_t)n * nef + c] = v;            // unsplit: the final epilogue's copy (cosine numerator, q)
             if (wcp_hi != nullptr) {                  // [nef][ncols]: B operand of the d_img GEMM's first term (backward only)
                 wcp_hi[(size_t)c * ncols + n] = hi;
                 wcp_lo[(size_t)c * ncols + n] = lo;
@@ -233,7 +236,9 @@ template <bool BWD>
 __global__ void __launch_bounds__(kWtThreads, 1)
     k_words_tc5(const __grid_constant__ CUtensorMap tm_xt_hi, const __grid_constant__ CUtensorMap tm_xt_lo,
                 const __grid_constant__ CUtensorMap tm_wt_hi, const __grid_constant__ CUtensorMap tm_wt_lo,
-                const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ CUtensorMap tm_x_lo, const WtParams p) {
+                const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ CUtensorMap tm_x_lo,
+                const __grid_constant__ CUtensorMap tm_wf, const __grid_constant__ CUtensorMap tm_q_hi,
+                const __grid_constant__ CUtensorMap tm_q_lo, const WtParams p) {
     const int nb = blockIdx.x, j = blockIdx.y;
     if (2 * nb >= p.plan->n_half) return;                      // the grid is sized for the worst packing
     [[maybe_unused]] const unsigned long long t_begin = WT_NOW();
@@ -257,7 +262,8 @@ __global__ void __launch_bounds__(kWtThreads, 1)
     // i.e. completion (k - 2) / 4 + 1 of bar_e_free[(k - 2) & 3], and saw completion (k - 2) / 4 one tile earlier.
     unsigned long long* bar_e_free = bar_e_ready + kEBufs;  // [4]
     unsigned long long* bar_d_full = bar_e_free + 4;        // [1]
-    uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(bar_d_full + 1);
+    unsigned long long* bar_w = bar_d_full + 1;             // [1] this block's W^T rows are in the (retired) operand ring
+    uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(bar_w + 1);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int nef = p.nef, MT = p.MT, RKC = p.RKC, KCH = nef / kKC;
@@ -269,6 +275,7 @@ __global__ void __launch_bounds__(kWtThreads, 1)
         for (int s = 0; s < kEBufs; ++s) mbar_init(smem_u32(&bar_e_ready[s]), 2);
         for (int s = 0; s < 4; ++s) mbar_init(smem_u32(&bar_e_free[s]), 1);
         mbar_init(smem_u32(bar_d_full), 1);
+        mbar_init(smem_u32(bar_w), 1);
         fence_barrier_init();
     }
     if (warp == kMmaWarp) tmem_alloc(smem_u32(tmem_base_s), 512);
@@ -315,6 +322,20 @@ __global__ void __launch_bounds__(kWtThreads, 1)
         }
         for (int q = 0; q < 4; ++q)
             if (4 * (MT - 1) + q < RKC) stage_g2(4 * (MT - 1) + q);
+        // The final epilogue wants this block's 128 rows of W^T (thread = column, all nef channels): read per thread from
+        // global memory that is a 16-byte piece of a different line per lane on every load (measured: 11 of a CTA's 40 us
+        // in the forward).  The operand ring is idle once its last stages have been consumed: KCH tiles of [128 rows][32
+        // channels] land there instead (nef <= 256: at most 8 x 16 KB = the ring), the same swizzled rows the MMAs read.
+        for (int st = 0; st < kStages; ++st) {
+            const int uses = (s - st + kStages - 1) / kStages;               // stages s' < s with s' % kStages == st
+            if (uses > 0) WT_WAIT(smem_u32(&bar_empty[st]), (uint32_t)(uses - 1) & 1u, 9);
+        }
+        if (elect_one()) {
+            const uint32_t full = smem_u32(bar_w);
+            mbar_expect_tx(full, (uint32_t)(KCH * kTileBytes));
+            for (int kc = 0; kc < KCH; ++kc) tma_load_2d(s_ring + kc * kTileBytes, &tm_wf, kc * kKC, nb * kNB, full);
+        }
+        __syncwarp();
     } else if (warp == kMmaWarp) {
         // ------------------------------- MMA issuer ------------------------------------------------------------------
         constexpr uint32_t kHi = desc_hi(1024, kSwizzle128B);
@@ -442,19 +463,15 @@ __global__ void __launch_bounds__(kWtThreads, 1)
                 sr[c] = __float_as_uint(run);
             }
             seg = 1.f;
-            [[maybe_unused]] float a1q[4];
+            [[maybe_unused]] float* a1o = p.a1 + ((size_t)j * p.ncols + ncol0) * p.RKP + 128 * m + 32 * q + lane;
 #pragma unroll
             for (int c = kHalf - 1; c >= 0; --c) {
                 seg = ((last >> c) & 1ull) ? mma::rcp_approx(__uint_as_float(sr[c])) : seg;
                 const float a1 = v[c] * seg;
                 // e = exp(gamma1 (a1 - 1)); padding columns and regions beyond R contribute nothing
                 v[c] = (rv && ((valid >> c) & 1ull)) ? mma::ex2_approx((a1 - 1.f) * p.g1l2e) : 0.f;
-                if constexpr (BWD) {             // phase A of the backward: a1 goes out, phase B does not recompute it
-                    a1q[c & 3] = a1;
-                    if ((c & 3) == 0 && rv)
-                        *reinterpret_cast<float4*>(p.a1 + ((size_t)j * p.R + 128 * m + 32 * q + lane) * p.ncols + ncol0 + c) =
-                            make_float4(a1q[0], a1q[1], a1q[2], a1q[3]);
-                }
+                // phase A of the backward: a1 goes out (phase B does not recompute it), one coalesced line per column
+                if constexpr (BWD) a1o[(size_t)c * p.RKP] = a1;
             }
             // column sums over this warp's 32 regions -> zp[k][column] (added in chunk order by the final epilogue)
             {
@@ -492,16 +509,17 @@ __global__ void __launch_bounds__(kWtThreads, 1)
             t_dfull = WT_NOW();
             tc_fence_after();
             float num = 0.f, wn2 = 0.f;
-            const float4* wh = reinterpret_cast<const float4*>(p.wt_hi + (size_t)ng * nef);
-            const float4* wl = reinterpret_cast<const float4*>(p.wt_lo + (size_t)ng * nef);
+            // row n of the W^T tiles in the ring: 128-byte rows in 8-row atoms, 16-byte chunks XOR-swizzled with n & 7
+            const unsigned char* wrow = smem_raw + (n >> 3) * 1024 + (n & 7) * 128;
+            WT_WAIT(smem_u32(bar_w), 0u, 8);
             for (int c0 = 0; c0 < nef; c0 += 32) {
                 uint32_t d[32];
                 tmem_ld<32>(tl + COL_D + c0, d);
                 tmem_wait_ld();
 #pragma unroll
                 for (int c4 = 0; c4 < 8; ++c4) {
-                    const float4 a = __ldg(wh + (c0 >> 2) + c4), b = __ldg(wl + (c0 >> 2) + c4);
-                    const float w[4] = {a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w};
+                    const float4 a = *reinterpret_cast<const float4*>(wrow + (c0 >> 5) * kTileBytes + ((c4 ^ (n & 7)) << 4));
+                    const float w[4] = {a.x, a.y, a.z, a.w};
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
                         const float wc = __uint_as_float(d[4 * c4 + e]);
@@ -561,19 +579,28 @@ __global__ void __launch_bounds__(kWtThreads, 1)
                 // <X_r, q_n> = alpha S[r, n] + beta V[r, n] is the whole d a2 that phase B needs - one GEMM instead of two
                 float* vh = p.v_hi + (size_t)j * nef * p.ncols + ng;
                 float* vl = p.v_lo + (size_t)j * nef * p.ncols + ng;
-                float4* th = reinterpret_cast<float4*>(p.wct_hi + ((size_t)j * p.ncols + ng) * nef);
-                float4* tlo = reinterpret_cast<float4*>(p.wct_lo + ((size_t)j * p.ncols + ng) * nef);
+                // q^T rows go out through the (retired) e chunk buffers: [128 columns][32 channels] tiles, hi and lo, in
+                // the swizzled layout of a TMA box - one tensor store per tile instead of a 16-byte piece of a different
+                // line per lane on every store; two tiles pairs alternate
+                const uint32_t qrow = (uint32_t)((n >> 3) * 1024 + (n & 7) * 128);
+                const bool issuer = ew == 0 && lane == 0;
                 __syncwarp();                    // (lane-dependent code above; tcgen05.ld is warp-collective)
                 tc_fence_after();
                 for (int c0 = 0; c0 < nef; c0 += 32) {
+                    const int kq = c0 >> 5;
+                    unsigned char* qs = g_e + (kq & 1) * kEBufBytes + qrow;           // hi tile; lo tile kTileBytes further
+                    if (kq >= 2) {                                                    // the store that last read this pair
+                        if (issuer) bulk_wait_read<1>();
+                        mma::named_bar_sync(2, 128);
+                    }
                     uint32_t d[32];
                     tmem_ld<32>(tl + COL_D + c0, d);
                     tmem_wait_ld();
 #pragma unroll
                     for (int c4 = 0; c4 < 8; ++c4) {
                         float hi[4], lo[4];
-                        const float4 a = __ldg(wh + (c0 >> 2) + c4), b = __ldg(wl + (c0 >> 2) + c4);
-                        const float w[4] = {a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w};
+                        const float4 a = *reinterpret_cast<const float4*>(wrow + (c0 >> 5) * kTileBytes + ((c4 ^ (n & 7)) << 4));
+                        const float w[4] = {a.x, a.y, a.z, a.w};
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
                             const float wc = __uint_as_float(d[4 * c4 + e]) * invZ;
@@ -585,10 +612,19 @@ __global__ void __launch_bounds__(kWtThreads, 1)
                             hi[e] = tf32_rna(qv);
                             lo[e] = tf32_rna(qv - hi[e]);
                         }
-                        th[(c0 >> 2) + c4] = make_float4(hi[0], hi[1], hi[2], hi[3]);
-                        tlo[(c0 >> 2) + c4] = make_float4(lo[0], lo[1], lo[2], lo[3]);
+                        *reinterpret_cast<float4*>(qs + ((c4 ^ (n & 7)) << 4)) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                        *reinterpret_cast<float4*>(qs + kTileBytes + ((c4 ^ (n & 7)) << 4)) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+                    }
+                    fence_proxy_async();
+                    mma::named_bar_sync(2, 128);
+                    if (issuer) {
+                        const uint32_t src = s_e + (kq & 1) * kEBufBytes;
+                        tma_store_2d(&tm_q_hi, c0, j * p.ncols + nb * kNB, src);
+                        tma_store_2d(&tm_q_lo, c0, j * p.ncols + nb * kNB, src + kTileBytes);
+                        bulk_commit();
                     }
                 }
+                if (issuer) bulk_wait<0>();          // the stores have left shared memory and landed before the CTA retires
             }
         }
         if (ew == 2 && lane == 0) {          // (q = 0 warp of the final epilogue: its tile loop is the longest)
@@ -625,7 +661,7 @@ struct WtBwdParams {
     const int* col_cap;
     const WtPlan* plan;
     const float4* scal;        // [B_img][ncols]  (alpha, beta, D, 1 / Z)
-    const float* a1;           // [B_img * R][ncols]
+    const float* a1;           // [B_img * ncols][RKP]
     float* u_hi;               // [B_img * R][ncols]  u^T and a2^T (regions = rows, columns contiguous), tf32 hi / lo:
     float* u_lo;               //                     the K-major A operands of the d_img GEMM
     float* a2_hi;
@@ -755,14 +791,11 @@ __global__ void __launch_bounds__(kWtThreads, 1)
             // shared memory.  (A version that also held 64 running sums in registers spilled 500-900 bytes per thread, and
             // with 194 KB of the SM's memory carved out for the operand ring that local memory lives in L2:
             // long-scoreboard stalls were 42 % of the kernel's samples.)
-            const float4* a1p = reinterpret_cast<const float4*>(p.a1 + orow);
+            const float* a1p = p.a1 + ((size_t)j * p.ncols + ncol0) * p.RKP + r;      // (every existing warp's r < RKP)
             float a1[kHalf];
             if (exists) {
 #pragma unroll
-                for (int c4 = 0; c4 < kHalf / 4; ++c4) {
-                    const float4 v4 = rv ? __ldcs(a1p + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    a1[4 * c4] = v4.x; a1[4 * c4 + 1] = v4.y; a1[4 * c4 + 2] = v4.z; a1[4 * c4 + 3] = v4.w;
-                }
+                for (int c = 0; c < kHalf; ++c) a1[c] = __ldcs(a1p + (size_t)c * p.RKP);
             }
             WT_WAIT(smem_u32(&bar_t_full[buf]), (uint32_t)(m >> 1) & 1u, 3);
             tc_fence_after();
@@ -1042,13 +1075,13 @@ constexpr size_t kWtBwdSmem = (size_t)kBStages * kBStageBytes + kNB * 16 + kMaxC
 static_assert(kWtBwdSmem <= 232448, "phase B: operand ring + caption totals must fit the 227 KB of one CTA");
 
 constexpr size_t kWtSmem = (size_t)kStages * kStageBytes + (size_t)kEBufs * kEBufBytes + (size_t)(kMaxChunks * kNB + kNB) * 4 +
-                           (2 * kStages + 4 + kEBufs + 4 + 2) * 8;
+                           (2 * kStages + 4 + kEBufs + 4 + 3) * 8;
 
 inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 struct WtLayout {
     int ncols, n_half_max, MT, RKC, RKP, RMP;
-    size_t plan, cap_col, col_cap, col_T, ww, wt_hi, wt_lo, x_hi, x_lo, xt_hi, xt_lo, total;
+    size_t plan, cap_col, col_cap, col_T, ww, wt_hi, wt_lo, wt_f, x_hi, x_lo, xt_hi, xt_lo, total;
     size_t wcp_hi, wcp_lo, scal, v_hi, v_lo, wct_hi, wct_lo, u_hi, u_lo, a2_hi, a2_lo;       // backward only
     size_t a1;                                                                               // backward only
     size_t kap, u2_hi, u2_lo, part;                                                          // word gradients only
@@ -1074,6 +1107,7 @@ WtLayout wt_layout(int B_img, int B_cap, int nef, int R, int Lw, bool bwd = fals
     w.ww = take((size_t)w.ncols * 4);
     w.wt_hi = take((size_t)w.ncols * nef * 4);
     w.wt_lo = take((size_t)w.ncols * nef * 4);
+    w.wt_f = take((size_t)w.ncols * nef * 4);
     w.x_hi = take((size_t)B_img * nef * w.RKP * 4);
     w.x_lo = take((size_t)B_img * nef * w.RKP * 4);
     w.xt_hi = take((size_t)B_img * w.RMP * nef * 4);
@@ -1090,7 +1124,7 @@ WtLayout wt_layout(int B_img, int B_cap, int nef, int R, int Lw, bool bwd = fals
         w.u_lo = take((size_t)B_img * R * w.ncols * 4);
         w.a2_hi = take((size_t)B_img * R * w.ncols * 4);
         w.a2_lo = take((size_t)B_img * R * w.ncols * 4);
-        w.a1 = take((size_t)B_img * R * w.ncols * 4);
+        w.a1 = take((size_t)B_img * w.ncols * w.RKP * 4);
     }
     w.splits = B_img < 16 ? B_img : 16;           // image splits of the d_words GEMM (partials added in order)
     if (bwd && dwords) {
@@ -1173,20 +1207,22 @@ int words_sim_fwd_tc5(const float* img, const float* words, const int* cap_lens,
     float* ww = reinterpret_cast<float*>(ws + w.ww);
     float* wt_hi = reinterpret_cast<float*>(ws + w.wt_hi);
     float* wt_lo = reinterpret_cast<float*>(ws + w.wt_lo);
+    float* wt_f = reinterpret_cast<float*>(ws + w.wt_f);
     float* x_hi = reinterpret_cast<float*>(ws + w.x_hi);
     float* x_lo = reinterpret_cast<float*>(ws + w.x_lo);
     float* xt_hi = reinterpret_cast<float*>(ws + w.xt_hi);
     float* xt_lo = reinterpret_cast<float*>(ws + w.xt_lo);
 
     k_wt_plan<<<1, 256, 0, st>>>(cap_lens, B_cap, Lw, cap_col, plan, col_cap, col_T, w.ncols);
-    k_wt_words<<<w.ncols / 8, 256, 0, st>>>(words, col_cap, cap_col, wt_hi, wt_lo, ww, nullptr, nullptr, w.ncols, nef, Lw);
+    k_wt_words<<<w.ncols / 8, 256, 0, st>>>(words, col_cap, cap_col, wt_hi, wt_lo, wt_f, ww, nullptr, nullptr, w.ncols, nef, Lw);
     k_wt_images<<<dim3(w.RMP / 32, nef / 32, B_img), 256, 0, st>>>(img, x_hi, x_lo, xt_hi, xt_lo, nef, R, w.RKP, w.RMP);
     add_launches(3);
     rc = check_launch("words_sim_fwd(tcgen05 pre-pass)");
     if (rc) return rc;
 
-    CUtensorMap tm[6];
-    rc = make_k128_map(&tm[0], xt_hi, (long long)B_img * w.RMP, nef, 128);
+    CUtensorMap tm[6], tm_wf;
+    rc = make_k128_map(&tm_wf, wt_f, w.ncols, nef, 128);
+    if (!rc) rc = make_k128_map(&tm[0], xt_hi, (long long)B_img * w.RMP, nef, 128);
     if (!rc) rc = make_k128_map(&tm[1], xt_lo, (long long)B_img * w.RMP, nef, 128);
     if (!rc) rc = make_k128_map(&tm[2], wt_hi, w.ncols, nef, 128);
     if (!rc) rc = make_k128_map(&tm[3], wt_lo, w.ncols, nef, 128);
@@ -1197,7 +1233,8 @@ int words_sim_fwd_tc5(const float* img, const float* words, const int* cap_lens,
     p.wt_hi = wt_hi; p.wt_lo = wt_lo; p.ww = ww; p.col_cap = col_cap; p.col_T = col_T; p.plan = plan; p.sim = sim;
     p.B_cap = B_cap; p.nef = nef; p.R = R; p.MT = w.MT; p.RKC = w.RKC;
     p.g1l2e = g1 * 1.4426950408889634f; p.g2 = g2; p.g3 = g3; p.eps = eps;
-    k_words_tc5<false><<<dim3(w.n_half_max / 2, B_img), kWtThreads, kWtSmem, st>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], p);
+    k_words_tc5<false><<<dim3(w.n_half_max / 2, B_img), kWtThreads, kWtSmem, st>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], tm_wf, tm_wf,
+                                                                                  tm_wf, p);      // (q^T maps: backward only)
     add_launches(1);
     return check_launch("words_sim_fwd(tcgen05)");
 }
@@ -1241,6 +1278,7 @@ int words_sim_bwd_tc5(const float* img, const float* words, const int* cap_lens,
     float* ww = reinterpret_cast<float*>(ws + w.ww);
     float* wt_hi = reinterpret_cast<float*>(ws + w.wt_hi);
     float* wt_lo = reinterpret_cast<float*>(ws + w.wt_lo);
+    float* wt_f = reinterpret_cast<float*>(ws + w.wt_f);
     float* x_hi = reinterpret_cast<float*>(ws + w.x_hi);
     float* x_lo = reinterpret_cast<float*>(ws + w.x_lo);
     float* xt_hi = reinterpret_cast<float*>(ws + w.xt_hi);
@@ -1263,14 +1301,15 @@ int words_sim_bwd_tc5(const float* img, const float* words, const int* cap_lens,
     float* part = dwords ? reinterpret_cast<float*>(ws + w.part) : nullptr;
 
     k_wt_plan<<<1, 256, 0, st>>>(cap_lens, B_cap, Lw, cap_col, plan, col_cap, col_T, w.ncols);
-    k_wt_words<<<w.ncols / 8, 256, 0, st>>>(words, col_cap, cap_col, wt_hi, wt_lo, ww, wcp_hi, wcp_lo, w.ncols, nef, Lw);
+    k_wt_words<<<w.ncols / 8, 256, 0, st>>>(words, col_cap, cap_col, wt_hi, wt_lo, wt_f, ww, wcp_hi, wcp_lo, w.ncols, nef, Lw);
     k_wt_images<<<dim3(w.RMP / 32, nef / 32, B_img), 256, 0, st>>>(img, x_hi, x_lo, xt_hi, xt_lo, nef, R, w.RKP, w.RMP);
     add_launches(3);
     rc = check_launch("words_sim_bwd(tcgen05 pre-pass)");
     if (rc) return rc;
 
-    CUtensorMap tm[18];
-    rc = make_k128_map(&tm[0], xt_hi, (long long)B_img * w.RMP, nef, 128);
+    CUtensorMap tm[18], tm_wf;
+    rc = make_k128_map(&tm_wf, wt_f, w.ncols, nef, 128);
+    if (!rc) rc = make_k128_map(&tm[0], xt_hi, (long long)B_img * w.RMP, nef, 128);
     if (!rc) rc = make_k128_map(&tm[1], xt_lo, (long long)B_img * w.RMP, nef, 128);
     if (!rc) rc = make_k128_map(&tm[2], wt_hi, w.ncols, nef, 128);
     if (!rc) rc = make_k128_map(&tm[3], wt_lo, w.ncols, nef, 128);
@@ -1298,9 +1337,9 @@ int words_sim_bwd_tc5(const float* img, const float* words, const int* cap_lens,
     p.B_cap = B_cap; p.nef = nef; p.R = R; p.MT = w.MT; p.RKC = w.RKC;
     p.g1l2e = g1 * 1.4426950408889634f; p.g2 = g2; p.g3 = g3; p.eps = eps;
     p.d_sim = d_sim; p.cap_col = cap_col; p.scal = scal; p.v_hi = v_hi; p.v_lo = v_lo; p.wct_hi = wct_hi; p.wct_lo = wct_lo;
-    p.ncols = w.ncols; p.g1 = g1; p.kap = kap; p.a1 = a1;
+    p.ncols = w.ncols; p.g1 = g1; p.kap = kap; p.a1 = a1; p.RKP = w.RKP;
     const dim3 grid(w.n_half_max / 2, B_img);
-    k_words_tc5<true><<<grid, kWtThreads, kWtSmem, st>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], p);
+    k_words_tc5<true><<<grid, kWtThreads, kWtSmem, st>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], tm_wf, tm[6], tm[7], p);
     rc = check_launch("words_sim_bwd(tcgen05 phase A)");
     if (rc) return rc;
     WtBwdParams b{};
