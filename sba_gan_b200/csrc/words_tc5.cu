@@ -656,7 +656,8 @@ __global__ void __launch_bounds__(kWtThreads, 1)
 // the CUDA-core kernel of words_loss.cu materialises the same u / a2).
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int kBStageBytes = 4 * kTileBytes;      // A hi, A lo, q hi, q lo: 64 KB
-constexpr int kBStages = 3;
+constexpr int kBStages = 2;
+constexpr int kBStageF4 = 2 * 32 * 8;             // float4 per epilogue warp: 32 columns of 32 regions, hi and lo (8 KB)
 struct WtBwdParams {
     const int* col_cap;
     const WtPlan* plan;
@@ -685,7 +686,8 @@ __global__ void __launch_bounds__(kWtThreads, 1)
     const uint32_t s_ring = sbase;
     float4* scs = reinterpret_cast<float4*>(smem_raw + kBStages * kBStageBytes);        // [128] per-column scalars
     float* tot_all = reinterpret_cast<float*>(scs + kNB);                               // [16 captions][256 epilogue threads]
-    unsigned long long* bars = reinterpret_cast<unsigned long long*>(tot_all + kMaxCapsPerHalf * 256);
+    float4* stg_all = reinterpret_cast<float4*>(tot_all + kMaxCapsPerHalf * 256);       // [8 warps][hi, lo][32 regions][8 x float4]
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(stg_all + 8 * kBStageF4);
     unsigned long long* bar_full = bars;                   // [kBStages]
     unsigned long long* bar_empty = bars + kBStages;       // [kBStages]
     unsigned long long* bar_t_full = bars + 2 * kBStages;  // [2]  T of a region tile is complete
@@ -784,7 +786,6 @@ __global__ void __launch_bounds__(kWtThreads, 1)
             const int buf = m & 1;
             const int r = 128 * m + 32 * q + lane;
             const bool rv = r < p.R;
-            const size_t orow = ((size_t)j * p.R + r) * p.ncols + ncol0;        // this region's row of a1 / u^T / a2^T
             // Both passes walk the 64 columns forward: a1 (written by phase A) is read from global memory once per tile,
             // all 16 loads in flight before the tile's T is waited for; T comes from tensor memory in 16-column pieces
             // in each pass, and the only state carried from the first pass to the second is one total per caption, in
@@ -806,6 +807,31 @@ __global__ void __launch_bounds__(kWtThreads, 1)
             }
             const uint32_t tT = tl + 128 * buf + hf * kHalf;
             float* tot = tot_all + ew * 32 + lane;               // [caption ordinal * 256]
+            // u^T / a2^T rows [region][column]: thread = region, so a thread's own row is a 16-byte piece of a different line
+            // per lane on every store.  32 columns of the warp's 32 regions are staged (float4 slots XOR-swizzled with
+            // region & 7: conflict-free both ways) and leave as whole 128-byte row pieces, four rows per store instruction.
+            float4* stg = stg_all + ew * kBStageF4;
+            const int r_base = 128 * m + 32 * q;
+            const size_t obase = ((size_t)j * p.R + r_base) * p.ncols + ncol0;
+            auto stage4 = [&](int c, const float (&h)[4], const float (&l)[4]) {      // columns c - 3 .. c of this lane's region
+                const int slot = lane * 8 + ((((c & 31) >> 2)) ^ (lane & 7));
+                stg[slot] = make_float4(h[0], h[1], h[2], h[3]);
+                stg[256 + slot] = make_float4(l[0], l[1], l[2], l[3]);
+            };
+            auto flush32 = [&](float* __restrict__ dst_hi, float* __restrict__ dst_lo, int col0) {
+                __syncwarp();
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int row = 4 * i + (lane >> 3), k4 = lane & 7;
+                    if (r_base + row < p.R) {
+                        const int slot = row * 8 + (k4 ^ (row & 7));
+                        const size_t o = obase + (size_t)row * p.ncols + col0 + 4 * k4;
+                        *reinterpret_cast<float4*>(dst_hi + o) = stg[slot];
+                        *reinterpret_cast<float4*>(dst_lo + o) = stg[256 + slot];
+                    }
+                }
+                __syncwarp();                                    // read out before the next 32 columns are staged
+            };
             // (1) t = a1 gamma1 a2 (T - D) summed per caption -> tot; a2 goes out
             {
                 float run = 0.f;
@@ -830,11 +856,9 @@ __global__ void __launch_bounds__(kWtThreads, 1)
                             ++ord;
                         }
                         split_tf32(a2, ah[k & 3], al[k & 3]);
-                        if ((k & 3) == 3 && rv) {
-                            *reinterpret_cast<float4*>(p.a2_hi + orow + c - 3) = make_float4(ah[0], ah[1], ah[2], ah[3]);
-                            *reinterpret_cast<float4*>(p.a2_lo + orow + c - 3) = make_float4(al[0], al[1], al[2], al[3]);
-                        }
+                        if ((k & 3) == 3) stage4(c, ah, al);
                     }
+                    if (g0 & 16) flush32(p.a2_hi, p.a2_lo, g0 - 16);
                 }
             }
             // (2) ds = t - a1 (sum of t over the caption), u = ds + alpha a2: the same walk again
@@ -866,11 +890,9 @@ __global__ void __launch_bounds__(kWtThreads, 1)
                             p.u2_hi[o2] = uh[k & 3];
                             p.u2_lo[o2] = ul[k & 3];
                         }
-                        if ((k & 3) == 3 && rv) {
-                            *reinterpret_cast<float4*>(p.u_hi + orow + c - 3) = make_float4(uh[0], uh[1], uh[2], uh[3]);
-                            *reinterpret_cast<float4*>(p.u_lo + orow + c - 3) = make_float4(ul[0], ul[1], ul[2], ul[3]);
-                        }
+                        if ((k & 3) == 3) stage4(c, uh, ul);
                     }
+                    if (g0 & 16) flush32(p.u_hi, p.u_lo, g0 - 16);
                 }
             }
             tc_fence_before();
@@ -1071,8 +1093,9 @@ __global__ void __launch_bounds__(256) k_wt_dwords(const float* __restrict__ par
     }
 }
 
-constexpr size_t kWtBwdSmem = (size_t)kBStages * kBStageBytes + kNB * 16 + kMaxCapsPerHalf * 256 * 4 + (2 * kBStages + 4 + 1) * 8;
-static_assert(kWtBwdSmem <= 232448, "phase B: operand ring + caption totals must fit the 227 KB of one CTA");
+constexpr size_t kWtBwdSmem = (size_t)kBStages * kBStageBytes + kNB * 16 + kMaxCapsPerHalf * 256 * 4 + 8 * kBStageF4 * 16 +
+                              (2 * kBStages + 4 + 1) * 8;
+static_assert(kWtBwdSmem <= 232448, "phase B: operand ring + caption totals + output staging must fit the 227 KB of one CTA");
 
 constexpr size_t kWtSmem = (size_t)kStages * kStageBytes + (size_t)kEBufs * kEBufBytes + (size_t)(kMaxChunks * kNB + kNB) * 4 +
                            (2 * kStages + 4 + kEBufs + 4 + 3) * 8;
