@@ -89,8 +89,9 @@ struct WtParams {
     float4* scal;              // [B_img][ncols] (alpha = d num, beta = d|wc| / |wc|, D = sum_r a2 da2, 1 / Z)
     float* v_hi;               // [B_img][nef][ncols]  beta * wc split in tf32 hi / lo: B operand of the d_img GEMM's second term
     float* v_lo;
-    float* wct_hi;             // [B_img][ncols][nef]  q = alpha w + beta wc split in tf32 hi / lo: B operand of T = X^T q in phase B
-    float* wct_lo;
+    float* qt_hi;              // [B_img][ncols][nef]  q^T, q = alpha w + beta wc, in tf32 hi / lo: B operand of T = X^T q in phase B (written
+                               //                      by TMA stores: the struct keeps the pointers for reference only)
+    float* qt_lo;
     float* a1;                 // [B_img * ncols][RKP] the caption softmax a1[n][r] of every pair (phase B reads it back;
                                //                      regions contiguous: thread = region on both sides, coalesced)
     int RKP;
@@ -1105,7 +1106,7 @@ inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
 struct WtLayout {
     int ncols, n_half_max, MT, RKC, RKP, RMP;
     size_t plan, cap_col, col_cap, col_T, ww, wt_hi, wt_lo, wt_f, x_hi, x_lo, xt_hi, xt_lo, total;
-    size_t wcp_hi, wcp_lo, scal, v_hi, v_lo, wct_hi, wct_lo, u_hi, u_lo, a2_hi, a2_lo;       // backward only
+    size_t wcp_hi, wcp_lo, scal, v_hi, v_lo, qt_hi, qt_lo, u_hi, u_lo, a2_hi, a2_lo;       // backward only
     size_t a1;                                                                               // backward only
     size_t kap, u2_hi, u2_lo, part;                                                          // word gradients only
     int splits;
@@ -1141,8 +1142,8 @@ WtLayout wt_layout(int B_img, int B_cap, int nef, int R, int Lw, bool bwd = fals
         w.scal = take((size_t)B_img * w.ncols * 16);
         w.v_hi = take((size_t)B_img * nef * w.ncols * 4);
         w.v_lo = take((size_t)B_img * nef * w.ncols * 4);
-        w.wct_hi = take((size_t)B_img * w.ncols * nef * 4);
-        w.wct_lo = take((size_t)B_img * w.ncols * nef * 4);
+        w.qt_hi = take((size_t)B_img * w.ncols * nef * 4);
+        w.qt_lo = take((size_t)B_img * w.ncols * nef * 4);
         w.u_hi = take((size_t)B_img * R * w.ncols * 4);
         w.u_lo = take((size_t)B_img * R * w.ncols * 4);
         w.a2_hi = take((size_t)B_img * R * w.ncols * 4);
@@ -1265,7 +1266,7 @@ int words_sim_fwd_tc5(const float* img, const float* words, const int* cap_lens,
 size_t words_tc5_bwd_workspace_bytes(int B_img, int B_cap, int nef, int R, int Lw, bool need_words) {
     if (!words_tc5_supports(B_img, B_cap, nef, R, Lw)) return 0;
     const WtLayout w = wt_layout(B_img, B_cap, nef, R, Lw, true, need_words);
-    if ((long long)B_img * w.ncols >= (1ll << 31) / 2) return 0;       // TMA row coordinates of wc^T
+    if ((long long)B_img * w.ncols >= (1ll << 31) / 2) return 0;       // TMA row coordinates of q^T
     return w.total;
 }
 
@@ -1311,8 +1312,8 @@ int words_sim_bwd_tc5(const float* img, const float* words, const int* cap_lens,
     float4* scal = reinterpret_cast<float4*>(ws + w.scal);
     float* v_hi = reinterpret_cast<float*>(ws + w.v_hi);
     float* v_lo = reinterpret_cast<float*>(ws + w.v_lo);
-    float* wct_hi = reinterpret_cast<float*>(ws + w.wct_hi);
-    float* wct_lo = reinterpret_cast<float*>(ws + w.wct_lo);
+    float* qt_hi = reinterpret_cast<float*>(ws + w.qt_hi);
+    float* qt_lo = reinterpret_cast<float*>(ws + w.qt_lo);
     float* u_hi = reinterpret_cast<float*>(ws + w.u_hi);
     float* u_lo = reinterpret_cast<float*>(ws + w.u_lo);
     float* a2_hi = reinterpret_cast<float*>(ws + w.a2_hi);
@@ -1338,8 +1339,8 @@ int words_sim_bwd_tc5(const float* img, const float* words, const int* cap_lens,
     if (!rc) rc = make_k128_map(&tm[3], wt_lo, w.ncols, nef, 128);
     if (!rc) rc = make_k128_map(&tm[4], x_hi, (long long)B_img * nef, w.RKP, nef);
     if (!rc) rc = make_k128_map(&tm[5], x_lo, (long long)B_img * nef, w.RKP, nef);
-    if (!rc) rc = make_k128_map(&tm[6], wct_hi, (long long)B_img * w.ncols, nef, 128);
-    if (!rc) rc = make_k128_map(&tm[7], wct_lo, (long long)B_img * w.ncols, nef, 128);
+    if (!rc) rc = make_k128_map(&tm[6], qt_hi, (long long)B_img * w.ncols, nef, 128);
+    if (!rc) rc = make_k128_map(&tm[7], qt_lo, (long long)B_img * w.ncols, nef, 128);
     // the d_img GEMM: A = u^T / a2^T [B_img * R][ncols] (tiles of 128 regions; rows past the last image read as zero),
     // B = wcp [nef][ncols] and v [B_img * nef][ncols]
     if (!rc) rc = make_k128_map(&tm[8], u_hi, (long long)B_img * R, w.ncols, 128);
@@ -1359,7 +1360,7 @@ int words_sim_bwd_tc5(const float* img, const float* words, const int* cap_lens,
     p.wt_hi = wt_hi; p.wt_lo = wt_lo; p.ww = ww; p.col_cap = col_cap; p.col_T = col_T; p.plan = plan; p.sim = nullptr;
     p.B_cap = B_cap; p.nef = nef; p.R = R; p.MT = w.MT; p.RKC = w.RKC;
     p.g1l2e = g1 * 1.4426950408889634f; p.g2 = g2; p.g3 = g3; p.eps = eps;
-    p.d_sim = d_sim; p.cap_col = cap_col; p.scal = scal; p.v_hi = v_hi; p.v_lo = v_lo; p.wct_hi = wct_hi; p.wct_lo = wct_lo;
+    p.d_sim = d_sim; p.cap_col = cap_col; p.scal = scal; p.v_hi = v_hi; p.v_lo = v_lo; p.qt_hi = qt_hi; p.qt_lo = qt_lo;
     p.ncols = w.ncols; p.g1 = g1; p.kap = kap; p.a1 = a1; p.RKP = w.RKP;
     const dim3 grid(w.n_half_max / 2, B_img);
     k_words_tc5<true><<<grid, kWtThreads, kWtSmem, st>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], tm_wf, tm[6], tm[7], p);
