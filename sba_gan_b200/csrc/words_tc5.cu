@@ -688,7 +688,8 @@ __global__ void __launch_bounds__(kWtThreads, 1)
     float4* scs = reinterpret_cast<float4*>(smem_raw + kBStages * kBStageBytes);        // [128] per-column scalars
     float* tot_all = reinterpret_cast<float*>(scs + kNB);                               // [16 captions][256 epilogue threads]
     float4* stg_all = reinterpret_cast<float4*>(tot_all + kMaxCapsPerHalf * 256);       // [8 warps][hi, lo][32 regions][8 x float4]
-    unsigned long long* bars = reinterpret_cast<unsigned long long*>(stg_all + 8 * kBStageF4);
+    float* stg2_all = reinterpret_cast<float*>(stg_all + 8 * kBStageF4);                // WORDS: [8 warps][hi, lo][8 columns][32 regions]
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(stg2_all + (WORDS ? 8 * 2 * 8 * 32 : 0));
     unsigned long long* bar_full = bars;                   // [kBStages]
     unsigned long long* bar_empty = bars + kBStages;       // [kBStages]
     unsigned long long* bar_t_full = bars + 2 * kBStages;  // [2]  T of a region tile is complete
@@ -886,10 +887,24 @@ __global__ void __launch_bounds__(kWtThreads, 1)
                         const float t = a1[c] * p.g1 * a2 * (__uint_as_float(t16[k]) - cs4.z);
                         const float uu = ok ? t - a1[c] * seg + cs4.x * a2 : 0.f;
                         split_tf32(uu, uh[k & 3], ul[k & 3]);
-                        if constexpr (WORDS) {           // every existing warp's regions are < RKP; zero beyond R
-                            const size_t o2 = ((size_t)j * p.ncols + ncol0 + c) * p.RKP + r;
-                            p.u2_hi[o2] = uh[k & 3];
-                            p.u2_lo[o2] = ul[k & 3];
+                        if constexpr (WORDS) {
+                            // u again as [column][region] (the d_words GEMM's K-major operand): 8 columns of the warp's 32
+                            // regions are staged and leave as 16-byte pieces along the regions - two store instructions per
+                            // array instead of eight (every existing warp's regions are < RKP; zero beyond R)
+                            float* s2 = stg2_all + ew * 512;
+                            s2[(k & 7) * 32 + lane] = uh[k & 3];
+                            s2[256 + (k & 7) * 32 + lane] = ul[k & 3];
+                            if ((k & 7) == 7) {
+                                __syncwarp();
+#pragma unroll
+                                for (int i = 0; i < 2; ++i) {
+                                    const int cc = 4 * i + (lane >> 3), r4 = (lane & 7) * 4;
+                                    const size_t o2 = ((size_t)j * p.ncols + ncol0 + c - 7 + cc) * p.RKP + r_base + r4;
+                                    *reinterpret_cast<float4*>(p.u2_hi + o2) = *reinterpret_cast<const float4*>(s2 + cc * 32 + r4);
+                                    *reinterpret_cast<float4*>(p.u2_lo + o2) = *reinterpret_cast<const float4*>(s2 + 256 + cc * 32 + r4);
+                                }
+                                __syncwarp();
+                            }
                         }
                         if ((k & 3) == 3) stage4(c, uh, ul);
                     }
@@ -1095,7 +1110,7 @@ __global__ void __launch_bounds__(256) k_wt_dwords(const float* __restrict__ par
 }
 
 constexpr size_t kWtBwdSmem = (size_t)kBStages * kBStageBytes + kNB * 16 + kMaxCapsPerHalf * 256 * 4 + 8 * kBStageF4 * 16 +
-                              (2 * kBStages + 4 + 1) * 8;
+                              8 * 2 * 8 * 32 * 4 /* WORDS: u2 staging */ + (2 * kBStages + 4 + 1) * 8;
 static_assert(kWtBwdSmem <= 232448, "phase B: operand ring + caption totals + output staging must fit the 227 KB of one CTA");
 
 constexpr size_t kWtSmem = (size_t)kStages * kStageBytes + (size_t)kEBufs * kEBufBytes + (size_t)(kMaxChunks * kNB + kNB) * 4 +
