@@ -87,8 +87,6 @@ struct WtParams {
     const float* d_sim;        // [B_img][B_cap]
     const int* cap_col;        // [B_cap] first column of each caption
     float4* scal;              // [B_img][ncols] (alpha = d num, beta = d|wc| / |wc|, D = sum_r a2 da2, 1 / Z)
-    float* v_hi;               // [B_img][nef][ncols]  beta * wc split in tf32 hi / lo: B operand of the d_img GEMM's second term
-    float* v_lo;
     float* qt_hi;              // [B_img][ncols][nef]  q^T, q = alpha w + beta wc, in tf32 hi / lo: B operand of T = X^T q in phase B (written
                                //                      by TMA stores: the struct keeps the pointers for reference only)
     float* qt_lo;
@@ -211,8 +209,9 @@ __global__ void __launch_bounds__(256) k_wt_images(const float* __restrict__ img
     }
 }
 
-// fp32 K-major operand tiles: rows of 32 floats (128 bytes), standard 128-byte swizzle
-int make_k128_map(CUtensorMap* out, const void* base, long long rows, int cols, int box_rows);
+// fp32 K-major operand tiles: rows of 32 floats (128 bytes), standard 128-byte swizzle; mn32 = true: [32 rows][32 floats]
+// boxes in the 32-byte-atom flavour of the 128-byte swizzle, the layout of a 32-bit MN-major UMMA operand
+int make_k128_map(CUtensorMap* out, const void* base, long long rows, int cols, int box_rows, bool mn32 = false);
 
 // lane l ends with the sum over lanes of v[l] in v[0] (31 shuffles)
 __device__ __forceinline__ void reduce_scatter32_sum(float (&v)[32], int lane) {
@@ -575,11 +574,9 @@ __global__ void __launch_bounds__(kWtThreads, 1)
                 }
                 p.scal[(size_t)j * p.ncols + ng] = make_float4(alpha, beta, D, invZ);
                 if (p.kap != nullptr) p.kap[(size_t)j * p.ncols + ng] = beta * wn * wn;      // = d_den |w| |wc| (losses.py:17)
-                // second pass over wc: v = beta wc in tf32 hi / lo (rows = channels: consecutive threads write consecutive columns) and
-                // q^T = alpha w + beta wc split into tf32 hi / lo (this thread's row, 128 contiguous bytes per chunk):
-                // <X_r, q_n> = alpha S[r, n] + beta V[r, n] is the whole d a2 that phase B needs - one GEMM instead of two
-                float* vh = p.v_hi + (size_t)j * nef * p.ncols + ng;
-                float* vl = p.v_lo + (size_t)j * nef * p.ncols + ng;
+                // second pass over wc: q^T = alpha w + beta wc split into tf32 hi / lo (this thread's row, 128 contiguous
+                // bytes per chunk): <X_r, q_n> = alpha S[r, n] + beta V[r, n] is the whole d a2 that phase B needs - one GEMM
+                // instead of two - and d_img = sum_n dS[r, n] w_n + sum_n a2[n, r] q_n needs no other per-image operand
                 // q^T rows go out through the (retired) e chunk buffers: [128 columns][32 channels] tiles, hi and lo, in
                 // the swizzled layout of a TMA box - one tensor store per tile instead of a 16-byte piece of a different
                 // line per lane on every store; two tiles pairs alternate
@@ -605,10 +602,6 @@ __global__ void __launch_bounds__(kWtThreads, 1)
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
                             const float wc = __uint_as_float(d[4 * c4 + e]) * invZ;
-                            float bh, bl;
-                            split_tf32(beta * wc, bh, bl);
-                            vh[(size_t)(c0 + 4 * c4 + e) * p.ncols] = bh;
-                            vl[(size_t)(c0 + 4 * c4 + e) * p.ncols] = bl;
                             const float qv = fmaf(alpha, w[e], beta * wc);
                             hi[e] = tf32_rna(qv);
                             lo[e] = tf32_rna(qv - hi[e]);
@@ -885,15 +878,17 @@ __global__ void __launch_bounds__(kWtThreads, 1)
                         }
                         const float a2 = ok ? mma::ex2_approx((a1[c] - 1.f) * p.g1l2e) * cs4.w : 0.f;
                         const float t = a1[c] * p.g1 * a2 * (__uint_as_float(t16[k]) - cs4.z);
-                        const float uu = ok ? t - a1[c] * seg + cs4.x * a2 : 0.f;
-                        split_tf32(uu, uh[k & 3], ul[k & 3]);
+                        const float dsv = ok ? t - a1[c] * seg : 0.f;                // d S[r, n]: the d_img GEMM's first term
+                        split_tf32(dsv, uh[k & 3], ul[k & 3]);
                         if constexpr (WORDS) {
+                            float u2h, u2l;                                          // u = ds + alpha a2: the d_words GEMM's operand
+                            split_tf32(ok ? dsv + cs4.x * a2 : 0.f, u2h, u2l);
                             // u again as [column][region] (the d_words GEMM's K-major operand): 8 columns of the warp's 32
                             // regions are staged and leave as 16-byte pieces along the regions - two store instructions per
                             // array instead of eight (every existing warp's regions are < RKP; zero beyond R)
                             float* s2 = stg2_all + ew * 512;
-                            s2[(k & 7) * 32 + lane] = uh[k & 3];
-                            s2[256 + (k & 7) * 32 + lane] = ul[k & 3];
+                            s2[(k & 7) * 32 + lane] = u2h;
+                            s2[256 + (k & 7) * 32 + lane] = u2l;
                             if ((k & 7) == 7) {
                                 __syncwarp();
 #pragma unroll
@@ -956,7 +951,7 @@ __global__ void __launch_bounds__(kGThreads, 1)
     k_words_dimg_tc5(const __grid_constant__ CUtensorMap tm_u_hi, const __grid_constant__ CUtensorMap tm_u_lo,
                      const __grid_constant__ CUtensorMap tm_a2_hi, const __grid_constant__ CUtensorMap tm_a2_lo,
                      const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
-                     const __grid_constant__ CUtensorMap tm_v_hi, const __grid_constant__ CUtensorMap tm_v_lo,
+                     const __grid_constant__ CUtensorMap tm_qmn_hi, const __grid_constant__ CUtensorMap tm_qmn_lo,
                      const WtGemmParams p) {
     const int m = blockIdx.x, j = blockIdx.y;           // WORDS: m = column block, j = split
     if (WORDS && 2 * m >= p.plan->n_half) return;
@@ -1006,29 +1001,43 @@ __global__ void __launch_bounds__(kGThreads, 1)
                     const int kc = (second ? s - KCH : s) * kKC;
                     tma_load_2d(dst, second ? &tm_a2_hi : &tm_u_hi, kc, j * p.R + m * 128, full);
                     tma_load_2d(dst + kTileBytes, second ? &tm_a2_lo : &tm_u_lo, kc, j * p.R + m * 128, full);
-                    tma_load_2d(dst + 2 * kTileBytes, second ? &tm_v_hi : &tm_w_hi, kc, second ? j * nef : 0, full);
-                    tma_load_2d(dst + 2 * kTileBytes + kGBTileBytes, second ? &tm_v_lo : &tm_w_lo, kc, second ? j * nef : 0, full);
+                    if (!second) {
+                        tma_load_2d(dst + 2 * kTileBytes, &tm_w_hi, kc, 0, full);
+                        tma_load_2d(dst + 2 * kTileBytes + kGBTileBytes, &tm_w_lo, kc, 0, full);
+                    } else {
+                        // q^T rows [32 columns n][32 channels] per box: the MN-major form of the [channel][column] operand
+                        for (int cb = 0; cb < nef / 32; ++cb) {
+                            tma_load_2d(dst + 2 * kTileBytes + cb * 4096, &tm_qmn_hi, cb * 32, j * p.ncols + kc, full);
+                            tma_load_2d(dst + 2 * kTileBytes + kGBTileBytes + cb * 4096, &tm_qmn_lo, cb * 32, j * p.ncols + kc, full);
+                        }
+                    }
                 }
             }
             __syncwarp();
         }
     } else if (warp == kMmaWarp) {
-        constexpr uint32_t kHi = desc_hi(1024, kSwizzle128B);
-        const uint32_t idesc = make_idesc(2, 0, 0, 128, nef);
+        constexpr uint32_t kHi = desc_hi(1024, kSwizzle128B), kMnHi = desc_hi(512, kSwizzle128B_Base32B);
+        const uint32_t idesc = make_idesc(2, 0, 0, 128, nef), idesc_mn = make_idesc(2, 0, 1, 128, nef);
         for (int s = 0; s < NS; ++s) {
             const int st = s % kStages;
             mbar_wait(smem_u32(&bar_full[st]), (uint32_t)(s / kStages) & 1u);
             tc_fence_after();
             const uint32_t base = sbase + st * kGStageBytes;
             const uint32_t a_hi = desc_lo(base, 16), a_lo = desc_lo(base + kTileBytes, 16);
-            const uint32_t b_hi = desc_lo(base + 2 * kTileBytes, 16), b_lo = desc_lo(base + 2 * kTileBytes + kGBTileBytes, 16);
+            // B: K-major [channel][32 columns] tiles (wcp; X in the d_words mode), or - second term of d_img - q^T boxes
+            // [32 columns][32 channels] as an MN-major operand: 4096 bytes between the 32-channel boxes, 4-row atoms of
+            // 512 bytes, 8 rows (one k-step) = 1024 bytes
+            const bool mn = !WORDS && s >= KCH;
+            const uint32_t lbo = mn ? 4096u : 16u;
+            const uint32_t b_hi = desc_lo(base + 2 * kTileBytes, lbo), b_lo = desc_lo(base + 2 * kTileBytes + kGBTileBytes, lbo);
+            const uint32_t kBh = mn ? kMnHi : kHi, id = mn ? idesc_mn : idesc, bstep = mn ? 64u : 2u;
             if (elect_one()) {
 #pragma unroll
                 for (int ks = 0; ks < kKC / 8; ++ks) {
-                    const uint32_t o = (uint32_t)(ks * 2);
-                    umma_ss<true>(tmem_base, a_hi + o, kHi, b_hi + o, kHi, idesc, (s > 0 || ks > 0) ? 1u : 0u);
-                    umma_ss<true>(tmem_base, a_hi + o, kHi, b_lo + o, kHi, idesc, 1u);
-                    umma_ss<true>(tmem_base, a_lo + o, kHi, b_hi + o, kHi, idesc, 1u);
+                    const uint32_t o = (uint32_t)(ks * 2), ob = (uint32_t)ks * bstep;
+                    umma_ss<true>(tmem_base, a_hi + o, kHi, b_hi + ob, kBh, id, (s > 0 || ks > 0) ? 1u : 0u);
+                    umma_ss<true>(tmem_base, a_hi + o, kHi, b_lo + ob, kBh, id, 1u);
+                    umma_ss<true>(tmem_base, a_lo + o, kHi, b_hi + ob, kBh, id, 1u);
                 }
                 umma_commit(smem_u32(&bar_empty[st]));
             }
@@ -1121,7 +1130,7 @@ inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
 struct WtLayout {
     int ncols, n_half_max, MT, RKC, RKP, RMP;
     size_t plan, cap_col, col_cap, col_T, ww, wt_hi, wt_lo, wt_f, x_hi, x_lo, xt_hi, xt_lo, total;
-    size_t wcp_hi, wcp_lo, scal, v_hi, v_lo, qt_hi, qt_lo, u_hi, u_lo, a2_hi, a2_lo;       // backward only
+    size_t wcp_hi, wcp_lo, scal, qt_hi, qt_lo, u_hi, u_lo, a2_hi, a2_lo;       // backward only
     size_t a1;                                                                               // backward only
     size_t kap, u2_hi, u2_lo, part;                                                          // word gradients only
     int splits;
@@ -1155,8 +1164,6 @@ WtLayout wt_layout(int B_img, int B_cap, int nef, int R, int Lw, bool bwd = fals
         w.wcp_hi = take((size_t)nef * w.ncols * 4);
         w.wcp_lo = take((size_t)nef * w.ncols * 4);
         w.scal = take((size_t)B_img * w.ncols * 16);
-        w.v_hi = take((size_t)B_img * nef * w.ncols * 4);
-        w.v_lo = take((size_t)B_img * nef * w.ncols * 4);
         w.qt_hi = take((size_t)B_img * w.ncols * nef * 4);
         w.qt_lo = take((size_t)B_img * w.ncols * nef * 4);
         w.u_hi = take((size_t)B_img * R * w.ncols * 4);
@@ -1179,7 +1186,7 @@ WtLayout wt_layout(int B_img, int B_cap, int nef, int R, int Lw, bool bwd = fals
 }  // namespace
 
 namespace {
-int make_k128_map(CUtensorMap* out, const void* base, long long rows, int cols, int box_rows) {
+int make_k128_map(CUtensorMap* out, const void* base, long long rows, int cols, int box_rows, bool mn32) {
     typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -1199,8 +1206,8 @@ int make_k128_map(CUtensorMap* out, const void* base, long long rows, int cols, 
     const cuuint32_t box[2] = {(cuuint32_t)kKC, (cuuint32_t)box_rows};
     const cuuint32_t estr[2] = {1, 1};
     CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim, gstride, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, mn32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled failed (CUresult %d) for a %lld x %d fp32 operand, box %d x %d", (int)r, rows, cols,
                   box_rows, kKC);
@@ -1325,8 +1332,6 @@ int words_sim_bwd_tc5(const float* img, const float* words, const int* cap_lens,
     float* wcp_hi = reinterpret_cast<float*>(ws + w.wcp_hi);
     float* wcp_lo = reinterpret_cast<float*>(ws + w.wcp_lo);
     float4* scal = reinterpret_cast<float4*>(ws + w.scal);
-    float* v_hi = reinterpret_cast<float*>(ws + w.v_hi);
-    float* v_lo = reinterpret_cast<float*>(ws + w.v_lo);
     float* qt_hi = reinterpret_cast<float*>(ws + w.qt_hi);
     float* qt_lo = reinterpret_cast<float*>(ws + w.qt_lo);
     float* u_hi = reinterpret_cast<float*>(ws + w.u_hi);
@@ -1357,15 +1362,15 @@ int words_sim_bwd_tc5(const float* img, const float* words, const int* cap_lens,
     if (!rc) rc = make_k128_map(&tm[6], qt_hi, (long long)B_img * w.ncols, nef, 128);
     if (!rc) rc = make_k128_map(&tm[7], qt_lo, (long long)B_img * w.ncols, nef, 128);
     // the d_img GEMM: A = u^T / a2^T [B_img * R][ncols] (tiles of 128 regions; rows past the last image read as zero),
-    // B = wcp [nef][ncols] and v [B_img * nef][ncols]
+    // B = wcp [nef][ncols] and q^T [B_img * ncols][nef] (MN-major)
     if (!rc) rc = make_k128_map(&tm[8], u_hi, (long long)B_img * R, w.ncols, 128);
     if (!rc) rc = make_k128_map(&tm[9], u_lo, (long long)B_img * R, w.ncols, 128);
     if (!rc) rc = make_k128_map(&tm[10], a2_hi, (long long)B_img * R, w.ncols, 128);
     if (!rc) rc = make_k128_map(&tm[11], a2_lo, (long long)B_img * R, w.ncols, 128);
     if (!rc) rc = make_k128_map(&tm[12], wcp_hi, nef, w.ncols, nef);
     if (!rc) rc = make_k128_map(&tm[13], wcp_lo, nef, w.ncols, nef);
-    if (!rc) rc = make_k128_map(&tm[14], v_hi, (long long)B_img * nef, w.ncols, nef);
-    if (!rc) rc = make_k128_map(&tm[15], v_lo, (long long)B_img * nef, w.ncols, nef);
+    if (!rc) rc = make_k128_map(&tm[14], qt_hi, (long long)B_img * w.ncols, nef, 32, true);      // q^T again, MN-major boxes
+    if (!rc) rc = make_k128_map(&tm[15], qt_lo, (long long)B_img * w.ncols, nef, 32, true);
     if (dwords) {
         if (!rc) rc = make_k128_map(&tm[16], u2_hi, (long long)B_img * w.ncols, w.RKP, 128);
         if (!rc) rc = make_k128_map(&tm[17], u2_lo, (long long)B_img * w.ncols, w.RKP, 128);
@@ -1375,7 +1380,7 @@ int words_sim_bwd_tc5(const float* img, const float* words, const int* cap_lens,
     p.wt_hi = wt_hi; p.wt_lo = wt_lo; p.ww = ww; p.col_cap = col_cap; p.col_T = col_T; p.plan = plan; p.sim = nullptr;
     p.B_cap = B_cap; p.nef = nef; p.R = R; p.MT = w.MT; p.RKC = w.RKC;
     p.g1l2e = g1 * 1.4426950408889634f; p.g2 = g2; p.g3 = g3; p.eps = eps;
-    p.d_sim = d_sim; p.cap_col = cap_col; p.scal = scal; p.v_hi = v_hi; p.v_lo = v_lo; p.qt_hi = qt_hi; p.qt_lo = qt_lo;
+    p.d_sim = d_sim; p.cap_col = cap_col; p.scal = scal; p.qt_hi = qt_hi; p.qt_lo = qt_lo;
     p.ncols = w.ncols; p.g1 = g1; p.kap = kap; p.a1 = a1; p.RKP = w.RKP;
     const dim3 grid(w.n_half_max / 2, B_img);
     k_words_tc5<true><<<grid, kWtThreads, kWtSmem, st>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], tm_wf, tm[6], tm[7], p);
@@ -1392,7 +1397,7 @@ int words_sim_bwd_tc5(const float* img, const float* words, const int* cap_lens,
     rc = check_launch("words_sim_bwd(tcgen05 phase B)");
     if (rc) return rc;
     WtGemmParams g{};
-    g.plan = plan; g.d_img = d_img; g.nef = nef; g.R = R;
+    g.plan = plan; g.d_img = d_img; g.nef = nef; g.R = R; g.ncols = w.ncols;
     k_words_dimg_tc5<false><<<dim3(w.MT, B_img), kGThreads, kWtGemmSmem, st>>>(tm[8], tm[9], tm[10], tm[11], tm[12], tm[13],
                                                                                 tm[14], tm[15], g);
     add_launches(3);
